@@ -1,0 +1,222 @@
+/* ls1b200.h -- C ABI of libls1b200.so: the B200-native short-range force path of ls1-MarDyn.
+ *
+ * This is the drop-in boundary. Every entry point below replaces one host-side call of the reference's
+ * time-step loop (Simulation::simulateOneTimestep, /root/reference/src/Simulation.cpp:1076-1300); the
+ * reference-side binding (a ParticleContainer / Integrator adapter compiled against ls1's headers) is shown in
+ * INTEGRATION.md. All "file:line" citations are relative to the reference tree (/root/reference).
+ *
+ * Conventions
+ *   - plain C types only; every function returns 0 on success, non-zero on error; the message is available
+ *     through ls1b200_last_error() (the reference aborts via MARDYN_EXIT -- utils/mardyn_assert.h -- the adapter
+ *     turns a non-zero return into exactly that);
+ *   - never throws, never falls back to a CPU path: without a CUDA device ls1b200_create() fails;
+ *   - one caller thread per context (the reference calls these phases from the serial master context of
+ *     simulateOneTimestep, Simulation.cpp:1104-1300); a context owns all of its device memory;
+ *   - host pointers are borrowed for the duration of a call only;
+ *   - molecule state is FP64 (as FullMolecule, molecules/FullMolecule.h:341-346), pair arithmetic is FP32 with
+ *     FP64 accumulation (LS1B200_MIXED == -DMARDYN_SPDP) or FP64 (LS1B200_DOUBLE == -DMARDYN_DPDP),
+ *     vectorization/SIMD_TYPES.h:108-110.
+ */
+#ifndef LS1B200_H
+#define LS1B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define LS1B200_ABI_VERSION 1
+
+typedef struct ls1b200_ctx ls1b200_ctx;
+
+enum { LS1B200_MIXED = 0, LS1B200_DOUBLE = 1 };
+/* How LinkedCells derives its cell length: LS1B200_GEOM_XML follows LinkedCells::rebuild (float cast of
+ * rc/cellsInCutoff, particleContainer/LinkedCells.cpp:148-166), LS1B200_GEOM_CTOR the (bBoxMin,bBoxMax,cutoff)
+ * constructor used by the reference's unit-test fixture (LinkedCells.cpp:47-58). */
+enum { LS1B200_GEOM_XML = 0, LS1B200_GEOM_CTOR = 1 };
+
+typedef struct ls1b200_config {
+	double box_min[3];      /* bounding box of THIS rank's domain (LinkedCells::_boundingBoxMin/Max)            */
+	double box_max[3];
+	double cutoff;          /* rc   (CellProcessor::_cutoffRadiusSquare = rc^2, adapter/CellProcessor.h:31)   */
+	double cutoff_lj;       /* rcLJ (CellProcessor::_LJCutoffRadiusSquare, :32); Simulation forces rc>=rcLJ  */
+	double epsilon_rf;      /* Domain::getepsilonRF(); enters dipole-dipole only (VectorizedCellProcessor.cpp:22) */
+	int32_t precision;      /* LS1B200_MIXED | LS1B200_DOUBLE                                                   */
+	int32_t geometry;       /* LS1B200_GEOM_XML | LS1B200_GEOM_CTOR                                             */
+	int32_t periodic[3];    /* 1: this rank wraps onto itself in that dimension (sequential DomainDecompBase,
+	                           parallel/DomainDecompBase.cpp:80-114); 0: no local periodic images are made --
+	                           open boundary (the unit-test fixture) or halo supplied by a neighbour rank via
+	                           ls1b200_halo_import                                                               */
+	int32_t device;         /* CUDA device ordinal                                                              */
+	int32_t reserved[4];
+} ls1b200_config;
+
+/* One Component (molecules/Component.h). Sites are listed LJ | charge | dipole | quadrupole, the order of
+ * CellDataSoA / ConcatenatedSites (utils/ConcatenatedSites.h:55-87). */
+typedef struct ls1b200_component {
+	uint32_t n_lj, n_charge, n_dipole, n_quadrupole;
+	uint32_t site_offset;   /* first row of this component in the site table                                    */
+	uint32_t lj_lookup_id;  /* Component::getLookUpID(): first row/column of this component in the LJ tables    */
+	uint32_t rot_dof;       /* Component::getRotationalDegreesOfFreedom()                                       */
+	uint32_t reserved;
+	double mass;            /* Component::m()                                                                   */
+	double inertia[3];      /* Component::I11(), I22(), I33() (principal axes)                                  */
+} ls1b200_component;
+
+/* One row of the site table: body-frame position, body-frame orientation (dipole / quadrupole; 0 otherwise) and
+ * the scalar the SoA carries for that site (charge q, |mu|, |Q|; unused for LJ), molecules/Site.h. */
+typedef struct ls1b200_site {
+	double r[3];
+	double e[3];
+	double param;
+} ls1b200_site;
+
+/* Macroscopic values of one traversal: what VectorizedCellProcessor::endTraversal hands to
+ * Domain::setLocalUpot / setLocalVirial (VectorizedCellProcessor.cpp:122-155). */
+typedef struct ls1b200_macro {
+	double upot;            /* U6_LJ/6 + U_xpoles + myRF                                                        */
+	double virial;          /* Virial + 3*myRF                                                                  */
+	double upot6lj, upot_xpoles, virial_raw, my_rf;   /* the four raw accumulators, for tests                  */
+} ls1b200_macro;
+
+/* What Leapfrog::transition2to3 hands to Domain::setLocalSummv2 / setLocalSumIw2 / setLocalNrotDOF
+ * (integrators/Leapfrog.cpp:139-143). */
+typedef struct ls1b200_kinetic {
+	double summv2;
+	double sum_iw2;
+	uint64_t n_molecules;
+	uint64_t rot_dof;
+} ls1b200_kinetic;
+
+/* Per-step record of ls1b200_simulate: the numbers of the reference's "Simstep" log line and ResultWriter
+ * (Simulation.cpp:1383-1386, io/ResultWriter.cpp:81). */
+typedef struct ls1b200_step_record {
+	double upot;        /* Domain::getGlobalUpot() (no long-range correction)                                   */
+	double virial;      /* Domain::_globalVirial   (no long-range correction)                                   */
+	double summv2, sum_iw2;
+	double temperature; /* Domain::getGlobalCurrentTemperature(), Domain.cpp:240-241                            */
+	double pressure;    /* Domain::getGlobalPressure(), Domain.cpp:142-146                                      */
+	double beta_trans, beta_rot;   /* Domain.cpp:248-252                                                        */
+} ls1b200_step_record;
+
+enum ls1b200_field {
+	LS1B200_F_ID = 0,   /* uint64 [n]                                                                           */
+	LS1B200_F_CID,      /* uint32 [n]                                                                           */
+	LS1B200_F_R,        /* double [n][3]                                                                        */
+	LS1B200_F_V,        /* double [n][3]                                                                        */
+	LS1B200_F_Q,        /* double [n][4]  (w,x,y,z)                                                             */
+	LS1B200_F_L,        /* double [n][3]  angular momentum D                                                    */
+	LS1B200_F_F,        /* double [n][3]  FullMolecule::_F after calcFM                                         */
+	LS1B200_F_M,        /* double [n][3]  FullMolecule::_M after calcFM                                         */
+	LS1B200_F_VI,       /* double [n][3]  FullMolecule::_Vi after calcFM                                        */
+	LS1B200_F_CELL,     /* uint64 [n]     LinkedCells cell index (incl. halo layer) of the molecule             */
+	LS1B200_F_COUNT
+};
+
+const char* ls1b200_last_error(void);
+int ls1b200_abi_version(void);
+/* Number of CUDA kernel launches issued by this library since load (bench.py's gpu_launches). */
+uint64_t ls1b200_kernel_launch_count(void);
+
+/* new LinkedCells + VectorizedCellProcessor + Leapfrog on one device
+ * (Simulation.cpp:484, :854, :181). */
+int ls1b200_create(const ls1b200_config* cfg, ls1b200_ctx** out);
+int ls1b200_destroy(ls1b200_ctx* ctx);
+
+/* Component list + the LJ pair tables VectorizedCellProcessor builds from Comp2Param
+ * (VectorizedCellProcessor.cpp:39-81): eps24[i*C+j] = 24*eps_ij, sig2 = sigma_ij^2, shift6 = 6*shift_ij,
+ * C = total number of LJ centres over all components. Values are FP64 and are cast to the calc type inside. */
+int ls1b200_set_components(ls1b200_ctx* ctx, uint32_t n_components, const ls1b200_component* comps,
+                           uint32_t n_sites, const ls1b200_site* sites,
+                           uint32_t n_lj_centers, const double* eps24, const double* sig2, const double* shift6);
+
+/* ParticleContainer::addParticles (ParticleContainer.h:134): replaces the molecule set. cid is 0-based.
+ * q may be NULL (identity), L may be NULL (zero). Molecules outside [box_min, box_max) are kept and treated
+ * exactly like the reference treats them at the next update (wrapped if periodic). */
+int ls1b200_upload(ls1b200_ctx* ctx, uint64_t n, const uint64_t* id, const uint32_t* cid,
+                   const double* r, const double* v, const double* q, const double* L);
+uint64_t ls1b200_num_molecules(const ls1b200_ctx* ctx);
+int ls1b200_download(ls1b200_ctx* ctx, int field, void* dst, uint64_t n);
+/* Overwrite one per-molecule field (R, V, Q, L or F, M) from host memory: the lazy host->device sync the adapter
+ * needs when a plugin modified molecules on the host. */
+int ls1b200_set_field(ls1b200_ctx* ctx, int field, const void* src, uint64_t n);
+
+/* LinkedCells geometry as the reference computes it (LinkedCells.cpp:47-58 / :148-166):
+ * cells per dimension incl. the halo layer, cell length, halo bounding box min. */
+int ls1b200_geometry(const ls1b200_ctx* ctx, int32_t cells_per_dim[3], double cell_length[3], double halo_min[3]);
+
+/* == LinkedCells::update() + DomainDecompBase::exchangeMolecules() + LinkedCells::updateMoleculeCaches()
+ * (Simulation.cpp:1417-1455): wraps leaving molecules (periodic dims), assigns every molecule to its cell
+ * bit-exactly like CellBorderAndFlagManager::getBorder (CellBorderAndFlagManager.h:134-152), creates the
+ * periodic halo copies (DomainDecompBase.cpp:317-376) and rebuilds the cell-sorted SoA. */
+int ls1b200_update(ls1b200_ctx* ctx);
+
+/* == ParticleContainer::traverseCells(VectorizedCellProcessor&) + Simulation::updateForces (calcFM)
+ * (Simulation.cpp:1161, :1178; LinkedCells.cpp:565-575; FullMolecule.cpp:548-626). Writes per-molecule F, M, Vi
+ * on the device; *out receives the macroscopic sums (may be NULL). */
+int ls1b200_traverse_cells(ls1b200_ctx* ctx, ls1b200_macro* out);
+
+/* == Leapfrog::eventNewTimestep -> transition1to2 -> upd_preF(dt) (Leapfrog.cpp:45-61, FullMolecule.cpp:331-361). */
+int ls1b200_leapfrog_pre(ls1b200_ctx* ctx, double dt);
+/* == Leapfrog::eventForcesCalculated -> transition2to3 -> upd_postF(dt/2) + sums (Leapfrog.cpp:63-147). */
+int ls1b200_leapfrog_post(ls1b200_ctx* ctx, double dt, ls1b200_kinetic* out);
+/* == VelocityScalingThermostat::apply, global variant (thermostats/VelocityScalingThermostat.cpp:68-89). */
+int ls1b200_scale_velocities(ls1b200_ctx* ctx, double beta_trans, double beta_rot);
+
+/* The whole hot path of Simulation::simulate for n_steps steps with the NVT velocity-scaling thermostat
+ * (target_temperature > 0) or NVE (<= 0), without any host round trip inside the loop:
+ *   leapfrog_pre -> update -> traverse_cells -> leapfrog_post -> Domain::calculateGlobalValues -> thermostat.
+ * Forces must be valid on entry (call ls1b200_update + ls1b200_traverse_cells once first, as
+ * Simulation::prepare_start does, Simulation.cpp:896-928). records (may be NULL) receives n_steps entries.
+ * global_n / global_volume: N and V of the whole system (for rho in p); pass 0 to use this context's own. */
+int ls1b200_simulate(ls1b200_ctx* ctx, uint64_t n_steps, double dt, double target_temperature,
+                     uint64_t global_n, double global_volume, ls1b200_step_record* records);
+
+/* ---- multi-GPU: 3D spatial decomposition (replaces parallel/DomainDecomposition.cpp + CommunicationPartner) ----
+ * The transport is the caller's (NCCL send/recv of the packed device buffers, or MPI in ls1); the library packs and
+ * unpacks on the device. Message layout: ls1b200_particle records (== ParticleDataFull, 13 doubles + id + cid,
+ * parallel/ParticleDataFull.h:30-35). */
+typedef struct ls1b200_particle {
+	uint64_t id;
+	uint32_t cid;
+	uint32_t flags;         /* bit0: 1 = halo copy (not owned by the receiver), 0 = leaving molecule (ownership moves) */
+	double r[3], v[3], q[4], L[3];
+} ls1b200_particle;
+
+/* Collects into a device buffer the molecules that have to go to the neighbour in direction dir[3] in {-1,0,1}^3
+ * (leaving molecules and halo copies, positions already shifted by shift[3] for periodic wrap); leaving molecules
+ * are removed from this context. Returns the device pointer and count. The buffer stays valid until the next call
+ * for the same direction. == DomainDecompMPIBase::exchangeMoleculesMPI(LEAVING_AND_HALO_COPIES), send side. */
+int ls1b200_halo_export(ls1b200_ctx* ctx, const int32_t dir[3], const double shift[3],
+                        void** device_buf, uint64_t* count);
+/* Receive side: adds leaving molecules as owned ones and halo copies as halo molecules for the next
+ * ls1b200_update (which must then be called with rebuild of the sorted SoA). device_buf is device memory. */
+int ls1b200_halo_import(ls1b200_ctx* ctx, const void* device_buf, uint64_t count);
+/* Same, from host memory (tests, MPI without GPU-direct). */
+int ls1b200_halo_import_host(ls1b200_ctx* ctx, const ls1b200_particle* host_buf, uint64_t count);
+
+/* ---- measurement helpers (bench.py) ---- */
+/* Device time (ms) spent in each phase since the last reset, measured with CUDA events on the library's stream:
+ * [0] update (binning+halo+SoA), [1] force kernels, [2] leapfrog pre, [3] leapfrog post + reductions. */
+int ls1b200_phase_times(ls1b200_ctx* ctx, double ms[4], uint64_t launches[4], int reset);
+/* Counts of the reference's FlopCounter for the current configuration (adapter/FlopCounter.cpp:20-74):
+ * molecule-distance evaluations and in-range pairs per potential, Newton-3 counting (each pair once). */
+typedef struct ls1b200_flopcount {
+	double mol_dist;        /* candidate molecule pairs the C08 traversal evaluates                             */
+	double lj, charge, charge_dipole, dipole, charge_quadrupole, dipole_quadrupole, quadrupole; /* site pairs   */
+	double lj_macro, charge_macro, charge_dipole_macro, dipole_macro, charge_quadrupole_macro,
+	       dipole_quadrupole_macro, quadrupole_macro;
+	double flops;           /* the FlopCounter total                                                            */
+} ls1b200_flopcount;
+int ls1b200_count_flops(ls1b200_ctx* ctx, ls1b200_flopcount* out);
+/* FP32 FMA micro-benchmark on this device: returns TFLOP/s (2 flops per FMA), the denominator of the
+ * "% of FP32 pair-rate peak" metric (MEASURED_PEAKS.json has no FP32 figure). */
+int ls1b200_measure_fp32_peak(int device, double* tflops);
+int ls1b200_measure_hbm_copy(int device, double* gbs);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* LS1B200_H */

@@ -1,0 +1,71 @@
+#!/usr/bin/env bash
+# Builds the UNMODIFIED ls1-MarDyn reference (sources where they lie under $LS1_REF, default
+# /root/reference) into oracle/_ref/<precision>/ with plain g++ -- no cmake, no copies of sources.
+# Test infrastructure only: the product (ls1_mardyn_b200) never links or runs anything built here.
+#
+#   oracle/_ref/mixed/MarDyn    PRECISION=MIXED  (-DMARDYN_SPDP), AVX2+FMA, OpenMP
+#   oracle/_ref/double/MarDyn   PRECISION=DOUBLE (-DMARDYN_DPDP), AVX2+FMA, OpenMP
+#   oracle/_ref/<prec>/refdump  our dump driver (oracle/refdump.cpp) linked against the same objects
+#
+# The source list mirrors what the reference's CMakeLists select for ENABLE_MPI=OFF, ENABLE_ADIOS2=OFF,
+# ENABLE_VTK=OFF, ENABLE_AUTOPAS=OFF, ENABLE_UNIT_TESTS=OFF, OPENMP=ON, VECTOR_INSTRUCTIONS=AVX2
+# (src/CMakeLists.txt and src/*/CMakeLists.txt; flags from cmake/modules/{options,vectorization,OpenMP}.cmake).
+set -euo pipefail
+HERE="$(cd "$(dirname "$0")" && pwd)"
+REF="${LS1_REF:-/root/reference}"
+PRECS="${1:-mixed double}"
+JOBS="${JOBS:-$(nproc)}"
+CXX="${REF_CXX:-/usr/bin/g++}"   # NB: /opt/gcc/bin/g++ (env CXX in this image) lacks libgomp.spec
+[ -d "$REF/src" ] || { echo "build_ref: $REF/src not found (reference absent) -- nothing to do"; exit 0; }
+
+MPI_ONLY="CommunicationBuffer CommunicationPartner DomainDecompMPIBase DomainDecomposition GeneralDomainDecomposition \
+KDDecomposition KDDStaticValues KDNode MPIKDNode NeighborAcquirer NeighbourCommunicationScheme NonBlockingMPIHandlerBase \
+NonBlockingMPIMultiStepHandler ParticleDataFull ParticleDataRMM ParticleForceData ResilienceComm \
+StaticIrregDomainDecomposition ALLLoadBalancer"
+
+list_sources() {
+  ( cd "$REF/src" && find . -name '*.cpp' \
+      ! -path '*/tests/*' ! -path './io/vtk/*' ! -path './bhfmm/fft/*' \
+      ! -path '*/AutoPasTemplateInstantiations/*' ! -name 'AutoPas*.cpp' ! -name 'Adios2*.cpp' \
+      | sed 's|^\./||' | sort ) | while read -r f; do
+        b="$(basename "$f" .cpp)"; skip=0
+        case "$f" in parallel/*) for m in $MPI_ONLY; do [ "$b" = "$m" ] && skip=1; done;; esac
+        [ $skip = 0 ] && echo "$f"
+      done
+}
+
+for prec in $PRECS; do
+  case "$prec" in
+    mixed)  PDEF=-DMARDYN_SPDP;;
+    double) PDEF=-DMARDYN_DPDP;;
+    *) echo "unknown precision $prec"; exit 2;;
+  esac
+  OUT="$HERE/_ref/$prec"; OBJ="$OUT/obj"; mkdir -p "$OBJ" "$OUT/gen"
+  # generated header (cmake's configure_file of src/MarDyn_version.h.in): written here, not copied
+  cat > "$OUT/gen/MarDyn_version.h" <<H
+#pragma once
+#include <string>
+const std::string MARDYN_VERSION = "1.2.0_oracle_ref_$prec";
+H
+  FLAGS="-std=c++17 -O3 -DNDEBUG -fopenmp -DENABLE_OPENMP -fopenmp-simd -mavx2 -mfma -DENABLE_VECTORIZED_CODE=1 \
+$PDEF -DTIMERS -w -I$OUT/gen -I$REF/src -I$REF/libs/rapidxml -I$REF/libs"
+  MK="$OUT/Makefile.gen"
+  { echo "CXX=$CXX"; echo "FLAGS=$FLAGS"; echo "OBJS="; } > "$MK"
+  for f in $(list_sources); do
+    o="$OBJ/$(echo "$f" | tr '/' '_' | sed 's/\.cpp$/.o/')"
+    echo "OBJS+=$o" >> "$MK"
+    printf '%s: %s\n\t@$(CXX) $(FLAGS) -c $< -o $@\n' "$o" "$REF/src/$f" >> "$MK"
+  done
+  cat >> "$MK" <<M
+LIBOBJS=\$(filter-out %/MarDyn.o,\$(OBJS))
+all: $OUT/MarDyn $OUT/refdump
+$OUT/MarDyn: \$(OBJS)
+	@\$(CXX) -fopenmp \$(OBJS) -o \$@
+$OUT/refdump.o: $HERE/refdump.cpp
+	@\$(CXX) \$(FLAGS) -c \$< -o \$@
+$OUT/refdump: \$(LIBOBJS) $OUT/refdump.o
+	@\$(CXX) -fopenmp \$(LIBOBJS) $OUT/refdump.o -o \$@
+M
+  if [ -f "$HERE/refdump.cpp" ]; then make -f "$MK" -j"$JOBS" all; else make -f "$MK" -j"$JOBS" "$OUT/MarDyn"; fi
+  echo "build_ref: built $OUT/MarDyn"
+done

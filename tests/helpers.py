@@ -1,0 +1,80 @@
+"""Shared helpers of the parity tests: golden-fixture loading and the comparison rule of SURVEY.md A.1."""
+from __future__ import annotations
+
+import glob
+import os
+
+import numpy as np
+
+from ls1_mardyn_b200.components import Ensemble
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+# north_star tolerances: 1e-10 relative in the double build, 1e-5 relative in the mixed build
+TOL = {"double": 1e-10, "mixed": 1e-5}
+
+
+# Fixtures whose forces are a near-total cancellation (r = r_min: F ~ 4e-8 from terms of order 24): compared
+# against the magnitude of the terms, like the reference's absolute tolerance (VectorizedCellProcessorTest.cpp:126-131).
+ABS_SCALE = {"force_ForceCalculationTestF0": 1.0}
+
+
+def golden_names(prefix):
+    return sorted(os.path.basename(p)[:-4] for p in glob.glob(os.path.join(GOLD, prefix + "*.npz")))
+
+
+def load(name):
+    g = dict(np.load(os.path.join(GOLD, name + ".npz")))
+    g["ensemble"] = Ensemble.from_arrays(g)
+    return g
+
+
+def rel_close(a, b, tol, scale=None):
+    """|a-b| <= tol * max(|b|, scale) elementwise; scale defaults to the RMS of b."""
+    a = np.asarray(a, dtype=np.float64); b = np.asarray(b, dtype=np.float64)
+    if scale is None:
+        scale = float(np.sqrt(np.mean(b * b))) if b.size else 0.0
+    bound = tol * np.maximum(np.abs(b), scale)
+    err = np.abs(a - b)
+    bad = err > bound
+    worst = float((err / np.maximum(bound, 1e-300)).max()) if err.size else 0.0
+    return (not bad.any()), worst
+
+
+def make_sim(cls, g, precision, tables_from_ref=False, **kw):
+    """Builds a simulation object (OracleSim or the CUDA Context wrapper -- same constructor) for golden case g."""
+    mode = str(g["mode"]); geom = str(g["geom"])
+    per = (1, 1, 1) if mode == "periodic" else (0, 0, 0)
+    sim = cls([0.0, 0.0, 0.0], list(g["length"]), float(g["cutoff"]), epsilon_rf=float(g["epsilon_rf"]),
+              precision=precision, geometry=geom, periodic=per, **kw)
+    tables = None
+    if tables_from_ref:
+        tables = (g["double_eps24"], g["double_sig2"], g["double_shift6"])
+    sim.set_components(g["ensemble"], tables)
+    sim.upload(g["in_id"], g["in_cid"], g["in_r"], g["in_v"], g["in_q"], g["in_L"])
+    return sim
+
+
+def ref_by_id(g, tag):
+    """Reference per-molecule outputs of the NON-halo records, ordered like the input ids."""
+    ids = g[f"{tag}_mol_id"]; halo = g[f"{tag}_mol_halo"].astype(bool)
+    sel = ~halo
+    order = {int(i): k for k, i in enumerate(ids[sel])}
+    idx = np.array([order[int(i)] for i in g["in_id"]])
+    out = {}
+    for k in ("F", "M", "Vi", "cell", "r"):
+        out[k] = g[f"{tag}_mol_{k}"][sel][idx]
+    return out
+
+
+def macro_close(m, g, tag, ref, abs_scale=None, tol=None):
+    """Upot / Virial of one traversal against the reference's Domain::getLocalUpot/Virial. The bound is relative to
+    the larger of |value| and the sum of per-molecule |Vi| (the magnitude of the terms that were summed)."""
+    tol = TOL[tag] if tol is None else tol
+    terms = float(np.abs(ref["Vi"]).sum())
+    for mine, theirs in ((m.upot, float(g[f"{tag}_upot"])), (m.virial, float(g[f"{tag}_virial"]))):
+        bound = tol * max(abs(theirs), terms, abs_scale or 0.0)
+        if not abs(mine - theirs) <= bound:
+            print("macro mismatch", mine, theirs, bound)
+            return False
+    return True

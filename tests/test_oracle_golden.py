@@ -1,0 +1,86 @@
+"""Pins the CPU oracle (oracle/oracle.cpp) against golden vectors produced by the unmodified reference
+(tests/golden/make_golden.py). Mirrors the reference's own VectorizedCellProcessorTest cases
+(src/particleContainer/adapter/tests/VectorizedCellProcessorTest.cpp:45-388)."""
+import numpy as np
+import pytest
+
+from helpers import ABS_SCALE, TOL, macro_close, golden_names, load, make_sim, ref_by_id, rel_close
+from oracle import oracle as orc
+
+FORCE = golden_names("force_")
+PERIODIC = golden_names("periodic_")
+
+
+def test_known_answers_U0_F0():
+    """testForcePotentialCalculationU0 / F0 (VectorizedCellProcessorTest.cpp:45-134): 4 LJ molecules on a square."""
+    g = load("force_ForceCalculationTestU0")
+    for prec, tol in (("double", 1e-8), ("mixed", 1e-4)):
+        s = make_sim(orc.OracleSim, g, prec); s.update(); m = s.traverse_cells()
+        F = s.download("F")
+        assert abs(m.upot) < tol and abs(m.virial - 96.0) < tol * 96
+        # molecule ids 1..4 at (1,1) (2,1) (1,2) (2,2): forces +-24 pointing outwards
+        expect = np.array([[-24, -24, 0], [24, -24, 0], [-24, 24, 0], [24, 24, 0]], dtype=float)
+        assert np.allclose(F, expect, atol=tol * 24)
+    g = load("force_ForceCalculationTestF0")
+    for prec, tol in (("double", 1e-8), ("mixed", 1e-4)):
+        s = make_sim(orc.OracleSim, g, prec); s.update(); m = s.traverse_cells()
+        assert abs(m.upot + 4.0) < tol * 4 and np.abs(s.download("F")).max() < max(tol, 1e-7)
+
+
+@pytest.mark.parametrize("name", FORCE + PERIODIC)
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_forces_vs_reference(name, prec):
+    g = load(name)
+    s = make_sim(orc.OracleSim, g, prec)
+    s.update()
+    m = s.traverse_cells()
+    ref = ref_by_id(g, prec)
+    tol = TOL[prec]
+    # bit-exact binning
+    assert np.array_equal(s.download("CELL"), ref["cell"]), "cell assignment differs"
+    for k, fld in (("F", "F"), ("M", "M"), ("Vi", "VI")):
+        ok, worst = rel_close(s.download(fld), ref[k], tol, ABS_SCALE.get(name))
+        assert ok, f"{name} {prec} {k}: worst err/bound = {worst:.3g}"
+    assert macro_close(m, g, prec, ref, ABS_SCALE.get(name))
+
+
+@pytest.mark.parametrize("name", FORCE)
+def test_vcp_vs_legacy_reference(name):
+    """The reference's own differential test: VectorizedCellProcessor (double) vs LegacyCellProcessor + potforce.h."""
+    g = load(name)
+    a, b = ref_by_id(g, "double"), ref_by_id(g, "legacy")
+    for k in ("F", "M", "Vi"):
+        assert np.allclose(a[k], b[k], atol=1e-11, rtol=0)
+
+
+@pytest.mark.parametrize("name", FORCE + PERIODIC)
+def test_lj_tables_and_components(name):
+    """Comp2Param / Component: both our host mirror (Ensemble.lj_tables) and the oracle's C++ restatement
+    against the parameter streams of the reference."""
+    g = load(name)
+    ens = g["ensemble"]
+    rc = float(g["cutoff"])
+    for tabs in (ens.lj_tables(rc), orc.lj_tables(ens, rc)):
+        for t, k in zip(tabs, ("eps24", "sig2", "shift6")):
+            assert np.allclose(t, g["double_" + k], rtol=1e-15, atol=0), k
+    cc, cs, ns = ens.pack()
+    ref = g["double_comp_ref"]
+    for i in range(len(ens.components)):
+        assert np.isclose(cc[i].mass, ref[i, 0], rtol=1e-15)
+        assert np.allclose(list(cc[i].inertia), ref[i, 1:4], rtol=1e-15, atol=0)
+        assert cc[i].rot_dof == int(ref[i, 4])
+
+
+@pytest.mark.parametrize("name", PERIODIC)
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_halo_copies_vs_reference(name, prec):
+    """DomainDecompBase::populateHaloLayerWithCopies: same multiset of (id, cell, position) halo records."""
+    g = load(name)
+    s = make_sim(orc.OracleSim, g, prec); s.update()
+    owner, r, cell = s.halo()
+    ids = g["in_id"][owner]
+    mine = sorted(zip(ids.tolist(), cell.tolist(), map(tuple, r.tolist())))
+    h = g[f"{prec}_mol_halo"].astype(bool)
+    theirs = sorted(zip(g[f"{prec}_mol_id"][h].tolist(), g[f"{prec}_mol_cell"][h].tolist(), map(tuple, g[f"{prec}_mol_r"][h].tolist())))
+    assert len(mine) == len(theirs)
+    assert mine == theirs
