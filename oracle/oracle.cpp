@@ -69,7 +69,10 @@ struct Geometry {
 		if (i == 1) return bmin[d];
 		if (i == cells[d] - 1) return bmax[d];
 		if (i == cells[d]) return hmax[d];
-		return i * clen[d] + hmin[d];
+		// NB: the reference binary evaluates index*_cellLength+_haloBoundingBoxMin as ONE fused multiply-add (g++ -mfma with
+		// the default -ffp-contract=fast; verified in the disassembly of ParticleCellBase::testInBox of oracle/_ref and by
+		// the golden fixture periodic_border_fma, whose molecules sit exactly on borders where fma != mul+add).
+		return std::fma((double) i, clen[d], hmin[d]);
 	}
 	// the unique i with border(i) <= x < border(i+1)  (FullParticleCell::testInBox via MoleculeInterface::inBox,
 	// molecules/MoleculeInterface.h:299-309); guess as LinkedCells.cpp:899. Returns -1 / cells if outside halo box.

@@ -118,12 +118,47 @@ def periodic():
         save_case("periodic_1clj_regular_12", read_phase_space(inp), 1.5, "periodic", "xml", inp)
 
 
+def border():
+    """Pins the cell-border arithmetic (CellBorderAndFlagManager::getBorder, one FMA in the reference binary): molecules
+    placed exactly ON, one ulp below and one ulp above every inner border, in each dimension, for borders where
+    fma(i, cellLength, haloMin) differs from i*cellLength + haloMin and for some where it does not."""
+    import math
+    from fractions import Fraction
+    from ls1_mardyn_b200.components import lj_fluid
+    L = 52.28; rc = 2.5
+    nb = int(math.floor(L / float(np.float32(rc)))); clen = L / nb; hmin = 0.0 - clen
+    vals = []
+    for i in range(2, nb + 1):
+        a = i * clen + hmin
+        f = float(Fraction(i) * Fraction(clen) + Fraction(hmin))
+        for b in {a, f}:
+            vals += [b, np.nextafter(b, -1e300), np.nextafter(b, 1e300)]
+    vals = np.array(sorted(set(vals)))
+    r = []
+    for d in range(3):
+        for k, x in enumerate(vals):
+            p = [0.0, 0.0, 0.0]
+            p[d] = x
+            p[(d + 1) % 3] = 1.3 + 1.7 * (k % 29)
+            p[(d + 2) % 3] = 1.1 + 1.7 * (k // 29) + 6.1 * d
+            r.append(p)
+    r = np.array(r); n = len(r)
+    rng = np.random.default_rng(5)
+    ps = PhaseSpace(np.array([L, L, L]), 0.85, 1e10, lj_fluid(rc=rc), np.arange(1, n + 1, dtype=np.uint64), np.zeros(n, dtype=np.uint32),
+                    r, rng.normal(size=(n, 3)), np.tile([1.0, 0, 0, 0], (n, 1)), np.zeros((n, 3)))
+    with tempfile.TemporaryDirectory() as td:
+        inp = os.path.join(td, "b.inp"); write_phase_space(inp, ps)
+        save_case("periodic_border_fma", read_phase_space(inp), rc, "periodic", "xml", inp)
+
+
 if __name__ == "__main__":
-    what = sys.argv[1:] or ["forces", "periodic", "traces"]
+    what = sys.argv[1:] or ["forces", "periodic", "border", "traces"]
     if "forces" in what:
         forces()
     if "periodic" in what:
         periodic()
+    if "border" in what:
+        border()
     if "traces" in what:
         from make_traces import traces  # noqa: E402
         traces()
