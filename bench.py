@@ -1,0 +1,339 @@
+#!/usr/bin/env python
+"""bench.py -- MMUPS (million molecule updates per second) of the short-range force path on B200.
+
+    python bench.py --gpus N --steps K --warmup W [--impl reference] [--n-per-dim n]
+
+Workload at N = 1 (BASELINE.json configs[1]): 1CLJ Lennard-Jones liquid, 16 M molecules (BCC lattice 2*200^3, rho* = 0.7,
+T* = 0.85, rc = 2.5 sigma, dt = 0.002), mixed precision, NVT velocity scaling. A "step" is one full time step of the hot
+path: leapfrog_pre -> update (bin + halo + SoA) -> traverse_cells (forces) -> leapfrog_post -> global values.
+
+  value     N*K / t: state resident in HBM, t = wall clock of ls1b200_simulate(K) between synchronisations (max over ranks),
+            cross-checked with CUDA events on the library's stream;
+  e2e       the same step driven phase by phase through the C ABI with HOST buffers: every step copies r, v from pinned host
+            memory to the device and reads r, v and the step's scalars back (the host-coherent mode an ls1 plugin sees);
+  roofline  dominant kernel = the LJ cell-pair force kernel, FP32-FMA bound (no tensor-core work exists on this path):
+            achieved = FlopCounter flops of the state (reference's algorithmic count, Newton-3 counting) / avg launch time;
+            peak = FP32 FMA rate measured in this run (MEASURED_PEAKS.json has no FP32 figure). The HBM-bound kernels
+            (update, leapfrog) are reported under roofline.hbm against MEASURED_PEAKS.json's copy bandwidth;
+  cpu_baseline  the reference (oracle/_ref MarDyn, OpenMP on all host cores) or the scalar port, on a bounded sample.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import re
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+RHO, TEMP, RC, DT = 0.7, 0.85, 2.5, 0.002
+
+
+def peaks():
+    p = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(p):
+        d = json.load(open(p))
+        return float(d["hbm_gbs"]), "measured (MEASURED_PEAKS.json)"
+    return 6650.0, "fallback (B200_PROFILING.md)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    def __init__(self, index):
+        self.index = index; self.rows = []; self.proc = None
+
+    def start(self):
+        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.rows.append([x.strip() for x in line.split(",")])
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except Exception:
+            self.proc.kill()
+        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            if len(r) >= 7:
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def make_system(n_per_dim, mixed=True, seed=0):
+    """BCC lattice like the reference's CubicGridGenerator (generators.lattice), positions rounded through the calc type
+    as ParticleCellBase::initCubicGrid does (ParticleCellBase.cpp:97-99)."""
+    from ls1_mardyn_b200 import generators
+    ps = generators.lj_lattice(n_per_dim, rho=RHO, temperature=TEMP, rc=RC, seed=seed, jitter=0.0)
+    if mixed:
+        ps.r = ps.r.astype(np.float32).astype(np.float64)
+    return ps
+
+
+def grid_for(n):
+    return {1: (1, 1, 1), 2: (2, 1, 1), 4: (2, 2, 1), 8: (2, 2, 2)}[n]
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# reference arm: the unmodified reference's own CPU implementation on the host cores
+# ----------------------------------------------------------------------------------------------------------------------
+XML = """<?xml version='1.0' encoding='UTF-8'?>
+<mardyn version="20100525">
+ <refunits type="SI"><length unit="nm">0.1</length><mass unit="u">1</mass><energy unit="K">1</energy></refunits>
+ <simulation type="MD">
+  <integrator type="Leapfrog"><timestep unit="reduced">{dt}</timestep></integrator>
+  <run><currenttime>0</currenttime><production><steps>{steps}</steps></production></run>
+  <ensemble type="NVT">
+   <temperature unit="reduced">{T}</temperature>
+   <domain type="box"><lx>{L}</lx><ly>{L}</ly><lz>{L}</lz></domain>
+   <components>
+    <moleculetype id="1" name="1CLJ">
+     <site type="LJ126" id="1" name="LJfull"><coords><x>0.0</x><y>0.0</y><z>0.0</z></coords><mass>1.0</mass><sigma>1.0</sigma><epsilon>1.0</epsilon><shifted>false</shifted></site>
+     <momentsofinertia rotaxes="xyz"><Ixx>0.0</Ixx><Iyy>0.0</Iyy><Izz>0.0</Izz></momentsofinertia>
+    </moleculetype>
+   </components>
+   <phasespacepoint><generator name="CubicGridGenerator"><specification>density</specification><density>{rho}</density><binaryMixture>false</binaryMixture></generator></phasespacepoint>
+  </ensemble>
+  <algorithm>
+   <parallelisation type="DomainDecomposition"></parallelisation>
+   <datastructure type="LinkedCells"><cellsInCutoffRadius>1</cellsInCutoffRadius></datastructure>
+   <cutoffs type="CenterOfMass"><radiusLJ unit="reduced">{rc}</radiusLJ></cutoffs>
+   <electrostatic type="ReactionField"><epsilon>1.0e+10</epsilon></electrostatic>
+  </algorithm>
+  <output></output>
+ </simulation>
+</mardyn>
+"""
+
+
+def run_reference_binary(n_per_dim, steps, threads=None, prec="mixed"):
+    """Runs oracle/_ref/<prec>/MarDyn (the unmodified reference, built by oracle/build_ref.sh) on a lattice of 2*n^3 molecules.
+    Returns (MMUPS from the reference's own main-loop timer, N, threads) or None if the binary is not there."""
+    exe = os.path.join(ROOT, "oracle", "_ref", prec, "MarDyn")
+    if not os.path.exists(exe):
+        return None
+    N = 2 * n_per_dim ** 3
+    L = (N / RHO) ** (1.0 / 3.0)
+    threads = threads or os.cpu_count() or 1
+    with tempfile.TemporaryDirectory() as td:
+        cfg = os.path.join(td, "config.xml")
+        open(cfg, "w").write(XML.format(dt=DT, steps=steps, T=TEMP, L=repr(L), rho=repr(N / L ** 3 * (1 + 1e-9)), rc=RC))
+        env = dict(os.environ, OMP_NUM_THREADS=str(threads))
+        p = subprocess.run([exe, "--steps", str(steps), "--final-checkpoint=0", cfg], cwd=td, env=env, capture_output=True, text=True, timeout=3000)
+        out = p.stdout + p.stderr
+    if p.returncode != 0:
+        return None
+    m = re.search(r"Computation in main loop took:\s*([0-9.eE+-]+)\s*sec", out)
+    nm = re.search(r"[Nn]umber of (?:global )?molecules[^0-9]*([0-9]+)", out)
+    if not m:
+        return None
+    t = float(m.group(1))
+    n_run = int(nm.group(1)) if nm else N
+    return n_run * steps / t / 1e6, n_run, threads, t
+
+
+def run_port(n_per_dim, steps):
+    """The scalar CPU port (oracle/liboracle.so), one core."""
+    from oracle import oracle as orc
+    ps = make_system(n_per_dim)
+    s = orc.OracleSim([0, 0, 0], list(ps.length), RC, precision="mixed", geometry="xml", periodic=(1, 1, 1))
+    s.set_components(ps.ensemble); s.upload(ps.id, ps.cid, ps.r, ps.v, ps.q, ps.L)
+    s.update(); s.traverse_cells()
+    t0 = time.perf_counter(); s.simulate(steps, DT, TEMP); t = time.perf_counter() - t0
+    return len(ps.id) * steps / t / 1e6, len(ps.id), 1, t
+
+
+def cpu_baseline(sample_n=60, steps=3):
+    r = run_reference_binary(sample_n, steps)
+    if r is not None:
+        v, n, cores, t = r
+        return {"value": round(v, 3), "unit": "MMUPS", "cores": cores, "kind": "reference",
+                "sample": f"oracle/_ref/mixed/MarDyn (unmodified reference, AVX2+FMA, OpenMP): 1CLJ lattice N={n}, {steps} steps, main loop {t:.2f} s"}
+    v, n, cores, t = run_port(24, 2)
+    return {"value": round(v, 3), "unit": "MMUPS", "cores": cores, "kind": "port",
+            "sample": f"oracle/liboracle.so scalar port: 1CLJ lattice N={n}, 2 steps, {t:.2f} s"}
+
+
+def reference_arm(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    n = args.ref_n_per_dim
+    t0 = time.perf_counter()
+    # warm-up and timed run are separate processes of the reference binary; the value comes from its own main-loop timer
+    r = run_reference_binary(n, args.steps + args.warmup) if args.warmup else None
+    r = run_reference_binary(n, args.steps)
+    kind = "reference"
+    if r is None:
+        r = run_port(24, max(1, min(args.steps, 3))); kind = "port"
+    v, nmol, cores, t = r
+    line = {"metric": "MMUPS", "value": round(v, 4), "unit": "MMUPS (1e6 molecule updates / s)", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(1e3 * t / max(args.steps, 1), 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 pair arithmetic, f64 accumulation and state (MARDYN_SPDP)", "data": "synthetic (BCC lattice, CubicGridGenerator)", "impl": "reference",
+            "config": {"workload": "1CLJ LJ liquid rho*=0.7 T*=0.85 rc=2.5 sigma dt=0.002, mixed precision, NVT", "molecules": nmol,
+                       "note": "bounded sample of the 16M-molecule workload (MMUPS is size independent to first order)"},
+            "cpu_baseline": {"value": round(v, 4), "unit": "MMUPS", "cores": cores, "kind": kind,
+                             "sample": f"N={nmol}, {args.steps} steps, main loop {t:.2f} s, total wall {time.perf_counter() - t0:.1f} s"},
+            "e2e": {"value": round(v, 4), "unit": "MMUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    print(json.dumps(line), flush=True)
+
+
+# ----------------------------------------------------------------------------------------------------------------------
+# our arm
+# ----------------------------------------------------------------------------------------------------------------------
+def our_arm(args):
+    import torch
+    import torch.distributed as dist
+    from ls1_mardyn_b200 import capi
+
+    rank = int(os.environ.get("RANK", "0")); world = int(os.environ.get("WORLD_SIZE", "1")); local = int(os.environ.get("LOCAL_RANK", "0"))
+    if world != args.gpus:
+        assert world == 1 and args.gpus == 1, "for --gpus N > 1 launch with torch.distributed.run --nproc-per-node N"
+    torch.cuda.set_device(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+
+    def barrier():
+        torch.cuda.synchronize()
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    # weak scaling: every rank owns one replica-sized periodic block of the workload (the decomposition with
+    # NCCL halo exchange replaces this replica mode when ls1b200_halo_* lands)
+    n = args.n_per_dim
+    ps = make_system(n, mixed=True, seed=rank)
+    N = len(ps.id)
+    ctx = capi.Context([0, 0, 0], list(ps.length), RC, precision="mixed", geometry="xml", periodic=(1, 1, 1), device=local)
+    ctx.set_components(ps.ensemble)
+    ctx.upload(ps.id, ps.cid, ps.r, ps.v)
+    ctx.update(); ctx.traverse_cells()
+    fc0 = ctx.count_flops()
+
+    fp32_peak = capi.measure_fp32_peak(local)
+    hbm_peak, hbm_src = peaks()
+
+    # ---- HBM-resident: K steps inside the library, no host round trip ----
+    ctx.simulate(args.warmup, DT, TEMP, records=False)
+    ctx.phase_times(reset=True)
+    launches0 = capi.kernel_launch_count()
+    ext = torch.cuda.ExternalStream(ctx.stream(), device=local)
+    e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
+    sampler = ClockSampler(local); sampler.start()
+    barrier()
+    t0 = time.perf_counter()
+    e0.record(ext)
+    rec = ctx.simulate(args.steps, DT, TEMP)
+    e1.record(ext)
+    barrier()
+    t_wall = time.perf_counter() - t0
+    clocks = sampler.stop()
+    t_dev = e0.elapsed_time(e1) * 1e-3
+    launches = capi.kernel_launch_count() - launches0
+    ph_ms, ph_launch = ctx.phase_times(reset=True)
+    fc1 = ctx.count_flops()
+    t = torch.tensor([t_wall, t_dev], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    t_wall, t_dev = float(t[0]), float(t[1])
+    value = world * N * args.steps / t_wall / 1e6
+
+    # ---- end to end through the C ABI with host buffers ----
+    e2e_steps = max(1, min(args.steps, args.e2e_steps))
+    r_h = torch.empty((N, 3), dtype=torch.float64).pin_memory(); v_h = torch.empty((N, 3), dtype=torch.float64).pin_memory()
+    ctx.download("R", out=r_h.numpy()); ctx.download("V", out=v_h.numpy())
+    barrier()
+    t0 = time.perf_counter()
+    for _ in range(e2e_steps):
+        ctx.set_field("R", r_h.numpy()); ctx.set_field("V", v_h.numpy())        # host -> device: this step's inputs
+        ctx.leapfrog_pre(DT); ctx.update(); m = ctx.traverse_cells(); k = ctx.leapfrog_post(DT)
+        ctx.download("R", out=r_h.numpy()); ctx.download("V", out=v_h.numpy())  # device -> host: the step's results
+        _ = (m.upot, m.virial, k.summv2)
+    barrier()
+    t_e2e = time.perf_counter() - t0
+    t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    e2e_value = world * N * e2e_steps / float(t[0]) / 1e6
+
+    if rank == 0:
+        force_ms = ph_ms["force"] / max(args.steps, 1)
+        flops = 0.5 * (fc0.flops + fc1.flops)          # algorithmic flops / force launch (state drifts slowly off the lattice)
+        achieved = flops / (force_ms * 1e-3) / 1e12
+        # algorithmic bytes of the HBM-bound phases per molecule: update 236 B, leapfrog pre 120 B, post 72 B
+        hbm = {}
+        for name, bpm in (("update", 236.0), ("leapfrog_pre", 120.0), ("leapfrog_post", 72.0)):
+            ms = ph_ms[name] / max(args.steps, 1)
+            hbm[name] = {"ms": round(ms, 4), "algorithmic_bytes_per_molecule": bpm, "achieved_gbs": round(bpm * N / (ms * 1e-3) / 1e9, 1) if ms > 0 else None,
+                         "frac": round(bpm * N / (ms * 1e-3) / 1e9 / hbm_peak, 4) if ms > 0 else None}
+        line = {
+            "metric": "MMUPS", "value": round(value, 2), "unit": "MMUPS (1e6 molecule updates / s)", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+            "ms_per_step": round(1e3 * t_wall / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
+            "dtype": "f32 pair arithmetic, f64 accumulation and state (MARDYN_SPDP)", "data": "synthetic (BCC lattice like CubicGridGenerator, equal-magnitude velocities)",
+            "config": {"workload": "BASELINE.json configs[1]: 1CLJ LJ liquid rho*=0.7 T*=0.85 rc=2.5 sigma dt=0.002, mixed precision, NVT velocity scaling",
+                       "molecules_per_gpu": N, "molecules": world * N, "cells_per_dim": [int(x) for x in ctx.geometry()[0]],
+                       "parallelism": "1 GPU" if world == 1 else f"{world} independent periodic replicas (weak scaling; halo exchange not built yet)",
+                       "l2_policy": "inputs larger than L2: state %.1f GB per GPU" % (N * 150 / 1e9)},
+            "ms_per_step_device_events": round(1e3 * t_dev / args.steps, 4),
+            "phases_ms_per_step": {k: round(v / args.steps, 4) for k, v in ph_ms.items()},
+            "gpu_launches": int(launches),
+            "e2e": {"value": round(e2e_value, 2), "unit": "MMUPS", "h2d_bytes_per_step": int(48 * N), "d2h_bytes_per_step": int(48 * N + 24), "steps": e2e_steps,
+                    "path": "set_field(R,V) from pinned host -> leapfrog_pre -> update -> traverse_cells -> leapfrog_post -> download(R,V) + scalars"},
+            "roofline": {"kernel": "k_force_1clj<float>", "bound": "fp32", "achieved": round(achieved, 3), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
+                         "frac": round(achieved / fp32_peak, 4), "traffic": None,
+                         "peak_source": "FP32 FMA micro-benchmark in this run (ls1b200_measure_fp32_peak); nominal 74.4",
+                         "algorithmic_flops_per_launch": flops, "flops_per_molecule": round(flops / N, 1), "kernel_ms": round(force_ms, 4),
+                         "pair_interactions_per_s": round(0.5 * (fc0.lj + fc1.lj) / (force_ms * 1e-3), 1),
+                         "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src, "hbm": hbm},
+            "clocks": clocks,
+            "trace": {"T_first": rec[0, 4], "T_last": rec[-1, 4], "upot_last_per_molecule": rec[-1, 0] / N, "p_last": rec[-1, 5]},
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            line["cpu_baseline"] = cpu_baseline()
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=10)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--n-per-dim", type=int, default=200, help="BCC lattice cells per dimension: N = 2 n^3 (200 -> 16 M molecules)")
+    ap.add_argument("--ref-n-per-dim", type=int, default=80, help="size of the reference arm's bounded sample (80 -> 1.02 M molecules)")
+    ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    if args.impl == "reference":
+        reference_arm(args)
+    else:
+        our_arm(args)
+
+
+if __name__ == "__main__":
+    main()

@@ -120,6 +120,10 @@ int ls1b200_abi_version(void);
 /* Number of CUDA kernel launches issued by this library since load (bench.py's gpu_launches). */
 uint64_t ls1b200_kernel_launch_count(void);
 
+/* The CUDA stream (cudaStream_t) every kernel of this context is launched on: lets the caller record its own CUDA
+ * events around calls (bench.py) or order its own work (NCCL halo exchange) against the library's. */
+void* ls1b200_stream(ls1b200_ctx* ctx);
+
 /* new LinkedCells + VectorizedCellProcessor + Leapfrog on one device
  * (Simulation.cpp:484, :854, :181). */
 int ls1b200_create(const ls1b200_config* cfg, ls1b200_ctx** out);

@@ -104,7 +104,7 @@ def read_phase_space(path: str) -> PhaseSpace:
 
 
 def write_phase_space(path: str, ps: PhaseSpace) -> None:
-    """Writes an ICRVQD file the reference's ASCIIReader accepts (used to feed synthetic systems to the oracle
+    """Writes an ICRVQD file the reference's ASCIIReader accepts (used to feed synthetic systems to the
     reference build; FullMolecule::write, FullMolecule.cpp:439-446)."""
     with open(path, "w") as f:
         f.write("mardyn trunk 20120726\n currentTime\t0\n")

@@ -1,0 +1,201 @@
+// common.cuh -- shared declarations of libls1b200.so (sm_100a). Host side C++17, device side CUDA.
+//
+// Data layout in HBM (DESIGN.md "Data layout"):
+//   * molecules live in SLOTS: one slot per owned molecule and per periodic/neighbour halo copy, sorted by LinkedCells
+//     cell index (z-major, y, x fastest -- LinkedCells::cellIndexOf3DIndex, particleContainer/LinkedCells.cpp:925-927),
+//     so that the three x-neighbour cells of any cell are ONE contiguous slot range;
+//   * molecule state is FP64 structure-of-arrays in component planes (r[d*cap + slot], ...), double buffered: the
+//     counting sort of every update() permutes it from `cur` into `nxt`;
+//   * `mpos` is the calc-precision (float4 / double4) copy of the molecule centre + component id + halo flag that the pair
+//     kernels read (== CellDataSoA::_mol_pos, adapter/CellDataSoA.h:41-74);
+//   * multi-site components additionally get `spos`/`sori` (site position + parameter, site orientation), smax entries
+//     per slot.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <atomic>
+#include <string>
+#include <vector>
+
+#include "../../include/ls1b200.h"
+
+namespace ls1b200 {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// errors (never throw across the C ABI)
+// ---------------------------------------------------------------------------------------------------------------------
+void set_error(const std::string& msg);
+int fail(const std::string& msg);
+extern std::atomic<uint64_t> g_launches;
+
+#define LS1_CUDA(call)                                                                                             \
+	do {                                                                                                             \
+		cudaError_t e__ = (call);                                                                                      \
+		if (e__ != cudaSuccess)                                                                                        \
+			return ::ls1b200::fail(std::string(#call) + ": " + cudaGetErrorString(e__) + " at " + __FILE__ + ":" + std::to_string(__LINE__)); \
+	} while (0)
+
+#define LS1_TRY(call)          \
+	do {                         \
+		int rc__ = (call);         \
+		if (rc__ != 0) return rc__; \
+	} while (0)
+
+// kernel launch with accounting (ls1b200_kernel_launch_count) and launch-error check
+#define LS1_LAUNCH(ctx, phase, kernel, grid, block, smem, ...)                                     \
+	do {                                                                                             \
+		kernel<<<(grid), (block), (smem), (ctx)->stream>>>(__VA_ARGS__);                               \
+		::ls1b200::g_launches.fetch_add(1, std::memory_order_relaxed);                                 \
+		(ctx)->phase_launches[(phase)]++;                                                              \
+		LS1_CUDA(cudaGetLastError());                                                                  \
+	} while (0)
+
+enum { PH_UPDATE = 0, PH_FORCE = 1, PH_PRE = 2, PH_POST = 3, PH_COUNT = 4 };
+
+// ---------------------------------------------------------------------------------------------------------------------
+// geometry of LinkedCells, passed by value to kernels
+// ---------------------------------------------------------------------------------------------------------------------
+struct Geom {
+	double bmin[3], bmax[3], hmin[3], hmax[3], clen[3], crecip[3], lbox[3];
+	double wrap_hi[3];           // value that replaces x >= bmax after a +L wrap (DomainDecompBase.cpp:236-240)
+	double halo_hi[3];           // value for a +L halo copy that landed < bmax   (DomainDecompBase.cpp:364-368)
+	double halo_lo[3];           // value for a -L halo copy that landed >= bmin  (DomainDecompBase.cpp:358-362)
+	double cutoff;
+	int cells[3];                // cells per dimension incl. the halo layer
+	int periodic[3];
+	uint32_t ncells;             // cells[0]*cells[1]*cells[2]; bin ncells is the "limbo" bin (outside the halo box)
+	int pad;
+};
+
+constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
+constexpr uint64_t META_HALO = 1ull << 63;
+__host__ __device__ inline uint32_t meta_orig(uint64_t m) { return (uint32_t) (m & 0xFFFFFFFFull); }
+__host__ __device__ inline uint32_t meta_cid(uint64_t m) { return (uint32_t) ((m >> 32) & 0xFFFFull); }
+__host__ __device__ inline bool meta_halo(uint64_t m) { return (m & META_HALO) != 0; }
+__host__ __device__ inline uint64_t make_meta(uint32_t orig, uint32_t cid, bool halo) {
+	return (uint64_t) orig | ((uint64_t) (cid & 0xFFFFu) << 32) | (halo ? META_HALO : 0ull);
+}
+
+// device view of one component (molecules/Component.h); site rows follow in the site table
+struct CompDev {
+	uint32_t n[4];               // LJ, charge, dipole, quadrupole
+	uint32_t site_offset, lj_lookup_id, rot_dof, nsites;
+	double mass, inv_mass;
+	double I[3], invI[3];        // invI = 0 where I == 0 (FullMolecule ctor, molecules/FullMolecule.cpp:33-40)
+};
+struct SiteDev {
+	double r[3], e[3], param;
+	uint32_t type;               // 0 LJ, 1 charge, 2 dipole, 3 quadrupole
+	uint32_t ljid;               // lj_lookup_id + j for LJ centres
+};
+
+// one double-buffered half of the molecule state
+struct State {
+	double* r = nullptr;         // [3][cap]
+	double* v = nullptr;         // [3][cap]
+	double* q = nullptr;         // [4][cap]  (only if the ensemble rotates)
+	double* L = nullptr;         // [3][cap]
+	uint64_t* meta = nullptr;    // [cap] orig index | cid << 32 | halo << 63
+};
+
+// scalars living on the device between kernels of one step
+struct DevScalars {
+	double upot6lj, upot_xpoles, virial, my_rf;   // force traversal
+	double summv2, sum_iw2;                       // leapfrog post
+	unsigned long long n_mol, rot_dof;
+	double beta_trans, beta_rot;                  // thermostat factors applied by the next leapfrog_pre
+	uint32_t n_slots2[2];                         // slots in use (owned + halo), ping-pong: [ctx->parity] is current
+	uint32_t overflow;                            // set if an update needed more than cap slots
+	uint32_t pad;
+};
+
+}  // namespace ls1b200
+
+// the opaque context of include/ls1b200.h
+struct ls1b200_ctx {
+	ls1b200_config cfg{};
+	ls1b200::Geom geom{};
+	int device = 0;
+	cudaStream_t stream = nullptr;
+	bool mixed = true;
+
+	// components
+	std::vector<ls1b200::CompDev> comps;
+	std::vector<ls1b200::SiteDev> sites;
+	ls1b200::CompDev* d_comps = nullptr;
+	ls1b200::SiteDev* d_sites = nullptr;
+	uint32_t n_lj = 0;
+	std::vector<double> h_eps24, h_sig2, h_shift6;
+	double* d_eps24 = nullptr; double* d_sig2 = nullptr; double* d_shift6 = nullptr;      // FP64 tables [n_lj*n_lj]
+	float* d_eps24f = nullptr; float* d_sig2f = nullptr; float* d_shift6f = nullptr;      // cast to calc (mixed)
+	uint32_t smax = 1;            // max sites per molecule
+	bool all_1clj = false;        // every component: exactly one LJ centre at the origin and nothing else
+	bool rotates = false;         // some component has rotational degrees of freedom
+	bool components_set = false;
+
+	// molecules
+	uint64_t n_owned = 0;         // molecules uploaded
+	uint64_t rot_dof_total = 0;   // sum of Component::getRotationalDegreesOfFreedom() over the owned molecules
+	uint64_t cap = 0;             // slot capacity of every per-slot array
+	uint32_t n_slots = 0;         // host copy (valid after a synchronising call)
+	uint32_t parity = 0;          // which DevScalars::n_slots2 entry is current
+	uint64_t* d_id = nullptr;     // [n_owned] molecule id, upload order (never permuted)
+	ls1b200::State cur, nxt;
+	double* F = nullptr; double* M = nullptr; double* Vi = nullptr;   // [3][cap] each, slot order
+	bool sorted = false;          // update() has run since the last upload
+	bool forces_valid = false;
+
+	// cells
+	uint32_t* cell_count = nullptr;   // [ncells+2]
+	uint32_t* cell_start = nullptr;   // [ncells+2] exclusive scan
+	uint32_t* cursor = nullptr;       // [ncells+2]
+	uint32_t* scan_tmp = nullptr;
+	uint32_t* key = nullptr;          // [cap] cell | shiftmask << 26 per source slot
+	uint32_t* entry = nullptr;        // [cap] src << 5 | shift code, per provisional slot
+	uint32_t* cell_of = nullptr;      // [cap] cell of provisional / final slot
+	uint32_t* cell_of2 = nullptr;     // [cap]
+
+	// calc-precision copies
+	void* mpos = nullptr;             // float4 / double4 [cap]
+	void* spos = nullptr;             // [cap*smax] float4 / double4: site position + parameter
+	void* sori = nullptr;             // [cap*smax] float4 / double4: site orientation
+	double* sf = nullptr;             // [cap*smax][9]: per-site force, virial, torque (general path)
+
+	// reductions
+	double* partials = nullptr;       // [n_partial_blocks][8]
+	uint32_t partial_blocks = 0;
+	ls1b200::DevScalars* d_scal = nullptr;
+	ls1b200::DevScalars* h_scal = nullptr;   // pinned
+	ls1b200_step_record* d_records = nullptr; uint64_t records_cap = 0;
+
+	// timing
+	std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
+	struct Span { int phase; cudaEvent_t a, b; };
+	std::vector<Span> spans;
+	double phase_ms[ls1b200::PH_COUNT] = {0, 0, 0, 0};
+	uint64_t phase_launches[ls1b200::PH_COUNT] = {0, 0, 0, 0};
+	bool timing = true;
+
+	// halo exchange buffers (multi-GPU)
+	void* export_buf[27] = {nullptr}; uint64_t export_cap[27] = {0};
+	uint32_t* d_export_count = nullptr;
+	void* import_buf = nullptr; uint64_t import_count = 0, import_cap = 0;
+};
+
+namespace ls1b200 {
+// implemented across the .cu files
+int ctx_alloc_molecules(ls1b200_ctx* c, uint64_t n_owned, uint64_t cap);
+void ctx_free_molecules(ls1b200_ctx* c);
+int span_begin(ls1b200_ctx* c, int phase);
+int span_end(ls1b200_ctx* c);
+int do_update(ls1b200_ctx* c);
+int do_forces(ls1b200_ctx* c);
+int do_leapfrog_pre(ls1b200_ctx* c, double dt, bool use_beta);
+int do_leapfrog_post(ls1b200_ctx* c, double dt);
+int do_globals(ls1b200_ctx* c, double target_T, uint64_t global_n, double global_volume, ls1b200_step_record* d_rec);
+int force_general(ls1b200_ctx* c);
+int force_1clj(ls1b200_ctx* c);
+int reduce_force_partials(ls1b200_ctx* c, uint32_t nblocks);
+}  // namespace ls1b200

@@ -1,0 +1,472 @@
+// context.cu -- C ABI of include/ls1b200.h: context life cycle, components, upload / download, geometry, timing.
+// Reference for the geometry: LinkedCells ctor / rebuild (particleContainer/LinkedCells.cpp:47-58, :148-166).
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+#include <mutex>
+
+#include "common.cuh"
+
+namespace ls1b200 {
+
+static thread_local std::string t_error;
+std::atomic<uint64_t> g_launches{0};
+void set_error(const std::string& msg) { t_error = msg; }
+int fail(const std::string& msg) { t_error = msg; return 1; }
+
+int span_begin(ls1b200_ctx* c, int phase) {
+	if (!c->timing) return 0;
+	if (c->ev_used + 2 > c->ev_pool.size()) {
+		if (c->ev_pool.size() >= 16384) return 0;   // stop recording rather than grow without bound
+		for (int i = 0; i < 64; i++) { cudaEvent_t e; LS1_CUDA(cudaEventCreate(&e)); c->ev_pool.push_back(e); }
+	}
+	ls1b200_ctx::Span s; s.phase = phase; s.a = c->ev_pool[c->ev_used++]; s.b = c->ev_pool[c->ev_used++];
+	LS1_CUDA(cudaEventRecord(s.a, c->stream));
+	c->spans.push_back(s);
+	return 0;
+}
+int span_end(ls1b200_ctx* c) {
+	if (!c->timing || c->spans.empty()) return 0;
+	LS1_CUDA(cudaEventRecord(c->spans.back().b, c->stream));
+	return 0;
+}
+static int spans_collect(ls1b200_ctx* c) {
+	LS1_CUDA(cudaStreamSynchronize(c->stream));
+	for (auto& s : c->spans) {
+		float ms = 0.f;
+		if (cudaEventElapsedTime(&ms, s.a, s.b) == cudaSuccess) c->phase_ms[s.phase] += ms;
+	}
+	c->spans.clear(); c->ev_used = 0;
+	return 0;
+}
+
+template <class T> static int dev_alloc(T** p, size_t n) {
+	*p = nullptr;
+	if (n == 0) n = 1;
+	LS1_CUDA(cudaMalloc((void**) p, n * sizeof(T)));
+	return 0;
+}
+template <class T> static void dev_free(T*& p) { if (p) cudaFree(p); p = nullptr; }
+
+static int alloc_state(State& s, uint64_t cap, bool rot) {
+	LS1_TRY(dev_alloc(&s.r, 3 * cap)); LS1_TRY(dev_alloc(&s.v, 3 * cap)); LS1_TRY(dev_alloc(&s.meta, cap));
+	if (rot) { LS1_TRY(dev_alloc(&s.q, 4 * cap)); LS1_TRY(dev_alloc(&s.L, 3 * cap)); }
+	return 0;
+}
+static void free_state(State& s) { dev_free(s.r); dev_free(s.v); dev_free(s.q); dev_free(s.L); dev_free(s.meta); }
+
+void ctx_free_molecules(ls1b200_ctx* c) {
+	free_state(c->cur); free_state(c->nxt);
+	dev_free(c->d_id); dev_free(c->F); dev_free(c->M); dev_free(c->Vi);
+	dev_free(c->key); dev_free(c->entry); dev_free(c->cell_of); dev_free(c->cell_of2);
+	if (c->mpos) cudaFree(c->mpos); c->mpos = nullptr;
+	if (c->spos) cudaFree(c->spos); c->spos = nullptr;
+	if (c->sori) cudaFree(c->sori); c->sori = nullptr;
+	dev_free(c->sf); dev_free(c->partials);
+	c->cap = 0; c->n_owned = 0; c->n_slots = 0;
+}
+
+int ctx_alloc_molecules(ls1b200_ctx* c, uint64_t n_owned, uint64_t cap) {
+	ctx_free_molecules(c);
+	if (cap >= (1ull << 27)) return fail("ls1b200: more than 2^27 slots per device are not supported");
+	c->cap = cap; c->n_owned = n_owned;
+	const bool rot = c->rotates;
+	LS1_TRY(alloc_state(c->cur, cap, rot)); LS1_TRY(alloc_state(c->nxt, cap, rot));
+	LS1_TRY(dev_alloc(&c->d_id, n_owned));
+	LS1_TRY(dev_alloc(&c->F, 3 * cap)); LS1_TRY(dev_alloc(&c->Vi, 3 * cap));
+	if (rot) LS1_TRY(dev_alloc(&c->M, 3 * cap));
+	LS1_TRY(dev_alloc(&c->key, cap)); LS1_TRY(dev_alloc(&c->entry, cap)); LS1_TRY(dev_alloc(&c->cell_of, cap)); LS1_TRY(dev_alloc(&c->cell_of2, cap));
+	const size_t v4 = c->mixed ? 16 : 32;
+	LS1_CUDA(cudaMalloc(&c->mpos, std::max<size_t>(cap, 1) * v4));
+	if (!c->all_1clj) {
+		LS1_CUDA(cudaMalloc(&c->spos, std::max<size_t>(cap, 1) * c->smax * v4));
+		LS1_CUDA(cudaMalloc(&c->sori, std::max<size_t>(cap, 1) * c->smax * v4));
+		LS1_TRY(dev_alloc(&c->sf, cap * c->smax * 9));
+	}
+	c->partial_blocks = (uint32_t) (((cap + 127) / 128) * std::max(c->smax, 1u) + 64);
+	LS1_TRY(dev_alloc(&c->partials, (size_t) c->partial_blocks * 8));
+	LS1_CUDA(cudaMemsetAsync(c->F, 0, sizeof(double) * 3 * cap, c->stream));
+	LS1_CUDA(cudaMemsetAsync(c->Vi, 0, sizeof(double) * 3 * cap, c->stream));
+	if (rot) LS1_CUDA(cudaMemsetAsync(c->M, 0, sizeof(double) * 3 * cap, c->stream));
+	return 0;
+}
+
+// LinkedCells geometry, host side (LinkedCells.cpp:47-58 ctor path, :148-166 XML path)
+static int init_geometry(ls1b200_ctx* c) {
+	Geom& g = c->geom;
+	const ls1b200_config& f = c->cfg;
+	uint64_t ncells = 1;
+	for (int d = 0; d < 3; d++) {
+		g.bmin[d] = f.box_min[d]; g.bmax[d] = f.box_max[d];
+		const double diff = g.bmax[d] - g.bmin[d];
+		if (!(diff > 0.)) return fail("ls1b200_create: empty bounding box");
+		int box_cells;
+		if (f.geometry == LS1B200_GEOM_CTOR) {
+			box_cells = (int) floor(diff / f.cutoff);                 // LinkedCells.cpp:47-58
+			if (box_cells == 0) box_cells = 1;
+		} else {
+			const float rc = (float) (f.cutoff / 1);                  // cellsInCutoff == 1; float cast: LinkedCells.cpp:148-166
+			box_cells = (int) floor(diff / rc);
+		}
+		if (box_cells < 1) return fail("ls1b200_create: bounding box smaller than the cutoff radius");
+		g.clen[d] = diff / box_cells;
+		g.crecip[d] = box_cells / diff;
+		g.hmin[d] = g.bmin[d] - g.clen[d];
+		g.hmax[d] = g.bmax[d] + g.clen[d];
+		g.cells[d] = box_cells + 2;
+		g.lbox[d] = diff;
+		g.periodic[d] = f.periodic[d] ? 1 : 0;
+		// clamp values of DomainDecompBase.cpp:236-240, :358-368 -- nexttoward in vcp_real_calc (float: mixed, double: double build)
+		if (c->mixed) {
+			const float rmax = (float) g.bmax[d], rmin = (float) g.bmin[d];
+			g.wrap_hi[d] = (double) nexttowardf(rmax, (long double) (rmax - 1.f));
+			g.halo_hi[d] = (double) nexttowardf(rmax, (long double) (rmax + 1.f));
+			g.halo_lo[d] = (double) nexttowardf(rmin, (long double) (rmin - 1.f));
+		} else {
+			const double rmax = g.bmax[d], rmin = g.bmin[d];
+			g.wrap_hi[d] = nexttoward(rmax, (long double) (rmax - 1.));
+			g.halo_hi[d] = nexttoward(rmax, (long double) (rmax + 1.));
+			g.halo_lo[d] = nexttoward(rmin, (long double) (rmin - 1.));
+		}
+		ncells *= (uint64_t) g.cells[d];
+	}
+	g.cutoff = f.cutoff;
+	if (ncells + 2 >= (1ull << 26)) return fail("ls1b200_create: more than 2^26 cells per device are not supported");
+	g.ncells = (uint32_t) ncells;
+	return 0;
+}
+
+__global__ void k_deinterleave(const double* __restrict__ src, double* __restrict__ dst, uint64_t n, uint64_t cap, int dim) {
+	const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n * dim) return;
+	const uint64_t m = i / dim; const int d = (int) (i % dim);
+	dst[(uint64_t) d * cap + m] = src[i];
+}
+__global__ void k_fill_q(double* __restrict__ q, uint64_t n, uint64_t cap) {
+	const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i >= n) return;
+	q[i] = 1.; q[cap + i] = 0.; q[2 * cap + i] = 0.; q[3 * cap + i] = 0.;
+}
+__global__ void k_make_meta(const uint32_t* __restrict__ cid, uint64_t* __restrict__ meta, uint64_t n) {
+	const uint64_t i = (uint64_t) blockIdx.x * blockDim.x + threadIdx.x;
+	if (i < n) meta[i] = make_meta((uint32_t) i, cid[i], false);
+}
+
+// out[orig][d] = plane[d][slot] for the owned molecule in every slot
+__global__ void k_download_planes(const double* __restrict__ planes, const uint64_t* __restrict__ meta, double* __restrict__ out, uint32_t n_slots, uint64_t cap, int dim) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_slots) return;
+	const uint64_t m = meta[t];
+	if (meta_halo(m)) return;
+	const uint64_t o = meta_orig(m);
+	for (int d = 0; d < dim; d++) out[o * dim + d] = planes[(uint64_t) d * cap + t];
+}
+__global__ void k_upload_planes(double* __restrict__ planes, const uint64_t* __restrict__ meta, const double* __restrict__ in, uint32_t n_slots, uint64_t cap, int dim) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_slots) return;
+	const uint64_t m = meta[t];
+	if (meta_halo(m)) return;
+	const uint64_t o = meta_orig(m);
+	for (int d = 0; d < dim; d++) planes[(uint64_t) d * cap + t] = in[o * dim + d];
+}
+__global__ void k_download_meta(const uint64_t* __restrict__ meta, const uint32_t* __restrict__ cell_of, uint32_t ncells, uint32_t* __restrict__ cid_out,
+                                uint64_t* __restrict__ cell_out, uint32_t n_slots) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= n_slots) return;
+	const uint64_t m = meta[t];
+	if (meta_halo(m)) return;
+	const uint64_t o = meta_orig(m);
+	if (cid_out) cid_out[o] = meta_cid(m);
+	if (cell_out) { const uint32_t c = cell_of[t]; cell_out[o] = (c >= ncells) ? ~0ull : (uint64_t) c; }
+}
+
+}  // namespace ls1b200
+
+using namespace ls1b200;
+
+extern "C" {
+
+const char* ls1b200_last_error(void) { return t_error.c_str(); }
+int ls1b200_abi_version(void) { return LS1B200_ABI_VERSION; }
+uint64_t ls1b200_kernel_launch_count(void) { return g_launches.load(); }
+
+int ls1b200_create(const ls1b200_config* cfg, ls1b200_ctx** out) {
+	if (!cfg || !out) return fail("ls1b200_create: null argument");
+	*out = nullptr;
+	int ndev = 0;
+	if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0)
+		return fail("ls1b200_create: no CUDA device (this library has no CPU path)");
+	if (cfg->device < 0 || cfg->device >= ndev) return fail("ls1b200_create: invalid device ordinal");
+	if (!(cfg->cutoff > 0.) || !(cfg->cutoff_lj > 0.)) return fail("ls1b200_create: cutoff radii must be positive");
+	if (cfg->precision != LS1B200_MIXED && cfg->precision != LS1B200_DOUBLE) return fail("ls1b200_create: unknown precision");
+	ls1b200_ctx* c = new (std::nothrow) ls1b200_ctx();
+	if (!c) return fail("ls1b200_create: out of host memory");
+	c->cfg = *cfg; c->device = cfg->device; c->mixed = cfg->precision == LS1B200_MIXED;
+	if (c->cfg.cutoff < c->cfg.cutoff_lj) c->cfg.cutoff = c->cfg.cutoff_lj;   // Simulation.cpp:267: rc = max(rc, rcLJ)
+	int rc = init_geometry(c);
+	if (rc) { delete c; return rc; }
+	auto cleanup = [&](int code) { ls1b200_destroy(c); return code; };
+	if (cudaSetDevice(c->device) != cudaSuccess) return cleanup(fail("ls1b200_create: cudaSetDevice failed"));
+	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail("ls1b200_create: cannot create stream"));
+	const size_t nb = (size_t) c->geom.ncells + 4;
+	if (dev_alloc(&c->cell_count, nb) || dev_alloc(&c->cell_start, nb) || dev_alloc(&c->cursor, nb) || dev_alloc(&c->scan_tmp, nb / 2048 + 16)) return cleanup(1);
+	if (dev_alloc(&c->d_scal, 1)) return cleanup(1);
+	if (cudaMallocHost((void**) &c->h_scal, sizeof(DevScalars)) != cudaSuccess) return cleanup(fail("ls1b200_create: cudaMallocHost failed"));
+	memset(c->h_scal, 0, sizeof(DevScalars));
+	c->h_scal->beta_trans = 1.; c->h_scal->beta_rot = 1.;
+	if (cudaMemcpy(c->d_scal, c->h_scal, sizeof(DevScalars), cudaMemcpyHostToDevice) != cudaSuccess) return cleanup(fail("ls1b200_create: memcpy failed"));
+	*out = c;
+	return 0;
+}
+
+int ls1b200_destroy(ls1b200_ctx* c) {
+	if (!c) return 0;
+	cudaSetDevice(c->device);
+	if (c->stream) cudaStreamSynchronize(c->stream);
+	ctx_free_molecules(c);
+	dev_free(c->d_comps); dev_free(c->d_sites);
+	dev_free(c->d_eps24); dev_free(c->d_sig2); dev_free(c->d_shift6); dev_free(c->d_eps24f); dev_free(c->d_sig2f); dev_free(c->d_shift6f);
+	dev_free(c->cell_count); dev_free(c->cell_start); dev_free(c->cursor); dev_free(c->scan_tmp);
+	dev_free(c->d_scal); dev_free(c->d_records);
+	if (c->h_scal) cudaFreeHost(c->h_scal);
+	for (auto e : c->ev_pool) cudaEventDestroy(e);
+	for (int i = 0; i < 27; i++) if (c->export_buf[i]) cudaFree(c->export_buf[i]);
+	dev_free(c->d_export_count);
+	if (c->import_buf) cudaFree(c->import_buf);
+	if (c->stream) cudaStreamDestroy(c->stream);
+	delete c;
+	return 0;
+}
+
+int ls1b200_set_components(ls1b200_ctx* c, uint32_t n_components, const ls1b200_component* comps, uint32_t n_sites, const ls1b200_site* sites,
+                           uint32_t n_lj, const double* eps24, const double* sig2, const double* shift6) {
+	if (!c || !comps || n_components == 0) return fail("ls1b200_set_components: null / empty argument");
+	if (n_components > 0xFFFF) return fail("ls1b200_set_components: too many components");
+	if (c->n_owned) return fail("ls1b200_set_components: must be called before ls1b200_upload");
+	LS1_CUDA(cudaSetDevice(c->device));
+	c->comps.clear(); c->sites.clear();
+	c->smax = 1; c->all_1clj = true; bool any_inertia = false;
+	for (uint32_t i = 0; i < n_components; i++) {
+		const ls1b200_component& s = comps[i];
+		CompDev d{};
+		d.n[0] = s.n_lj; d.n[1] = s.n_charge; d.n[2] = s.n_dipole; d.n[3] = s.n_quadrupole;
+		d.nsites = s.n_lj + s.n_charge + s.n_dipole + s.n_quadrupole;
+		d.site_offset = s.site_offset; d.lj_lookup_id = s.lj_lookup_id; d.rot_dof = s.rot_dof;
+		if (d.site_offset + d.nsites > n_sites) return fail("ls1b200_set_components: site table too short");
+		if (!(s.mass > 0.)) return fail("ls1b200_set_components: component mass must be positive");
+		d.mass = s.mass; d.inv_mass = 1. / s.mass;
+		for (int k = 0; k < 3; k++) { d.I[k] = s.inertia[k]; d.invI[k] = (s.inertia[k] != 0.) ? 1. / s.inertia[k] : 0.; if (s.inertia[k] != 0.) any_inertia = true; }
+		c->smax = std::max(c->smax, d.nsites);
+		bool one_clj = d.n[0] == 1 && d.nsites == 1 && d.lj_lookup_id == i;
+		if (one_clj) { const ls1b200_site& st = sites[d.site_offset]; one_clj = st.r[0] == 0. && st.r[1] == 0. && st.r[2] == 0.; }
+		c->all_1clj = c->all_1clj && one_clj;
+		c->comps.push_back(d);
+	}
+	c->sites.resize(n_sites);
+	for (uint32_t i = 0; i < n_components; i++) {
+		const CompDev& d = c->comps[i];
+		uint32_t k = d.site_offset;
+		for (int t = 0; t < 4; t++) for (uint32_t j = 0; j < d.n[t]; j++, k++) {
+			SiteDev& o = c->sites[k];
+			for (int x = 0; x < 3; x++) { o.r[x] = sites[k].r[x]; o.e[x] = sites[k].e[x]; }
+			o.param = sites[k].param; o.type = (uint32_t) t; o.ljid = (t == 0) ? d.lj_lookup_id + j : 0u;
+			if (t == 0 && o.ljid >= n_lj) return fail("ls1b200_set_components: LJ lookup id outside the pair tables");
+		}
+	}
+	c->rotates = !c->all_1clj || any_inertia;
+	c->n_lj = n_lj;
+	const size_t nt = (size_t) n_lj * n_lj;
+	if (nt && (!eps24 || !sig2 || !shift6)) return fail("ls1b200_set_components: LJ tables missing");
+	c->h_eps24.assign(eps24, eps24 + nt); c->h_sig2.assign(sig2, sig2 + nt); c->h_shift6.assign(shift6, shift6 + nt);
+	if (nt == 0) { c->h_eps24.assign(1, 0.); c->h_sig2.assign(1, 0.); c->h_shift6.assign(1, 0.); }
+	dev_free(c->d_comps); dev_free(c->d_sites);
+	dev_free(c->d_eps24); dev_free(c->d_sig2); dev_free(c->d_shift6); dev_free(c->d_eps24f); dev_free(c->d_sig2f); dev_free(c->d_shift6f);
+	LS1_TRY(dev_alloc(&c->d_comps, c->comps.size())); LS1_TRY(dev_alloc(&c->d_sites, c->sites.size()));
+	LS1_CUDA(cudaMemcpy(c->d_comps, c->comps.data(), sizeof(CompDev) * c->comps.size(), cudaMemcpyHostToDevice));
+	if (!c->sites.empty()) LS1_CUDA(cudaMemcpy(c->d_sites, c->sites.data(), sizeof(SiteDev) * c->sites.size(), cudaMemcpyHostToDevice));
+	const size_t na = c->h_eps24.size();
+	std::vector<float> f24(na), fs2(na), fsh(na);
+	for (size_t i = 0; i < na; i++) { f24[i] = (float) c->h_eps24[i]; fs2[i] = (float) c->h_sig2[i]; fsh[i] = (float) c->h_shift6[i]; }
+	LS1_TRY(dev_alloc(&c->d_eps24, na)); LS1_TRY(dev_alloc(&c->d_sig2, na)); LS1_TRY(dev_alloc(&c->d_shift6, na));
+	LS1_TRY(dev_alloc(&c->d_eps24f, na)); LS1_TRY(dev_alloc(&c->d_sig2f, na)); LS1_TRY(dev_alloc(&c->d_shift6f, na));
+	LS1_CUDA(cudaMemcpy(c->d_eps24, c->h_eps24.data(), 8 * na, cudaMemcpyHostToDevice));
+	LS1_CUDA(cudaMemcpy(c->d_sig2, c->h_sig2.data(), 8 * na, cudaMemcpyHostToDevice));
+	LS1_CUDA(cudaMemcpy(c->d_shift6, c->h_shift6.data(), 8 * na, cudaMemcpyHostToDevice));
+	LS1_CUDA(cudaMemcpy(c->d_eps24f, f24.data(), 4 * na, cudaMemcpyHostToDevice));
+	LS1_CUDA(cudaMemcpy(c->d_sig2f, fs2.data(), 4 * na, cudaMemcpyHostToDevice));
+	LS1_CUDA(cudaMemcpy(c->d_shift6f, fsh.data(), 4 * na, cudaMemcpyHostToDevice));
+	c->components_set = true;
+	return 0;
+}
+
+uint64_t ls1b200_num_molecules(const ls1b200_ctx* c) { return c ? c->n_owned : 0; }
+void* ls1b200_stream(ls1b200_ctx* c) { return c ? (void*) c->stream : nullptr; }
+
+int ls1b200_geometry(const ls1b200_ctx* c, int32_t cells_per_dim[3], double cell_length[3], double halo_min[3]) {
+	if (!c) return fail("ls1b200_geometry: null context");
+	for (int d = 0; d < 3; d++) { cells_per_dim[d] = c->geom.cells[d]; cell_length[d] = c->geom.clen[d]; halo_min[d] = c->geom.hmin[d]; }
+	return 0;
+}
+
+int ls1b200_upload(ls1b200_ctx* c, uint64_t n, const uint64_t* id, const uint32_t* cid, const double* r, const double* v, const double* q, const double* L) {
+	if (!c) return fail("ls1b200_upload: null context");
+	if (!c->components_set) return fail("ls1b200_upload: call ls1b200_set_components first");
+	if (n && (!id || !cid || !r || !v)) return fail("ls1b200_upload: null array");
+	LS1_CUDA(cudaSetDevice(c->device));
+	for (uint64_t i = 0; i < n; i++) if (cid[i] >= c->comps.size()) return fail("ls1b200_upload: component id out of range");
+	// slot capacity: owned molecules + periodic halo copies (boundary layer of width rc on every periodic face) with head room
+	double fac = 1.;
+	for (int d = 0; d < 3; d++) if (c->geom.periodic[d] || c->cfg.reserved[0]) fac *= 1. + 2. * std::min(1., c->geom.cutoff / c->geom.lbox[d]);
+	const uint64_t cap = n + (uint64_t) ((fac - 1.) * 1.5 * (double) n) + 4096;
+	LS1_TRY(ctx_alloc_molecules(c, n, cap));
+	c->rot_dof_total = 0;
+	for (uint64_t i = 0; i < n; i++) c->rot_dof_total += c->comps[cid[i]].rot_dof;
+	if (n) {
+		double* stage = nullptr; uint32_t* cstage = nullptr;
+		LS1_TRY(dev_alloc(&stage, 4 * n)); LS1_TRY(dev_alloc(&cstage, n));
+		const uint32_t g3 = (uint32_t) ((3 * n + 255) / 256), g4 = (uint32_t) ((4 * n + 255) / 256), g1 = (uint32_t) ((n + 255) / 256);
+		auto put = [&](const double* src, double* planes, int dim) -> int {
+			LS1_CUDA(cudaMemcpyAsync(stage, src, sizeof(double) * dim * n, cudaMemcpyHostToDevice, c->stream));
+			k_deinterleave<<<dim == 3 ? g3 : g4, 256, 0, c->stream>>>(stage, planes, n, cap, dim);
+			g_launches++;
+			LS1_CUDA(cudaGetLastError());
+			return 0;
+		};
+		LS1_TRY(put(r, c->cur.r, 3)); LS1_TRY(put(v, c->cur.v, 3));
+		if (c->rotates) {
+			if (q) LS1_TRY(put(q, c->cur.q, 4)); else { k_fill_q<<<g1, 256, 0, c->stream>>>(c->cur.q, n, cap); g_launches++; }
+			if (L) LS1_TRY(put(L, c->cur.L, 3)); else LS1_CUDA(cudaMemsetAsync(c->cur.L, 0, sizeof(double) * 3 * cap, c->stream));
+		}
+		LS1_CUDA(cudaMemcpyAsync(cstage, cid, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
+		k_make_meta<<<g1, 256, 0, c->stream>>>(cstage, c->cur.meta, n); g_launches++;
+		LS1_CUDA(cudaMemcpyAsync(c->d_id, id, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, c->stream));
+		LS1_CUDA(cudaStreamSynchronize(c->stream));
+		cudaFree(stage); cudaFree(cstage);
+	}
+	c->parity = 0; c->n_slots = (uint32_t) n;
+	c->h_scal->n_slots2[0] = (uint32_t) n; c->h_scal->n_slots2[1] = 0; c->h_scal->overflow = 0;
+	c->h_scal->beta_trans = 1.; c->h_scal->beta_rot = 1.;
+	LS1_CUDA(cudaMemcpy(c->d_scal, c->h_scal, sizeof(DevScalars), cudaMemcpyHostToDevice));
+	c->sorted = false; c->forces_valid = false;
+	return 0;
+}
+
+// brings n_slots / overflow to the host (synchronises the stream)
+static int sync_scalars(ls1b200_ctx* c) {
+	LS1_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
+	LS1_CUDA(cudaStreamSynchronize(c->stream));
+	c->n_slots = std::min<uint64_t>(c->h_scal->n_slots2[c->parity], c->cap);
+	if (c->h_scal->overflow) return fail("ls1b200: slot capacity exceeded (more halo copies than reserved)");
+	return 0;
+}
+
+int ls1b200_update(ls1b200_ctx* c) {
+	if (!c) return fail("ls1b200_update: null context");
+	LS1_CUDA(cudaSetDevice(c->device));
+	LS1_TRY(do_update(c));
+	return sync_scalars(c);
+}
+
+int ls1b200_traverse_cells(ls1b200_ctx* c, ls1b200_macro* out) {
+	if (!c) return fail("ls1b200_traverse_cells: null context");
+	if (!c->sorted) return fail("ls1b200_traverse_cells: call ls1b200_update first");
+	LS1_CUDA(cudaSetDevice(c->device));
+	LS1_TRY(do_forces(c));
+	LS1_TRY(sync_scalars(c));
+	if (out) {
+		const DevScalars& s = *c->h_scal;
+		out->upot6lj = s.upot6lj; out->upot_xpoles = s.upot_xpoles; out->virial_raw = s.virial; out->my_rf = s.my_rf;
+		out->upot = s.upot6lj / 6.0 + s.upot_xpoles + s.my_rf;      // VectorizedCellProcessor.cpp:153-154
+		out->virial = s.virial + 3.0 * s.my_rf;
+	}
+	return 0;
+}
+
+int ls1b200_download(ls1b200_ctx* c, int field, void* dst, uint64_t n) {
+	if (!c || !dst) return fail("ls1b200_download: null argument");
+	if (n != c->n_owned) return fail("ls1b200_download: n does not match the number of molecules");
+	if (n == 0) return 0;
+	LS1_CUDA(cudaSetDevice(c->device));
+	LS1_TRY(sync_scalars(c));
+	const uint32_t ns = c->n_slots, g = (ns + 255) / 256;
+	const double* planes = nullptr; int dim = 3;
+	switch (field) {
+		case LS1B200_F_ID: LS1_CUDA(cudaMemcpy(dst, c->d_id, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost)); return 0;
+		case LS1B200_F_R: planes = c->cur.r; break;
+		case LS1B200_F_V: planes = c->cur.v; break;
+		case LS1B200_F_Q: planes = c->cur.q; dim = 4; break;
+		case LS1B200_F_L: planes = c->cur.L; break;
+		case LS1B200_F_F: planes = c->F; break;
+		case LS1B200_F_M: planes = c->M; break;
+		case LS1B200_F_VI: planes = c->Vi; break;
+		case LS1B200_F_CID: case LS1B200_F_CELL: break;
+		default: return fail("ls1b200_download: unknown field");
+	}
+	if (field == LS1B200_F_CID || field == LS1B200_F_CELL) {
+		if (field == LS1B200_F_CELL && !c->sorted) return fail("ls1b200_download: cell indices need ls1b200_update first");
+		void* tmp = nullptr; const size_t es = field == LS1B200_F_CID ? 4 : 8;
+		LS1_CUDA(cudaMalloc(&tmp, es * n));
+		k_download_meta<<<g, 256, 0, c->stream>>>(c->cur.meta, c->cell_of2, c->geom.ncells, field == LS1B200_F_CID ? (uint32_t*) tmp : nullptr,
+		                                         field == LS1B200_F_CELL ? (uint64_t*) tmp : nullptr, ns);
+		g_launches++;
+		cudaError_t e = cudaMemcpyAsync(dst, tmp, es * n, cudaMemcpyDeviceToHost, c->stream);
+		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+		cudaFree(tmp);
+		LS1_CUDA(e);
+		return 0;
+	}
+	if (!planes) {   // fields a non-rotating ensemble does not store: identity orientation, zero angular momentum / torque
+		double* o = (double*) dst;
+		for (uint64_t i = 0; i < n * dim; i++) o[i] = 0.;
+		if (field == LS1B200_F_Q) for (uint64_t i = 0; i < n; i++) o[4 * i] = 1.;
+		return 0;
+	}
+	double* tmp = nullptr;
+	LS1_CUDA(cudaMalloc((void**) &tmp, sizeof(double) * dim * n));
+	k_download_planes<<<g, 256, 0, c->stream>>>(planes, c->cur.meta, tmp, ns, c->cap, dim);
+	g_launches++;
+	cudaError_t e = cudaMemcpyAsync(dst, tmp, sizeof(double) * dim * n, cudaMemcpyDeviceToHost, c->stream);
+	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
+	cudaFree(tmp);
+	LS1_CUDA(e);
+	return 0;
+}
+
+int ls1b200_set_field(ls1b200_ctx* c, int field, const void* src, uint64_t n) {
+	if (!c || !src) return fail("ls1b200_set_field: null argument");
+	if (n != c->n_owned) return fail("ls1b200_set_field: n does not match the number of molecules");
+	if (n == 0) return 0;
+	LS1_CUDA(cudaSetDevice(c->device));
+	LS1_TRY(sync_scalars(c));
+	double* planes = nullptr; int dim = 3;
+	switch (field) {
+		case LS1B200_F_R: planes = c->cur.r; c->forces_valid = false; break;
+		case LS1B200_F_V: planes = c->cur.v; break;
+		case LS1B200_F_Q: planes = c->cur.q; dim = 4; break;
+		case LS1B200_F_L: planes = c->cur.L; break;
+		case LS1B200_F_F: planes = c->F; break;
+		case LS1B200_F_M: planes = c->M; break;
+		default: return fail("ls1b200_set_field: field cannot be set");
+	}
+	if (!planes) return 0;   // non-rotating ensemble: nothing to store
+	double* tmp = nullptr;
+	LS1_CUDA(cudaMalloc((void**) &tmp, sizeof(double) * dim * n));
+	cudaError_t e = cudaMemcpyAsync(tmp, src, sizeof(double) * dim * n, cudaMemcpyHostToDevice, c->stream);
+	const uint32_t ns = c->n_slots;
+	if (e == cudaSuccess) { k_upload_planes<<<(ns + 255) / 256, 256, 0, c->stream>>>(planes, c->cur.meta, tmp, ns, c->cap, dim); g_launches++; e = cudaStreamSynchronize(c->stream); }
+	cudaFree(tmp);
+	LS1_CUDA(e);
+	return 0;
+}
+
+int ls1b200_phase_times(ls1b200_ctx* c, double ms[4], uint64_t launches[4], int reset) {
+	if (!c) return fail("ls1b200_phase_times: null context");
+	LS1_CUDA(cudaSetDevice(c->device));
+	LS1_TRY(spans_collect(c));
+	for (int i = 0; i < PH_COUNT; i++) { if (ms) ms[i] = c->phase_ms[i]; if (launches) launches[i] = c->phase_launches[i]; }
+	if (reset) for (int i = 0; i < PH_COUNT; i++) { c->phase_ms[i] = 0.; c->phase_launches[i] = 0; }
+	return 0;
+}
+
+}  // extern "C"

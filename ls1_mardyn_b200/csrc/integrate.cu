@@ -1,0 +1,252 @@
+// integrate.cu -- Leapfrog integrator, velocity-scaling thermostat, Domain's global values and the fused multi-step loop.
+//
+// Reference: Leapfrog::transition1to2 / transition2to3 (integrators/Leapfrog.cpp:45-61, :63-147);
+//   FullMolecule::upd_preF / upd_postF (molecules/FullMolecule.cpp:331-361, :363-386);
+//   Quaternion::rotateinv / differentiate (molecules/Quaternion.cpp:66-103);
+//   Domain::calculateGlobalValues, getGlobalPressure (Domain.cpp:157-252, :142-146);
+//   VelocityScalingThermostat::apply (thermostats/VelocityScalingThermostat.cpp:68-89);
+//   Simulation::simulateOneTimestep for the order of the phases (Simulation.cpp:1076-1261).
+// All kernels here are HBM-bound streaming kernels over the FP64 state planes.
+#include "pairs.cuh"
+#include "types.cuh"
+
+namespace ls1b200 {
+
+__device__ __forceinline__ void q_rotateinv(const double* q, const double* d, double* o) {
+	if (d[0] == 0. && d[1] == 0. && d[2] == 0.) { o[0] = o[1] = o[2] = 0.; return; }
+	const double w = q[0], x = q[1], y = q[2], z = q[3];
+	const double ww = w * w, xx = x * x, yy = y * y, zz = z * z, wx = w * x, wy = w * y, wz = w * z, xy = x * y, xz = x * z, yz = y * z;
+	o[0] = (ww + xx - yy - zz) * d[0] + 2. * (xy + wz) * d[1] + 2. * (xz - wy) * d[2];
+	o[1] = 2. * (xy - wz) * d[0] + (ww - xx + yy - zz) * d[1] + 2. * (yz + wx) * d[2];
+	o[2] = 2. * (xz + wy) * d[0] + 2. * (yz - wx) * d[1] + (ww - xx - yy + zz) * d[2];
+}
+__device__ __forceinline__ void q_differentiate(const double* q, const double* w, double* dq) {
+	dq[0] = .5 * (-q[1] * w[0] - q[2] * w[1] - q[3] * w[2]);
+	dq[1] = .5 * (q[0] * w[0] - q[3] * w[1] + q[2] * w[2]);
+	dq[2] = .5 * (q[3] * w[0] + q[0] * w[1] - q[1] * w[2]);
+	dq[3] = .5 * (-q[2] * w[0] + q[1] * w[1] + q[0] * w[2]);
+}
+
+// upd_preF, with the thermostat factors of the previous step applied on load (v *= beta_trans, L *= beta_rot is what
+// VelocityScalingThermostat::apply does between two steps; nothing reads v or L in between).
+__global__ void __launch_bounds__(256) k_leapfrog_pre(State st, const double* __restrict__ F, const double* __restrict__ M, uint32_t cap,
+                                                       const CompDev* __restrict__ comps, double dt, const DevScalars* __restrict__ scal,
+                                                       uint32_t parity, int use_beta, int rotates) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= min(scal->n_slots2[parity], cap)) return;
+	const uint64_t meta = st.meta[t];
+	if (meta_halo(meta)) return;
+	const CompDev& cp = comps[meta_cid(meta)];
+	const double bt = use_beta ? scal->beta_trans : 1., br = use_beta ? scal->beta_rot : 1.;
+	const double dth = .5 * dt, dtInv2m = dth / cp.mass;
+	const size_t c = cap;
+	#pragma unroll
+	for (int d = 0; d < 3; d++) {
+		double v = st.v[d * c + t];
+		if (use_beta) v *= bt;
+		v += dtInv2m * F[d * c + t];
+		st.v[d * c + t] = v;
+		st.r[d * c + t] += dt * v;
+	}
+	if (rotates) {
+		double q[4], L[3], w[3], qh[4], qi[4];
+		for (int k = 0; k < 4; k++) q[k] = st.q[k * c + t];
+		for (int d = 0; d < 3; d++) { L[d] = st.L[d * c + t]; if (use_beta) L[d] *= br; }
+		q_rotateinv(q, L, w);
+		for (int d = 0; d < 3; d++) w[d] *= cp.invI[d];
+		q_differentiate(q, w, qh);
+		for (int k = 0; k < 4; k++) qh[k] = qh[k] * dth + q[k];
+		double qc = 1. / sqrt(qh[0] * qh[0] + qh[1] * qh[1] + qh[2] * qh[2] + qh[3] * qh[3]);
+		for (int k = 0; k < 4; k++) qh[k] *= qc;
+		for (int d = 0; d < 3; d++) L[d] += dth * M[d * c + t];
+		q_rotateinv(qh, L, w);
+		for (int d = 0; d < 3; d++) w[d] *= cp.invI[d];
+		q_differentiate(qh, w, qi);
+		for (int k = 0; k < 4; k++) q[k] += qi[k] * dt;
+		qc = 1. / sqrt(q[0] * q[0] + q[1] * q[1] + q[2] * q[2] + q[3] * q[3]);
+		for (int k = 0; k < 4; k++) st.q[k * c + t] = q[k] * qc;
+		for (int d = 0; d < 3; d++) st.L[d * c + t] = L[d];
+	}
+}
+
+// upd_postF + the sums of Leapfrog::transition2to3 (Leapfrog.cpp:113-143)
+__global__ void __launch_bounds__(256) k_leapfrog_post(State st, const double* __restrict__ F, const double* __restrict__ M, uint32_t cap,
+                                                        const CompDev* __restrict__ comps, double dt, const DevScalars* __restrict__ scal,
+                                                        uint32_t parity, int rotates, double* __restrict__ partials) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	double acc[2] = {0., 0.};
+	if (t < min(scal->n_slots2[parity], cap)) {
+		const uint64_t meta = st.meta[t];
+		if (!meta_halo(meta)) {
+			const CompDev& cp = comps[meta_cid(meta)];
+			const double dth = .5 * dt, dtInv2m = dth / cp.mass;
+			const size_t c = cap;
+			double v2 = 0.;
+			#pragma unroll
+			for (int d = 0; d < 3; d++) {
+				const double v = st.v[d * c + t] + dtInv2m * F[d * c + t];
+				st.v[d * c + t] = v;
+				v2 += v * v;
+			}
+			acc[0] = cp.mass * v2;
+			if (rotates) {
+				double q[4], L[3], w[3];
+				for (int k = 0; k < 4; k++) q[k] = st.q[k * c + t];
+				for (int d = 0; d < 3; d++) { L[d] = st.L[d * c + t] + dth * M[d * c + t]; st.L[d * c + t] = L[d]; }
+				q_rotateinv(q, L, w);
+				double Iw2 = 0.;
+				for (int d = 0; d < 3; d++) { w[d] *= cp.invI[d]; Iw2 += cp.I[d] * w[d] * w[d]; }
+				acc[1] = Iw2;
+			}
+		}
+	}
+	block_reduce_store<2>(acc, partials, blockIdx.x);
+}
+
+__global__ void __launch_bounds__(1024) k_reduce_kinetic(const double* __restrict__ partials, uint32_t nblocks, DevScalars* scal) {
+	double v[2] = {0., 0.};
+	for (uint32_t b = threadIdx.x; b < nblocks; b += blockDim.x) { v[0] += partials[(size_t) b * 8]; v[1] += partials[(size_t) b * 8 + 1]; }
+	__shared__ double out[8];
+	block_reduce_store<2>(v, out, 0);
+	__syncthreads();
+	if (threadIdx.x == 0) { scal->summv2 = out[0]; scal->sum_iw2 = out[1]; }
+}
+
+__global__ void __launch_bounds__(256) k_scale(State st, uint32_t cap, double bt, double br, const DevScalars* __restrict__ scal, uint32_t parity,
+                                               int from_scal, int rotates) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= min(scal->n_slots2[parity], cap)) return;
+	if (meta_halo(st.meta[t])) return;
+	if (from_scal) { bt = scal->beta_trans; br = scal->beta_rot; }
+	const size_t c = cap;
+	#pragma unroll
+	for (int d = 0; d < 3; d++) st.v[d * c + t] *= bt;
+	if (rotates) for (int d = 0; d < 3; d++) st.L[d * c + t] *= br;
+}
+
+// Domain::calculateGlobalValues + getGlobalPressure for one rank (Domain.cpp:157-252, :142-146)
+__global__ void k_globals(DevScalars* scal, double target_T, unsigned long long N, unsigned long long rot_dof, double volume, ls1b200_step_record* rec) {
+	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	const double upot = scal->upot6lj / 6.0 + scal->upot_xpoles + scal->my_rf;
+	const double virial = scal->virial + 3.0 * scal->my_rf;
+	const double summv2 = scal->summv2;
+	const double sumIw2 = rot_dof > 0 ? scal->sum_iw2 : 0.0;
+	const double T = (N > 0) ? (summv2 + sumIw2) / (double) (3 * N + rot_dof) : target_T;
+	double bt = 1., br = 1.;
+	if (target_T > 0. && N > 0) {
+		bt = pow(3.0 * (double) N * target_T / summv2, 0.4);
+		br = (sumIw2 == 0.0) ? 1.0 : pow((double) rot_dof * target_T / sumIw2, 0.4);
+	}
+	const double rho = (double) N / volume;
+	const double p = T * rho + rho * (virial / (double) N) / 3.;
+	scal->beta_trans = bt; scal->beta_rot = br;
+	if (rec) { rec->upot = upot; rec->virial = virial; rec->summv2 = summv2; rec->sum_iw2 = sumIw2; rec->temperature = T; rec->pressure = p; rec->beta_trans = bt; rec->beta_rot = br; }
+}
+
+int do_forces(ls1b200_ctx* c) {
+	if (c->n_owned == 0) { c->forces_valid = true; return 0; }
+	LS1_TRY(span_begin(c, PH_FORCE));
+	LS1_TRY(c->all_1clj ? force_1clj(c) : force_general(c));
+	LS1_TRY(span_end(c));
+	c->forces_valid = true;
+	return 0;
+}
+
+int do_leapfrog_pre(ls1b200_ctx* c, double dt, bool use_beta) {
+	if (c->n_owned == 0) return 0;
+	LS1_TRY(span_begin(c, PH_PRE));
+	const uint32_t g = (uint32_t) ((c->cap + 255) / 256);
+	LS1_LAUNCH(c, PH_PRE, k_leapfrog_pre, g, 256, 0, c->cur, c->F, c->M, (uint32_t) c->cap, c->d_comps, dt, c->d_scal, c->parity, (int) use_beta, (int) c->rotates);
+	LS1_TRY(span_end(c));
+	c->forces_valid = false;
+	return 0;
+}
+
+int do_leapfrog_post(ls1b200_ctx* c, double dt) {
+	if (c->n_owned == 0) return 0;
+	LS1_TRY(span_begin(c, PH_POST));
+	const uint32_t g = (uint32_t) ((c->cap + 255) / 256);
+	if (g > c->partial_blocks) return fail("leapfrog_post: partials buffer too small");
+	LS1_LAUNCH(c, PH_POST, k_leapfrog_post, g, 256, 0, c->cur, c->F, c->M, (uint32_t) c->cap, c->d_comps, dt, c->d_scal, c->parity, (int) c->rotates, c->partials);
+	LS1_LAUNCH(c, PH_POST, k_reduce_kinetic, 1, 1024, 0, c->partials, g, c->d_scal);
+	LS1_TRY(span_end(c));
+	return 0;
+}
+
+int do_globals(ls1b200_ctx* c, double target_T, uint64_t global_n, double global_volume, ls1b200_step_record* d_rec) {
+	const uint64_t N = global_n ? global_n : c->n_owned;
+	double V = global_volume;
+	if (!(V > 0.)) V = c->geom.lbox[0] * c->geom.lbox[1] * c->geom.lbox[2];
+	LS1_LAUNCH(c, PH_POST, k_globals, 1, 32, 0, c->d_scal, target_T, (unsigned long long) N, (unsigned long long) c->rot_dof_total, V, d_rec);
+	return 0;
+}
+
+}  // namespace ls1b200
+
+using namespace ls1b200;
+
+extern "C" {
+
+int ls1b200_leapfrog_pre(ls1b200_ctx* c, double dt) {
+	if (!c) return fail("ls1b200_leapfrog_pre: null context");
+	LS1_CUDA(cudaSetDevice(c->device));
+	return do_leapfrog_pre(c, dt, false);
+}
+
+int ls1b200_leapfrog_post(ls1b200_ctx* c, double dt, ls1b200_kinetic* out) {
+	if (!c) return fail("ls1b200_leapfrog_post: null context");
+	LS1_CUDA(cudaSetDevice(c->device));
+	LS1_TRY(do_leapfrog_post(c, dt));
+	if (out) {
+		LS1_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
+		LS1_CUDA(cudaStreamSynchronize(c->stream));
+		out->summv2 = c->h_scal->summv2; out->sum_iw2 = c->h_scal->sum_iw2;
+		out->n_molecules = c->n_owned; out->rot_dof = c->rot_dof_total;
+	}
+	return 0;
+}
+
+int ls1b200_scale_velocities(ls1b200_ctx* c, double beta_trans, double beta_rot) {
+	if (!c) return fail("ls1b200_scale_velocities: null context");
+	LS1_CUDA(cudaSetDevice(c->device));
+	if (c->n_owned == 0) return 0;
+	const uint32_t g = (uint32_t) ((c->cap + 255) / 256);
+	LS1_LAUNCH(c, PH_POST, k_scale, g, 256, 0, c->cur, (uint32_t) c->cap, beta_trans, beta_rot, c->d_scal, c->parity, 0, (int) c->rotates);
+	return 0;
+}
+
+int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_temperature, uint64_t global_n, double global_volume,
+                     ls1b200_step_record* records) {
+	if (!c) return fail("ls1b200_simulate: null context");
+	if (!c->forces_valid) return fail("ls1b200_simulate: forces are not valid (call ls1b200_update + ls1b200_traverse_cells first)");
+	LS1_CUDA(cudaSetDevice(c->device));
+	if (n_steps == 0) return 0;
+	if (c->records_cap < n_steps) {
+		if (c->d_records) cudaFree(c->d_records);
+		c->d_records = nullptr; c->records_cap = 0;
+		LS1_CUDA(cudaMalloc((void**) &c->d_records, sizeof(ls1b200_step_record) * n_steps));
+		c->records_cap = n_steps;
+	}
+	// thermostat factors of the previous call have already been applied: start from 1
+	c->h_scal->beta_trans = 1.; c->h_scal->beta_rot = 1.;
+	LS1_CUDA(cudaMemcpyAsync(&c->d_scal->beta_trans, &c->h_scal->beta_trans, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	for (uint64_t s = 0; s < n_steps; s++) {
+		LS1_TRY(do_leapfrog_pre(c, dt, target_temperature > 0.));
+		LS1_TRY(do_update(c));
+		LS1_TRY(do_forces(c));
+		LS1_TRY(do_leapfrog_post(c, dt));
+		LS1_TRY(do_globals(c, target_temperature, global_n, global_volume, c->d_records + s));
+	}
+	if (target_temperature > 0.) {   // the scaling the next leapfrog_pre would have applied on load
+		const uint32_t g = (uint32_t) ((c->cap + 255) / 256);
+		LS1_LAUNCH(c, PH_POST, k_scale, g, 256, 0, c->cur, (uint32_t) c->cap, 1., 1., c->d_scal, c->parity, 1, (int) c->rotates);
+	}
+	if (records) LS1_CUDA(cudaMemcpyAsync(records, c->d_records, sizeof(ls1b200_step_record) * n_steps, cudaMemcpyDeviceToHost, c->stream));
+	LS1_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
+	LS1_CUDA(cudaStreamSynchronize(c->stream));
+	c->n_slots = std::min<uint64_t>(c->h_scal->n_slots2[c->parity], c->cap);
+	if (c->h_scal->overflow) return fail("ls1b200_simulate: slot capacity exceeded (more halo copies than reserved)");
+	return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,260 @@
+// update.cu -- ls1b200_update(): LinkedCells::update() + DomainDecompBase::exchangeMolecules() (periodic, one rank) +
+// LinkedCells::updateMoleculeCaches() as a deterministic counting sort on the device.
+//
+// Reference: Simulation::updateParticleContainerAndDecomposition (Simulation.cpp:1417-1455);
+//   LinkedCells::update_via_copies (particleContainer/LinkedCells.cpp:303-355) -- which cell a molecule belongs to;
+//   DomainDecompBase::handleDomainLeavingParticles / populateHaloLayerWithCopies (parallel/DomainDecompBase.cpp:199-249,
+//   :317-376) -- wrap + periodic halo copies;
+//   FullParticleCell::buildSoACaches / FullMolecule::setupSoACache (FullParticleCell.cpp:141-191, FullMolecule.cpp:711-767)
+//   -- calc-precision SoA (site expansion).
+//
+// Kernels (all HBM-bound; algorithmic bytes per molecule in DESIGN.md):
+//   k_key      wrap, cell index (bit exact), histogram of owned molecules + periodic copies
+//   k_scan_*   exclusive scan of the histogram -> cell_start
+//   k_scatter  provisional slot per molecule / copy (atomic cursor, order not yet deterministic)
+//   k_gather   deterministic rank inside the cell (by source slot, shift code), permutes the FP64 state cur -> nxt,
+//              writes the calc-precision molecule record mpos
+//   k_sites    quaternion -> site positions / orientations in calc precision (multi-site components only)
+#include "geom.cuh"
+#include "types.cuh"
+
+namespace ls1b200 {
+
+constexpr int SHIFT_BITS = 26;   // key = bin | shiftmask << 26  (bin <= ncells < 2^26)
+
+struct UpdArgs {
+	Geom g;
+	uint32_t cap;
+	uint32_t parity;     // DevScalars::n_slots2[parity] = source slots of this update, [parity^1] receives the new count
+};
+
+__device__ __forceinline__ bool code_valid(uint32_t mask, int a, int b, int c) {
+	return (a == 0 || ((mask >> (a - 1)) & 1u)) && (b == 0 || ((mask >> (2 + b - 1)) & 1u)) && (c == 0 || ((mask >> (4 + c - 1)) & 1u));
+}
+
+__global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __restrict__ key, uint32_t* __restrict__ count, const DevScalars* __restrict__ scal) {
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= min(scal->n_slots2[a.parity], a.cap)) return;
+	const uint64_t meta = cur.meta[s];
+	if (meta_halo(meta)) { key[s] = KEY_NONE; return; }
+	const Geom& g = a.g;
+	double x = cur.r[s], y = cur.r[(size_t) a.cap + s], z = cur.r[2 * (size_t) a.cap + s];
+	if (g.periodic[0]) { double w = wrap_coord<0>(g, x); if (w != x) { x = w; cur.r[s] = w; } }
+	if (g.periodic[1]) { double w = wrap_coord<1>(g, y); if (w != y) { y = w; cur.r[(size_t) a.cap + s] = w; } }
+	if (g.periodic[2]) { double w = wrap_coord<2>(g, z); if (w != z) { z = w; cur.r[2 * (size_t) a.cap + s] = w; } }
+	const int cx = cell1d<0>(g, x), cy = cell1d<1>(g, y), cz = cell1d<2>(g, z);
+	const bool out = cx < 0 || cy < 0 || cz < 0 || cx >= g.cells[0] || cy >= g.cells[1] || cz >= g.cells[2];
+	if (out) {
+		key[s] = g.ncells;
+		atomicAdd(&count[g.ncells], 1u);
+		return;
+	}
+	const uint32_t bin = cell_index(g, cx, cy, cz);
+	const uint32_t mask = shift_mask<0>(g, x) | (shift_mask<1>(g, y) << 2) | (shift_mask<2>(g, z) << 4);
+	key[s] = bin | (mask << SHIFT_BITS);
+	atomicAdd(&count[bin], 1u);
+	if (mask) {
+		for (int c3 = 0; c3 < 3; c3++) for (int b3 = 0; b3 < 3; b3++) for (int a3 = 0; a3 < 3; a3++) {
+			if ((a3 | b3 | c3) == 0 || !code_valid(mask, a3, b3, c3)) continue;
+			const int hx = cell1d<0>(g, halo_coord<0>(g, x, a3)), hy = cell1d<1>(g, halo_coord<1>(g, y, b3)), hz = cell1d<2>(g, halo_coord<2>(g, z, c3));
+			atomicAdd(&count[cell_index(g, hx, hy, hz)], 1u);
+		}
+	}
+}
+
+// ---- exclusive scan (three small kernels; n = ncells + 1 bins) ----------------------------------------------------
+constexpr int SCAN_T = 256, SCAN_V = 8, SCAN_B = SCAN_T * SCAN_V;
+
+__device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* total, uint32_t* sh /*[32]*/) {
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint32_t inc = v;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+	if (lane == 31) sh[w] = inc;
+	__syncthreads();
+	if (w == 0) {
+		uint32_t x = (lane < (blockDim.x >> 5)) ? sh[lane] : 0u, xi = x;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += t; }
+		sh[lane] = xi - x;
+		if (lane == 31) *total = xi;
+	}
+	__syncthreads();
+	uint32_t r = sh[w] + inc - v;
+	__syncthreads();
+	return r;
+}
+
+__global__ void __launch_bounds__(SCAN_T) k_scan_block(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* __restrict__ bsum, uint32_t n) {
+	__shared__ uint32_t sh[32]; __shared__ uint32_t tot;
+	const uint32_t base = blockIdx.x * SCAN_B + threadIdx.x * SCAN_V;
+	uint32_t v[SCAN_V], sum = 0;
+	#pragma unroll
+	for (int k = 0; k < SCAN_V; k++) { v[k] = (base + k < n) ? in[base + k] : 0u; sum += v[k]; }
+	uint32_t off = block_exclusive_scan(sum, &tot, sh);
+	#pragma unroll
+	for (int k = 0; k < SCAN_V; k++) { if (base + k < n) out[base + k] = off; off += v[k]; }
+	if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(SCAN_T) k_scan_top(uint32_t* __restrict__ bsum, uint32_t nb, uint32_t* __restrict__ grand_total) {
+	__shared__ uint32_t sh[32]; __shared__ uint32_t tot;
+	uint32_t carry = 0;
+	for (uint32_t b0 = 0; b0 < nb; b0 += SCAN_T) {
+		const uint32_t i = b0 + threadIdx.x;
+		const uint32_t v = (i < nb) ? bsum[i] : 0u;
+		const uint32_t off = block_exclusive_scan(v, &tot, sh);
+		if (i < nb) bsum[i] = carry + off;
+		carry += tot;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) *grand_total = carry;
+}
+// adds the block offsets; writes cell_start[0..n] (cell_start[n] = total), the scatter cursor, and the slot count
+__global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict__ start, uint32_t* __restrict__ cursor, const uint32_t* __restrict__ bsum,
+                                                      const uint32_t* __restrict__ grand_total, uint32_t n, uint32_t cap, uint32_t parity, DevScalars* scal) {
+	const uint32_t base = blockIdx.x * SCAN_B + threadIdx.x * SCAN_V;
+	const uint32_t off = bsum[blockIdx.x];
+	#pragma unroll
+	for (int k = 0; k < SCAN_V; k++) if (base + k < n) { uint32_t v = start[base + k] + off; start[base + k] = v; cursor[base + k] = v; }
+	if (blockIdx.x == 0 && threadIdx.x == 0) {
+		const uint32_t total = *grand_total;
+		start[n] = total;
+		scal->n_slots2[parity ^ 1u] = total;
+		if (total > cap) scal->overflow = 1;
+	}
+}
+
+__global__ void __launch_bounds__(256) k_scatter(UpdArgs a, State cur, const uint32_t* __restrict__ key, uint32_t* __restrict__ cursor,
+                                                  uint32_t* __restrict__ entry, uint32_t* __restrict__ cell_of, const DevScalars* __restrict__ scal) {
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= min(scal->n_slots2[a.parity], a.cap)) return;
+	const uint32_t k = key[s];
+	if (k == KEY_NONE) return;
+	const Geom& g = a.g;
+	const uint32_t bin = k & ((1u << SHIFT_BITS) - 1u), mask = k >> SHIFT_BITS;
+	uint32_t p = atomicAdd(&cursor[bin], 1u);
+	if (p < a.cap) { entry[p] = s << 5; cell_of[p] = bin; }
+	if (mask) {
+		const double x = cur.r[s], y = cur.r[(size_t) a.cap + s], z = cur.r[2 * (size_t) a.cap + s];
+		for (int c3 = 0; c3 < 3; c3++) for (int b3 = 0; b3 < 3; b3++) for (int a3 = 0; a3 < 3; a3++) {
+			if ((a3 | b3 | c3) == 0 || !code_valid(mask, a3, b3, c3)) continue;
+			const int hx = cell1d<0>(g, halo_coord<0>(g, x, a3)), hy = cell1d<1>(g, halo_coord<1>(g, y, b3)), hz = cell1d<2>(g, halo_coord<2>(g, z, c3));
+			const uint32_t hb = cell_index(g, hx, hy, hz);
+			p = atomicAdd(&cursor[hb], 1u);
+			if (p < a.cap) { entry[p] = (s << 5) | (uint32_t) (a3 + 3 * b3 + 9 * c3); cell_of[p] = hb; }
+		}
+	}
+}
+
+template <class C>
+__global__ void __launch_bounds__(256) k_gather(UpdArgs a, State cur, State nxt, const uint32_t* __restrict__ entry, const uint32_t* __restrict__ cell_of,
+                                                 const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_of2,
+                                                 typename Vec4<C>::type* __restrict__ mpos, const DevScalars* __restrict__ scal, int rotates) {
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t n_slots = min(scal->n_slots2[a.parity ^ 1u], a.cap);
+	if (p >= n_slots) return;
+	const Geom& g = a.g;
+	const uint32_t e = entry[p], c = cell_of[p];
+	const uint32_t b = cell_start[c], en = min(cell_start[c + 1], a.cap);
+	uint32_t rank = 0;
+	for (uint32_t u = b; u < en; u++) rank += (entry[u] < e) ? 1u : 0u;
+	const uint32_t t = b + rank, s = e >> 5, code = e & 31u;
+	const size_t cap = a.cap;
+	double x = cur.r[s], y = cur.r[cap + s], z = cur.r[2 * cap + s];
+	uint64_t meta = cur.meta[s];
+	if (code) {
+		const int a3 = code % 3, b3 = (code / 3) % 3, c3 = code / 9;
+		x = halo_coord<0>(g, x, a3); y = halo_coord<1>(g, y, b3); z = halo_coord<2>(g, z, c3);
+		meta |= META_HALO;
+	}
+	nxt.r[t] = x; nxt.r[cap + t] = y; nxt.r[2 * cap + t] = z;
+	nxt.meta[t] = meta;
+	#pragma unroll
+	for (int d = 0; d < 3; d++) nxt.v[d * cap + t] = cur.v[d * cap + s];
+	if (rotates) {
+		#pragma unroll
+		for (int d = 0; d < 4; d++) nxt.q[d * cap + t] = cur.q[d * cap + s];
+		#pragma unroll
+		for (int d = 0; d < 3; d++) nxt.L[d * cap + t] = cur.L[d * cap + s];
+	}
+	cell_of2[t] = c;
+	// the limbo bin and halo cells never hold "i" molecules: flag them like halo copies in the calc record
+	const bool inert = code != 0 || c >= g.ncells || is_halo_cell(g, c);
+	mpos[t] = make_mrec<C>(x, y, z, meta_cid(meta) | (inert ? 0x80000000u : 0u));
+}
+
+// ---- site expansion (FullMolecule::setupSoACache, molecules/FullMolecule.cpp:711-767; Quaternion::rotate, Quaternion.cpp:43-64)
+__device__ __forceinline__ void q_rotate(const double* q, const double* d, double* o) {
+	if (d[0] == 0. && d[1] == 0. && d[2] == 0.) { o[0] = o[1] = o[2] = 0.; return; }
+	const double w = q[0], x = q[1], y = q[2], z = q[3];
+	const double ww = w * w, xx = x * x, yy = y * y, zz = z * z, wx = w * x, wy = w * y, wz = w * z, xy = x * y, xz = x * z, yz = y * z;
+	o[0] = (ww + xx - yy - zz) * d[0] + 2. * (xy - wz) * d[1] + 2. * (wy + xz) * d[2];
+	o[1] = 2. * (wz + xy) * d[0] + (ww - xx + yy - zz) * d[1] + 2. * (yz - wx) * d[2];
+	o[2] = 2. * (xz - wy) * d[0] + 2. * (wx + yz) * d[1] + (ww - xx - yy + zz) * d[2];
+}
+
+template <class C>
+__global__ void __launch_bounds__(128) k_sites(State st, uint32_t cap, uint32_t smax, const CompDev* __restrict__ comps, const SiteDev* __restrict__ sites,
+                                                typename Vec4<C>::type* __restrict__ spos, typename Vec4<C>::type* __restrict__ sori,
+                                                const DevScalars* __restrict__ scal, uint32_t parity, int rotates) {
+	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (t >= min(scal->n_slots2[parity], cap)) return;
+	const uint64_t meta = st.meta[t];
+	const CompDev& cp = comps[meta_cid(meta)];
+	const double r[3] = {st.r[t], st.r[(size_t) cap + t], st.r[2 * (size_t) cap + t]};
+	double qn[4] = {1., 0., 0., 0.};
+	if (rotates) {
+		for (int k = 0; k < 4; k++) qn[k] = st.q[(size_t) k * cap + t];
+		const double sc = 1. / sqrt(qn[0] * qn[0] + qn[1] * qn[1] + qn[2] * qn[2] + qn[3] * qn[3]);
+		for (int k = 0; k < 4; k++) qn[k] *= sc;
+	}
+	for (uint32_t k = 0; k < cp.nsites; k++) {
+		const SiteDev& sd = sites[cp.site_offset + k];
+		double d3[3], e3[3] = {0., 0., 0.};
+		q_rotate(qn, sd.r, d3);
+		if (sd.type >= 2) q_rotate(qn, sd.e, e3);
+		C w = (C) sd.param;
+		if (sd.type == 0) {
+			if (sizeof(C) == 4) w = (C) __uint_as_float(sd.ljid); else w = (C) __longlong_as_double((long long) sd.ljid);
+		}
+		spos[(size_t) t * smax + k] = make_c4<C>((C) (d3[0] + r[0]), (C) (d3[1] + r[1]), (C) (d3[2] + r[2]), w);
+		sori[(size_t) t * smax + k] = make_c4<C>((C) e3[0], (C) e3[1], (C) e3[2], (C) 0);
+	}
+}
+
+int do_update(ls1b200_ctx* c) {
+	if (!c->components_set) return fail("ls1b200_update: components not set");
+	if (c->n_owned == 0) { c->sorted = true; return 0; }
+	LS1_TRY(span_begin(c, PH_UPDATE));
+	UpdArgs a; a.g = c->geom; a.cap = (uint32_t) c->cap; a.parity = c->parity;
+	const uint32_t nb = c->geom.ncells + 1;   // + limbo bin
+	LS1_CUDA(cudaMemsetAsync(c->cell_count, 0, sizeof(uint32_t) * (nb + 1), c->stream));
+	// slot counts are only known on the device: every per-slot kernel is launched over the capacity, threads beyond exit
+	const uint32_t gs = (uint32_t) ((c->cap + 255) / 256);
+	LS1_LAUNCH(c, PH_UPDATE, k_key, gs, 256, 0, a, c->cur, c->key, c->cell_count, c->d_scal);
+	const uint32_t sb = (nb + SCAN_B - 1) / SCAN_B;
+	LS1_LAUNCH(c, PH_UPDATE, k_scan_block, sb, SCAN_T, 0, c->cell_count, c->cell_start, c->scan_tmp, nb);
+	LS1_LAUNCH(c, PH_UPDATE, k_scan_top, 1, SCAN_T, 0, c->scan_tmp, sb, c->scan_tmp + sb);
+	LS1_LAUNCH(c, PH_UPDATE, k_scan_add, sb, SCAN_T, 0, c->cell_start, c->cursor, c->scan_tmp, c->scan_tmp + sb, nb, (uint32_t) c->cap, a.parity, c->d_scal);
+	LS1_LAUNCH(c, PH_UPDATE, k_scatter, gs, 256, 0, a, c->cur, c->key, c->cursor, c->entry, c->cell_of, c->d_scal);
+	const uint32_t gc = gs;
+	if (c->mixed)
+		LS1_LAUNCH(c, PH_UPDATE, k_gather<float>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, c->cell_start, c->cell_of2, (float4*) c->mpos, c->d_scal, (int) c->rotates);
+	else
+		LS1_LAUNCH(c, PH_UPDATE, k_gather<double>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, c->cell_start, c->cell_of2, (double4*) c->mpos, c->d_scal, (int) c->rotates);
+	std::swap(c->cur, c->nxt);
+	c->parity ^= 1u;
+	if (!c->all_1clj) {
+		const uint32_t g2 = (uint32_t) ((c->cap + 127) / 128);
+		if (c->mixed)
+			LS1_LAUNCH(c, PH_UPDATE, k_sites<float>, g2, 128, 0, c->cur, (uint32_t) c->cap, c->smax, c->d_comps, c->d_sites, (float4*) c->spos, (float4*) c->sori, c->d_scal, c->parity, (int) c->rotates);
+		else
+			LS1_LAUNCH(c, PH_UPDATE, k_sites<double>, g2, 128, 0, c->cur, (uint32_t) c->cap, c->smax, c->d_comps, c->d_sites, (double4*) c->spos, (double4*) c->sori, c->d_scal, c->parity, (int) c->rotates);
+	}
+	LS1_TRY(span_end(c));
+	c->sorted = true;
+	c->forces_valid = false;
+	return 0;
+}
+
+}  // namespace ls1b200

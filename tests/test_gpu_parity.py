@@ -1,0 +1,221 @@
+"""Parity of the CUDA path (libls1b200.so through its C ABI) against (a) the golden vectors produced by the unmodified
+reference build and (b) the CPU oracle on seeded synthetic inputs. Needs a B200: run with -m gpu.
+
+Mirrors the reference's own VectorizedCellProcessorTest (known answers U0/F0, the 11 differential Vectorization*
+fixtures) and LinkedCellsTest (cell assignment, halo), plus multi-step T / U / p traces.
+Tolerances (north_star): bit-exact cell binning; F, M, Vi, Upot, Virial within 1e-10 relative (double) / 1e-5 (mixed)."""
+import numpy as np
+import pytest
+
+from helpers import ABS_SCALE, TOL, macro_close, golden_names, load, make_sim, ref_by_id, rel_close
+
+pytestmark = pytest.mark.gpu
+
+FORCE = golden_names("force_")
+PERIODIC = golden_names("periodic_")
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from ls1_mardyn_b200 import capi
+    capi.lib()
+    return capi
+
+
+def test_known_answers_U0_F0(capi):
+    g = load("force_ForceCalculationTestU0")
+    for prec, tol in (("double", 1e-8), ("mixed", 1e-4)):
+        s = make_sim(capi.Context, g, prec); s.update(); m = s.traverse_cells()
+        F = s.download("F")
+        assert abs(m.upot) < tol and abs(m.virial - 96.0) < tol * 96
+        expect = np.array([[-24, -24, 0], [24, -24, 0], [-24, 24, 0], [24, 24, 0]], dtype=float)
+        assert np.allclose(F, expect, atol=tol * 24)
+    g = load("force_ForceCalculationTestF0")
+    for prec, tol in (("double", 1e-8), ("mixed", 1e-4)):
+        s = make_sim(capi.Context, g, prec); s.update(); m = s.traverse_cells()
+        assert abs(m.upot + 4.0) < tol * 4 and np.abs(s.download("F")).max() < max(tol, 1e-7) * 24
+
+
+@pytest.mark.parametrize("name", FORCE + PERIODIC)
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_forces_vs_reference_golden(capi, name, prec):
+    g = load(name)
+    s = make_sim(capi.Context, g, prec)
+    s.update()
+    m = s.traverse_cells()
+    ref = ref_by_id(g, prec)
+    tol = TOL[prec]
+    assert np.array_equal(s.download("CELL"), ref["cell"]), "cell assignment differs from the reference"
+    for k, fld in (("F", "F"), ("M", "M"), ("Vi", "VI")):
+        ok, worst = rel_close(s.download(fld), ref[k], tol, ABS_SCALE.get(name))
+        assert ok, f"{name} {prec} {k}: worst err/bound = {worst:.3g}"
+    assert macro_close(m, g, prec, ref, ABS_SCALE.get(name))
+    assert np.array_equal(s.download("ID"), g["in_id"]) and np.array_equal(s.download("CID"), g["in_cid"])
+
+
+def _lattice_case(n_per_dim, seed, jitter=0.1, ens=None, rho=0.7, T=0.85, rc=2.5):
+    from ls1_mardyn_b200 import generators
+    from ls1_mardyn_b200.components import lj_fluid
+    ens = ens or lj_fluid(rc=rc)
+    return generators.lattice(ens, n_per_dim, rho, T, seed=seed, jitter=jitter, rc=rc)
+
+
+def _mk(cls, ps, rc, prec, periodic=(1, 1, 1)):
+    s = cls([0, 0, 0], list(ps.length), rc, epsilon_rf=ps.epsilon_rf, precision=prec, geometry="xml", periodic=periodic)
+    s.set_components(ps.ensemble)
+    s.upload(ps.id, ps.cid, ps.r, ps.v, ps.q, ps.L)
+    return s
+
+
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_1clj_lattice_vs_oracle(capi, prec):
+    """16k-molecule periodic 1CLJ liquid: bit-exact cells, forces / virial / energy against the CPU oracle."""
+    from oracle import oracle as orc
+    ps = _lattice_case(20, seed=11)
+    a = _mk(capi.Context, ps, 2.5, prec); b = _mk(orc.OracleSim, ps, 2.5, prec)
+    a.update(); b.update()
+    assert np.array_equal(a.download("CELL"), b.download("CELL"))
+    assert np.array_equal(a.download("R"), b.download("R"))   # periodic wrap is bit-exact
+    ma, mb = a.traverse_cells(), b.traverse_cells()
+    tol = TOL[prec]
+    for f in ("F", "VI"):
+        ok, worst = rel_close(a.download(f), b.download(f), tol)
+        assert ok, (f, worst)
+    assert abs(ma.upot - mb.upot) <= tol * abs(mb.upot) and abs(ma.virial - mb.virial) <= tol * max(abs(mb.virial), np.abs(b.download("VI")).sum())
+    # FlopCounter counts (pair set identity): integers, must agree exactly
+    fa, fb = a.count_flops(), b.count_flops()
+    for k, _ in fa._fields_:
+        assert getattr(fa, k) == getattr(fb, k), k
+
+
+def test_multicomponent_1clj_fast_path(capi):
+    """Two single-centre LJ components (Lorentz-Berthelot mixing): the 1CLJ fast path with table lookups."""
+    from oracle import oracle as orc
+    from ls1_mardyn_b200.components import Component, Ensemble, LJcenter
+    ens = Ensemble([Component(ljcenters=[LJcenter((0, 0, 0), 1.0, 1.0, 1.0, 2.5, False)]),
+                    Component(ljcenters=[LJcenter((0, 0, 0), 2.0, 0.7, 1.15, 2.5, True)])],
+                   xi=np.array([[1, 0.9], [1, 1]]), eta=np.array([[1, 1.05], [1, 1]]))
+    ps = _lattice_case(8, seed=5, ens=ens, rho=0.6)
+    for prec in ("double", "mixed"):
+        a = _mk(capi.Context, ps, 2.5, prec); b = _mk(orc.OracleSim, ps, 2.5, prec)
+        a.update(); b.update(); ma, mb = a.traverse_cells(), b.traverse_cells()
+        for f in ("F", "VI"):
+            ok, worst = rel_close(a.download(f), b.download(f), TOL[prec])
+            assert ok, (prec, f, worst)
+        assert abs(ma.upot - mb.upot) <= TOL[prec] * abs(mb.upot)
+
+
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_leapfrog_and_thermostat_steps_vs_oracle(capi, prec):
+    """Phase-by-phase: pre -> update -> traverse -> post -> scale, 5 steps, state compared after every phase."""
+    from oracle import oracle as orc
+    g = load("periodic_water_432")
+    a = make_sim(capi.Context, g, prec); b = make_sim(orc.OracleSim, g, prec)
+    for s in (a, b):
+        s.update(); s.traverse_cells()
+    dt = 0.5
+    tol = 1e-9 if prec == "double" else 2e-5
+    for step in range(5):
+        for s in (a, b):
+            s.leapfrog_pre(dt)
+        for f in ("R", "V", "Q", "L"):
+            ok, worst = rel_close(a.download(f), b.download(f), tol); assert ok, (step, "pre", f, worst)
+        for s in (a, b):
+            s.update()
+        assert np.array_equal(a.download("CELL"), b.download("CELL"))
+        ma, mb = a.traverse_cells(), b.traverse_cells()
+        for f in ("F", "M", "VI"):
+            ok, worst = rel_close(a.download(f), b.download(f), 10 * tol); assert ok, (step, "force", f, worst)
+        ka, kb = a.leapfrog_post(dt), b.leapfrog_post(dt)
+        assert ka.n_molecules == kb.n_molecules and ka.rot_dof == kb.rot_dof
+        assert abs(ka.summv2 - kb.summv2) <= tol * kb.summv2 and abs(ka.sum_iw2 - kb.sum_iw2) <= 10 * tol * kb.sum_iw2
+        for s in (a, b):
+            s.scale_velocities(0.999, 1.002)
+        for f in ("V", "L"):
+            ok, worst = rel_close(a.download(f), b.download(f), tol); assert ok, (step, "scale", f, worst)
+
+
+@pytest.mark.parametrize("name,dt,nsteps", [("periodic_1clj_1458", 0.002, 100), ("periodic_water_432", 0.0667516, 40), ("periodic_multi_250", 0.0667516, 40)])
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_simulate_trace_vs_oracle(capi, name, dt, nsteps, prec):
+    """Fused multi-step loop (NVT velocity scaling): T, U_pot, p per step against the oracle's loop."""
+    from oracle import oracle as orc
+    g = load(name)
+    a = make_sim(capi.Context, g, prec); b = make_sim(orc.OracleSim, g, prec)
+    for s in (a, b):
+        s.update(); s.traverse_cells()
+    T = float(g["temperature"])
+    ra = a.simulate(nsteps, dt, T); rb = b.simulate(nsteps, dt, T)
+    cols = dict(upot=0, virial=1, summv2=2, temperature=4, pressure=5, beta_trans=6)
+    tol = 1e-9 if prec == "double" else 1e-6
+    for k, i in cols.items():
+        scale = np.abs(rb[:, i]).max()
+        # p = rho*T + rho*W/3N is a near cancellation: compare against the size of its terms (hard parts)
+        if k == "pressure":
+            N = len(g["in_id"]); V = float(np.prod(g["length"]))
+            scale = max(scale, (N / V) * np.abs(rb[:, 4]).max())
+        err = np.abs(ra[:, i] - rb[:, i]).max() / scale
+        assert err <= tol, f"{name} {prec} {k}: {err:.3g}"
+    ok, worst = rel_close(a.download("R"), b.download("R"), 1e-7 if prec == "double" else 1e-4, scale=1.0)
+    assert ok, worst
+
+
+def test_simulate_equals_phase_calls(capi):
+    """ls1b200_simulate is the same arithmetic as the individual phase calls (thermostat applied on load)."""
+    g = load("periodic_1clj_1458")
+    a = make_sim(capi.Context, g, "double"); b = make_sim(capi.Context, g, "double")
+    for s in (a, b):
+        s.update(); s.traverse_cells()
+    dt, T, n = 0.002, 0.85, 6
+    ra = a.simulate(n, dt, T)
+    N = len(g["in_id"])
+    for i in range(n):
+        b.leapfrog_pre(dt); b.update(); m = b.traverse_cells(); k = b.leapfrog_post(dt)
+        bt = (3.0 * N * T / k.summv2) ** 0.4
+        assert abs(m.upot - ra[i, 0]) <= 1e-12 * abs(m.upot) and abs(bt - ra[i, 6]) <= 1e-13
+        b.scale_velocities(bt, 1.0)
+    assert np.allclose(a.download("V"), b.download("V"), rtol=1e-12, atol=1e-14)
+    assert np.allclose(a.download("R"), b.download("R"), rtol=1e-13, atol=1e-13)
+
+
+def test_update_is_deterministic_and_idempotent(capi):
+    ps = _lattice_case(12, seed=3, jitter=0.2)
+    a = _mk(capi.Context, ps, 2.5, "mixed"); b = _mk(capi.Context, ps, 2.5, "mixed")
+    a.update(); a.traverse_cells(); b.update(); b.update(); b.update(); b.traverse_cells()
+    assert np.array_equal(a.download("CELL"), b.download("CELL"))
+    assert np.array_equal(a.download("F"), b.download("F"))          # bit-identical: order inside a cell is deterministic
+    assert np.array_equal(a.download("R"), b.download("R"))
+
+
+def test_edge_cases(capi):
+    from ls1_mardyn_b200.components import lj_fluid
+    ens = lj_fluid()
+    # empty container
+    s = capi.Context([0, 0, 0], [10, 10, 10], 2.5); s.set_components(ens)
+    s.upload(np.zeros(0, np.uint64), np.zeros(0, np.uint32), np.zeros((0, 3)), np.zeros((0, 3)))
+    s.update(); m = s.traverse_cells(); assert m.upot == 0 and m.virial == 0
+    # a single molecule, and two molecules interacting only through the periodic image
+    s = capi.Context([0, 0, 0], [10, 10, 10], 2.5, precision="double"); s.set_components(ens)
+    s.upload(np.array([7], np.uint64), np.zeros(1, np.uint32), np.array([[0.1, 5, 5]]), np.zeros((1, 3)))
+    s.update(); m = s.traverse_cells(); assert m.upot == 0 and np.all(s.download("F") == 0)
+    s.upload(np.array([1, 2], np.uint64), np.zeros(2, np.uint32), np.array([[0.5, 5, 5], [9.5, 5, 5]]), np.zeros((2, 3)))
+    s.update(); m = s.traverse_cells()
+    r = 1.0; u = 4 * (r ** -12 - r ** -6); f = 24 * (2 * r ** -12 - r ** -6) / r
+    F = s.download("F")
+    assert abs(m.upot - u) < 1e-12 and abs(F[0, 0] - f) < 1e-10 * f and abs(F[1, 0] + f) < 1e-10 * f
+    assert abs(m.virial - f * r) < 1e-10 * f
+    # molecules that left the box are wrapped by update() exactly like DomainDecompBase::handleDomainLeavingParticles
+    s.upload(np.array([1, 2], np.uint64), np.zeros(2, np.uint32), np.array([[-0.25, 5, 5], [10.0, 11.5, -1e-17]]), np.zeros((2, 3)))
+    s.update(); R = s.download("R")
+    assert R[0, 0] == 9.75 and R[1, 0] == 0.0 and R[1, 1] == 1.5 and 0 <= R[1, 2] < 10
+    # errors are reported, never thrown past the ABI
+    with pytest.raises(capi.Ls1B200Error):
+        capi.Context([0, 0, 0], [1, 1, 1], 2.5)
+    with pytest.raises(capi.Ls1B200Error):
+        s2 = capi.Context([0, 0, 0], [10, 10, 10], 2.5); s2.update()
+
+
+def test_kernels_were_launched(capi):
+    assert capi.kernel_launch_count() > 0
