@@ -163,6 +163,11 @@ struct ls1b200_ctx {
 	void* sori = nullptr;             // [cap*smax] float4 / double4: site orientation
 	double* sf = nullptr;             // [cap*smax][9]: per-site force, virial, torque (general path)
 
+	// chunk list of the tiled 1CLJ kernel (force_1clj_tiled.cu)
+	void* chunks = nullptr; uint32_t* chunk_row_count = nullptr; uint32_t* chunk_row_start = nullptr; uint32_t* work_counter = nullptr;
+	int sm_count = 148;
+	int lj_kernel = 0;                // 0: tiled (shared-memory windows, TMA), 1: global-memory variant (force_1clj.cu)
+
 	// reductions
 	double* partials = nullptr;       // [n_partial_blocks][8]
 	uint32_t partial_blocks = 0;
@@ -197,5 +202,6 @@ int do_leapfrog_post(ls1b200_ctx* c, double dt);
 int do_globals(ls1b200_ctx* c, double target_T, uint64_t global_n, double global_volume, ls1b200_step_record* d_rec);
 int force_general(ls1b200_ctx* c);
 int force_1clj(ls1b200_ctx* c);
+int force_1clj_tiled(ls1b200_ctx* c);
 int reduce_force_partials(ls1b200_ctx* c, uint32_t nblocks);
 }  // namespace ls1b200

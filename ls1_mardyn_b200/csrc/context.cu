@@ -1,6 +1,7 @@
 // context.cu -- C ABI of include/ls1b200.h: context life cycle, components, upload / download, geometry, timing.
 // Reference for the geometry: LinkedCells ctor / rebuild (particleContainer/LinkedCells.cpp:47-58, :148-166).
 #include <math.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include <algorithm>
@@ -78,13 +79,21 @@ int ctx_alloc_molecules(ls1b200_ctx* c, uint64_t n_owned, uint64_t cap) {
 	if (rot) LS1_TRY(dev_alloc(&c->M, 3 * cap));
 	LS1_TRY(dev_alloc(&c->key, cap)); LS1_TRY(dev_alloc(&c->entry, cap)); LS1_TRY(dev_alloc(&c->cell_of, cap)); LS1_TRY(dev_alloc(&c->cell_of2, cap));
 	const size_t v4 = c->mixed ? 16 : 32;
-	LS1_CUDA(cudaMalloc(&c->mpos, std::max<size_t>(cap, 1) * v4));
+	// + 64 padding records; mpos[cap] is the far-away sentinel the 1CLJ kernel pads odd neighbour lists with
+	LS1_CUDA(cudaMalloc(&c->mpos, (cap + 64) * v4));
+	{
+		const double far_d[4] = {1e18, 1e18, 1e18, 0.}; const float far_f[4] = {1e18f, 1e18f, 1e18f, 0.f};
+		for (int k = 0; k < 64; k++)
+			LS1_CUDA(cudaMemcpyAsync((char*) c->mpos + (cap + k) * v4, c->mixed ? (const void*) far_f : (const void*) far_d, v4, cudaMemcpyHostToDevice, c->stream));
+		LS1_CUDA(cudaStreamSynchronize(c->stream));
+	}
 	if (!c->all_1clj) {
 		LS1_CUDA(cudaMalloc(&c->spos, std::max<size_t>(cap, 1) * c->smax * v4));
 		LS1_CUDA(cudaMalloc(&c->sori, std::max<size_t>(cap, 1) * c->smax * v4));
 		LS1_TRY(dev_alloc(&c->sf, cap * c->smax * 9));
 	}
-	c->partial_blocks = (uint32_t) (((cap + 127) / 128) * std::max(c->smax, 1u) + 64);
+	c->partial_blocks = (uint32_t) (((cap + 63) / 64) * std::max(c->smax, 1u) + 64);
+	if (c->all_1clj) c->partial_blocks = std::max<uint32_t>(c->partial_blocks, c->geom.ncells + 64);   // one partial per chunk
 	LS1_TRY(dev_alloc(&c->partials, (size_t) c->partial_blocks * 8));
 	LS1_CUDA(cudaMemsetAsync(c->F, 0, sizeof(double) * 3 * cap, c->stream));
 	LS1_CUDA(cudaMemsetAsync(c->Vi, 0, sizeof(double) * 3 * cap, c->stream));
@@ -211,6 +220,14 @@ int ls1b200_create(const ls1b200_config* cfg, ls1b200_ctx** out) {
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail("ls1b200_create: cannot create stream"));
 	const size_t nb = (size_t) c->geom.ncells + 4;
 	if (dev_alloc(&c->cell_count, nb) || dev_alloc(&c->cell_start, nb) || dev_alloc(&c->cursor, nb) || dev_alloc(&c->scan_tmp, nb / 2048 + 16)) return cleanup(1);
+	{
+		const size_t nrows = (size_t) c->geom.cells[1] * c->geom.cells[2] + 8;
+		if (cudaMalloc(&c->chunks, ((size_t) c->geom.ncells + 8) * 8) != cudaSuccess) return cleanup(fail("ls1b200_create: out of device memory"));
+		if (dev_alloc(&c->chunk_row_count, nrows) || dev_alloc(&c->chunk_row_start, nrows) || dev_alloc(&c->work_counter, 4)) return cleanup(1);
+		cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
+		const char* k = getenv("LS1B200_LJ_KERNEL");
+		c->lj_kernel = (k && std::string(k) == "global") ? 1 : 0;
+	}
 	if (dev_alloc(&c->d_scal, 1)) return cleanup(1);
 	if (cudaMallocHost((void**) &c->h_scal, sizeof(DevScalars)) != cudaSuccess) return cleanup(fail("ls1b200_create: cudaMallocHost failed"));
 	memset(c->h_scal, 0, sizeof(DevScalars));
@@ -229,6 +246,8 @@ int ls1b200_destroy(ls1b200_ctx* c) {
 	dev_free(c->d_eps24); dev_free(c->d_sig2); dev_free(c->d_shift6); dev_free(c->d_eps24f); dev_free(c->d_sig2f); dev_free(c->d_shift6f);
 	dev_free(c->cell_count); dev_free(c->cell_start); dev_free(c->cursor); dev_free(c->scan_tmp);
 	dev_free(c->d_scal); dev_free(c->d_records);
+	if (c->chunks) cudaFree(c->chunks);
+	dev_free(c->chunk_row_count); dev_free(c->chunk_row_start); dev_free(c->work_counter);
 	if (c->h_scal) cudaFreeHost(c->h_scal);
 	for (auto e : c->ev_pool) cudaEventDestroy(e);
 	for (int i = 0; i < 27; i++) if (c->export_buf[i]) cudaFree(c->export_buf[i]);
@@ -254,8 +273,10 @@ int ls1b200_set_components(ls1b200_ctx* c, uint32_t n_components, const ls1b200_
 		d.nsites = s.n_lj + s.n_charge + s.n_dipole + s.n_quadrupole;
 		d.site_offset = s.site_offset; d.lj_lookup_id = s.lj_lookup_id; d.rot_dof = s.rot_dof;
 		if (d.site_offset + d.nsites > n_sites) return fail("ls1b200_set_components: site table too short");
-		if (!(s.mass > 0.)) return fail("ls1b200_set_components: component mass must be positive");
-		d.mass = s.mass; d.inv_mass = 1. / s.mass;
+		// components made of massless sites only (dipoles / quadrupoles, as in the reference's Vectorization*.inp force fixtures)
+		// have m = 0: forces are defined, integration is not (the reference divides by m as well)
+		if (!(s.mass >= 0.)) return fail("ls1b200_set_components: negative component mass");
+		d.mass = s.mass; d.inv_mass = s.mass > 0. ? 1. / s.mass : 0.;
 		for (int k = 0; k < 3; k++) { d.I[k] = s.inertia[k]; d.invI[k] = (s.inertia[k] != 0.) ? 1. / s.inertia[k] : 0.; if (s.inertia[k] != 0.) any_inertia = true; }
 		c->smax = std::max(c->smax, d.nsites);
 		bool one_clj = d.n[0] == 1 && d.nsites == 1 && d.lj_lookup_id == i;

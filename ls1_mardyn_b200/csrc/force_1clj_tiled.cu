@@ -1,0 +1,432 @@
+// force_1clj_tiled.cu -- the production 1CLJ cell-pair kernel: neighbour-cell tiles staged in shared memory by TMA bulk
+// copies, per-thread neighbour lists in shared memory, no global-memory access inside the pair loops.
+//
+// Reference: same arithmetic as force_1clj.cu (VectorizedCellProcessor::_calculatePairs LJ block,
+// adapter/VectorizedCellProcessor.cpp:1029-1178; _loopBodyLJ :171-224; calcDistLookup,
+// vectorization/SIMD_VectorizedCellProcessorHelpers.h:427-472; FullMolecule::calcFM, molecules/FullMolecule.cpp:548-626).
+// The cell pairs are those of the C08 traversal (LinkedCellTraversals/C08BasedTraversals.h:48-99), visited from both ends.
+//
+// Work decomposition ("chunks"): a chunk is a run of consecutive inner cells [xa, xb] of one x-row of the cell grid whose
+// molecules (the "i" molecules, <= TPB) become the threads of one CTA pass. Because slots are sorted by cell index with x
+// fastest, the candidates "j" of ALL molecules of the chunk are exactly 9 CONTIGUOUS slot ranges (one per (dy, dz) row
+// offset, cells xa-1 .. xb+1), at most W records each. k_chunks_count / k_chunks_write build the chunk list on the device
+// after every update (greedy, deterministic); chunks that do not fit (a cell denser than the tile) are flagged BIG and
+// take a slow generic path inside the same kernel.
+//
+// Kernel (persistent CTAs pulling chunks from an atomic work counter):
+//   1. one thread arms an mbarrier and issues 9 cp.async.bulk (TMA) copies global -> shared of the 9 windows;
+//   2. phase 1, thread per i: molecule-distance test of the reference (bit-identical FP32 / FP64 sequence) against its
+//      3x9 neighbour cells read from shared memory; hits are appended to a per-thread u16 list in shared memory;
+//   3. phase 2: dense LJ 12-6 over the list (positions again from shared memory), FP32 partial sums folded into FP64;
+//   4. F, Vi written coalesced; per-chunk partial sums of 6*U and the virial (deterministic final reduction).
+#include "pairs.cuh"
+#include "types.cuh"
+
+namespace ls1b200 {
+
+struct Chunk { uint32_t cell0; uint16_t ncells; uint16_t flags; };
+constexpr uint16_t CHUNK_BIG = 1;
+constexpr int CH_MAXC = 24;        // max cells per chunk (size of the cell_start cache)
+
+#ifndef LS1_TILE_RI_F
+// measured on B200, 16 M molecules (profiles/r01_tile_sweep.md): RI/TPB/W/LCAP = 1/128/176/64 -> 5.61 ms per traversal,
+// 2/64/176/64 -> 6.51, 1/64/112/64 -> 6.16, 2/32/112/64 -> 6.99, 2/64/176/80 -> 7.25
+#define LS1_TILE_RI_F 1
+#define LS1_TILE_TPB_F 128
+#define LS1_TILE_W_F 176
+#define LS1_TILE_LCAP_F 64
+#endif
+template <class C> struct TileCfg;
+// TPB threads, each owning RI molecules of ONE cell (RI > 1 is register blocking: one shared-memory load of a candidate
+// serves RI distance tests); W records per window row; LCAP list entries per molecule.
+template <> struct TileCfg<float> { static constexpr int RI = LS1_TILE_RI_F, TPB = LS1_TILE_TPB_F, W = LS1_TILE_W_F, LCAP = LS1_TILE_LCAP_F; };
+template <> struct TileCfg<double> { static constexpr int RI = 2, TPB = 32, W = 112, LCAP = 64; };
+
+// ---------------------------------------------------------------------------------------------------------------------
+// chunk list
+// ---------------------------------------------------------------------------------------------------------------------
+struct ChunkGeo { int nx, ny, nz; int tpb, w, ri; };
+
+template <bool WRITE>
+__device__ __forceinline__ uint32_t walk_row(const ChunkGeo& g, const uint32_t* __restrict__ cs, uint32_t r, Chunk* __restrict__ out) {
+	const int cy = 1 + (int) (r % (uint32_t) (g.ny - 2)), cz = 1 + (int) (r / (uint32_t) (g.ny - 2));
+	const uint32_t R = (uint32_t) (cz * g.ny + cy) * g.nx;
+	uint32_t rows[9];
+	for (int k = 0; k < 9; k++) rows[k] = (uint32_t) ((cz + k / 3 - 1) * g.ny + (cy + k % 3 - 1)) * g.nx;
+	uint32_t n = 0;
+	int xa = 1;
+	while (xa <= g.nx - 2) {
+		int xb = xa;
+		// does [xa, x] fit into one tile?
+		auto fits = [&](int x) -> bool {
+			if (x - xa + 1 > CH_MAXC) return false;
+			uint32_t nthr = 0;
+			for (int cxx = xa; cxx <= x; cxx++) nthr += (cs[R + cxx + 1] - cs[R + cxx] + (uint32_t) g.ri - 1u) / (uint32_t) g.ri;      // RI molecules of one cell per thread
+			if (nthr > (uint32_t) g.tpb) return false;
+			for (int k = 0; k < 9; k++) if (cs[rows[k] + x + 2] - cs[rows[k] + xa - 1] > (uint32_t) g.w) return false;
+			return true;
+		};
+		const bool ok = fits(xa);
+		if (ok) while (xb + 1 <= g.nx - 2 && fits(xb + 1)) xb++;
+		if (cs[R + xb + 1] - cs[R + xa] > 0) {       // chunks without molecules are dropped
+			if (WRITE) { Chunk c; c.cell0 = R + xa; c.ncells = (uint16_t) (xb - xa + 1); c.flags = ok ? 0 : CHUNK_BIG; out[n] = c; }
+			n++;
+		}
+		xa = xb + 1;
+	}
+	return n;
+}
+__global__ void __launch_bounds__(128) k_chunks_count(ChunkGeo g, const uint32_t* __restrict__ cs, uint32_t nrows, uint32_t* __restrict__ cnt) {
+	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < nrows) cnt[r] = walk_row<false>(g, cs, r, nullptr);
+}
+__global__ void __launch_bounds__(128) k_chunks_write(ChunkGeo g, const uint32_t* __restrict__ cs, uint32_t nrows, const uint32_t* __restrict__ start, Chunk* __restrict__ chunks) {
+	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
+	if (r < nrows) walk_row<true>(g, cs, r, chunks + start[r]);
+}
+// single-block exclusive scan of the per-row counts (a few thousand rows); start[nrows] = total; resets the work counter
+__global__ void __launch_bounds__(1024) k_chunks_scan(const uint32_t* __restrict__ cnt, uint32_t* __restrict__ start, uint32_t nrows, uint32_t* __restrict__ work_counter) {
+	__shared__ uint32_t sh[32]; __shared__ uint32_t carry_s;
+	if (threadIdx.x == 0) { carry_s = 0; *work_counter = 0; }
+	__syncthreads();
+	for (uint32_t b0 = 0; b0 < nrows; b0 += blockDim.x) {
+		const uint32_t i = b0 + threadIdx.x;
+		const uint32_t v = i < nrows ? cnt[i] : 0u;
+		const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+		uint32_t inc = v;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+		if (lane == 31) sh[w] = inc;
+		__syncthreads();
+		if (w == 0) {
+			uint32_t x = sh[lane], xi = x;
+			#pragma unroll
+			for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += t; }
+			sh[lane] = xi - x;
+		}
+		__syncthreads();
+		const uint32_t carry = carry_s;
+		if (i < nrows) start[i] = carry + sh[w] + inc - v;
+		__syncthreads();
+		if (threadIdx.x == blockDim.x - 1) carry_s = carry + sh[w] + inc;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) start[nrows] = carry_s;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+// shared-memory / TMA helpers (inline PTX; cp.async.bulk shows up as UBLKCP in SASS)
+// ---------------------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t) __cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count) { asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(bar), "r"(count)); }
+__device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes) {
+	asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(bar), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity) {
+	uint32_t ok;
+	do {
+		asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+		             : "=r"(ok) : "r"(bar), "r"(parity) : "memory");
+	} while (!ok);
+}
+__device__ __forceinline__ void tma_bulk_g2s(uint32_t dst, const void* src, uint32_t bytes, uint32_t bar) {
+	asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+	             :: "r"(dst), "l"(src), "r"(bytes), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void sts16(uint32_t addr, uint32_t v) { asm volatile("st.shared.u16 [%0], %1;" :: "r"(addr), "h"((unsigned short) v) : "memory"); }
+__device__ __forceinline__ uint32_t lds16(uint32_t addr) { unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(addr) : "memory"); return v; }
+__device__ __forceinline__ uint32_t lds_u32(uint32_t addr) { uint32_t v; asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(addr) : "memory"); return v; }
+template <class C> __device__ __forceinline__ typename Vec4<C>::type lds_v4(uint32_t addr);
+template <> __device__ __forceinline__ float4 lds_v4<float>(uint32_t addr) {
+	float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(addr) : "memory"); return v;
+}
+template <> __device__ __forceinline__ double4 lds_v4<double>(uint32_t addr) {
+	double4 v;
+	asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "r"(addr) : "memory");
+	asm volatile("ld.shared.v2.f64 {%0, %1}, [%2];" : "=d"(v.z), "=d"(v.w) : "r"(addr + 16) : "memory");
+	return v;
+}
+
+template <class C> __device__ __forceinline__ C rcp_fast(C x);
+template <> __device__ __forceinline__ float rcp_fast<float>(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
+template <> __device__ __forceinline__ double rcp_fast<double>(double x) { return 1.0 / x; }
+
+template <class C>
+struct TArgs {
+	const typename Vec4<C>::type* mpos;
+	const uint32_t* cell_start;
+	const uint32_t* cell_of;
+	const C* eps24; const C* sig2; const C* shift6;
+	double* F; double* M; double* Vi;
+	double* partials;
+	const Chunk* chunks;
+	const uint32_t* n_chunks;     // -> row_start[nrows]
+	uint32_t* work_counter;
+	uint32_t cap, n_lj;
+	int nx, ny, nz;
+	C ljrc2;
+	C eps24_0, sig2_0, shift6_0;
+};
+
+// LJ 12-6 of one pair, accumulated into FP32 partial sums (slot u)
+#define LJ_PAIR_ACCUM(u, mj)                                                                   \
+	{                                                                                           \
+		const C dx = mi.x - (mj).x, dy = mi.y - (mj).y, dz = mi.z - (mj).z;                      \
+		const C r2 = dx * dx + dy * dy + dz * dz;                                                 \
+		if (!SINGLE) {                                                                            \
+			const size_t ti = (size_t) cid_i * a.n_lj + (wbits<C>((mj).w) & 0xFFFFu);              \
+			eps24 = a.eps24[ti]; sig2 = a.sig2[ti]; shift6 = a.shift6[ti];                          \
+		}                                                                                         \
+		const C r2inv = rcp_fast<C>(r2);                                                          \
+		const C lj2 = sig2 * r2inv, lj6 = lj2 * lj2 * lj2, lj12 = lj6 * lj6, lj12m6 = lj12 - lj6;  \
+		const C scale = eps24 * r2inv * (lj12 + lj12m6);                                          \
+		const C px = dx * scale, py = dy * scale, pz = dz * scale;                                \
+		fx[u] += px; fy[u] += py; fz[u] += pz;                                                    \
+		vx[u] += dx * px; vy[u] += dy * py; vz[u] += dz * pz;                                     \
+		if (SINGLE) up[u] += lj12m6; else up[u] += eps24 * lj12m6 + shift6;                       \
+	}
+
+template <class C, bool SINGLE>
+__global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a) {
+	typedef typename Vec4<C>::type V4;
+	constexpr int TPB = TileCfg<C>::TPB, W = TileCfg<C>::W, LCAP = TileCfg<C>::LCAP, RI = TileCfg<C>::RI;
+	constexpr uint32_t VB = sizeof(V4), LSTRIDE = (uint32_t) TPB * 2u * RI;      // bytes between consecutive entries of one list
+	extern __shared__ __align__(128) unsigned char smem_raw[];
+	V4* win = reinterpret_cast<V4*>(smem_raw);                                         // [9][W] (+1 sentinel record at [9*W])
+	uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw + (size_t) (9 * W + 1) * VB);   // [LCAP+1][RI][TPB]
+	uint32_t* cs = reinterpret_cast<uint32_t*>(list + (size_t) (LCAP + 1) * RI * TPB);   // [9][CH_MAXC+3]
+	__shared__ uint32_t s_tb[CH_MAXC + 1];
+	__shared__ __align__(8) unsigned long long s_bar;
+	__shared__ uint32_t s_chunk;
+	const uint32_t win_s = smem_u32(win), list_s = smem_u32(list) + threadIdx.x * 2, bar = smem_u32(&s_bar);
+	const uint32_t n_chunks = *a.n_chunks;
+	if (threadIdx.x == 0) {
+		mbar_init(bar, 1);
+		// sentinel record: a point far away from everything, pads odd lists (all LJ terms underflow to 0)
+		win[9 * W] = make_c4<C>((C) 1e18, (C) 1e18, (C) 1e18, (C) 0);
+	}
+	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+	fence_proxy_async();
+	__syncthreads();
+	uint32_t parity = 0;
+	for (;;) {
+		if (threadIdx.x == 0) s_chunk = atomicAdd(a.work_counter, 1u);
+		__syncthreads();
+		const uint32_t ch = s_chunk;
+		if (ch >= n_chunks) break;
+		const Chunk cd = a.chunks[ch];
+		const int nc = cd.ncells;
+		const uint32_t R = cd.cell0 / (uint32_t) a.nx;                 // row index cz*ny + cy
+		const int xa = (int) (cd.cell0 % (uint32_t) a.nx);
+		double acc[2] = {0., 0.};
+		if (cd.flags & CHUNK_BIG) {
+			// ---- slow generic path: a cell denser than the tile. Global loads, pair evaluated as soon as it is found. ----
+			const uint32_t ib = a.cell_start[cd.cell0], ie = a.cell_start[cd.cell0 + nc];
+			for (uint32_t t = ib + threadIdx.x; t < ie; t += TPB) {
+				const V4 mi = a.mpos[t];
+				const uint32_t cid_i = wbits<C>(mi.w) & 0xFFFFu;
+				const int cx = (int) (a.cell_of[t] % (uint32_t) a.nx);
+				C eps24 = a.eps24_0, sig2 = a.sig2_0, shift6 = a.shift6_0;
+				double Fd[3] = {0., 0., 0.}, Vd[3] = {0., 0., 0.}, Ud = 0.;
+				for (int r = 0; r < 9; r++) {
+					const uint32_t row = (uint32_t) ((int) R + (r / 3 - 1) * a.ny + (r % 3 - 1)) * a.nx + cx - 1;
+					const uint32_t jb = a.cell_start[row], je = a.cell_start[row + 3];
+					for (uint32_t j0 = jb; j0 < je; j0 += 32) {
+						C fx[1] = {C(0)}, fy[1] = {C(0)}, fz[1] = {C(0)}, vx[1] = {C(0)}, vy[1] = {C(0)}, vz[1] = {C(0)}, up[1] = {C(0)};
+						int nh = 0;
+						for (uint32_t j = j0; j < min(je, j0 + 32); j++) {
+							const V4 mj = a.mpos[j];
+							const C r2t = molpair_r2<C>(mi.x, mi.y, mi.z, mj.x, mj.y, mj.z);
+							if ((r2t < a.ljrc2) && (r2t != C(0))) { LJ_PAIR_ACCUM(0, mj); nh++; }
+						}
+						Fd[0] += (double) fx[0]; Fd[1] += (double) fy[0]; Fd[2] += (double) fz[0];
+						Vd[0] += (double) vx[0]; Vd[1] += (double) vy[0]; Vd[2] += (double) vz[0];
+						Ud += SINGLE ? (double) (eps24 * up[0] + (C) nh * shift6) : (double) up[0];
+					}
+				}
+				acc[0] += 0.5 * Ud; acc[1] += 0.5 * (Vd[0] + Vd[1] + Vd[2]);
+				const size_t cp = a.cap;
+				a.F[t] = Fd[0]; a.F[cp + t] = Fd[1]; a.F[2 * cp + t] = Fd[2];
+				a.Vi[t] = 0.5 * Vd[0]; a.Vi[cp + t] = 0.5 * Vd[1]; a.Vi[2 * cp + t] = 0.5 * Vd[2];
+				if (a.M) { a.M[t] = 0.; a.M[cp + t] = 0.; a.M[2 * cp + t] = 0.; }
+			}
+			block_reduce_store<2>(acc, a.partials, ch);
+			__syncthreads();
+			continue;
+		}
+		// ---- 1. cell_start cache of the 9 rows (cells xa-1 .. xb+2 -> nc+3 entries each) and the TMA loads ----
+		for (int k = threadIdx.x; k < 9 * (nc + 3); k += TPB) {
+			const int r = k / (nc + 3), c = k % (nc + 3);
+			const uint32_t row = (uint32_t) ((int) R + (r / 3 - 1) * a.ny + (r % 3 - 1)) * a.nx;
+			cs[r * (CH_MAXC + 3) + c] = a.cell_start[row + xa - 1 + c];
+		}
+		__syncthreads();
+		if (threadIdx.x == 0) {
+			uint32_t total = 0;
+			for (int r = 0; r < 9; r++) total += (cs[r * (CH_MAXC + 3) + nc + 2] - cs[r * (CH_MAXC + 3)]) * VB;
+			if (total) {
+				fence_proxy_async();      // the previous chunk's generic-proxy reads of the windows precede these async-proxy writes
+				mbar_expect_tx(bar, total);
+				for (int r = 0; r < 9; r++) {
+					const uint32_t b = cs[r * (CH_MAXC + 3)], len = cs[r * (CH_MAXC + 3) + nc + 2] - b;
+					if (len) tma_bulk_g2s(win_s + (uint32_t) (r * W) * VB, a.mpos + b, len * VB, bar);
+				}
+			}
+			// thread -> (cell, molecule pair): prefix of ceil(n_c / 2) over the cells of the chunk
+			uint32_t tb = 0;
+			for (int c = 0; c < nc; c++) { s_tb[c] = tb; tb += (cs[4 * (CH_MAXC + 3) + c + 2] - cs[4 * (CH_MAXC + 3) + c + 1] + (uint32_t) RI - 1u) / (uint32_t) RI; }
+			s_tb[nc] = tb;
+		}
+		__syncthreads();
+		const uint32_t* csc = cs + 4 * (CH_MAXC + 3);          // centre row
+		int kx = 0;
+		while (kx + 1 < nc && s_tb[kx + 1] <= threadIdx.x) kx++;
+		const bool have0 = threadIdx.x < s_tb[nc];
+		const uint32_t t0 = csc[kx + 1] + (uint32_t) RI * (threadIdx.x - s_tb[kx]);      // my first molecule (slot); the others follow
+		mbar_wait(bar, parity); parity ^= 1u;
+		// ---- 2. phase 1: distance tests from shared memory -> RI u16 lists of (row * W + k) ----
+		V4 mi[RI]; bool have[RI];
+		#pragma unroll
+		for (int l = 0; l < RI; l++) {
+			have[l] = have0 && (t0 + l < csc[kx + 2]);
+			mi[l] = make_c4<C>((C) 1e18, (C) 1e18, (C) 1e18, (C) 0);      // an absent molecule: no candidate is ever in range
+			if (have[l]) mi[l] = lds_v4<C>(win_s + (uint32_t) (4 * W + (int) (t0 + l - csc[0])) * VB);
+		}
+		double Fd[RI][3], Vd[RI][3], Ud[RI];
+		#pragma unroll
+		for (int l = 0; l < RI; l++) { Fd[l][0] = Fd[l][1] = Fd[l][2] = Vd[l][0] = Vd[l][1] = Vd[l][2] = Ud[l] = 0.; }
+		// dense LJ over list l (entries [0, cnt)); FP32 partial sums in two interleaved slots, folded into FP64
+		auto process_list = [&](const int l, const int cnt) {
+			const uint32_t cid_i = wbits<C>(mi[l].w) & 0xFFFFu;
+			const V4 mi_ = mi[l];
+			const uint32_t lbase = list_s + (uint32_t) l * (TPB * 2);
+			C fx[2] = {C(0), C(0)}, fy[2] = {C(0), C(0)}, fz[2] = {C(0), C(0)}, vx[2] = {C(0), C(0)}, vy[2] = {C(0), C(0)}, vz[2] = {C(0), C(0)}, up[2] = {C(0), C(0)};
+			C eps24 = a.eps24_0, sig2 = a.sig2_0, shift6 = a.shift6_0;
+			if (cnt & 1) sts16(lbase + (uint32_t) cnt * LSTRIDE, 9 * W);      // pad with the sentinel record
+			#pragma unroll 1
+			for (int e = 0; e < cnt; e += 2) {
+				const uint32_t i0 = lds16(lbase + (uint32_t) e * LSTRIDE), i1 = lds16(lbase + (uint32_t) (e + 1) * LSTRIDE);
+				const V4 m0 = lds_v4<C>(win_s + i0 * VB), m1 = lds_v4<C>(win_s + i1 * VB);
+				#define mi mi_
+				LJ_PAIR_ACCUM(0, m0);
+				if (SINGLE || i1 != 9 * W) LJ_PAIR_ACCUM(1, m1);
+				#undef mi
+			}
+			if (SINGLE) { up[0] = eps24 * (up[0] + up[1]) + (C) cnt * shift6; up[1] = C(0); }
+			Fd[l][0] += (double) fx[0] + (double) fx[1]; Fd[l][1] += (double) fy[0] + (double) fy[1]; Fd[l][2] += (double) fz[0] + (double) fz[1];
+			Vd[l][0] += (double) vx[0] + (double) vx[1]; Vd[l][1] += (double) vy[0] + (double) vy[1]; Vd[l][2] += (double) vz[0] + (double) vz[1];
+			Ud[l] += (double) up[0] + (double) up[1];
+		};
+		uint32_t w[RI];      // list write cursors (shared-window addresses)
+		#pragma unroll
+		for (int l = 0; l < RI; l++) w[l] = list_s + (uint32_t) l * (TPB * 2);
+		#pragma unroll 1
+		for (int r = 0; r < 9; r++) {
+			uint32_t kb = 0, ke = 0;
+			if (have0) {
+				const uint32_t base = cs[r * (CH_MAXC + 3)];
+				kb = cs[r * (CH_MAXC + 3) + kx] - base; ke = cs[r * (CH_MAXC + 3) + kx + 3] - base;      // cells cx-1 .. cx+1 of this row
+			}
+			const bool self_row = r == 4;
+			uint32_t src = win_s + (uint32_t) (r * W + (int) kb) * VB;
+			uint32_t idx = (uint32_t) (r * W) + kb;
+			// every candidate is loaded once (LDS.128) and tested against all of my molecules: strict <, bit-identical to
+			// calcDistLookup; in my own row SingleCellPolicy_ additionally masks pairs at distance 0 (the molecule itself).
+			// A list that could overflow during the next four candidates is evaluated and emptied first (lane-local, rare).
+			#define LJ_TESTS(m, off)                                                                                   \
+				_Pragma("unroll") for (int l = 0; l < RI; l++) {                                                        \
+					const C rr = molpair_r2<C>(mi[l].x, mi[l].y, mi[l].z, (m).x, (m).y, (m).z);                          \
+					if ((rr < a.ljrc2) && (!self_row || rr != C(0))) { sts16(w[l], idx + (off)); w[l] += LSTRIDE; }      \
+				}
+			#define LJ_ROOM()                                                                                          \
+				_Pragma("unroll") for (int l = 0; l < RI; l++) {                                                        \
+					if (w[l] > list_s + (uint32_t) l * (TPB * 2) + (uint32_t) (LCAP - 4) * LSTRIDE) {                    \
+						process_list(l, (int) ((w[l] - list_s - (uint32_t) l * (TPB * 2)) / LSTRIDE));                    \
+						w[l] = list_s + (uint32_t) l * (TPB * 2);                                                          \
+					}                                                                                                    \
+				}
+			uint32_t k = kb;
+			for (; k + 4 <= ke; k += 4, src += 4 * VB, idx += 4) {
+				const V4 m0 = lds_v4<C>(src), m1 = lds_v4<C>(src + VB), m2 = lds_v4<C>(src + 2 * VB), m3 = lds_v4<C>(src + 3 * VB);
+				LJ_ROOM();
+				LJ_TESTS(m0, 0); LJ_TESTS(m1, 1); LJ_TESTS(m2, 2); LJ_TESTS(m3, 3);
+			}
+			if (k < ke) {
+				LJ_ROOM();
+				for (; k < ke; k++, src += VB, idx++) {
+					const V4 mj = lds_v4<C>(src);
+					LJ_TESTS(mj, 0);
+				}
+			}
+			#undef LJ_TESTS
+			#undef LJ_ROOM
+		}
+		// ---- 3. phase 2 ----
+		#pragma unroll
+		for (int l = 0; l < RI; l++) process_list(l, (int) ((w[l] - list_s - (uint32_t) l * (TPB * 2)) / LSTRIDE));
+		// ---- 4. results ----
+		#pragma unroll
+		for (int l = 0; l < RI; l++) {
+			if (have[l]) {
+				const size_t cp = a.cap;
+				const uint32_t t = t0 + l;
+				acc[0] += 0.5 * Ud[l];                          // every pair is visited from both of its ends
+				acc[1] += 0.5 * (Vd[l][0] + Vd[l][1] + Vd[l][2]);
+				a.F[t] = Fd[l][0]; a.F[cp + t] = Fd[l][1]; a.F[2 * cp + t] = Fd[l][2];
+				a.Vi[t] = 0.5 * Vd[l][0]; a.Vi[cp + t] = 0.5 * Vd[l][1]; a.Vi[2 * cp + t] = 0.5 * Vd[l][2];
+				if (a.M) { a.M[t] = 0.; a.M[cp + t] = 0.; a.M[2 * cp + t] = 0.; }
+			}
+		}
+		block_reduce_store<2>(acc, a.partials, ch);
+		__syncthreads();      // windows, lists and cs are reused by the next chunk
+	}
+}
+
+__global__ void __launch_bounds__(1024) k_reduce_force_chunks(const double* __restrict__ partials, const uint32_t* __restrict__ n_chunks, DevScalars* scal) {
+	double v[2] = {0., 0.};
+	const uint32_t n = *n_chunks;
+	for (uint32_t b = threadIdx.x; b < n; b += blockDim.x) { v[0] += partials[(size_t) b * 8]; v[1] += partials[(size_t) b * 8 + 1]; }
+	__shared__ double out[8];
+	block_reduce_store<2>(v, out, 0);
+	__syncthreads();
+	if (threadIdx.x == 0) { scal->upot6lj = out[0]; scal->upot_xpoles = 0.; scal->virial = out[1]; scal->my_rf = 0.; }
+}
+
+template <class C>
+static int launch_tiled(ls1b200_ctx* c) {
+	typedef typename Vec4<C>::type V4;
+	constexpr int TPB = TileCfg<C>::TPB, W = TileCfg<C>::W, LCAP = TileCfg<C>::LCAP, RI = TileCfg<C>::RI;
+	const Geom& g = c->geom;
+	const uint32_t nrows = (uint32_t) (g.cells[1] - 2) * (uint32_t) (g.cells[2] - 2);
+	ChunkGeo cg; cg.nx = g.cells[0]; cg.ny = g.cells[1]; cg.nz = g.cells[2]; cg.tpb = TPB; cg.w = W; cg.ri = RI;
+	Chunk* chunks = (Chunk*) c->chunks;
+	const uint32_t gr = (nrows + 127) / 128;
+	LS1_LAUNCH(c, PH_FORCE, k_chunks_count, gr, 128, 0, cg, c->cell_start, nrows, c->chunk_row_count);
+	LS1_LAUNCH(c, PH_FORCE, k_chunks_scan, 1, 1024, 0, c->chunk_row_count, c->chunk_row_start, nrows, c->work_counter);
+	LS1_LAUNCH(c, PH_FORCE, k_chunks_write, gr, 128, 0, cg, c->cell_start, nrows, c->chunk_row_start, chunks);
+	TArgs<C> a;
+	a.mpos = (const V4*) c->mpos; a.cell_start = c->cell_start; a.cell_of = c->cell_of2;
+	if (sizeof(C) == 4) { a.eps24 = (const C*) c->d_eps24f; a.sig2 = (const C*) c->d_sig2f; a.shift6 = (const C*) c->d_shift6f; }
+	else { a.eps24 = (const C*) c->d_eps24; a.sig2 = (const C*) c->d_sig2; a.shift6 = (const C*) c->d_shift6; }
+	a.F = c->F; a.M = c->rotates ? c->M : nullptr; a.Vi = c->Vi; a.partials = c->partials;
+	a.chunks = chunks; a.n_chunks = c->chunk_row_start + nrows; a.work_counter = c->work_counter;
+	a.cap = (uint32_t) c->cap; a.n_lj = c->n_lj; a.nx = g.cells[0]; a.ny = g.cells[1]; a.nz = g.cells[2];
+	const double rclj = c->cfg.cutoff_lj;
+	a.ljrc2 = (C) (rclj * rclj);
+	a.eps24_0 = (C) c->h_eps24[0]; a.sig2_0 = (C) c->h_sig2[0]; a.shift6_0 = (C) c->h_shift6[0];
+	const size_t smem = (size_t) (9 * W + 1) * sizeof(V4) + (size_t) (LCAP + 1) * RI * TPB * 2 + 9 * (CH_MAXC + 3) * 4;
+	auto kern = c->comps.size() == 1 ? k_force_1clj_tiled<C, true> : k_force_1clj_tiled<C, false>;
+	LS1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
+	int per_sm = 0;
+	LS1_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, smem));
+	if (per_sm < 1) return fail("force_1clj_tiled: kernel does not fit on an SM");
+	const uint32_t grid = (uint32_t) (c->sm_count * per_sm);
+	LS1_LAUNCH(c, PH_FORCE, kern, grid, TPB, smem, a);
+	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks, 1, 1024, 0, c->partials, c->chunk_row_start + nrows, c->d_scal);
+	return 0;
+}
+
+int force_1clj_tiled(ls1b200_ctx* c) { return c->mixed ? launch_tiled<float>(c) : launch_tiled<double>(c); }
+
+}  // namespace ls1b200

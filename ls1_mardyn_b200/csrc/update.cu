@@ -149,7 +149,8 @@ __global__ void __launch_bounds__(256) k_scatter(UpdArgs a, State cur, const uin
 template <class C>
 __global__ void __launch_bounds__(256) k_gather(UpdArgs a, State cur, State nxt, const uint32_t* __restrict__ entry, const uint32_t* __restrict__ cell_of,
                                                  const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_of2,
-                                                 typename Vec4<C>::type* __restrict__ mpos, const DevScalars* __restrict__ scal, int rotates) {
+                                                 typename Vec4<C>::type* __restrict__ mpos, const DevScalars* __restrict__ scal, int rotates,
+                                                 double* __restrict__ F, double* __restrict__ Vi, double* __restrict__ M) {
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t n_slots = min(scal->n_slots2[a.parity ^ 1u], a.cap);
 	if (p >= n_slots) return;
@@ -181,6 +182,9 @@ __global__ void __launch_bounds__(256) k_gather(UpdArgs a, State cur, State nxt,
 	// the limbo bin and halo cells never hold "i" molecules: flag them like halo copies in the calc record
 	const bool inert = code != 0 || c >= g.ncells || is_halo_cell(g, c);
 	mpos[t] = make_mrec<C>(x, y, z, meta_cid(meta) | (inert ? 0x80000000u : 0u));
+	if (inert && code == 0) {   // an owned molecule no force kernel visits (halo-cell resident, limbo): its force is zero
+		for (int d = 0; d < 3; d++) { F[d * cap + t] = 0.; Vi[d * cap + t] = 0.; if (M) M[d * cap + t] = 0.; }
+	}
 }
 
 // ---- site expansion (FullMolecule::setupSoACache, molecules/FullMolecule.cpp:711-767; Quaternion::rotate, Quaternion.cpp:43-64)
@@ -239,9 +243,9 @@ int do_update(ls1b200_ctx* c) {
 	LS1_LAUNCH(c, PH_UPDATE, k_scatter, gs, 256, 0, a, c->cur, c->key, c->cursor, c->entry, c->cell_of, c->d_scal);
 	const uint32_t gc = gs;
 	if (c->mixed)
-		LS1_LAUNCH(c, PH_UPDATE, k_gather<float>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, c->cell_start, c->cell_of2, (float4*) c->mpos, c->d_scal, (int) c->rotates);
+		LS1_LAUNCH(c, PH_UPDATE, k_gather<float>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, c->cell_start, c->cell_of2, (float4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M);
 	else
-		LS1_LAUNCH(c, PH_UPDATE, k_gather<double>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, c->cell_start, c->cell_of2, (double4*) c->mpos, c->d_scal, (int) c->rotates);
+		LS1_LAUNCH(c, PH_UPDATE, k_gather<double>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, c->cell_start, c->cell_of2, (double4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M);
 	std::swap(c->cur, c->nxt);
 	c->parity ^= 1u;
 	if (!c->all_1clj) {
