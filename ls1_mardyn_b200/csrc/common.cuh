@@ -170,6 +170,7 @@ struct ls1b200_ctx {
 
 	// reductions
 	double* partials = nullptr;       // [n_partial_blocks][8]
+	double* partials2 = nullptr;      // [1024][8] second reduction level
 	uint32_t partial_blocks = 0;
 	ls1b200::DevScalars* d_scal = nullptr;
 	ls1b200::DevScalars* h_scal = nullptr;   // pinned

@@ -228,7 +228,7 @@ int ls1b200_create(const ls1b200_config* cfg, ls1b200_ctx** out) {
 		const char* k = getenv("LS1B200_LJ_KERNEL");
 		c->lj_kernel = (k && std::string(k) == "global") ? 1 : 0;
 	}
-	if (dev_alloc(&c->d_scal, 1)) return cleanup(1);
+	if (dev_alloc(&c->d_scal, 1) || dev_alloc(&c->partials2, 1024 * 8)) return cleanup(1);
 	if (cudaMallocHost((void**) &c->h_scal, sizeof(DevScalars)) != cudaSuccess) return cleanup(fail("ls1b200_create: cudaMallocHost failed"));
 	memset(c->h_scal, 0, sizeof(DevScalars));
 	c->h_scal->beta_trans = 1.; c->h_scal->beta_rot = 1.;
@@ -245,7 +245,7 @@ int ls1b200_destroy(ls1b200_ctx* c) {
 	dev_free(c->d_comps); dev_free(c->d_sites);
 	dev_free(c->d_eps24); dev_free(c->d_sig2); dev_free(c->d_shift6); dev_free(c->d_eps24f); dev_free(c->d_sig2f); dev_free(c->d_shift6f);
 	dev_free(c->cell_count); dev_free(c->cell_start); dev_free(c->cursor); dev_free(c->scan_tmp);
-	dev_free(c->d_scal); dev_free(c->d_records);
+	dev_free(c->d_scal); dev_free(c->d_records); dev_free(c->partials2);
 	if (c->chunks) cudaFree(c->chunks);
 	dev_free(c->chunk_row_count); dev_free(c->chunk_row_start); dev_free(c->work_counter);
 	if (c->h_scal) cudaFreeHost(c->h_scal);

@@ -55,20 +55,24 @@ __device__ __forceinline__ uint32_t walk_row(const ChunkGeo& g, const uint32_t* 
 	for (int k = 0; k < 9; k++) rows[k] = (uint32_t) ((cz + k / 3 - 1) * g.ny + (cy + k % 3 - 1)) * g.nx;
 	uint32_t n = 0;
 	int xa = 1;
+	// greedy, incremental: the chunk [xa, xb] grows by one cell while its threads fit into the CTA and each of its 9 windows
+	// (cells xa-1 .. xb+1 of the neighbour rows) fits into W records
 	while (xa <= g.nx - 2) {
-		int xb = xa;
-		// does [xa, x] fit into one tile?
-		auto fits = [&](int x) -> bool {
-			if (x - xa + 1 > CH_MAXC) return false;
-			uint32_t nthr = 0;
-			for (int cxx = xa; cxx <= x; cxx++) nthr += (cs[R + cxx + 1] - cs[R + cxx] + (uint32_t) g.ri - 1u) / (uint32_t) g.ri;      // RI molecules of one cell per thread
-			if (nthr > (uint32_t) g.tpb) return false;
-			for (int k = 0; k < 9; k++) if (cs[rows[k] + x + 2] - cs[rows[k] + xa - 1] > (uint32_t) g.w) return false;
-			return true;
-		};
-		const bool ok = fits(xa);
-		if (ok) while (xb + 1 <= g.nx - 2 && fits(xb + 1)) xb++;
-		if (cs[R + xb + 1] - cs[R + xa] > 0) {       // chunks without molecules are dropped
+		uint32_t lo[9];
+		for (int k = 0; k < 9; k++) lo[k] = cs[rows[k] + xa - 1];
+		uint32_t nthr = 0, nmol = 0;
+		int xb = xa - 1;
+		bool ok = true;
+		for (int x = xa; x <= g.nx - 2 && x - xa + 1 <= CH_MAXC; x++) {
+			const uint32_t nc = cs[R + x + 1] - cs[R + x];
+			const uint32_t t2 = nthr + (nc + (uint32_t) g.ri - 1u) / (uint32_t) g.ri;      // RI molecules of one cell per thread
+			bool f = t2 <= (uint32_t) g.tpb;
+			for (int k = 0; k < 9 && f; k++) f = cs[rows[k] + x + 2] - lo[k] <= (uint32_t) g.w;
+			if (!f) break;
+			nthr = t2; nmol += nc; xb = x;
+		}
+		if (xb < xa) { ok = false; xb = xa; nmol = cs[R + xa + 1] - cs[R + xa]; }      // a single cell that does not fit: BIG chunk
+		if (nmol > 0) {       // chunks without molecules are dropped
 			if (WRITE) { Chunk c; c.cell0 = R + xa; c.ncells = (uint16_t) (xb - xa + 1); c.flags = ok ? 0 : CHUNK_BIG; out[n] = c; }
 			n++;
 		}
@@ -76,11 +80,11 @@ __device__ __forceinline__ uint32_t walk_row(const ChunkGeo& g, const uint32_t* 
 	}
 	return n;
 }
-__global__ void __launch_bounds__(128) k_chunks_count(ChunkGeo g, const uint32_t* __restrict__ cs, uint32_t nrows, uint32_t* __restrict__ cnt) {
+__global__ void __launch_bounds__(32) k_chunks_count(ChunkGeo g, const uint32_t* __restrict__ cs, uint32_t nrows, uint32_t* __restrict__ cnt) {
 	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r < nrows) cnt[r] = walk_row<false>(g, cs, r, nullptr);
 }
-__global__ void __launch_bounds__(128) k_chunks_write(ChunkGeo g, const uint32_t* __restrict__ cs, uint32_t nrows, const uint32_t* __restrict__ start, Chunk* __restrict__ chunks) {
+__global__ void __launch_bounds__(32) k_chunks_write(ChunkGeo g, const uint32_t* __restrict__ cs, uint32_t nrows, const uint32_t* __restrict__ start, Chunk* __restrict__ chunks) {
 	const uint32_t r = blockIdx.x * blockDim.x + threadIdx.x;
 	if (r < nrows) walk_row<true>(g, cs, r, chunks + start[r]);
 }
@@ -383,10 +387,19 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 	}
 }
 
-__global__ void __launch_bounds__(1024) k_reduce_force_chunks(const double* __restrict__ partials, const uint32_t* __restrict__ n_chunks, DevScalars* scal) {
+// deterministic two-level reduction of the per-chunk partial sums (fixed assignment chunk -> block -> thread, fixed order)
+constexpr int RED_BLOCKS = 128;
+__global__ void __launch_bounds__(256) k_reduce_force_chunks1(const double* __restrict__ partials, const uint32_t* __restrict__ n_chunks, double* __restrict__ partials2) {
 	double v[2] = {0., 0.};
 	const uint32_t n = *n_chunks;
-	for (uint32_t b = threadIdx.x; b < n; b += blockDim.x) { v[0] += partials[(size_t) b * 8]; v[1] += partials[(size_t) b * 8 + 1]; }
+	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
+		const double2 p = *reinterpret_cast<const double2*>(partials + (size_t) b * 8);
+		v[0] += p.x; v[1] += p.y;
+	}
+	block_reduce_store<2>(v, partials2, blockIdx.x);
+}
+__global__ void __launch_bounds__(RED_BLOCKS) k_reduce_force_chunks2(const double* __restrict__ partials2, DevScalars* scal) {
+	double v[2] = {partials2[(size_t) threadIdx.x * 8], partials2[(size_t) threadIdx.x * 8 + 1]};
 	__shared__ double out[8];
 	block_reduce_store<2>(v, out, 0);
 	__syncthreads();
@@ -401,10 +414,10 @@ static int launch_tiled(ls1b200_ctx* c) {
 	const uint32_t nrows = (uint32_t) (g.cells[1] - 2) * (uint32_t) (g.cells[2] - 2);
 	ChunkGeo cg; cg.nx = g.cells[0]; cg.ny = g.cells[1]; cg.nz = g.cells[2]; cg.tpb = TPB; cg.w = W; cg.ri = RI;
 	Chunk* chunks = (Chunk*) c->chunks;
-	const uint32_t gr = (nrows + 127) / 128;
-	LS1_LAUNCH(c, PH_FORCE, k_chunks_count, gr, 128, 0, cg, c->cell_start, nrows, c->chunk_row_count);
+	const uint32_t gr = (nrows + 31) / 32;
+	LS1_LAUNCH(c, PH_FORCE, k_chunks_count, gr, 32, 0, cg, c->cell_start, nrows, c->chunk_row_count);
 	LS1_LAUNCH(c, PH_FORCE, k_chunks_scan, 1, 1024, 0, c->chunk_row_count, c->chunk_row_start, nrows, c->work_counter);
-	LS1_LAUNCH(c, PH_FORCE, k_chunks_write, gr, 128, 0, cg, c->cell_start, nrows, c->chunk_row_start, chunks);
+	LS1_LAUNCH(c, PH_FORCE, k_chunks_write, gr, 32, 0, cg, c->cell_start, nrows, c->chunk_row_start, chunks);
 	TArgs<C> a;
 	a.mpos = (const V4*) c->mpos; a.cell_start = c->cell_start; a.cell_of = c->cell_of2;
 	if (sizeof(C) == 4) { a.eps24 = (const C*) c->d_eps24f; a.sig2 = (const C*) c->d_sig2f; a.shift6 = (const C*) c->d_shift6f; }
@@ -423,7 +436,8 @@ static int launch_tiled(ls1b200_ctx* c) {
 	if (per_sm < 1) return fail("force_1clj_tiled: kernel does not fit on an SM");
 	const uint32_t grid = (uint32_t) (c->sm_count * per_sm);
 	LS1_LAUNCH(c, PH_FORCE, kern, grid, TPB, smem, a);
-	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks, 1, 1024, 0, c->partials, c->chunk_row_start + nrows, c->d_scal);
+	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks1, RED_BLOCKS, 256, 0, c->partials, c->chunk_row_start + nrows, c->partials2);
+	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks2, 1, RED_BLOCKS, 0, c->partials2, c->d_scal);
 	return 0;
 }
 

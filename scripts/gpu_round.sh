@@ -1,0 +1,20 @@
+#!/usr/bin/env bash
+# One gpurun call: parity tests, bench line, ncu launch list and one full capture of the dominant kernel.
+# Usage (from the repo root): gpurun --timeout 1500 -- 'bash scripts/gpu_round.sh <tag>'
+set -u
+TAG="${1:-r01}"
+OUT=gpurun_out/$TAG; mkdir -p "$OUT"
+nvidia-smi --query-gpu=name,clocks.sm,clocks.max.sm,power.draw --format=csv > "$OUT/gpu.txt" 2>&1
+python __graft_entry__.py smoke > "$OUT/smoke.log" 2>&1; echo "smoke rc=$?" | tee -a "$OUT/summary.txt"
+timeout 900 python -m pytest tests -m gpu -x -q > "$OUT/pytest_gpu.log" 2>&1; echo "pytest rc=$?" | tee -a "$OUT/summary.txt"
+tail -3 "$OUT/pytest_gpu.log"
+timeout 600 python bench.py --steps 50 --warmup 5 > "$OUT/bench.json" 2> "$OUT/bench.err"; echo "bench rc=$?" | tee -a "$OUT/summary.txt"
+cat "$OUT/bench.json"
+timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_ref.json" 2> "$OUT/bench_ref.err"; cat "$OUT/bench_ref.json"
+# launch list of the same command (shares, not absolutes), reduced steps
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > "$OUT/bench_under_ncu.log" 2>&1
+# full capture of the force kernel on a 2 M molecule system (keeps the ~40 replays short)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_force -s 2 -c 2 -o "$OUT/force_full" -f \
+    python bench.py --steps 3 --warmup 3 --n-per-dim 100 --no-cpu-baseline --e2e-steps 1 > "$OUT/ncu_full.log" 2>&1
+ls -la "$OUT"
