@@ -1,0 +1,48 @@
+#include "integrators/LeapfrogB200.h"
+
+#include "Domain.h"
+#include "particleContainer/LinkedCellsB200.h"
+#include "utils/Logger.h"
+#include "utils/mardyn_assert.h"
+#include "utils/xmlfileUnits.h"
+
+#include "ls1b200.h"
+
+static LinkedCellsB200* deviceContainer(ParticleContainer* pc) {
+	LinkedCellsB200* c = dynamic_cast<LinkedCellsB200*>(pc);
+	if (!c) {
+		std::ostringstream error_message;
+		error_message << "LeapfrogB200 needs <datastructure type=\"LinkedCellsB200\">" << std::endl;
+		MARDYN_EXIT(error_message.str());
+	}
+	return c;
+}
+
+void LeapfrogB200::readXML(XMLfileUnits& xmlconfig) {
+	_timestepLength = 0;
+	xmlconfig.getNodeValueReduced("timestep", _timestepLength);      // as Leapfrog::readXML (Leapfrog.cpp:23-28)
+	Log::global_log->info() << "Timestep: " << _timestepLength << std::endl;
+	mardyn_assert(_timestepLength > 0);
+}
+
+void LeapfrogB200::eventNewTimestep(ParticleContainer* moleculeContainer, Domain* domain) {
+	LinkedCellsB200* c = deviceContainer(moleculeContainer);
+	if (!c->deviceMode()) return;
+	// VelocityScalingThermostat::apply of the previous step found an empty iterator range (device mode); its factors are
+	// Domain's global betas (Domain.cpp:248-252) and are applied here, before the kick, which is the same arithmetic
+	// (Simulation.cpp:1235-1261; single global thermostat -- the component-wise variant needs a per-component factor table).
+	if (!domain->NVE() && !domain->severalThermostats()) {
+		if (ls1b200_scale_velocities(c->context(), domain->getGlobalBetaTrans(), domain->getGlobalBetaRot()) != 0) MARDYN_EXIT(ls1b200_last_error());
+	}
+	if (ls1b200_leapfrog_pre(c->context(), _timestepLength) != 0) MARDYN_EXIT(ls1b200_last_error());
+}
+
+void LeapfrogB200::eventForcesCalculated(ParticleContainer* moleculeContainer, Domain* domain) {
+	LinkedCellsB200* c = deviceContainer(moleculeContainer);
+	if (!c->deviceMode()) return;
+	ls1b200_kinetic kin{};
+	if (ls1b200_leapfrog_post(c->context(), _timestepLength, &kin) != 0) MARDYN_EXIT(ls1b200_last_error());
+	domain->setLocalSummv2(kin.summv2, 0);                        // Leapfrog.cpp:139-143
+	domain->setLocalSumIw2(kin.sum_iw2, 0);
+	domain->setLocalNrotDOF(0, kin.n_molecules, kin.rot_dof);
+}

@@ -1,0 +1,14 @@
+// LeapfrogB200 -- <integrator type="LeapfrogB200">: the Leapfrog integrator (integrators/Leapfrog.cpp) on the device state
+// of a LinkedCellsB200 container. Falls back to nothing: with any other container it aborts (MARDYN_EXIT).
+#pragma once
+
+#include "integrators/Integrator.h"
+
+class LeapfrogB200 : public Integrator {
+public:
+	LeapfrogB200() {}
+	void readXML(XMLfileUnits& xmlconfig) override;
+	void init() override {}
+	void eventNewTimestep(ParticleContainer* moleculeContainer, Domain* domain) override;       // transition1to2: upd_preF
+	void eventForcesCalculated(ParticleContainer* moleculeContainer, Domain* domain) override;  // transition2to3: upd_postF + sums
+};

@@ -1,0 +1,50 @@
+// LinkedCellsB200 -- the ls1-MarDyn side of the drop-in: a ParticleContainer that keeps the molecules on a B200 through
+// libls1b200.so (include/ls1b200.h). Compiled AGAINST ls1's headers (this file is added to ls1's src/ by
+// adapter/build_adapter.sh; it is not part of libls1b200.so).
+//
+// It derives from the reference's own LinkedCells, which stays the host mirror: input readers / generators fill it through
+// addParticle(s) / initCubicGrid exactly as before (Simulation::prepare_start), and plugins that iterate molecules see it
+// after a lazy device -> host sync. From the first update() on the device copy is authoritative ("device mode"): the
+// per-step host loops of the stock time step find an empty iterator range and cost nothing.
+// Precedent in the reference for a container that ignores the CellProcessor's kernels and writes Upot / Virial itself:
+// AutoPasContainer::traverseCells (particleContainer/AutoPasContainer.cpp:554-606).
+#pragma once
+
+#include "particleContainer/LinkedCells.h"
+
+struct ls1b200_ctx;
+
+class LinkedCellsB200 : public LinkedCells {
+public:
+	LinkedCellsB200() : LinkedCells() {}
+	~LinkedCellsB200() override;
+
+	// <datastructure type="LinkedCellsB200"> takes the same children as LinkedCells (readXML is inherited).
+	void update() override;                                  // -> ls1b200_update (first call: upload the host mirror)
+	void traverseCells(CellProcessor& cellProcessor) override;   // -> ls1b200_traverse_cells, Domain::setLocalUpot/Virial
+	void updateMoleculeCaches() override { if (!_deviceMode) LinkedCells::updateMoleculeCaches(); }
+	void updateInnerMoleculeCaches() override { if (!_deviceMode) LinkedCells::updateInnerMoleculeCaches(); }
+	void updateBoundaryAndHaloMoleculeCaches() override { if (!_deviceMode) LinkedCells::updateBoundaryAndHaloMoleculeCaches(); }
+	void deleteOuterParticles() override { if (!_deviceMode) LinkedCells::deleteOuterParticles(); }   // halo is transient device data
+	unsigned long getNumberOfParticles(ParticleIterator::Type t = ParticleIterator::ALL_CELLS) override;
+
+	// In device mode the host loops of the time step (Leapfrog, exchangeMolecules, updateForces, thermostat) iterate nothing;
+	// a caller that really wants the molecules (writers, checkpoints, RDF) calls syncToHost() first -- or sets hostView(true).
+	ParticleIterator iterator(ParticleIterator::Type t) override;
+	RegionParticleIterator regionIterator(const double startRegion[3], const double endRegion[3], ParticleIterator::Type type) override;
+
+	void syncToHost();            // device -> host Molecule objects (r, v, q, D, F, M, Vi), then the host cell structure
+	void syncToDevice();          // host -> device after a plugin changed molecules
+	void hostView(bool on) { _hostView = on; }
+	ls1b200_ctx* context() { return _ctx; }
+	bool deviceMode() const { return _deviceMode; }
+
+private:
+	void createContext();
+	void uploadAll();
+
+	ls1b200_ctx* _ctx = nullptr;
+	bool _deviceMode = false;
+	bool _hostView = false;
+	unsigned long _numMolecules = 0;
+};

@@ -205,6 +205,9 @@ def reference_arm(args):
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
 def our_arm(args):
+    # exactly ONE line on stdout: libraries that chat on fd 1 (NCCL prints its version there) are sent to stderr
+    real_stdout = os.dup(1)
+    os.dup2(2, 1)
     import torch
     import torch.distributed as dist
     from ls1_mardyn_b200 import capi
@@ -222,14 +225,35 @@ def our_arm(args):
             dist.barrier()
         torch.cuda.synchronize()
 
-    # weak scaling: every rank owns one replica-sized periodic block of the workload (the decomposition with
-    # NCCL halo exchange replaces this replica mode when ls1b200_halo_* lands)
+    # weak scaling: the box grows with the number of GPUs; every rank owns one block of the 3D decomposition
+    # with the same 2 n^3 molecules, generates only its own part of the lattice, and exchanges leaving molecules and halo
+    # copies with its neighbours over NCCL inside the library every step
     n = args.n_per_dim
-    ps = make_system(n, mixed=True, seed=rank)
+    from ls1_mardyn_b200 import generators
+    from ls1_mardyn_b200.components import lj_fluid
+    from ls1_mardyn_b200.decomposition import DomainDecomposition
+    if world == 1:
+        ps = make_system(n, mixed=True, seed=rank)
+        dd = None
+        ctx = capi.Context([0, 0, 0], list(ps.length), RC, precision="mixed", geometry="xml", periodic=(1, 1, 1), device=local)
+        ctx.set_components(ps.ensemble)
+    else:
+        grid = grid_for(world)
+        dd0 = DomainDecomposition(rank, world, [1.0, 1.0, 1.0], grid)
+        ps = generators.lattice_block(lj_fluid(rc=RC), n, RHO, TEMP, dd0.coords, grid, seed=0)
+        ps.r = ps.r.astype(np.float32).astype(np.float64)
+        dd = DomainDecomposition(rank, world, ps.length, grid)
+        ctx = capi.Context(list(dd.box_min()), list(dd.box_max()), RC, precision="mixed", geometry="xml", periodic=dd.periodic(), device=local)
+        ctx.set_components(ps.ensemble)
+        uid = [capi.nccl_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(uid, src=0, device=torch.device("cuda", local))
+        ctx.decomp_attach(dd, uid[0])
     N = len(ps.id)
-    ctx = capi.Context([0, 0, 0], list(ps.length), RC, precision="mixed", geometry="xml", periodic=(1, 1, 1), device=local)
-    ctx.set_components(ps.ensemble)
+    N_global = world * N
+    V_global = float(np.prod(ps.length))
     ctx.upload(ps.id, ps.cid, ps.r, ps.v)
+    if dd is not None:
+        ctx.exchange()
     ctx.update(); ctx.traverse_cells()
     fc0 = ctx.count_flops()
 
@@ -237,7 +261,7 @@ def our_arm(args):
     hbm_peak, hbm_src = peaks()
 
     # ---- HBM-resident: K steps inside the library, no host round trip ----
-    ctx.simulate(args.warmup, DT, TEMP, records=False)
+    ctx.simulate(args.warmup, DT, TEMP, global_n=N_global, global_volume=V_global, records=False)
     ctx.phase_times(reset=True)
     launches0 = capi.kernel_launch_count()
     ext = torch.cuda.ExternalStream(ctx.stream(), device=local)
@@ -246,7 +270,7 @@ def our_arm(args):
     barrier()
     t0 = time.perf_counter()
     e0.record(ext)
-    rec = ctx.simulate(args.steps, DT, TEMP)
+    rec = ctx.simulate(args.steps, DT, TEMP, global_n=N_global, global_volume=V_global)
     e1.record(ext)
     barrier()
     t_wall = time.perf_counter() - t0
@@ -263,14 +287,26 @@ def our_arm(args):
 
     # ---- end to end through the C ABI with host buffers ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
-    r_h = torch.empty((N, 3), dtype=torch.float64).pin_memory(); v_h = torch.empty((N, 3), dtype=torch.float64).pin_memory()
-    ctx.download("R", out=r_h.numpy()); ctx.download("V", out=v_h.numpy())
+    cap_h = int(N * 1.1) + 4096      # decomposed: the number of molecules a rank owns changes from step to step
+    r_h = torch.empty((cap_h, 3), dtype=torch.float64).pin_memory(); v_h = torch.empty((cap_h, 3), dtype=torch.float64).pin_memory()
+    n_now = ctx.num_molecules() if dd is not None else N
+    ctx.download("R", out=r_h.numpy()[:n_now]); ctx.download("V", out=v_h.numpy()[:n_now])
+    h2d = d2h = 0
+    ctx.set_field("R", r_h.numpy()[:n_now]); ctx.set_field("V", v_h.numpy()[:n_now])      # untimed: first touch of the staging buffers
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        ctx.set_field("R", r_h.numpy()); ctx.set_field("V", v_h.numpy())        # host -> device: this step's inputs
-        ctx.leapfrog_pre(DT); ctx.update(); m = ctx.traverse_cells(); k = ctx.leapfrog_post(DT)
-        ctx.download("R", out=r_h.numpy()); ctx.download("V", out=v_h.numpy())  # device -> host: the step's results
+        ctx.set_field("R", r_h.numpy()[:n_now]); ctx.set_field("V", v_h.numpy()[:n_now])        # host -> device: this step's inputs
+        h2d += 48 * n_now
+        ctx.leapfrog_pre(DT)
+        if dd is not None:
+            ctx.exchange()
+        ctx.update(); m = ctx.traverse_cells(); k = ctx.leapfrog_post(DT)
+        if dd is not None:
+            m, k = ctx.allreduce_macro()
+            n_now = ctx.num_molecules()
+        ctx.download("R", out=r_h.numpy()[:n_now]); ctx.download("V", out=v_h.numpy()[:n_now])  # device -> host: the step's results
+        d2h += 48 * n_now + 24
         _ = (m.upot, m.virial, k.summv2)
     barrier()
     t_e2e = time.perf_counter() - t0
@@ -295,12 +331,13 @@ def our_arm(args):
             "dtype": "f32 pair arithmetic, f64 accumulation and state (MARDYN_SPDP)", "data": "synthetic (BCC lattice like CubicGridGenerator, equal-magnitude velocities)",
             "config": {"workload": "BASELINE.json configs[1]: 1CLJ LJ liquid rho*=0.7 T*=0.85 rc=2.5 sigma dt=0.002, mixed precision, NVT velocity scaling",
                        "molecules_per_gpu": N, "molecules": world * N, "cells_per_dim": [int(x) for x in ctx.geometry()[0]],
-                       "parallelism": "1 GPU" if world == 1 else f"{world} independent periodic replicas (weak scaling; halo exchange not built yet)",
+                       "parallelism": "1 GPU" if world == 1 else "3D block decomposition %dx%dx%d, one process per GPU, leaving molecules + halo copies over NCCL send/recv every step, allreduce of 6 doubles" % grid_for(world),
+                       "box": [float(x) for x in ps.length],
                        "l2_policy": "inputs larger than L2: state %.1f GB per GPU" % (N * 150 / 1e9)},
             "ms_per_step_device_events": round(1e3 * t_dev / args.steps, 4),
             "phases_ms_per_step": {k: round(v / args.steps, 4) for k, v in ph_ms.items()},
             "gpu_launches": int(launches),
-            "e2e": {"value": round(e2e_value, 2), "unit": "MMUPS", "h2d_bytes_per_step": int(48 * N), "d2h_bytes_per_step": int(48 * N + 24), "steps": e2e_steps,
+            "e2e": {"value": round(e2e_value, 2), "unit": "MMUPS", "h2d_bytes_per_step": int(h2d / e2e_steps), "d2h_bytes_per_step": int(d2h / e2e_steps), "steps": e2e_steps,
                     "path": "set_field(R,V) from pinned host -> leapfrog_pre -> update -> traverse_cells -> leapfrog_post -> download(R,V) + scalars"},
             "roofline": {"kernel": "k_force_1clj<float>", "bound": "fp32", "achieved": round(achieved, 3), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
                          "frac": round(achieved / fp32_peak, 4), "traffic": None,
@@ -309,11 +346,11 @@ def our_arm(args):
                          "pair_interactions_per_s": round(0.5 * (fc0.lj + fc1.lj) / (force_ms * 1e-3), 1),
                          "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src, "hbm": hbm},
             "clocks": clocks,
-            "trace": {"T_first": rec[0, 4], "T_last": rec[-1, 4], "upot_last_per_molecule": rec[-1, 0] / N, "p_last": rec[-1, 5]},
+            "trace": {"T_first": rec[0, 4], "T_last": rec[-1, 4], "upot_last_per_molecule": rec[-1, 0] / N_global, "p_last": rec[-1, 5]},
         }
         if world == 1 and not args.no_cpu_baseline:
             line["cpu_baseline"] = cpu_baseline()
-        print(json.dumps(line), flush=True)
+        os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

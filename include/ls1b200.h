@@ -27,7 +27,7 @@
 extern "C" {
 #endif
 
-#define LS1B200_ABI_VERSION 1
+#define LS1B200_ABI_VERSION 2
 
 typedef struct ls1b200_ctx ls1b200_ctx;
 
@@ -178,10 +178,31 @@ int ls1b200_scale_velocities(ls1b200_ctx* ctx, double beta_trans, double beta_ro
 int ls1b200_simulate(ls1b200_ctx* ctx, uint64_t n_steps, double dt, double target_temperature,
                      uint64_t global_n, double global_volume, ls1b200_step_record* records);
 
-/* ---- multi-GPU: 3D spatial decomposition (replaces parallel/DomainDecomposition.cpp + CommunicationPartner) ----
- * The transport is the caller's (NCCL send/recv of the packed device buffers, or MPI in ls1); the library packs and
- * unpacks on the device. Message layout: ls1b200_particle records (== ParticleDataFull, 13 doubles + id + cid,
- * parallel/ParticleDataFull.h:30-35). */
+/* ---- multi-GPU: 3D block decomposition (replaces parallel/DomainDecomposition.cpp, DomainDecompMPIBase.cpp and
+ * CommunicationPartner.cpp; one process and one context per GPU) ----
+ * The box is cut into grid[0] x grid[1] x grid[2] equal blocks (DomainDecomposition::getBoundingBoxMin/Max,
+ * DomainDecomposition.cpp:130-139); rank = (coords[0]*grid[1] + coords[1])*grid[2] + coords[2] (MPI_Cart order).
+ * The context of a rank is created with ITS block as box_min/box_max and periodic[d] = (grid[d] == 1): dimensions that
+ * are not cut wrap locally (DomainDecompBase), cut dimensions get their halo from the neighbour ranks.
+ * Per step, between leapfrog_pre and update, leaving molecules and halo copies are exchanged dimension by dimension
+ * (x, then y, then z; copies received in one stage are forwarded by the next, which covers edges and corners) --
+ * == DomainDecompMPIBase::exchangeMoleculesMPI(LEAVING_AND_HALO_COPIES) with the indirect neighbour scheme. Positions that
+ * cross the global periodic boundary are shifted by the global box length with the reference's clamps
+ * (CommunicationPartner.cpp:526-563). Full-shell halo: no force exchange (C08CellPairTraversal.h:35). */
+typedef struct ls1b200_decomp {
+	int32_t rank, n_ranks;
+	int32_t grid[3];
+	int32_t coords[3];
+	double global_min[3], global_max[3];   /* Domain: the whole periodic box                                          */
+	uint8_t nccl_unique_id[128];           /* ncclUniqueId of ls1b200_nccl_unique_id(), identical on all ranks;
+	                                          ignored when use_nccl == 0                                             */
+	int32_t use_nccl;                      /* 1: the library owns an NCCL communicator and ls1b200_exchange /
+	                                          ls1b200_simulate do the transport (NVLink); 0: the caller moves the
+	                                          messages itself with ls1b200_halo_export / ls1b200_halo_import*         */
+	int32_t reserved[3];
+} ls1b200_decomp;
+
+/* Message record == ParticleDataFull (parallel/ParticleDataFull.h:30-35: id, cid, r, v, q, D). */
 typedef struct ls1b200_particle {
 	uint64_t id;
 	uint32_t cid;
@@ -189,14 +210,33 @@ typedef struct ls1b200_particle {
 	double r[3], v[3], q[4], L[3];
 } ls1b200_particle;
 
-/* Collects into a device buffer the molecules that have to go to the neighbour in direction dir[3] in {-1,0,1}^3
- * (leaving molecules and halo copies, positions already shifted by shift[3] for periodic wrap); leaving molecules
- * are removed from this context. Returns the device pointer and count. The buffer stays valid until the next call
- * for the same direction. == DomainDecompMPIBase::exchangeMoleculesMPI(LEAVING_AND_HALO_COPIES), send side. */
-int ls1b200_halo_export(ls1b200_ctx* ctx, const int32_t dir[3], const double shift[3],
-                        void** device_buf, uint64_t* count);
-/* Receive side: adds leaving molecules as owned ones and halo copies as halo molecules for the next
- * ls1b200_update (which must then be called with rebuild of the sorted SoA). device_buf is device memory. */
+/* ncclGetUniqueId on the calling rank (rank 0 calls it and broadcasts the 128 bytes with whatever it has: MPI,
+ * torch.distributed, a file). NCCL is loaded at run time (dlopen libnccl.so.2); fails loudly if it is absent. */
+int ls1b200_nccl_unique_id(uint8_t out[128]);
+/* Must be called after ls1b200_set_components and before ls1b200_upload; collective over all ranks when use_nccl == 1
+ * (ncclCommInitRank). After it, ls1b200_upload takes only the molecules of this rank's block, ids travel with the
+ * molecules, and ls1b200_download returns the molecules this rank owns NOW, in slot order (download LS1B200_F_ID
+ * to match them; ls1b200_num_molecules gives the count). */
+int ls1b200_decomp_attach(ls1b200_ctx* ctx, const ls1b200_decomp* dd);
+/* One exchange (all stages) over NCCL on the context's stream; collective. ls1b200_simulate calls it every step;
+ * phase-by-phase drivers call it between ls1b200_leapfrog_pre and ls1b200_update (and once before the first update). */
+int ls1b200_exchange(ls1b200_ctx* ctx);
+/* Sums the macroscopic values of the last traversal / leapfrog_post over all ranks (ncclAllReduce; replaces the
+ * collective communication of Domain::calculateGlobalValues, Domain.cpp:176-182, :220-230); collective. */
+int ls1b200_allreduce_macro(ls1b200_ctx* ctx, ls1b200_macro* macro, ls1b200_kinetic* kinetic);
+
+/* Transport-agnostic stage (use_nccl == 0, or MPI inside ls1): packs on the device what has to go to the neighbour on
+ * `side` (0 low, 1 high) of dimension `dim` -- leaving molecules (they stay behind as this rank's halo copy) and halo
+ * copies, positions already shifted for the periodic wrap -- and returns the device buffer of ls1b200_particle records
+ * and their count. Both sides of a dimension must be exported before anything of that stage is imported. The buffer
+ * stays valid until the next export for the same side. */
+int ls1b200_halo_export(ls1b200_ctx* ctx, int32_t dim, int32_t side, void** device_buf, uint64_t* count);
+/* Same, with the records copied to host memory; if host_cap is too small the call fails and *count holds the need --
+ * NB: the export has then already happened (leaving molecules were converted), so size the buffer generously. */
+int ls1b200_halo_export_host(ls1b200_ctx* ctx, int32_t dim, int32_t side, ls1b200_particle* host_buf, uint64_t host_cap,
+                             uint64_t* count);
+/* Receive side: appends leaving molecules as owned ones and halo copies as halo molecules; they are binned by the next
+ * ls1b200_update. device_buf is device memory of this context's device. */
 int ls1b200_halo_import(ls1b200_ctx* ctx, const void* device_buf, uint64_t count);
 /* Same, from host memory (tests, MPI without GPU-direct). */
 int ls1b200_halo_import_host(ls1b200_ctx* ctx, const ls1b200_particle* host_buf, uint64_t count);

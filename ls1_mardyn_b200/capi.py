@@ -30,7 +30,8 @@ EXPORTS = ["ls1b200_last_error", "ls1b200_abi_version", "ls1b200_kernel_launch_c
            "ls1b200_geometry", "ls1b200_update", "ls1b200_traverse_cells", "ls1b200_leapfrog_pre", "ls1b200_leapfrog_post",
            "ls1b200_scale_velocities", "ls1b200_simulate", "ls1b200_halo_export", "ls1b200_halo_import",
            "ls1b200_halo_import_host", "ls1b200_phase_times", "ls1b200_count_flops", "ls1b200_measure_fp32_peak",
-           "ls1b200_measure_hbm_copy", "ls1b200_stream"]
+           "ls1b200_measure_hbm_copy", "ls1b200_stream", "ls1b200_nccl_unique_id", "ls1b200_decomp_attach", "ls1b200_exchange",
+           "ls1b200_allreduce_macro", "ls1b200_halo_export_host"]
 
 
 class Ls1B200Error(RuntimeError):
@@ -56,6 +57,18 @@ class StepRecord(C.Structure):
 
 
 RECORD_FIELDS = [k for k, _ in StepRecord._fields_]
+
+
+class Decomp(C.Structure):
+    """ls1b200_decomp"""
+    _fields_ = [("rank", C.c_int32), ("n_ranks", C.c_int32), ("grid", C.c_int32 * 3), ("coords", C.c_int32 * 3),
+                ("global_min", C.c_double * 3), ("global_max", C.c_double * 3), ("nccl_unique_id", C.c_uint8 * 128),
+                ("use_nccl", C.c_int32), ("reserved", C.c_int32 * 3)]
+
+
+# ls1b200_particle (== ParticleDataFull): the record of the halo / leaving-molecule messages
+PARTICLE = np.dtype([("id", "<u8"), ("cid", "<u4"), ("flags", "<u4"), ("r", "<f8", 3), ("v", "<f8", 3), ("q", "<f8", 4), ("L", "<f8", 3)])
+assert PARTICLE.itemsize == 120
 
 
 class FlopCount(C.Structure):
@@ -95,6 +108,14 @@ def lib():
         L.ls1b200_count_flops.argtypes = [C.c_void_p, C.c_void_p]
         L.ls1b200_measure_fp32_peak.argtypes = [C.c_int, C.c_void_p]
         L.ls1b200_measure_hbm_copy.argtypes = [C.c_int, C.c_void_p]
+        L.ls1b200_nccl_unique_id.argtypes = [C.c_void_p]
+        L.ls1b200_decomp_attach.argtypes = [C.c_void_p, C.c_void_p]
+        L.ls1b200_exchange.argtypes = [C.c_void_p]
+        L.ls1b200_allreduce_macro.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ls1b200_halo_export_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p]
+        L.ls1b200_halo_import_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.ls1b200_halo_import.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
+        L.ls1b200_halo_export.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_void_p]
         _LIB = L
     return _LIB
 
@@ -110,6 +131,11 @@ def _vp(a):
 
 def kernel_launch_count() -> int:
     return int(lib().ls1b200_kernel_launch_count())
+
+
+def nccl_unique_id() -> bytes:
+    """ncclGetUniqueId (rank 0 calls it and broadcasts the 128 bytes)."""
+    b = (C.c_uint8 * 128)(); _check(lib().ls1b200_nccl_unique_id(b)); return bytes(b)
 
 
 def measure_fp32_peak(device: int = 0) -> float:
@@ -134,6 +160,7 @@ class Context:
         self.cfg = cfg
         self.h = C.c_void_p()
         self.n = 0
+        self.decomposed = False
         _check(lib().ls1b200_create(C.byref(cfg), C.byref(self.h)))
 
     def close(self):
@@ -167,6 +194,41 @@ class Context:
         _check(lib().ls1b200_upload(self.h, n, _vp(id), _vp(cid), _vp(r), _vp(v), _vp(q), _vp(L)))
         self.n = n
 
+    # ---- multi-GPU block decomposition (ls1_mardyn_b200.decomposition.DomainDecomposition) ----
+    def decomp_attach(self, dd, unique_id: bytes | None = None):
+        """ls1b200_decomp_attach; collective when unique_id is given (NCCL transport inside the library)."""
+        d = Decomp()
+        d.rank = dd.rank; d.n_ranks = dd.n_ranks
+        for k in range(3):
+            d.grid[k] = int(dd.grid[k]); d.coords[k] = int(dd.coords[k]); d.global_min[k] = 0.0; d.global_max[k] = float(dd.global_length[k])
+        d.use_nccl = 0
+        if unique_id is not None:
+            d.use_nccl = 1
+            for k in range(128):
+                d.nccl_unique_id[k] = unique_id[k]
+        _check(lib().ls1b200_decomp_attach(self.h, C.byref(d)))
+        self.decomposed = True
+
+    def num_molecules(self) -> int:
+        return int(lib().ls1b200_num_molecules(self.h))
+
+    def exchange(self):
+        _check(lib().ls1b200_exchange(self.h))
+
+    def allreduce_macro(self):
+        m = Macro(); k = Kinetic(); _check(lib().ls1b200_allreduce_macro(self.h, C.byref(m), C.byref(k))); return m, k
+
+    def halo_export(self, dim, side, cap=None):
+        """Records (numpy, dtype PARTICLE) for the neighbour on `side` of dimension `dim`."""
+        cap = int(cap or max(4096, self.n)) + 1
+        buf = np.zeros(cap, dtype=PARTICLE); cnt = C.c_uint64()
+        _check(lib().ls1b200_halo_export_host(self.h, dim, side, _vp(buf), cap, C.byref(cnt)))
+        return buf[:cnt.value].copy()
+
+    def halo_import(self, records):
+        records = np.ascontiguousarray(records, dtype=PARTICLE)
+        _check(lib().ls1b200_halo_import_host(self.h, _vp(records), len(records)))
+
     def stream(self) -> int:
         """cudaStream_t of this context as an integer (torch.cuda.ExternalStream(ctx.stream()))."""
         return int(lib().ls1b200_stream(self.h))
@@ -178,6 +240,8 @@ class Context:
 
     def update(self):
         _check(lib().ls1b200_update(self.h))
+        if self.decomposed:
+            self.n = self.num_molecules()
 
     def traverse_cells(self):
         m = Macro(); _check(lib().ls1b200_traverse_cells(self.h, C.byref(m))); return m
@@ -194,6 +258,8 @@ class Context:
     def download(self, field, out=None):
         f = FIELDS[field] if isinstance(field, str) else field
         dt, shp = _FIELD_SHAPE[f]
+        if self.decomposed:
+            self.n = self.num_molecules()
         if out is None:
             out = np.zeros((self.n,) + shp, dtype=dt)
         _check(lib().ls1b200_download(self.h, f, _vp(out), self.n))
@@ -202,11 +268,13 @@ class Context:
     def set_field(self, field, a):
         f = FIELDS[field] if isinstance(field, str) else field
         a = np.ascontiguousarray(a, dtype=_FIELD_SHAPE[f][0])
-        _check(lib().ls1b200_set_field(self.h, f, _vp(a), self.n))
+        _check(lib().ls1b200_set_field(self.h, f, _vp(a), len(a)))
 
     def simulate(self, nsteps, dt, target_temperature, global_n=0, global_volume=0.0, records=True):
         rec = (StepRecord * nsteps)() if records else None
         _check(lib().ls1b200_simulate(self.h, nsteps, dt, target_temperature, global_n, global_volume, rec))
+        if self.decomposed:
+            self.n = self.num_molecules()
         if not records:
             return None
         return np.frombuffer(rec, dtype=np.float64).reshape(nsteps, len(RECORD_FIELDS)).copy()

@@ -71,6 +71,10 @@ struct Geom {
 
 constexpr uint32_t KEY_NONE = 0xFFFFFFFFu;
 constexpr uint64_t META_HALO = 1ull << 63;
+// a halo copy that arrived (or was retained) during the halo exchange of THIS step: unlike a stale halo slot of the previous
+// sort it takes part in the next binning (and is forwarded by the later stages of the exchange); always set with META_HALO
+constexpr uint64_t META_FRESH = 1ull << 62;
+__host__ __device__ inline bool meta_fresh(uint64_t m) { return (m & META_FRESH) != 0; }
 __host__ __device__ inline uint32_t meta_orig(uint64_t m) { return (uint32_t) (m & 0xFFFFFFFFull); }
 __host__ __device__ inline uint32_t meta_cid(uint64_t m) { return (uint32_t) ((m >> 32) & 0xFFFFull); }
 __host__ __device__ inline bool meta_halo(uint64_t m) { return (m & META_HALO) != 0; }
@@ -97,7 +101,8 @@ struct State {
 	double* v = nullptr;         // [3][cap]
 	double* q = nullptr;         // [4][cap]  (only if the ensemble rotates)
 	double* L = nullptr;         // [3][cap]
-	uint64_t* meta = nullptr;    // [cap] orig index | cid << 32 | halo << 63
+	uint64_t* meta = nullptr;    // [cap] orig index | cid << 32 | fresh << 62 | halo << 63
+	uint64_t* id = nullptr;      // [cap] molecule id, travels with the molecule (decomposed mode only; otherwise ids stay in d_id)
 };
 
 // scalars living on the device between kernels of one step
@@ -107,8 +112,8 @@ struct DevScalars {
 	unsigned long long n_mol, rot_dof;
 	double beta_trans, beta_rot;                  // thermostat factors applied by the next leapfrog_pre
 	uint32_t n_slots2[2];                         // slots in use (owned + halo), ping-pong: [ctx->parity] is current
-	uint32_t overflow;                            // set if an update needed more than cap slots
-	uint32_t pad;
+	uint32_t overflow;                            // 1: an update needed more than cap slots, 2: a halo message buffer was too small
+	uint32_t n_owned_dev;                         // owned molecules counted by the last count_owned() (decomposed mode)
 };
 
 }  // namespace ls1b200
@@ -176,6 +181,9 @@ struct ls1b200_ctx {
 	ls1b200::DevScalars* h_scal = nullptr;   // pinned
 	ls1b200_step_record* d_records = nullptr; uint64_t records_cap = 0;
 
+	// staging buffer of download / set_field (grow-only: no cudaMalloc / cudaFree per call on the host-coherent path)
+	void* stage = nullptr; size_t stage_bytes = 0;
+
 	// timing
 	std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
 	struct Span { int phase; cudaEvent_t a, b; };
@@ -184,10 +192,23 @@ struct ls1b200_ctx {
 	uint64_t phase_launches[ls1b200::PH_COUNT] = {0, 0, 0, 0};
 	bool timing = true;
 
-	// halo exchange buffers (multi-GPU)
-	void* export_buf[27] = {nullptr}; uint64_t export_cap[27] = {0};
-	uint32_t* d_export_count = nullptr;
-	void* import_buf = nullptr; uint64_t import_count = 0, import_cap = 0;
+	// ---- 3D block decomposition (halo.cu; replaces parallel/DomainDecomposition.cpp + CommunicationPartner.cpp) ----
+	struct Decomp {
+		bool active = false;
+		int rank = 0, n_ranks = 1;
+		int grid[3] = {1, 1, 1}, coords[3] = {0, 0, 0};
+		double gmin[3] = {0, 0, 0}, gmax[3] = {0, 0, 0};
+		double wrap_hi[3], halo_hi[3], halo_lo[3];      // clamps against the GLOBAL box (CommunicationPartner.cpp:526-563)
+		int nbr[3][2];                                   // neighbour rank per dimension, [0] low side, [1] high side
+		void* comm = nullptr;                            // ncclComm_t
+		uint64_t rot_dof_global = 0; bool rot_dof_valid = false;
+	} dd;
+	unsigned char* msg_out[2] = {nullptr, nullptr};    // [low, high] message: 16-byte header (count) + records
+	unsigned char* msg_in[2] = {nullptr, nullptr};
+	uint64_t msg_cap = 0;                               // records per message
+	ls1b200_particle* import_stage = nullptr; uint64_t import_stage_cap = 0;   // host-staged imports (ls1b200_halo_import_host)
+	uint64_t* ekey = nullptr;                           // [cap] (id << 5 | shift code) per provisional slot: content-based in-cell order
+	uint64_t n_owned_local = 0;                         // owned molecules of this rank (host copy, decomposed mode)
 };
 
 namespace ls1b200 {
@@ -205,4 +226,9 @@ int force_general(ls1b200_ctx* c);
 int force_1clj(ls1b200_ctx* c);
 int force_1clj_tiled(ls1b200_ctx* c);
 int reduce_force_partials(ls1b200_ctx* c, uint32_t nblocks);
+int do_exchange(ls1b200_ctx* c);                    // NCCL halo + leaving-molecule exchange of one step (no-op if not decomposed)
+int do_allreduce_scalars(ls1b200_ctx* c);           // sums the 6 leading doubles of DevScalars over the ranks
+int count_owned(ls1b200_ctx* c, bool want_index);   // decomposed mode: n_owned_local (+ entry[slot] = index among owned slots)
+int decomp_alloc(ls1b200_ctx* c);
+void decomp_free(ls1b200_ctx* c);
 }  // namespace ls1b200

@@ -50,12 +50,13 @@ template <class T> static int dev_alloc(T** p, size_t n) {
 }
 template <class T> static void dev_free(T*& p) { if (p) cudaFree(p); p = nullptr; }
 
-static int alloc_state(State& s, uint64_t cap, bool rot) {
+static int alloc_state(State& s, uint64_t cap, bool rot, bool ids) {
 	LS1_TRY(dev_alloc(&s.r, 3 * cap)); LS1_TRY(dev_alloc(&s.v, 3 * cap)); LS1_TRY(dev_alloc(&s.meta, cap));
+	if (ids) LS1_TRY(dev_alloc(&s.id, cap));
 	if (rot) { LS1_TRY(dev_alloc(&s.q, 4 * cap)); LS1_TRY(dev_alloc(&s.L, 3 * cap)); }
 	return 0;
 }
-static void free_state(State& s) { dev_free(s.r); dev_free(s.v); dev_free(s.q); dev_free(s.L); dev_free(s.meta); }
+static void free_state(State& s) { dev_free(s.r); dev_free(s.v); dev_free(s.q); dev_free(s.L); dev_free(s.meta); dev_free(s.id); }
 
 void ctx_free_molecules(ls1b200_ctx* c) {
 	free_state(c->cur); free_state(c->nxt);
@@ -65,6 +66,7 @@ void ctx_free_molecules(ls1b200_ctx* c) {
 	if (c->spos) cudaFree(c->spos); c->spos = nullptr;
 	if (c->sori) cudaFree(c->sori); c->sori = nullptr;
 	dev_free(c->sf); dev_free(c->partials);
+	decomp_free(c);
 	c->cap = 0; c->n_owned = 0; c->n_slots = 0;
 }
 
@@ -73,7 +75,7 @@ int ctx_alloc_molecules(ls1b200_ctx* c, uint64_t n_owned, uint64_t cap) {
 	if (cap >= (1ull << 27)) return fail("ls1b200: more than 2^27 slots per device are not supported");
 	c->cap = cap; c->n_owned = n_owned;
 	const bool rot = c->rotates;
-	LS1_TRY(alloc_state(c->cur, cap, rot)); LS1_TRY(alloc_state(c->nxt, cap, rot));
+	LS1_TRY(alloc_state(c->cur, cap, rot, c->dd.active)); LS1_TRY(alloc_state(c->nxt, cap, rot, c->dd.active));
 	LS1_TRY(dev_alloc(&c->d_id, n_owned));
 	LS1_TRY(dev_alloc(&c->F, 3 * cap)); LS1_TRY(dev_alloc(&c->Vi, 3 * cap));
 	if (rot) LS1_TRY(dev_alloc(&c->M, 3 * cap));
@@ -95,6 +97,7 @@ int ctx_alloc_molecules(ls1b200_ctx* c, uint64_t n_owned, uint64_t cap) {
 	c->partial_blocks = (uint32_t) (((cap + 63) / 64) * std::max(c->smax, 1u) + 64);
 	if (c->all_1clj) c->partial_blocks = std::max<uint32_t>(c->partial_blocks, c->geom.ncells + 64);   // one partial per chunk
 	LS1_TRY(dev_alloc(&c->partials, (size_t) c->partial_blocks * 8));
+	if (c->dd.active) LS1_TRY(decomp_alloc(c));
 	LS1_CUDA(cudaMemsetAsync(c->F, 0, sizeof(double) * 3 * cap, c->stream));
 	LS1_CUDA(cudaMemsetAsync(c->Vi, 0, sizeof(double) * 3 * cap, c->stream));
 	if (rot) LS1_CUDA(cudaMemsetAsync(c->M, 0, sizeof(double) * 3 * cap, c->stream));
@@ -163,29 +166,33 @@ __global__ void k_make_meta(const uint32_t* __restrict__ cid, uint64_t* __restri
 }
 
 // out[orig][d] = plane[d][slot] for the owned molecule in every slot
-__global__ void k_download_planes(const double* __restrict__ planes, const uint64_t* __restrict__ meta, double* __restrict__ out, uint32_t n_slots, uint64_t cap, int dim) {
+__global__ void k_download_planes(const double* __restrict__ planes, const uint64_t* __restrict__ meta, double* __restrict__ out, uint32_t n_slots, uint64_t cap, int dim,
+                                  const uint32_t* __restrict__ owned_index) {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n_slots) return;
 	const uint64_t m = meta[t];
 	if (meta_halo(m)) return;
-	const uint64_t o = meta_orig(m);
+	const uint64_t o = owned_index ? owned_index[t] : meta_orig(m);      // decomposed mode: slot order of the molecules owned now
 	for (int d = 0; d < dim; d++) out[o * dim + d] = planes[(uint64_t) d * cap + t];
 }
-__global__ void k_upload_planes(double* __restrict__ planes, const uint64_t* __restrict__ meta, const double* __restrict__ in, uint32_t n_slots, uint64_t cap, int dim) {
+__global__ void k_upload_planes(double* __restrict__ planes, const uint64_t* __restrict__ meta, const double* __restrict__ in, uint32_t n_slots, uint64_t cap, int dim,
+                                const uint32_t* __restrict__ owned_index) {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n_slots) return;
 	const uint64_t m = meta[t];
 	if (meta_halo(m)) return;
-	const uint64_t o = meta_orig(m);
+	const uint64_t o = owned_index ? owned_index[t] : meta_orig(m);
 	for (int d = 0; d < dim; d++) planes[(uint64_t) d * cap + t] = in[o * dim + d];
 }
 __global__ void k_download_meta(const uint64_t* __restrict__ meta, const uint32_t* __restrict__ cell_of, uint32_t ncells, uint32_t* __restrict__ cid_out,
-                                uint64_t* __restrict__ cell_out, uint32_t n_slots) {
+                                uint64_t* __restrict__ cell_out, uint32_t n_slots, const uint32_t* __restrict__ owned_index, const uint64_t* __restrict__ id_plane,
+                                uint64_t* __restrict__ id_out) {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= n_slots) return;
 	const uint64_t m = meta[t];
 	if (meta_halo(m)) return;
-	const uint64_t o = meta_orig(m);
+	const uint64_t o = owned_index ? owned_index[t] : meta_orig(m);
+	if (id_out) id_out[o] = id_plane[t];
 	if (cid_out) cid_out[o] = meta_cid(m);
 	if (cell_out) { const uint32_t c = cell_of[t]; cell_out[o] = (c >= ncells) ? ~0ull : (uint64_t) c; }
 }
@@ -250,9 +257,8 @@ int ls1b200_destroy(ls1b200_ctx* c) {
 	dev_free(c->chunk_row_count); dev_free(c->chunk_row_start); dev_free(c->work_counter);
 	if (c->h_scal) cudaFreeHost(c->h_scal);
 	for (auto e : c->ev_pool) cudaEventDestroy(e);
-	for (int i = 0; i < 27; i++) if (c->export_buf[i]) cudaFree(c->export_buf[i]);
-	dev_free(c->d_export_count);
-	if (c->import_buf) cudaFree(c->import_buf);
+	decomp_free(c);
+	if (c->stage) cudaFree(c->stage);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
 	return 0;
@@ -321,7 +327,7 @@ int ls1b200_set_components(ls1b200_ctx* c, uint32_t n_components, const ls1b200_
 	return 0;
 }
 
-uint64_t ls1b200_num_molecules(const ls1b200_ctx* c) { return c ? c->n_owned : 0; }
+uint64_t ls1b200_num_molecules(const ls1b200_ctx* c) { return c ? (c->dd.active ? c->n_owned_local : c->n_owned) : 0; }
 void* ls1b200_stream(ls1b200_ctx* c) { return c ? (void*) c->stream : nullptr; }
 
 int ls1b200_geometry(const ls1b200_ctx* c, int32_t cells_per_dim[3], double cell_length[3], double halo_min[3]) {
@@ -338,8 +344,9 @@ int ls1b200_upload(ls1b200_ctx* c, uint64_t n, const uint64_t* id, const uint32_
 	for (uint64_t i = 0; i < n; i++) if (cid[i] >= c->comps.size()) return fail("ls1b200_upload: component id out of range");
 	// slot capacity: owned molecules + periodic halo copies (boundary layer of width rc on every periodic face) with head room
 	double fac = 1.;
-	for (int d = 0; d < 3; d++) if (c->geom.periodic[d] || c->cfg.reserved[0]) fac *= 1. + 2. * std::min(1., c->geom.cutoff / c->geom.lbox[d]);
-	const uint64_t cap = n + (uint64_t) ((fac - 1.) * 1.5 * (double) n) + 4096;
+	for (int d = 0; d < 3; d++) if (c->geom.periodic[d] || c->cfg.reserved[0] || c->dd.active) fac *= 1. + 2. * std::min(1., c->geom.cutoff / c->geom.lbox[d]);
+	// decomposed mode: + 10 % for molecules migrating in
+	const uint64_t cap = n + (uint64_t) ((fac - 1.) * 1.5 * (double) n) + (c->dd.active ? n / 10 + 16384 : 0) + 4096;
 	LS1_TRY(ctx_alloc_molecules(c, n, cap));
 	c->rot_dof_total = 0;
 	for (uint64_t i = 0; i < n; i++) c->rot_dof_total += c->comps[cid[i]].rot_dof;
@@ -362,9 +369,11 @@ int ls1b200_upload(ls1b200_ctx* c, uint64_t n, const uint64_t* id, const uint32_
 		LS1_CUDA(cudaMemcpyAsync(cstage, cid, sizeof(uint32_t) * n, cudaMemcpyHostToDevice, c->stream));
 		k_make_meta<<<g1, 256, 0, c->stream>>>(cstage, c->cur.meta, n); g_launches++;
 		LS1_CUDA(cudaMemcpyAsync(c->d_id, id, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, c->stream));
+		if (c->dd.active) LS1_CUDA(cudaMemcpyAsync(c->cur.id, id, sizeof(uint64_t) * n, cudaMemcpyHostToDevice, c->stream));
 		LS1_CUDA(cudaStreamSynchronize(c->stream));
 		cudaFree(stage); cudaFree(cstage);
 	}
+	c->n_owned_local = n; c->dd.rot_dof_valid = false;
 	c->parity = 0; c->n_slots = (uint32_t) n;
 	c->h_scal->n_slots2[0] = (uint32_t) n; c->h_scal->n_slots2[1] = 0; c->h_scal->overflow = 0;
 	c->h_scal->beta_trans = 1.; c->h_scal->beta_rot = 1.;
@@ -373,8 +382,17 @@ int ls1b200_upload(ls1b200_ctx* c, uint64_t n, const uint64_t* id, const uint32_
 	return 0;
 }
 
+static int stage_reserve(ls1b200_ctx* c, size_t bytes) {
+	if (bytes <= c->stage_bytes) return 0;
+	if (c->stage) { LS1_CUDA(cudaStreamSynchronize(c->stream)); cudaFree(c->stage); c->stage = nullptr; c->stage_bytes = 0; }
+	LS1_CUDA(cudaMalloc(&c->stage, bytes));
+	c->stage_bytes = bytes;
+	return 0;
+}
+
 // brings n_slots / overflow to the host (synchronises the stream)
-static int sync_scalars(ls1b200_ctx* c) {
+static int sync_scalars(ls1b200_ctx* c, bool owned_index = false) {
+	if (c->dd.active && c->cap) LS1_TRY(count_owned(c, owned_index));
 	LS1_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
 	LS1_CUDA(cudaStreamSynchronize(c->stream));
 	c->n_slots = std::min<uint64_t>(c->h_scal->n_slots2[c->parity], c->cap);
@@ -406,14 +424,19 @@ int ls1b200_traverse_cells(ls1b200_ctx* c, ls1b200_macro* out) {
 
 int ls1b200_download(ls1b200_ctx* c, int field, void* dst, uint64_t n) {
 	if (!c || !dst) return fail("ls1b200_download: null argument");
-	if (n != c->n_owned) return fail("ls1b200_download: n does not match the number of molecules");
-	if (n == 0) return 0;
 	LS1_CUDA(cudaSetDevice(c->device));
-	LS1_TRY(sync_scalars(c));
+	if (c->dd.active) {
+		if (!c->cap) return fail("ls1b200_download: call ls1b200_upload first");
+		LS1_TRY(sync_scalars(c, true));      // entry[slot] = index among the owned slots
+		if (n != c->n_owned_local) return fail("ls1b200_download: n does not match ls1b200_num_molecules()");
+	} else if (n != c->n_owned) return fail("ls1b200_download: n does not match the number of molecules");
+	if (n == 0) return 0;
+	if (!c->dd.active) LS1_TRY(sync_scalars(c));
+	const uint32_t* oi = c->dd.active ? c->entry : nullptr;
 	const uint32_t ns = c->n_slots, g = (ns + 255) / 256;
 	const double* planes = nullptr; int dim = 3;
 	switch (field) {
-		case LS1B200_F_ID: LS1_CUDA(cudaMemcpy(dst, c->d_id, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost)); return 0;
+		case LS1B200_F_ID: if (c->dd.active) break; LS1_CUDA(cudaMemcpy(dst, c->d_id, sizeof(uint64_t) * n, cudaMemcpyDeviceToHost)); return 0;
 		case LS1B200_F_R: planes = c->cur.r; break;
 		case LS1B200_F_V: planes = c->cur.v; break;
 		case LS1B200_F_Q: planes = c->cur.q; dim = 4; break;
@@ -424,17 +447,16 @@ int ls1b200_download(ls1b200_ctx* c, int field, void* dst, uint64_t n) {
 		case LS1B200_F_CID: case LS1B200_F_CELL: break;
 		default: return fail("ls1b200_download: unknown field");
 	}
-	if (field == LS1B200_F_CID || field == LS1B200_F_CELL) {
+	if (field == LS1B200_F_CID || field == LS1B200_F_CELL || field == LS1B200_F_ID) {
 		if (field == LS1B200_F_CELL && !c->sorted) return fail("ls1b200_download: cell indices need ls1b200_update first");
-		void* tmp = nullptr; const size_t es = field == LS1B200_F_CID ? 4 : 8;
-		LS1_CUDA(cudaMalloc(&tmp, es * n));
+		const size_t es = field == LS1B200_F_CID ? 4 : 8;
+		LS1_TRY(stage_reserve(c, es * n));
+		void* tmp = c->stage;
 		k_download_meta<<<g, 256, 0, c->stream>>>(c->cur.meta, c->cell_of2, c->geom.ncells, field == LS1B200_F_CID ? (uint32_t*) tmp : nullptr,
-		                                         field == LS1B200_F_CELL ? (uint64_t*) tmp : nullptr, ns);
+		                                         field == LS1B200_F_CELL ? (uint64_t*) tmp : nullptr, ns, oi, c->cur.id, field == LS1B200_F_ID ? (uint64_t*) tmp : nullptr);
 		g_launches++;
-		cudaError_t e = cudaMemcpyAsync(dst, tmp, es * n, cudaMemcpyDeviceToHost, c->stream);
-		if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-		cudaFree(tmp);
-		LS1_CUDA(e);
+		LS1_CUDA(cudaMemcpyAsync(dst, tmp, es * n, cudaMemcpyDeviceToHost, c->stream));
+		LS1_CUDA(cudaStreamSynchronize(c->stream));
 		return 0;
 	}
 	if (!planes) {   // fields a non-rotating ensemble does not store: identity orientation, zero angular momentum / torque
@@ -443,23 +465,26 @@ int ls1b200_download(ls1b200_ctx* c, int field, void* dst, uint64_t n) {
 		if (field == LS1B200_F_Q) for (uint64_t i = 0; i < n; i++) o[4 * i] = 1.;
 		return 0;
 	}
-	double* tmp = nullptr;
-	LS1_CUDA(cudaMalloc((void**) &tmp, sizeof(double) * dim * n));
-	k_download_planes<<<g, 256, 0, c->stream>>>(planes, c->cur.meta, tmp, ns, c->cap, dim);
+	LS1_TRY(stage_reserve(c, sizeof(double) * dim * n));
+	double* tmp = (double*) c->stage;
+	k_download_planes<<<g, 256, 0, c->stream>>>(planes, c->cur.meta, tmp, ns, c->cap, dim, oi);
 	g_launches++;
-	cudaError_t e = cudaMemcpyAsync(dst, tmp, sizeof(double) * dim * n, cudaMemcpyDeviceToHost, c->stream);
-	if (e == cudaSuccess) e = cudaStreamSynchronize(c->stream);
-	cudaFree(tmp);
-	LS1_CUDA(e);
+	LS1_CUDA(cudaGetLastError());
+	LS1_CUDA(cudaMemcpyAsync(dst, tmp, sizeof(double) * dim * n, cudaMemcpyDeviceToHost, c->stream));
+	LS1_CUDA(cudaStreamSynchronize(c->stream));
 	return 0;
 }
 
 int ls1b200_set_field(ls1b200_ctx* c, int field, const void* src, uint64_t n) {
 	if (!c || !src) return fail("ls1b200_set_field: null argument");
-	if (n != c->n_owned) return fail("ls1b200_set_field: n does not match the number of molecules");
-	if (n == 0) return 0;
 	LS1_CUDA(cudaSetDevice(c->device));
-	LS1_TRY(sync_scalars(c));
+	if (c->dd.active) {
+		LS1_TRY(sync_scalars(c, true));
+		if (n != c->n_owned_local) return fail("ls1b200_set_field: n does not match ls1b200_num_molecules()");
+	} else if (n != c->n_owned) return fail("ls1b200_set_field: n does not match the number of molecules");
+	if (n == 0) return 0;
+	if (!c->dd.active) LS1_TRY(sync_scalars(c));
+	const uint32_t* oi = c->dd.active ? c->entry : nullptr;
 	double* planes = nullptr; int dim = 3;
 	switch (field) {
 		case LS1B200_F_R: planes = c->cur.r; c->forces_valid = false; break;
@@ -471,13 +496,14 @@ int ls1b200_set_field(ls1b200_ctx* c, int field, const void* src, uint64_t n) {
 		default: return fail("ls1b200_set_field: field cannot be set");
 	}
 	if (!planes) return 0;   // non-rotating ensemble: nothing to store
-	double* tmp = nullptr;
-	LS1_CUDA(cudaMalloc((void**) &tmp, sizeof(double) * dim * n));
-	cudaError_t e = cudaMemcpyAsync(tmp, src, sizeof(double) * dim * n, cudaMemcpyHostToDevice, c->stream);
+	LS1_TRY(stage_reserve(c, sizeof(double) * dim * n));
+	double* tmp = (double*) c->stage;
+	LS1_CUDA(cudaMemcpyAsync(tmp, src, sizeof(double) * dim * n, cudaMemcpyHostToDevice, c->stream));
 	const uint32_t ns = c->n_slots;
-	if (e == cudaSuccess) { k_upload_planes<<<(ns + 255) / 256, 256, 0, c->stream>>>(planes, c->cur.meta, tmp, ns, c->cap, dim); g_launches++; e = cudaStreamSynchronize(c->stream); }
-	cudaFree(tmp);
-	LS1_CUDA(e);
+	k_upload_planes<<<(ns + 255) / 256, 256, 0, c->stream>>>(planes, c->cur.meta, tmp, ns, c->cap, dim, oi);
+	g_launches++;
+	LS1_CUDA(cudaGetLastError());
+	LS1_CUDA(cudaStreamSynchronize(c->stream));      // src is borrowed for the duration of the call only
 	return 0;
 }
 

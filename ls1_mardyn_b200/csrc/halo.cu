@@ -1,13 +1,500 @@
-// halo.cu -- multi-GPU halo / leaving-molecule exchange buffers (see include/ls1b200.h). Placeholder until the
-// decomposition row of SURVEY.md section 8(e) is built: the entry points exist and fail loudly.
+// halo.cu -- multi-GPU 3D block decomposition: leaving-molecule + halo-copy exchange and the global reductions.
+//
+// Replaces (one process and one context per GPU): parallel/DomainDecomposition.cpp (:130-139 block bounds),
+// DomainDecompMPIBase::exchangeMoleculesMPI(LEAVING_AND_HALO_COPIES) with the indirect (x, y, z staged) neighbour scheme
+// (parallel/NeighbourCommunicationScheme.cpp), CommunicationPartner::collectMoleculesInRegion (CommunicationPartner.cpp:
+// 435-575: which molecules, the periodic shift and its clamps) and the collective of Domain::calculateGlobalValues
+// (Domain.cpp:176-182, :220-230).
+//
+// Per stage (dimension d with grid[d] > 1), all on the context's stream:
+//   k_export   one pass over the slots: owned molecules outside [bmin, bmax) in d are packed as LEAVING for that neighbour
+//              and stay behind as this rank's halo copy (META_FRESH); owned molecules and fresh halo copies within rc of
+//              a face are packed as HALO copies. Records go straight into the two outgoing message buffers
+//              (16-byte header holding the count + fixed-capacity record array), positions already shifted.
+//   ncclGroup  { send low, send high, recv from high, recv from low }   -- NVLink / NVSwitch peer copies
+//   k_import   appends the records of both incoming messages to the slot arrays (owned or fresh halo)
+// The following ls1b200_update bins owned molecules and fresh halo copies alike and makes the local periodic copies of
+// the dimensions that are not cut. In-cell order is by (molecule id, shift code), i.e. independent of message order.
+// NCCL is bound at run time (dlopen), so the library loads -- and the single-GPU path runs -- without it.
+#include <dlfcn.h>
+#include <math.h>
+#include <string.h>
+
+#include <algorithm>
+
 #include "common.cuh"
+
+namespace ls1b200 {
+
+// ---------------------------------------------------------------------------------------------------------------------
+// NCCL, bound at run time
+// ---------------------------------------------------------------------------------------------------------------------
+namespace {
+typedef struct { char internal[128]; } nccl_uid;
+struct Nccl {
+	void* h = nullptr;
+	int (*GetUniqueId)(nccl_uid*) = nullptr;
+	int (*CommInitRank)(void**, int, nccl_uid, int) = nullptr;
+	int (*CommDestroy)(void*) = nullptr;
+	int (*Send)(const void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+	int (*Recv)(void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+	int (*AllReduce)(const void*, void*, size_t, int, int, void*, cudaStream_t) = nullptr;
+	int (*GroupStart)() = nullptr;
+	int (*GroupEnd)() = nullptr;
+	const char* (*GetErrorString)(int) = nullptr;
+};
+Nccl g_nccl;
+constexpr int NCCL_UINT8 = 1, NCCL_FLOAT64 = 8, NCCL_SUM = 0;   // ncclDataType_t / ncclRedOp_t values of nccl.h (stable since 2.0)
+
+int nccl_load() {
+	if (g_nccl.h) return 0;
+	void* h = dlopen("libnccl.so.2", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) h = dlopen("libnccl.so", RTLD_NOW | RTLD_GLOBAL);
+	if (!h) return fail(std::string("ls1b200: cannot load NCCL (libnccl.so.2): ") + dlerror());
+	Nccl n; n.h = h;
+	#define SYM(field, name) *(void**) (&n.field) = dlsym(h, name); if (!n.field) return fail("ls1b200: NCCL symbol " name " not found")
+	SYM(GetUniqueId, "ncclGetUniqueId"); SYM(CommInitRank, "ncclCommInitRank"); SYM(CommDestroy, "ncclCommDestroy");
+	SYM(Send, "ncclSend"); SYM(Recv, "ncclRecv"); SYM(AllReduce, "ncclAllReduce");
+	SYM(GroupStart, "ncclGroupStart"); SYM(GroupEnd, "ncclGroupEnd"); SYM(GetErrorString, "ncclGetErrorString");
+	#undef SYM
+	g_nccl = n;
+	return 0;
+}
+#define LS1_NCCL(call)                                                                                               \
+	do {                                                                                                               \
+		int e__ = (call);                                                                                                \
+		if (e__ != 0) return ::ls1b200::fail(std::string(#call) + ": " + g_nccl.GetErrorString(e__));                    \
+	} while (0)
+}  // namespace
+
+// ---------------------------------------------------------------------------------------------------------------------
+// message records
+// ---------------------------------------------------------------------------------------------------------------------
+constexpr size_t MSG_HEADER = 16;
+struct RecCompact { uint64_t id; uint32_t cid; uint32_t flags; double r[3], v[3]; };      // non-rotating ensembles over NCCL: 64 B
+static_assert(sizeof(RecCompact) == 64 && sizeof(ls1b200_particle) == 120, "record layout");
+
+struct XArgs {
+	int dim;
+	double bmin, bmax, rc;                 // this rank's block in dimension dim, halo width (== cutoff, DomainDecompBase.cpp:329)
+	double glen, gmin, gmax;               // global box in dimension dim
+	double wrap_hi, halo_hi, halo_lo;      // clamps against the global box
+	int lo_wrap, hi_wrap;                  // the low / high neighbour lies across the global periodic boundary
+	uint32_t cap, parity, msg_cap;
+	int rotates;
+};
+
+template <bool FULL>
+__device__ __forceinline__ void pack(unsigned char* msg, uint32_t msg_cap, DevScalars* scal, const State& st, size_t cap, uint32_t s, uint64_t meta,
+                                     int dim, double xd, uint32_t flags, int rotates) {
+	const uint32_t k = atomicAdd(reinterpret_cast<uint32_t*>(msg), 1u);
+	if (k >= msg_cap) { scal->overflow = 2; return; }
+	double r[3] = {st.r[s], st.r[cap + s], st.r[2 * cap + s]};
+	r[dim] = xd;
+	if (FULL) {
+		ls1b200_particle* p = reinterpret_cast<ls1b200_particle*>(msg + MSG_HEADER) + k;
+		p->id = st.id[s]; p->cid = meta_cid(meta); p->flags = flags;
+		for (int d = 0; d < 3; d++) { p->r[d] = r[d]; p->v[d] = st.v[d * cap + s]; }
+		if (rotates) {
+			for (int d = 0; d < 4; d++) p->q[d] = st.q[d * cap + s];
+			for (int d = 0; d < 3; d++) p->L[d] = st.L[d * cap + s];
+		} else {
+			p->q[0] = 1.; p->q[1] = p->q[2] = p->q[3] = 0.; p->L[0] = p->L[1] = p->L[2] = 0.;
+		}
+	} else {
+		RecCompact* p = reinterpret_cast<RecCompact*>(msg + MSG_HEADER) + k;
+		p->id = st.id[s]; p->cid = meta_cid(meta); p->flags = flags;
+		for (int d = 0; d < 3; d++) { p->r[d] = r[d]; p->v[d] = st.v[d * cap + s]; }
+	}
+}
+
+// which == 3: both sides (the NCCL path), 1: low side only, 2: high side only (the staged C ABI exports one side per call;
+// a leaving molecule is converted by the call for ITS side, so low + high together equal one which == 3 pass)
+template <bool FULL>
+__global__ void __launch_bounds__(256) k_export(XArgs a, State st, unsigned char* __restrict__ out_lo, unsigned char* __restrict__ out_hi, DevScalars* scal, int which) {
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= min(scal->n_slots2[a.parity], a.cap)) return;
+	const uint64_t meta = st.meta[s];
+	const bool halo = meta_halo(meta);
+	if (halo && !meta_fresh(meta)) return;                       // stale halo slot of the previous sort
+	const size_t cap = a.cap;
+	const double x = st.r[(size_t) a.dim * cap + s];
+	if (!halo && x < a.bmin) {
+		if (!(which & 1)) return;
+		// leaving through the low face: LEAVING shift + clamp (CommunicationPartner.cpp:550-562) ...
+		double xn = x;
+		if (a.lo_wrap) { xn = __dadd_rn(x, a.glen); if (xn >= a.gmax) xn = a.wrap_hi; }
+		pack<FULL>(out_lo, a.msg_cap, scal, st, cap, s, meta, a.dim, xn, 0u, a.rotates);
+		// ... and it stays behind as my halo copy of the molecule its new owner now holds (HALO shift + clamp, :533-547)
+		double xh = xn;
+		if (a.lo_wrap) { xh = __dsub_rn(xn, a.glen); if (xh >= a.gmin) xh = a.halo_lo; }
+		st.r[(size_t) a.dim * cap + s] = xh;
+		st.meta[s] = meta | META_HALO | META_FRESH;
+		return;
+	}
+	if (!halo && x >= a.bmax) {
+		if (!(which & 2)) return;
+		double xn = x;
+		if (a.hi_wrap) { xn = __dsub_rn(x, a.glen); if (xn < a.gmin) xn = a.gmin; }
+		pack<FULL>(out_hi, a.msg_cap, scal, st, cap, s, meta, a.dim, xn, 0u, a.rotates);
+		double xh = xn;
+		if (a.hi_wrap) { xh = __dadd_rn(xn, a.glen); if (xh < a.gmax) xh = a.halo_hi; }
+		st.r[(size_t) a.dim * cap + s] = xh;
+		st.meta[s] = meta | META_HALO | META_FRESH;
+		return;
+	}
+	// halo copies: an owned molecule inside the boundary layer, or a fresh halo copy of an earlier stage (forwarded to the
+	// edge / corner neighbours; it may lie outside [bmin, bmax) in this dimension if its owner is about to hand it over)
+	if ((which & 1) && x < __dadd_rn(a.bmin, a.rc)) {
+		double xn = x;
+		if (a.lo_wrap) { xn = __dadd_rn(x, a.glen); if (x >= a.bmin && xn < a.gmax) xn = a.halo_hi; }
+		pack<FULL>(out_lo, a.msg_cap, scal, st, cap, s, meta, a.dim, xn, 1u, a.rotates);
+	}
+	if ((which & 2) && x >= __dsub_rn(a.bmax, a.rc)) {
+		double xn = x;
+		if (a.hi_wrap) { xn = __dsub_rn(x, a.glen); if (x < a.bmax && xn >= a.gmin) xn = a.halo_lo; }
+		pack<FULL>(out_hi, a.msg_cap, scal, st, cap, s, meta, a.dim, xn, 1u, a.rotates);
+	}
+}
+
+// appends the records of one message behind the slots in use (+ the records of the message imported just before)
+template <bool FULL>
+__global__ void __launch_bounds__(256) k_import(const unsigned char* __restrict__ msg, const unsigned char* __restrict__ prev_msg, State st, uint32_t cap, uint32_t parity,
+                                                 uint32_t msg_cap, int rotates, DevScalars* scal) {
+	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
+	const uint32_t n = min(*reinterpret_cast<const uint32_t*>(msg), msg_cap);
+	if (i >= n) return;
+	uint32_t base = scal->n_slots2[parity];
+	if (prev_msg) base += min(*reinterpret_cast<const uint32_t*>(prev_msg), msg_cap);
+	const uint32_t t = base + i;
+	if (t >= cap) { scal->overflow = 1; return; }
+	const size_t c = cap;
+	uint64_t id; uint32_t cid, flags; const double *r, *v;
+	if (FULL) {
+		const ls1b200_particle* p = reinterpret_cast<const ls1b200_particle*>(msg + MSG_HEADER) + i;
+		id = p->id; cid = p->cid; flags = p->flags; r = p->r; v = p->v;
+		if (rotates) {
+			for (int d = 0; d < 4; d++) st.q[d * c + t] = p->q[d];
+			for (int d = 0; d < 3; d++) st.L[d * c + t] = p->L[d];
+		}
+	} else {
+		const RecCompact* p = reinterpret_cast<const RecCompact*>(msg + MSG_HEADER) + i;
+		id = p->id; cid = p->cid; flags = p->flags; r = p->r; v = p->v;
+	}
+	for (int d = 0; d < 3; d++) { st.r[d * c + t] = r[d]; st.v[d * c + t] = v[d]; }
+	st.id[t] = id;
+	st.meta[t] = make_meta(0u, cid, false) | ((flags & 1u) ? (META_HALO | META_FRESH) : 0ull);
+}
+__global__ void k_import_bump(const unsigned char* __restrict__ m0, const unsigned char* __restrict__ m1, uint32_t cap, uint32_t parity, uint32_t msg_cap, DevScalars* scal) {
+	if (threadIdx.x || blockIdx.x) return;
+	uint32_t n = scal->n_slots2[parity] + min(*reinterpret_cast<const uint32_t*>(m0), msg_cap);
+	if (m1) n += min(*reinterpret_cast<const uint32_t*>(m1), msg_cap);
+	if (n > cap) { scal->overflow = 1; n = cap; }
+	scal->n_slots2[parity] = n;
+}
+
+// ---- owned-molecule count / compaction index (decomposed mode: the set a rank owns changes every step) ----------------
+__global__ void __launch_bounds__(256) k_flag_owned(const uint64_t* __restrict__ meta, uint32_t* __restrict__ flag, uint32_t cap, uint32_t parity, const DevScalars* __restrict__ scal) {
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= cap) return;
+	flag[s] = (s < min(scal->n_slots2[parity], cap) && !meta_halo(meta[s])) ? 1u : 0u;
+}
+constexpr int CS_T = 256, CS_V = 8, CS_B = CS_T * CS_V;
+__device__ __forceinline__ uint32_t cs_block_scan(uint32_t v, uint32_t* total, uint32_t* sh) {
+	const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
+	uint32_t inc = v;
+	#pragma unroll
+	for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, inc, o); if (lane >= o) inc += t; }
+	if (lane == 31) sh[w] = inc;
+	__syncthreads();
+	if (w == 0) {
+		uint32_t x = (lane < (blockDim.x >> 5)) ? sh[lane] : 0u, xi = x;
+		#pragma unroll
+		for (int o = 1; o < 32; o <<= 1) { uint32_t t = __shfl_up_sync(0xffffffffu, xi, o); if (lane >= o) xi += t; }
+		sh[lane] = xi - x;
+		if (lane == 31) *total = xi;
+	}
+	__syncthreads();
+	const uint32_t r = sh[w] + inc - v;
+	__syncthreads();
+	return r;
+}
+__global__ void __launch_bounds__(CS_T) k_cs_block(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* __restrict__ bsum, uint32_t n) {
+	__shared__ uint32_t sh[32]; __shared__ uint32_t tot;
+	const uint32_t base = blockIdx.x * CS_B + threadIdx.x * CS_V;
+	uint32_t v[CS_V], sum = 0;
+	#pragma unroll
+	for (int k = 0; k < CS_V; k++) { v[k] = (base + k < n) ? in[base + k] : 0u; sum += v[k]; }
+	uint32_t off = cs_block_scan(sum, &tot, sh);
+	#pragma unroll
+	for (int k = 0; k < CS_V; k++) { if (base + k < n) out[base + k] = off; off += v[k]; }
+	if (threadIdx.x == 0) bsum[blockIdx.x] = tot;
+}
+__global__ void __launch_bounds__(CS_T) k_cs_top(uint32_t* __restrict__ bsum, uint32_t nb, DevScalars* scal) {
+	__shared__ uint32_t sh[32]; __shared__ uint32_t tot;
+	uint32_t carry = 0;
+	for (uint32_t b0 = 0; b0 < nb; b0 += CS_T) {
+		const uint32_t i = b0 + threadIdx.x;
+		const uint32_t v = (i < nb) ? bsum[i] : 0u;
+		const uint32_t off = cs_block_scan(v, &tot, sh);
+		if (i < nb) bsum[i] = carry + off;
+		carry += tot;
+		__syncthreads();
+	}
+	if (threadIdx.x == 0) scal->n_owned_dev = carry;
+}
+__global__ void __launch_bounds__(CS_T) k_cs_add(uint32_t* __restrict__ out, const uint32_t* __restrict__ bsum, uint32_t n) {
+	const uint32_t base = blockIdx.x * CS_B + threadIdx.x * CS_V;
+	const uint32_t off = bsum[blockIdx.x];
+	#pragma unroll
+	for (int k = 0; k < CS_V; k++) if (base + k < n) out[base + k] += off;
+}
+
+int count_owned(ls1b200_ctx* c, bool want_index) {
+	const uint32_t cap = (uint32_t) c->cap, g = (cap + 255) / 256, sb = (cap + CS_B - 1) / CS_B;
+	uint32_t* bsum = reinterpret_cast<uint32_t*>(c->msg_out[0] + MSG_HEADER);      // scratch: the message buffers are idle here
+	if ((uint64_t) sb * 4 > c->msg_cap * sizeof(RecCompact)) return fail("count_owned: scratch too small");
+	LS1_LAUNCH(c, PH_UPDATE, k_flag_owned, g, 256, 0, c->cur.meta, c->key, cap, c->parity, c->d_scal);
+	LS1_LAUNCH(c, PH_UPDATE, k_cs_block, sb, CS_T, 0, c->key, c->entry, bsum, cap);
+	LS1_LAUNCH(c, PH_UPDATE, k_cs_top, 1, CS_T, 0, bsum, sb, c->d_scal);
+	if (want_index) LS1_LAUNCH(c, PH_UPDATE, k_cs_add, sb, CS_T, 0, c->entry, bsum, cap);
+	LS1_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
+	LS1_CUDA(cudaStreamSynchronize(c->stream));
+	c->n_owned_local = c->h_scal->n_owned_dev;
+	return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------------------
+static XArgs stage_args(const ls1b200_ctx* c, int d) {
+	const ls1b200_ctx::Decomp& dd = c->dd;
+	XArgs a;
+	a.dim = d; a.bmin = c->geom.bmin[d]; a.bmax = c->geom.bmax[d]; a.rc = c->geom.cutoff;
+	a.gmin = dd.gmin[d]; a.gmax = dd.gmax[d]; a.glen = dd.gmax[d] - dd.gmin[d];
+	a.wrap_hi = dd.wrap_hi[d]; a.halo_hi = dd.halo_hi[d]; a.halo_lo = dd.halo_lo[d];
+	a.lo_wrap = dd.coords[d] == 0; a.hi_wrap = dd.coords[d] == dd.grid[d] - 1;
+	a.cap = (uint32_t) c->cap; a.parity = c->parity; a.msg_cap = (uint32_t) c->msg_cap; a.rotates = c->rotates;
+	return a;
+}
+
+int decomp_alloc(ls1b200_ctx* c) {
+	decomp_free(c);
+	// records per message: the boundary layer of one face incl. forwarded copies, with head room
+	double frac = 0.;
+	for (int d = 0; d < 3; d++) if (c->dd.grid[d] > 1) frac = std::max(frac, std::min(1., c->geom.cutoff / c->geom.lbox[d]));
+	double ring = 1.;
+	for (int d = 0; d < 3; d++) ring *= 1. + 2. * std::min(1., c->geom.cutoff / c->geom.lbox[d]);
+	c->msg_cap = (uint64_t) (1.6 * frac * ring * (double) std::max<uint64_t>(c->n_owned, 1)) + 8192;
+	const size_t bytes = MSG_HEADER + c->msg_cap * sizeof(ls1b200_particle);
+	for (int k = 0; k < 2; k++) {
+		LS1_CUDA(cudaMalloc((void**) &c->msg_out[k], bytes));
+		LS1_CUDA(cudaMalloc((void**) &c->msg_in[k], bytes));
+		LS1_CUDA(cudaMemsetAsync(c->msg_out[k], 0, MSG_HEADER, c->stream));
+		LS1_CUDA(cudaMemsetAsync(c->msg_in[k], 0, MSG_HEADER, c->stream));
+	}
+	LS1_CUDA(cudaMalloc((void**) &c->ekey, sizeof(uint64_t) * c->cap));
+	return 0;
+}
+void decomp_free(ls1b200_ctx* c) {
+	for (int k = 0; k < 2; k++) {
+		if (c->msg_out[k]) cudaFree(c->msg_out[k]); c->msg_out[k] = nullptr;
+		if (c->msg_in[k]) cudaFree(c->msg_in[k]); c->msg_in[k] = nullptr;
+	}
+	if (c->ekey) cudaFree(c->ekey); c->ekey = nullptr;
+	if (c->import_stage) cudaFree(c->import_stage); c->import_stage = nullptr; c->import_stage_cap = 0;
+	c->msg_cap = 0;
+}
+
+int do_exchange(ls1b200_ctx* c) {
+	if (!c->dd.active) return 0;
+	if (!c->dd.comm) return fail("ls1b200_exchange: this context was attached with use_nccl = 0 (move the messages with ls1b200_halo_export / import)");
+	if (!c->msg_out[0]) return fail("ls1b200_exchange: call ls1b200_upload first");
+	LS1_TRY(span_begin(c, PH_UPDATE));
+	const bool full = c->rotates;
+	const size_t rec = full ? sizeof(ls1b200_particle) : sizeof(RecCompact);
+	const size_t bytes = MSG_HEADER + c->msg_cap * rec;
+	const uint32_t g = (uint32_t) ((c->cap + 255) / 256), gi = (uint32_t) ((c->msg_cap + 255) / 256);
+	for (int d = 0; d < 3; d++) {
+		if (c->dd.grid[d] == 1) continue;
+		const XArgs a = stage_args(c, d);
+		LS1_CUDA(cudaMemsetAsync(c->msg_out[0], 0, MSG_HEADER, c->stream));
+		LS1_CUDA(cudaMemsetAsync(c->msg_out[1], 0, MSG_HEADER, c->stream));
+		if (full) LS1_LAUNCH(c, PH_UPDATE, k_export<true>, g, 256, 0, a, c->cur, c->msg_out[0], c->msg_out[1], c->d_scal, 3);
+		else LS1_LAUNCH(c, PH_UPDATE, k_export<false>, g, 256, 0, a, c->cur, c->msg_out[0], c->msg_out[1], c->d_scal, 3);
+		// fixed-size messages (the count travels in the header): no host round trip, the whole step stays asynchronous
+		LS1_NCCL(g_nccl.GroupStart());
+		LS1_NCCL(g_nccl.Send(c->msg_out[0], bytes, NCCL_UINT8, c->dd.nbr[d][0], c->dd.comm, c->stream));
+		LS1_NCCL(g_nccl.Send(c->msg_out[1], bytes, NCCL_UINT8, c->dd.nbr[d][1], c->dd.comm, c->stream));
+		LS1_NCCL(g_nccl.Recv(c->msg_in[0], bytes, NCCL_UINT8, c->dd.nbr[d][1], c->dd.comm, c->stream));      // the high neighbour's low message
+		LS1_NCCL(g_nccl.Recv(c->msg_in[1], bytes, NCCL_UINT8, c->dd.nbr[d][0], c->dd.comm, c->stream));      // the low neighbour's high message
+		LS1_NCCL(g_nccl.GroupEnd());
+		if (full) {
+			LS1_LAUNCH(c, PH_UPDATE, k_import<true>, gi, 256, 0, c->msg_in[0], (const unsigned char*) nullptr, c->cur, (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, (int) c->rotates, c->d_scal);
+			LS1_LAUNCH(c, PH_UPDATE, k_import<true>, gi, 256, 0, c->msg_in[1], c->msg_in[0], c->cur, (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, (int) c->rotates, c->d_scal);
+		} else {
+			LS1_LAUNCH(c, PH_UPDATE, k_import<false>, gi, 256, 0, c->msg_in[0], (const unsigned char*) nullptr, c->cur, (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, (int) c->rotates, c->d_scal);
+			LS1_LAUNCH(c, PH_UPDATE, k_import<false>, gi, 256, 0, c->msg_in[1], c->msg_in[0], c->cur, (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, (int) c->rotates, c->d_scal);
+		}
+		LS1_LAUNCH(c, PH_UPDATE, k_import_bump, 1, 32, 0, c->msg_in[0], c->msg_in[1], (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, c->d_scal);
+	}
+	LS1_TRY(span_end(c));
+	c->sorted = false;
+	return 0;
+}
+
+int do_allreduce_scalars(ls1b200_ctx* c) {
+	if (!c->dd.active || !c->dd.comm) return 0;
+	// upot6lj, upot_xpoles, virial, my_rf, summv2, sum_iw2: the six leading doubles of DevScalars
+	LS1_NCCL(g_nccl.AllReduce(c->d_scal, c->d_scal, 6, NCCL_FLOAT64, NCCL_SUM, c->dd.comm, c->stream));
+	return 0;
+}
+
+}  // namespace ls1b200
 
 using namespace ls1b200;
 
 extern "C" {
 
-int ls1b200_halo_export(ls1b200_ctx*, const int32_t*, const double*, void**, uint64_t*) { return fail("ls1b200_halo_export: not implemented yet"); }
-int ls1b200_halo_import(ls1b200_ctx*, const void*, uint64_t) { return fail("ls1b200_halo_import: not implemented yet"); }
-int ls1b200_halo_import_host(ls1b200_ctx*, const ls1b200_particle*, uint64_t) { return fail("ls1b200_halo_import_host: not implemented yet"); }
-
+int ls1b200_nccl_unique_id(uint8_t out[128]) {
+	if (!out) return fail("ls1b200_nccl_unique_id: null argument");
+	LS1_TRY(nccl_load());
+	nccl_uid id;
+	LS1_NCCL(g_nccl.GetUniqueId(&id));
+	memcpy(out, id.internal, 128);
+	return 0;
 }
+
+int ls1b200_decomp_attach(ls1b200_ctx* c, const ls1b200_decomp* dd) {
+	if (!c || !dd) return fail("ls1b200_decomp_attach: null argument");
+	if (!c->components_set) return fail("ls1b200_decomp_attach: call ls1b200_set_components first");
+	if (c->cap) return fail("ls1b200_decomp_attach: must be called before ls1b200_upload");
+	if (dd->n_ranks < 1 || dd->grid[0] * dd->grid[1] * dd->grid[2] != dd->n_ranks) return fail("ls1b200_decomp_attach: grid does not match the number of ranks");
+	if (dd->rank < 0 || dd->rank >= dd->n_ranks) return fail("ls1b200_decomp_attach: rank out of range");
+	LS1_CUDA(cudaSetDevice(c->device));
+	ls1b200_ctx::Decomp& o = c->dd;
+	o = ls1b200_ctx::Decomp();
+	o.rank = dd->rank; o.n_ranks = dd->n_ranks;
+	for (int d = 0; d < 3; d++) {
+		o.grid[d] = dd->grid[d]; o.coords[d] = dd->coords[d];
+		o.gmin[d] = dd->global_min[d]; o.gmax[d] = dd->global_max[d];
+		if (o.coords[d] < 0 || o.coords[d] >= o.grid[d]) return fail("ls1b200_decomp_attach: coordinates outside the grid");
+		if ((o.grid[d] == 1) != (c->geom.periodic[d] != 0) )
+			return fail("ls1b200_decomp_attach: the context must be created with periodic[d] = (grid[d] == 1)");
+		if (o.grid[d] > 1 && c->geom.lbox[d] < 2. * c->geom.cutoff) return fail("ls1b200_decomp_attach: a block must be at least two cutoff radii wide");
+		// clamps of the periodic shift, in the calc type, against the global box (CommunicationPartner.cpp:533-562)
+		if (c->mixed) {
+			const float rmax = (float) o.gmax[d], rmin = (float) o.gmin[d];
+			o.wrap_hi[d] = (double) nexttowardf(rmax, (long double) (rmax - 1.f));
+			o.halo_hi[d] = (double) nexttowardf(rmax, (long double) (rmax + 1.f));
+			o.halo_lo[d] = (double) nexttowardf(rmin, (long double) (rmin - 1.f));
+		} else {
+			const double rmax = o.gmax[d], rmin = o.gmin[d];
+			o.wrap_hi[d] = nexttoward(rmax, (long double) (rmax - 1.));
+			o.halo_hi[d] = nexttoward(rmax, (long double) (rmax + 1.));
+			o.halo_lo[d] = nexttoward(rmin, (long double) (rmin - 1.));
+		}
+	}
+	for (int d = 0; d < 3; d++) for (int side = 0; side < 2; side++) {
+		int cc[3] = {o.coords[0], o.coords[1], o.coords[2]};
+		cc[d] = (cc[d] + (side ? 1 : -1) + o.grid[d]) % o.grid[d];
+		o.nbr[d][side] = (cc[0] * o.grid[1] + cc[1]) * o.grid[2] + cc[2];
+	}
+	{
+		int cc = (o.coords[0] * o.grid[1] + o.coords[1]) * o.grid[2] + o.coords[2];
+		if (cc != o.rank) return fail("ls1b200_decomp_attach: rank != (coords[0]*grid[1] + coords[1])*grid[2] + coords[2]");
+	}
+	if (dd->use_nccl) {
+		LS1_TRY(nccl_load());
+		nccl_uid id; memcpy(id.internal, dd->nccl_unique_id, 128);
+		LS1_NCCL(g_nccl.CommInitRank(&o.comm, o.n_ranks, id, o.rank));
+	}
+	o.active = true;
+	return 0;
+}
+
+int ls1b200_exchange(ls1b200_ctx* c) {
+	if (!c) return fail("ls1b200_exchange: null context");
+	LS1_CUDA(cudaSetDevice(c->device));
+	return do_exchange(c);
+}
+
+int ls1b200_allreduce_macro(ls1b200_ctx* c, ls1b200_macro* m, ls1b200_kinetic* k) {
+	if (!c) return fail("ls1b200_allreduce_macro: null context");
+	LS1_CUDA(cudaSetDevice(c->device));
+	LS1_TRY(do_allreduce_scalars(c));
+	LS1_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
+	LS1_CUDA(cudaStreamSynchronize(c->stream));
+	const DevScalars& s = *c->h_scal;
+	if (m) {
+		m->upot6lj = s.upot6lj; m->upot_xpoles = s.upot_xpoles; m->virial_raw = s.virial; m->my_rf = s.my_rf;
+		m->upot = s.upot6lj / 6.0 + s.upot_xpoles + s.my_rf; m->virial = s.virial + 3.0 * s.my_rf;
+	}
+	if (k) { k->summv2 = s.summv2; k->sum_iw2 = s.sum_iw2; }
+	return 0;
+}
+
+int ls1b200_halo_export(ls1b200_ctx* c, int32_t dim, int32_t side, void** device_buf, uint64_t* count) {
+	if (!c || !device_buf || !count) return fail("ls1b200_halo_export: null argument");
+	if (!c->dd.active) return fail("ls1b200_halo_export: no decomposition attached");
+	if (dim < 0 || dim > 2 || side < 0 || side > 1 || c->dd.grid[dim] == 1) return fail("ls1b200_halo_export: this dimension is not cut / bad side");
+	if (!c->msg_out[0]) return fail("ls1b200_halo_export: call ls1b200_upload first");
+	LS1_CUDA(cudaSetDevice(c->device));
+	const XArgs a = stage_args(c, dim);
+	LS1_CUDA(cudaMemsetAsync(c->msg_out[side], 0, MSG_HEADER, c->stream));
+	LS1_LAUNCH(c, PH_UPDATE, k_export<true>, (uint32_t) ((c->cap + 255) / 256), 256, 0, a, c->cur, c->msg_out[0], c->msg_out[1], c->d_scal, side ? 2 : 1);
+	uint32_t n = 0;
+	LS1_CUDA(cudaMemcpyAsync(&n, c->msg_out[side], 4, cudaMemcpyDeviceToHost, c->stream));
+	LS1_CUDA(cudaStreamSynchronize(c->stream));
+	if (n > c->msg_cap) return fail("ls1b200_halo_export: message buffer too small");
+	*device_buf = c->msg_out[side] + MSG_HEADER; *count = n;
+	c->sorted = false;
+	return 0;
+}
+
+}  // extern "C" (helpers below are C++)
+
+static int export_side(ls1b200_ctx* c, int32_t dim, int32_t side, void** device_buf, uint64_t* count) { return ls1b200_halo_export(c, dim, side, device_buf, count); }
+
+extern "C" {
+
+/* ls1b200_halo_export + copy of the records to host memory (tests, MPI without GPU-direct). */
+int ls1b200_halo_export_host(ls1b200_ctx* c, int32_t dim, int32_t side, ls1b200_particle* host_buf, uint64_t host_cap, uint64_t* count) {
+	if (!count) return fail("ls1b200_halo_export_host: null argument");
+	void* dbuf = nullptr;
+	LS1_TRY(export_side(c, dim, side, &dbuf, count));
+	if (*count > host_cap) return fail("ls1b200_halo_export_host: host buffer too small (count returned)");
+	if (*count) {
+		if (!host_buf) return fail("ls1b200_halo_export_host: null buffer");
+		LS1_CUDA(cudaMemcpyAsync(host_buf, dbuf, *count * sizeof(ls1b200_particle), cudaMemcpyDeviceToHost, c->stream));
+		LS1_CUDA(cudaStreamSynchronize(c->stream));
+	}
+	return 0;
+}
+
+static int import_records(ls1b200_ctx* c, const void* buf, uint64_t count, cudaMemcpyKind kind) {
+	if (!c->dd.active) return fail("ls1b200_halo_import: no decomposition attached");
+	if (!c->msg_in[0]) return fail("ls1b200_halo_import: call ls1b200_upload first");
+	if (count == 0) return 0;
+	if (!buf) return fail("ls1b200_halo_import: null buffer");
+	if (count > c->msg_cap) return fail("ls1b200_halo_import: more records than the message capacity");
+	LS1_CUDA(cudaSetDevice(c->device));
+	const uint32_t n = (uint32_t) count;
+	LS1_CUDA(cudaMemcpyAsync(c->msg_in[0], &n, 4, cudaMemcpyHostToDevice, c->stream));
+	LS1_CUDA(cudaMemcpyAsync(c->msg_in[0] + MSG_HEADER, buf, count * sizeof(ls1b200_particle), kind, c->stream));
+	LS1_LAUNCH(c, PH_UPDATE, k_import<true>, (uint32_t) ((count + 255) / 256), 256, 0, c->msg_in[0], (const unsigned char*) nullptr, c->cur, (uint32_t) c->cap, c->parity,
+	           (uint32_t) c->msg_cap, (int) c->rotates, c->d_scal);
+	LS1_LAUNCH(c, PH_UPDATE, k_import_bump, 1, 32, 0, c->msg_in[0], (const unsigned char*) nullptr, (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, c->d_scal);
+	LS1_CUDA(cudaStreamSynchronize(c->stream));      // n and a pageable host buffer are read by the copies above
+	c->sorted = false;
+	return 0;
+}
+
+int ls1b200_halo_import(ls1b200_ctx* c, const void* device_buf, uint64_t count) {
+	if (!c) return fail("ls1b200_halo_import: null context");
+	return import_records(c, device_buf, count, cudaMemcpyDeviceToDevice);
+}
+int ls1b200_halo_import_host(ls1b200_ctx* c, const ls1b200_particle* host_buf, uint64_t count) {
+	if (!c) return fail("ls1b200_halo_import_host: null context");
+	return import_records(c, host_buf, count, cudaMemcpyHostToDevice);
+}
+
+}  // extern "C"

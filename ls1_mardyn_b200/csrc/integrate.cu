@@ -144,7 +144,7 @@ __global__ void k_globals(DevScalars* scal, double target_T, unsigned long long 
 }
 
 int do_forces(ls1b200_ctx* c) {
-	if (c->n_owned == 0) { c->forces_valid = true; return 0; }
+	if (c->n_owned == 0 && !c->dd.active) { c->forces_valid = true; return 0; }
 	LS1_TRY(span_begin(c, PH_FORCE));
 	LS1_TRY(c->all_1clj ? (c->lj_kernel == 0 ? force_1clj_tiled(c) : force_1clj(c)) : force_general(c));
 	LS1_TRY(span_end(c));
@@ -153,7 +153,7 @@ int do_forces(ls1b200_ctx* c) {
 }
 
 int do_leapfrog_pre(ls1b200_ctx* c, double dt, bool use_beta) {
-	if (c->n_owned == 0) return 0;
+	if (c->n_owned == 0 && !c->dd.active) return 0;
 	LS1_TRY(span_begin(c, PH_PRE));
 	const uint32_t g = (uint32_t) ((c->cap + 255) / 256);
 	LS1_LAUNCH(c, PH_PRE, k_leapfrog_pre, g, 256, 0, c->cur, c->F, c->M, (uint32_t) c->cap, c->d_comps, dt, c->d_scal, c->parity, (int) use_beta, (int) c->rotates);
@@ -163,7 +163,7 @@ int do_leapfrog_pre(ls1b200_ctx* c, double dt, bool use_beta) {
 }
 
 int do_leapfrog_post(ls1b200_ctx* c, double dt) {
-	if (c->n_owned == 0) return 0;
+	if (c->n_owned == 0 && !c->dd.active) return 0;
 	LS1_TRY(span_begin(c, PH_POST));
 	const uint32_t g = (uint32_t) ((c->cap + 255) / 256);
 	if (g > c->partial_blocks) return fail("leapfrog_post: partials buffer too small");
@@ -177,7 +177,8 @@ int do_globals(ls1b200_ctx* c, double target_T, uint64_t global_n, double global
 	const uint64_t N = global_n ? global_n : c->n_owned;
 	double V = global_volume;
 	if (!(V > 0.)) V = c->geom.lbox[0] * c->geom.lbox[1] * c->geom.lbox[2];
-	LS1_LAUNCH(c, PH_POST, k_globals, 1, 32, 0, c->d_scal, target_T, (unsigned long long) N, (unsigned long long) c->rot_dof_total, V, d_rec);
+	const uint64_t rdof = c->dd.active ? c->dd.rot_dof_global : c->rot_dof_total;
+	LS1_LAUNCH(c, PH_POST, k_globals, 1, 32, 0, c->d_scal, target_T, (unsigned long long) N, (unsigned long long) rdof, V, d_rec);
 	return 0;
 }
 
@@ -201,7 +202,7 @@ int ls1b200_leapfrog_post(ls1b200_ctx* c, double dt, ls1b200_kinetic* out) {
 		LS1_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
 		LS1_CUDA(cudaStreamSynchronize(c->stream));
 		out->summv2 = c->h_scal->summv2; out->sum_iw2 = c->h_scal->sum_iw2;
-		out->n_molecules = c->n_owned; out->rot_dof = c->rot_dof_total;
+		out->n_molecules = c->dd.active ? c->n_owned_local : c->n_owned; out->rot_dof = c->rot_dof_total;
 	}
 	return 0;
 }
@@ -209,7 +210,7 @@ int ls1b200_leapfrog_post(ls1b200_ctx* c, double dt, ls1b200_kinetic* out) {
 int ls1b200_scale_velocities(ls1b200_ctx* c, double beta_trans, double beta_rot) {
 	if (!c) return fail("ls1b200_scale_velocities: null context");
 	LS1_CUDA(cudaSetDevice(c->device));
-	if (c->n_owned == 0) return 0;
+	if (c->n_owned == 0 && !c->dd.active) return 0;
 	const uint32_t g = (uint32_t) ((c->cap + 255) / 256);
 	LS1_LAUNCH(c, PH_POST, k_scale, g, 256, 0, c->cur, (uint32_t) c->cap, beta_trans, beta_rot, c->d_scal, c->parity, 0, (int) c->rotates);
 	return 0;
@@ -221,6 +222,21 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 	if (!c->forces_valid) return fail("ls1b200_simulate: forces are not valid (call ls1b200_update + ls1b200_traverse_cells first)");
 	LS1_CUDA(cudaSetDevice(c->device));
 	if (n_steps == 0) return 0;
+	if (c->dd.active) {
+		if (global_n == 0 || !(global_volume > 0.)) return fail("ls1b200_simulate: a decomposed context needs global_n and global_volume");
+		if (!c->dd.comm) return fail("ls1b200_simulate: a decomposed context needs use_nccl = 1 (or drive the phases and move the messages yourself)");
+		if (!c->dd.rot_dof_valid) {      // rotational degrees of freedom of the whole system (Domain.cpp:220-230), once per upload
+			double v = (double) c->rot_dof_total;
+			LS1_CUDA(cudaMemcpyAsync(&c->d_scal->summv2, &v, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+			double zero[5] = {0., 0., 0., 0., 0.};
+			LS1_CUDA(cudaMemcpyAsync(&c->d_scal->upot6lj, zero, 4 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+			LS1_CUDA(cudaMemcpyAsync(&c->d_scal->sum_iw2, zero, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+			LS1_TRY(do_allreduce_scalars(c));
+			LS1_CUDA(cudaMemcpyAsync(&v, &c->d_scal->summv2, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+			LS1_CUDA(cudaStreamSynchronize(c->stream));
+			c->dd.rot_dof_global = (uint64_t) (v + 0.5); c->dd.rot_dof_valid = true;
+		}
+	}
 	if (c->records_cap < n_steps) {
 		if (c->d_records) cudaFree(c->d_records);
 		c->d_records = nullptr; c->records_cap = 0;
@@ -232,9 +248,11 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 	LS1_CUDA(cudaMemcpyAsync(&c->d_scal->beta_trans, &c->h_scal->beta_trans, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
 	for (uint64_t s = 0; s < n_steps; s++) {
 		LS1_TRY(do_leapfrog_pre(c, dt, target_temperature > 0.));
+		LS1_TRY(do_exchange(c));                 // multi-GPU: leaving molecules + halo copies over NCCL (no-op on one GPU)
 		LS1_TRY(do_update(c));
 		LS1_TRY(do_forces(c));
 		LS1_TRY(do_leapfrog_post(c, dt));
+		LS1_TRY(do_allreduce_scalars(c));        // multi-GPU: Upot, virial, sum m v^2, sum I w^2 over the ranks
 		LS1_TRY(do_globals(c, target_temperature, global_n, global_volume, c->d_records + s));
 	}
 	if (target_temperature > 0.) {   // the scaling the next leapfrog_pre would have applied on load
@@ -245,7 +263,8 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 	LS1_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
 	LS1_CUDA(cudaStreamSynchronize(c->stream));
 	c->n_slots = std::min<uint64_t>(c->h_scal->n_slots2[c->parity], c->cap);
-	if (c->h_scal->overflow) return fail("ls1b200_simulate: slot capacity exceeded (more halo copies than reserved)");
+	if (c->h_scal->overflow) return fail(c->h_scal->overflow == 2 ? "ls1b200_simulate: a halo message buffer was too small" : "ls1b200_simulate: slot capacity exceeded (more halo copies than reserved)");
+	if (c->dd.active) LS1_TRY(count_owned(c, false));
 	return 0;
 }
 

@@ -91,7 +91,7 @@ int ls1b200_count_flops(ls1b200_ctx* c, ls1b200_flopcount* out) {
 	if (!c->sorted) return fail("ls1b200_count_flops: call ls1b200_update first");
 	LS1_CUDA(cudaSetDevice(c->device));
 	memset(out, 0, sizeof(*out));
-	if (c->n_owned == 0) return 0;
+	if (c->n_owned == 0 && !c->dd.active) return 0;
 	LS1_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
 	LS1_CUDA(cudaStreamSynchronize(c->stream));
 	const uint32_t ns = (uint32_t) std::min<uint64_t>(c->h_scal->n_slots2[c->parity], c->cap);

@@ -36,7 +36,7 @@ __global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __r
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= min(scal->n_slots2[a.parity], a.cap)) return;
 	const uint64_t meta = cur.meta[s];
-	if (meta_halo(meta)) { key[s] = KEY_NONE; return; }
+	if (meta_halo(meta) && !meta_fresh(meta)) { key[s] = KEY_NONE; return; }      // stale halo slot; fresh halo copies (halo.cu) are binned
 	const Geom& g = a.g;
 	double x = cur.r[s], y = cur.r[(size_t) a.cap + s], z = cur.r[2 * (size_t) a.cap + s];
 	if (g.periodic[0]) { double w = wrap_coord<0>(g, x); if (w != x) { x = w; cur.r[s] = w; } }
@@ -125,7 +125,8 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict__ star
 }
 
 __global__ void __launch_bounds__(256) k_scatter(UpdArgs a, State cur, const uint32_t* __restrict__ key, uint32_t* __restrict__ cursor,
-                                                  uint32_t* __restrict__ entry, uint32_t* __restrict__ cell_of, const DevScalars* __restrict__ scal) {
+                                                  uint32_t* __restrict__ entry, uint32_t* __restrict__ cell_of, const DevScalars* __restrict__ scal,
+                                                  uint64_t* __restrict__ ekey) {
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	if (s >= min(scal->n_slots2[a.parity], a.cap)) return;
 	const uint32_t k = key[s];
@@ -133,7 +134,8 @@ __global__ void __launch_bounds__(256) k_scatter(UpdArgs a, State cur, const uin
 	const Geom& g = a.g;
 	const uint32_t bin = k & ((1u << SHIFT_BITS) - 1u), mask = k >> SHIFT_BITS;
 	uint32_t p = atomicAdd(&cursor[bin], 1u);
-	if (p < a.cap) { entry[p] = s << 5; cell_of[p] = bin; }
+	const uint64_t idk = ekey ? (cur.id[s] << 5) : 0ull;      // decomposed mode: in-cell order by (molecule id, shift code)
+	if (p < a.cap) { entry[p] = s << 5; cell_of[p] = bin; if (ekey) ekey[p] = idk; }
 	if (mask) {
 		const double x = cur.r[s], y = cur.r[(size_t) a.cap + s], z = cur.r[2 * (size_t) a.cap + s];
 		for (int c3 = 0; c3 < 3; c3++) for (int b3 = 0; b3 < 3; b3++) for (int a3 = 0; a3 < 3; a3++) {
@@ -141,7 +143,7 @@ __global__ void __launch_bounds__(256) k_scatter(UpdArgs a, State cur, const uin
 			const int hx = cell1d<0>(g, halo_coord<0>(g, x, a3)), hy = cell1d<1>(g, halo_coord<1>(g, y, b3)), hz = cell1d<2>(g, halo_coord<2>(g, z, c3));
 			const uint32_t hb = cell_index(g, hx, hy, hz);
 			p = atomicAdd(&cursor[hb], 1u);
-			if (p < a.cap) { entry[p] = (s << 5) | (uint32_t) (a3 + 3 * b3 + 9 * c3); cell_of[p] = hb; }
+			if (p < a.cap) { entry[p] = (s << 5) | (uint32_t) (a3 + 3 * b3 + 9 * c3); cell_of[p] = hb; if (ekey) ekey[p] = idk | (uint64_t) (a3 + 3 * b3 + 9 * c3); }
 		}
 	}
 }
@@ -150,7 +152,7 @@ template <class C>
 __global__ void __launch_bounds__(256) k_gather(UpdArgs a, State cur, State nxt, const uint32_t* __restrict__ entry, const uint32_t* __restrict__ cell_of,
                                                  const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_of2,
                                                  typename Vec4<C>::type* __restrict__ mpos, const DevScalars* __restrict__ scal, int rotates,
-                                                 double* __restrict__ F, double* __restrict__ Vi, double* __restrict__ M) {
+                                                 double* __restrict__ F, double* __restrict__ Vi, double* __restrict__ M, const uint64_t* __restrict__ ekey) {
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t n_slots = min(scal->n_slots2[a.parity ^ 1u], a.cap);
 	if (p >= n_slots) return;
@@ -158,7 +160,8 @@ __global__ void __launch_bounds__(256) k_gather(UpdArgs a, State cur, State nxt,
 	const uint32_t e = entry[p], c = cell_of[p];
 	const uint32_t b = cell_start[c], en = min(cell_start[c + 1], a.cap);
 	uint32_t rank = 0;
-	for (uint32_t u = b; u < en; u++) rank += (entry[u] < e) ? 1u : 0u;
+	if (ekey) { const uint64_t ek = ekey[p]; for (uint32_t u = b; u < en; u++) rank += (ekey[u] < ek) ? 1u : 0u; }
+	else for (uint32_t u = b; u < en; u++) rank += (entry[u] < e) ? 1u : 0u;
 	const uint32_t t = b + rank, s = e >> 5, code = e & 31u;
 	const size_t cap = a.cap;
 	double x = cur.r[s], y = cur.r[cap + s], z = cur.r[2 * cap + s];
@@ -168,6 +171,8 @@ __global__ void __launch_bounds__(256) k_gather(UpdArgs a, State cur, State nxt,
 		x = halo_coord<0>(g, x, a3); y = halo_coord<1>(g, y, b3); z = halo_coord<2>(g, z, c3);
 		meta |= META_HALO;
 	}
+	meta &= ~META_FRESH;      // a fresh halo copy of this step's exchange is an ordinary (stale after this sort) halo slot from here on
+	if (ekey) nxt.id[t] = cur.id[s];
 	nxt.r[t] = x; nxt.r[cap + t] = y; nxt.r[2 * cap + t] = z;
 	nxt.meta[t] = meta;
 	#pragma unroll
@@ -180,9 +185,9 @@ __global__ void __launch_bounds__(256) k_gather(UpdArgs a, State cur, State nxt,
 	}
 	cell_of2[t] = c;
 	// the limbo bin and halo cells never hold "i" molecules: flag them like halo copies in the calc record
-	const bool inert = code != 0 || c >= g.ncells || is_halo_cell(g, c);
+	const bool inert = meta_halo(meta) || c >= g.ncells || is_halo_cell(g, c);
 	mpos[t] = make_mrec<C>(x, y, z, meta_cid(meta) | (inert ? 0x80000000u : 0u));
-	if (inert && code == 0) {   // an owned molecule no force kernel visits (halo-cell resident, limbo): its force is zero
+	if (inert && !meta_halo(meta)) {   // an owned molecule no force kernel visits (halo-cell resident, limbo): its force is zero
 		for (int d = 0; d < 3; d++) { F[d * cap + t] = 0.; Vi[d * cap + t] = 0.; if (M) M[d * cap + t] = 0.; }
 	}
 }
@@ -228,7 +233,8 @@ __global__ void __launch_bounds__(128) k_sites(State st, uint32_t cap, uint32_t 
 
 int do_update(ls1b200_ctx* c) {
 	if (!c->components_set) return fail("ls1b200_update: components not set");
-	if (c->n_owned == 0) { c->sorted = true; return 0; }
+	if (c->n_owned == 0 && !c->dd.active) { c->sorted = true; return 0; }
+	if (c->cap == 0) return fail("ls1b200_update: call ls1b200_upload first");
 	LS1_TRY(span_begin(c, PH_UPDATE));
 	UpdArgs a; a.g = c->geom; a.cap = (uint32_t) c->cap; a.parity = c->parity;
 	const uint32_t nb = c->geom.ncells + 1;   // + limbo bin
@@ -240,12 +246,12 @@ int do_update(ls1b200_ctx* c) {
 	LS1_LAUNCH(c, PH_UPDATE, k_scan_block, sb, SCAN_T, 0, c->cell_count, c->cell_start, c->scan_tmp, nb);
 	LS1_LAUNCH(c, PH_UPDATE, k_scan_top, 1, SCAN_T, 0, c->scan_tmp, sb, c->scan_tmp + sb);
 	LS1_LAUNCH(c, PH_UPDATE, k_scan_add, sb, SCAN_T, 0, c->cell_start, c->cursor, c->scan_tmp, c->scan_tmp + sb, nb, (uint32_t) c->cap, a.parity, c->d_scal);
-	LS1_LAUNCH(c, PH_UPDATE, k_scatter, gs, 256, 0, a, c->cur, c->key, c->cursor, c->entry, c->cell_of, c->d_scal);
+	LS1_LAUNCH(c, PH_UPDATE, k_scatter, gs, 256, 0, a, c->cur, c->key, c->cursor, c->entry, c->cell_of, c->d_scal, c->dd.active ? c->ekey : (uint64_t*) nullptr);
 	const uint32_t gc = gs;
 	if (c->mixed)
-		LS1_LAUNCH(c, PH_UPDATE, k_gather<float>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, c->cell_start, c->cell_of2, (float4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M);
+		LS1_LAUNCH(c, PH_UPDATE, k_gather<float>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, c->cell_start, c->cell_of2, (float4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr);
 	else
-		LS1_LAUNCH(c, PH_UPDATE, k_gather<double>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, c->cell_start, c->cell_of2, (double4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M);
+		LS1_LAUNCH(c, PH_UPDATE, k_gather<double>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, c->cell_start, c->cell_of2, (double4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr);
 	std::swap(c->cur, c->nxt);
 	c->parity ^= 1u;
 	if (!c->all_1clj) {

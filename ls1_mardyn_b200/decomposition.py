@@ -1,0 +1,111 @@
+"""Host side of the multi-GPU block decomposition: the mirror of the reference's DomainDecomposition
+(src/parallel/DomainDecomposition.cpp) -- process grid, block bounds, neighbour ranks -- and a transport-agnostic driver
+of the staged leaving-molecule + halo exchange for callers that move the messages themselves (MPI inside ls1,
+torch.distributed with gloo in the CPU tests). The production transport is NCCL inside libls1b200.so
+(Context.decomp_attach(dd, unique_id) + Context.simulate / Context.exchange): nothing here is on that path.
+
+One process per GPU; rank = (coords[0]*grid[1] + coords[1])*grid[2] + coords[2] (MPI_Cart_create order)."""
+from __future__ import annotations
+
+import numpy as np
+
+
+def dims_create(n: int):
+    """MPI_Dims_create(n, 3): factors as balanced as possible, in non-increasing order (DomainDecomposition.cpp:44)."""
+    best = None
+    for a in range(1, n + 1):
+        if n % a:
+            continue
+        for b in range(1, n // a + 1):
+            if (n // a) % b:
+                continue
+            c = n // a // b
+            t = tuple(sorted((a, b, c), reverse=True))
+            if best is None or (t[0] - t[2], t) < (best[0] - best[2], best):
+                best = t
+    return best
+
+
+class DomainDecomposition:
+    """Equal blocks of a periodic box of size global_length (origin 0): getBoundingBoxMin/Max as
+    DomainDecomposition.cpp:130-139 (coords * L / grid, the last block ends exactly at L)."""
+
+    def __init__(self, rank: int, n_ranks: int, global_length, grid=None):
+        self.rank, self.n_ranks = int(rank), int(n_ranks)
+        self.global_length = np.asarray(global_length, dtype=np.float64)
+        self.grid = tuple(int(g) for g in (grid if grid is not None else dims_create(n_ranks)))
+        if self.grid[0] * self.grid[1] * self.grid[2] != n_ranks:
+            raise ValueError("DomainDecomposition: Wrong grid size given!")
+        self.coords = self.coords_of(rank)
+
+    def coords_of(self, rank):
+        g = self.grid
+        return (rank // (g[1] * g[2]), (rank // g[2]) % g[1], rank % g[2])
+
+    def rank_of(self, coords):
+        g = self.grid
+        c = [coords[d] % g[d] for d in range(3)]
+        return (c[0] * g[1] + c[1]) * g[2] + c[2]
+
+    def box_min(self, coords=None):
+        c = self.coords if coords is None else coords
+        return np.array([c[d] * self.global_length[d] / self.grid[d] for d in range(3)])
+
+    def box_max(self, coords=None):
+        c = self.coords if coords is None else coords
+        return np.array([self.global_length[d] if c[d] + 1 == self.grid[d] else (c[d] + 1) * self.global_length[d] / self.grid[d] for d in range(3)])
+
+    def periodic(self):
+        """Dimensions that are not cut wrap locally (the sequential DomainDecompBase treatment)."""
+        return tuple(int(g == 1) for g in self.grid)
+
+    def neighbour(self, dim: int, side: int) -> int:
+        c = list(self.coords); c[dim] += 1 if side else -1
+        return self.rank_of(c)
+
+    def owner_of(self, r):
+        """Rank owning each position (for distributing an initial phase space)."""
+        r = np.asarray(r, dtype=np.float64)
+        idx = []
+        for d in range(3):
+            edges = np.array([self.box_min((k,) * 3)[d] for k in range(self.grid[d])])
+            idx.append(np.clip(np.searchsorted(edges, r[:, d], side="right") - 1, 0, self.grid[d] - 1))
+        return (idx[0] * self.grid[1] + idx[1]) * self.grid[2] + idx[2]
+
+    def cut_dims(self):
+        return [d for d in range(3) if self.grid[d] > 1]
+
+
+def exchange_local(ranks, dds):
+    """All ranks live in this process (tests; several contexts on one GPU): the staged exchange of one step.
+    ranks[k] offers halo_export(dim, side) -> records and halo_import(records)."""
+    for d in dds[0].cut_dims():
+        outs = [(r.halo_export(d, 0), r.halo_export(d, 1)) for r in ranks]
+        for k, r in enumerate(ranks):
+            r.halo_import(outs[dds[k].neighbour(d, 1)][0])      # the high neighbour's low-side message
+            r.halo_import(outs[dds[k].neighbour(d, 0)][1])      # the low neighbour's high-side message
+
+
+def exchange_dist(rank_obj, dd, dist, record_dtype):
+    """One process per rank, messages over torch.distributed point-to-point (gloo on CPU; also MPI-like transports).
+    Counts travel first, then the records as bytes."""
+    import torch
+    for d in dd.cut_dims():
+        out = (rank_obj.halo_export(d, 0), rank_obj.halo_export(d, 1))
+        peers = (dd.neighbour(d, 0), dd.neighbour(d, 1))
+        # sizes
+        n_out = [torch.tensor([len(out[0])], dtype=torch.int64), torch.tensor([len(out[1])], dtype=torch.int64)]
+        n_in = [torch.zeros(1, dtype=torch.int64), torch.zeros(1, dtype=torch.int64)]
+        ops = [dist.P2POp(dist.isend, n_out[0], peers[0], tag=10 + d), dist.P2POp(dist.isend, n_out[1], peers[1], tag=20 + d),
+               dist.P2POp(dist.irecv, n_in[0], peers[1], tag=10 + d), dist.P2POp(dist.irecv, n_in[1], peers[0], tag=20 + d)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        sz = record_dtype.itemsize
+        t_out = [torch.from_numpy(np.frombuffer(np.ascontiguousarray(o).tobytes() + b"\0", dtype=np.uint8).copy()) for o in out]
+        t_in = [torch.zeros(int(n_in[0]) * sz + 1, dtype=torch.uint8), torch.zeros(int(n_in[1]) * sz + 1, dtype=torch.uint8)]
+        ops = [dist.P2POp(dist.isend, t_out[0], peers[0], tag=30 + d), dist.P2POp(dist.isend, t_out[1], peers[1], tag=40 + d),
+               dist.P2POp(dist.irecv, t_in[0], peers[1], tag=30 + d), dist.P2POp(dist.irecv, t_in[1], peers[0], tag=40 + d)]
+        for w in dist.batch_isend_irecv(ops):
+            w.wait()
+        for t, n in zip(t_in, n_in):
+            rank_obj.halo_import(np.frombuffer(t.numpy()[:int(n) * sz].tobytes(), dtype=record_dtype))

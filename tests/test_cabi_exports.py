@@ -24,7 +24,7 @@ def declared_symbols():
 def test_header_declares_the_path():
     syms = declared_symbols()
     for s in ("ls1b200_create", "ls1b200_update", "ls1b200_traverse_cells", "ls1b200_leapfrog_pre", "ls1b200_leapfrog_post",
-              "ls1b200_simulate", "ls1b200_halo_export", "ls1b200_halo_import"):
+              "ls1b200_simulate", "ls1b200_halo_export", "ls1b200_halo_import", "ls1b200_decomp_attach", "ls1b200_exchange"):
         assert s in syms
 
 
@@ -35,7 +35,7 @@ def test_library_exports_every_declared_symbol(libpath):
     from ls1_mardyn_b200 import capi
     assert sorted(capi.EXPORTS) == declared_symbols()
     lib.ls1b200_abi_version.restype = C.c_int
-    assert lib.ls1b200_abi_version() == 1
+    assert lib.ls1b200_abi_version() == 2
 
 
 def test_struct_layouts_match_header(libpath):
@@ -45,6 +45,7 @@ def test_struct_layouts_match_header(libpath):
     assert C.sizeof(CComponent) == 32 + 32 and C.sizeof(CSite) == 56
     assert C.sizeof(capi.Macro) == 48 and C.sizeof(capi.Kinetic) == 32 and C.sizeof(capi.StepRecord) == 64
     assert C.sizeof(capi.FlopCount) == 128
+    assert C.sizeof(capi.Decomp) == 4 * 8 + 8 * 6 + 128 + 16 and capi.PARTICLE.itemsize == 120
 
 
 def test_no_cpu_fallback(libpath):

@@ -1,0 +1,159 @@
+"""Multi-GPU block decomposition on the device (halo.cu), through the C ABI. Needs a B200: run with -m gpu.
+
+(1) several contexts -- one per block -- on ONE device, messages staged through the host (ls1b200_halo_export_host /
+    ls1b200_halo_import_host): every exported record and every force is compared with the decomposed CPU oracle and with the
+    single-domain CUDA path; (2) with >= 2 GPUs, the NCCL transport inside the library (torchrun, one process per GPU)."""
+import os
+import subprocess
+import sys
+
+import numpy as np
+import pytest
+
+from helpers import TOL, rel_close
+from test_decomposition import gather, make_ranks, split
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+@pytest.fixture(scope="module")
+def capi():
+    import torch
+    assert torch.cuda.is_available(), "GPU tests need a CUDA device"
+    from ls1_mardyn_b200 import capi
+    capi.lib()
+    return capi
+
+
+class Recorder:
+    """Wraps a rank object and keeps what it exported (to compare CUDA and oracle message by message)."""
+
+    def __init__(self, inner):
+        self.inner = inner; self.log = []
+
+    def halo_export(self, dim, side):
+        r = self.inner.halo_export(dim, side); self.log.append((dim, side, r)); return r
+
+    def __getattr__(self, k):
+        return getattr(self.inner, k)
+
+
+def make_gpu_ranks(capi, ps, dds, owner, prec, rc):
+    ranks = []
+    for dd in dds:
+        c = capi.Context(list(dd.box_min()), list(dd.box_max()), rc, epsilon_rf=ps.epsilon_rf, precision=prec, geometry="xml", periodic=dd.periodic())
+        c.set_components(ps.ensemble)
+        c.decomp_attach(dd)
+        m = owner == dd.rank
+        c.upload(ps.id[m], ps.cid[m], ps.r[m], ps.v[m], ps.q[m], ps.L[m])
+        ranks.append(c)
+    return ranks
+
+
+def same_records(a, b, exact):
+    """Same molecules with the same role; positions bit-identical while the two states are (step 0), afterwards within the
+    drift the force tolerance allows."""
+    if len(a) != len(b):
+        return False
+    a = np.sort(a, order=["flags", "id", "r"]); b = np.sort(b, order=["flags", "id", "r"])
+    if not (np.array_equal(a["id"], b["id"]) and np.array_equal(a["cid"], b["cid"]) and np.array_equal(a["flags"], b["flags"])):
+        return False
+    lv = a["flags"] == 0
+    if exact:
+        return np.array_equal(a["r"], b["r"]) and np.array_equal(a["v"][lv], b["v"][lv]) and np.array_equal(a["q"][lv], b["q"][lv])
+    return np.allclose(a["r"], b["r"], rtol=0, atol=1e-4) and np.allclose(a["v"][lv], b["v"][lv], rtol=1e-3, atol=1e-3)
+
+
+@pytest.mark.parametrize("n_ranks,grid", [(2, None), (4, None), (8, None), (3, (1, 3, 1))])
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_blocks_on_one_device_vs_oracle(capi, n_ranks, grid, prec):
+    from ls1_mardyn_b200 import generators
+    from ls1_mardyn_b200.decomposition import exchange_local
+    from oracle import oracle as orc
+    ps = generators.lj_lattice(9, seed=4, jitter=0.15); ps.v *= 6.0
+    rc, dt = 2.0, 0.005
+    dds, owner = split(ps, n_ranks, grid)
+    G = [Recorder(k) for k in make_gpu_ranks(capi, ps, dds, owner, prec, rc)]
+    O = [Recorder(k) for k in make_ranks(ps, dds, owner, prec, rc)]
+    one = capi.Context([0, 0, 0], list(ps.length), rc, epsilon_rf=ps.epsilon_rf, precision=prec, geometry="xml", periodic=(1, 1, 1))
+    one.set_components(ps.ensemble); one.upload(ps.id, ps.cid, ps.r, ps.v, ps.q, ps.L)
+    one.update(); m1 = one.traverse_cells()
+    o1 = np.argsort(one.download("ID"))
+    for step in range(8):
+        # step 0: both sides see bit-identical inputs -> the north-star tolerance. Later steps compare two trajectories of a hot,
+        # jittered (stiff) system whose states have drifted apart by the force tolerance: the bound is widened accordingly.
+        tol = TOL[prec] * (1 if step == 0 else 50)
+        if step:
+            for k in G + O:
+                k.leapfrog_pre(dt)
+            one.leapfrog_pre(dt); one.update(); m1 = one.traverse_cells()
+        exchange_local(G, dds); exchange_local(O, dds)
+        # message by message: same molecules, bit-identical shifted positions (integer / exact work: no tolerance)
+        for g, o in zip(G, O):
+            assert len(g.log) == len(o.log)
+            for (d, s, a), (_, _, b) in zip(g.log, o.log):
+                assert same_records(a, b, exact=(step == 0)), (step, g.inner.cfg.box_min[:], d, s, len(a), len(b))
+            g.log.clear(); o.log.clear()
+        for k in G + O:
+            k.update()
+        mg = [k.traverse_cells() for k in G]; mo = [k.traverse_cells() for k in O]
+        for g, o in zip(G, O):
+            assert np.array_equal(np.sort(g.download("ID")), np.sort(o.download("ID")))      # same owners
+        ids, Fg = gather(G, "F"); _, Fo = gather(O, "F")
+        ok, worst = rel_close(Fg, Fo, tol); assert ok, (step, worst)
+        ok, worst = rel_close(Fg, one.download("F")[o1], 3 * tol); assert ok, (step, "vs single domain", worst)      # other cells, other summation order
+        up = sum(m.upot for m in mg)
+        assert abs(up - sum(m.upot for m in mo)) <= tol * abs(up) and abs(up - m1.upot) <= 3 * tol * abs(up)
+        vir = sum(m.virial for m in mg)
+        assert abs(vir - m1.virial) <= 3 * tol * max(abs(m1.virial), np.abs(one.download("VI")).sum())
+        kg = [k.leapfrog_post(dt) for k in G]; ko = [k.leapfrog_post(dt) for k in O]; k1 = one.leapfrog_post(dt)
+        assert sum(k.n_molecules for k in kg) == len(ps.id)
+        assert abs(sum(k.summv2 for k in kg) - k1.summv2) <= 10 * tol * k1.summv2
+    ids, Rg = gather(G, "R")
+    assert np.abs(Rg - one.download("R")[o1]).max() <= (1e-9 if prec == "double" else 1e-4)
+
+
+def test_multisite_blocks(capi):
+    """Rotating multi-site molecules (water-like golden fixture): orientation and angular momentum travel with the molecule."""
+    from helpers import load
+    from ls1_mardyn_b200.ascii_reader import PhaseSpace
+    from ls1_mardyn_b200.decomposition import DomainDecomposition, exchange_local
+    g = load("periodic_water_432")
+    L = np.asarray(g["length"], dtype=float); rc = float(g["cutoff"])
+    if L.min() < 4 * rc:
+        pytest.skip("fixture box too small for two blocks of two cutoff radii")
+    ps = PhaseSpace(L, float(g["temperature"]), float(g["epsilon_rf"]), g["ensemble"], g["in_id"], g["in_cid"], g["in_r"], g["in_v"], g["in_q"], g["in_L"])
+    dds, owner = split(ps, 2)
+    G = make_gpu_ranks(capi, ps, dds, owner, "double", rc)
+    one = capi.Context([0, 0, 0], list(L), rc, epsilon_rf=ps.epsilon_rf, precision="double", geometry="xml", periodic=(1, 1, 1))
+    one.set_components(ps.ensemble); one.upload(ps.id, ps.cid, ps.r, ps.v, ps.q, ps.L)
+    one.update(); one.traverse_cells(); o1 = np.argsort(one.download("ID"))
+    dt = 0.0667516
+    for step in range(4):
+        if step:
+            for k in G:
+                k.leapfrog_pre(dt)
+            one.leapfrog_pre(dt); one.update(); one.traverse_cells()
+        exchange_local(G, dds)
+        for k in G:
+            k.update()
+        for k in G:
+            k.traverse_cells()
+        for f in ("F", "M"):
+            _, a = gather(G, f)
+            ok, worst = rel_close(a, one.download(f)[o1], 1e-9); assert ok, (step, f, worst)
+        for k in G:
+            k.leapfrog_post(dt)
+        one.leapfrog_post(dt)
+
+
+def test_nccl_two_gpus(capi, tmp_path):
+    """The NCCL transport (ls1b200_exchange inside ls1b200_simulate), one process per GPU."""
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
+    cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29641",
+           os.path.join(ROOT, "tests", "nccl_decomposition_worker.py")]
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PYTHONPATH=ROOT))
+    assert p.returncode == 0 and "NCCL-DECOMP-OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
