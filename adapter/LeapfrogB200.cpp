@@ -28,10 +28,11 @@ void LeapfrogB200::readXML(XMLfileUnits& xmlconfig) {
 void LeapfrogB200::eventNewTimestep(ParticleContainer* moleculeContainer, Domain* domain) {
 	LinkedCellsB200* c = deviceContainer(moleculeContainer);
 	if (!c->deviceMode()) return;
+	c->hostView(false);                     // from here on the device state is authoritative; host loops of the step iterate nothing
 	// VelocityScalingThermostat::apply of the previous step found an empty iterator range (device mode); its factors are
 	// Domain's global betas (Domain.cpp:248-252) and are applied here, before the kick, which is the same arithmetic
 	// (Simulation.cpp:1235-1261; single global thermostat -- the component-wise variant needs a per-component factor table).
-	if (!domain->NVE() && !domain->severalThermostats()) {
+	if (_thermostatPending && !domain->NVE() && !domain->severalThermostats()) {
 		if (ls1b200_scale_velocities(c->context(), domain->getGlobalBetaTrans(), domain->getGlobalBetaRot()) != 0) MARDYN_EXIT(ls1b200_last_error());
 	}
 	if (ls1b200_leapfrog_pre(c->context(), _timestepLength) != 0) MARDYN_EXIT(ls1b200_last_error());
@@ -45,4 +46,5 @@ void LeapfrogB200::eventForcesCalculated(ParticleContainer* moleculeContainer, D
 	domain->setLocalSummv2(kin.summv2, 0);                        // Leapfrog.cpp:139-143
 	domain->setLocalSumIw2(kin.sum_iw2, 0);
 	domain->setLocalNrotDOF(0, kin.n_molecules, kin.rot_dof);
+	_thermostatPending = true;
 }

@@ -11,4 +11,6 @@ public:
 	void init() override {}
 	void eventNewTimestep(ParticleContainer* moleculeContainer, Domain* domain) override;       // transition1to2: upd_preF
 	void eventForcesCalculated(ParticleContainer* moleculeContainer, Domain* domain) override;  // transition2to3: upd_postF + sums
+private:
+	bool _thermostatPending = false;   // a step has completed: its velocity-scaling factors are applied before the next kick
 };

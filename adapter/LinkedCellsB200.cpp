@@ -103,18 +103,25 @@ void LinkedCellsB200::uploadAll() {
 }
 
 void LinkedCellsB200::update() {
-	if (!_deviceMode) {
-		LinkedCells::update();                 // host mirror: the state the readers / generators produced
-		if (!_ctx) createContext();
-		uploadAll();
-		_deviceMode = true;
-		Log::global_log->info() << "LinkedCellsB200: " << _numMolecules << " molecules now live on the device" << std::endl;
-	}
+	// Before the first force calculation (input readers, Simulation::initialize) this is the stock host container: the
+	// pair-parameter streams the device tables are built from do not exist yet (Domain::initParameterStreams runs in
+	// Simulation::prepare_start).
+	if (!_deviceMode) { LinkedCells::update(); return; }
 	B200_CHECK(ls1b200_update(_ctx));          // == update() + exchangeMolecules() + updateMoleculeCaches()
 }
 
 void LinkedCellsB200::traverseCells(CellProcessor& cellProcessor) {
-	if (_deviceMode && (dynamic_cast<VectorizedCellProcessor*>(&cellProcessor) || dynamic_cast<LegacyCellProcessor*>(&cellProcessor))) {
+	const bool forceProcessor = dynamic_cast<VectorizedCellProcessor*>(&cellProcessor) || dynamic_cast<LegacyCellProcessor*>(&cellProcessor);
+	if (!_deviceMode && forceProcessor) {
+		// first force calculation (Simulation::prepare_start, Simulation.cpp:908-912): the molecules move to the device
+		LinkedCells::deleteOuterParticles();   // the host halo copies made by exchangeMolecules are not owned molecules
+		if (!_ctx) createContext();
+		uploadAll();
+		_deviceMode = true;
+		B200_CHECK(ls1b200_update(_ctx));
+		Log::global_log->info() << "LinkedCellsB200: " << _numMolecules << " molecules now live on the device" << std::endl;
+	}
+	if (_deviceMode && forceProcessor) {
 		ls1b200_macro mac{};
 		B200_CHECK(ls1b200_traverse_cells(_ctx, &mac));      // forces, torques, per-molecule virial stay on the device
 		Domain* domain = global_simulation->getDomain();

@@ -4,7 +4,7 @@
 //
 // It derives from the reference's own LinkedCells, which stays the host mirror: input readers / generators fill it through
 // addParticle(s) / initCubicGrid exactly as before (Simulation::prepare_start), and plugins that iterate molecules see it
-// after a lazy device -> host sync. From the first update() on the device copy is authoritative ("device mode"): the
+// after a lazy device -> host sync. From the first force traversal on the device copy is authoritative ("device mode"): the
 // per-step host loops of the stock time step find an empty iterator range and cost nothing.
 // Precedent in the reference for a container that ignores the CellProcessor's kernels and writes Upot / Virial itself:
 // AutoPasContainer::traverseCells (particleContainer/AutoPasContainer.cpp:554-606).
@@ -20,14 +20,17 @@ public:
 	~LinkedCellsB200() override;
 
 	// <datastructure type="LinkedCellsB200"> takes the same children as LinkedCells (readXML is inherited).
-	void update() override;                                  // -> ls1b200_update (first call: upload the host mirror)
-	void traverseCells(CellProcessor& cellProcessor) override;   // -> ls1b200_traverse_cells, Domain::setLocalUpot/Virial
+	void update() override;                                  // -> ls1b200_update once the molecules live on the device
+	void traverseCells(CellProcessor& cellProcessor) override;   // -> ls1b200_traverse_cells, Domain::setLocalUpot/Virial (first call: upload)
 	void updateMoleculeCaches() override { if (!_deviceMode) LinkedCells::updateMoleculeCaches(); }
 	void updateInnerMoleculeCaches() override { if (!_deviceMode) LinkedCells::updateInnerMoleculeCaches(); }
 	void updateBoundaryAndHaloMoleculeCaches() override { if (!_deviceMode) LinkedCells::updateBoundaryAndHaloMoleculeCaches(); }
 	void deleteOuterParticles() override { if (!_deviceMode) LinkedCells::deleteOuterParticles(); }   // halo is transient device data
 	unsigned long getNumberOfParticles(ParticleIterator::Type t = ParticleIterator::ALL_CELLS) override;
+	bool requiresForceExchange() const override { return false; }   // full-shell on the device, like plain C08 (C08CellPairTraversal.h:35)
 
+	// Until LeapfrogB200 starts the first time step the host mirror still equals the device state and stays visible
+	// (Domain::calculateVelocitySums etc. in Simulation::prepare_start, Simulation.cpp:986-992, need it).
 	// In device mode the host loops of the time step (Leapfrog, exchangeMolecules, updateForces, thermostat) iterate nothing;
 	// a caller that really wants the molecules (writers, checkpoints, RDF) calls syncToHost() first -- or sets hostView(true).
 	ParticleIterator iterator(ParticleIterator::Type t) override;
@@ -45,6 +48,6 @@ private:
 
 	ls1b200_ctx* _ctx = nullptr;
 	bool _deviceMode = false;
-	bool _hostView = false;
+	bool _hostView = true;        // until the first time step: the init-time loops of prepare_start read the host mirror
 	unsigned long _numMolecules = 0;
 };

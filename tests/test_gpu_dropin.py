@@ -1,0 +1,52 @@
+"""The drop-in proof: the UNMODIFIED ls1-MarDyn Simulation loop, XML input and ResultWriter, with
+<datastructure type="LinkedCellsB200"> + <integrator type="LeapfrogB200"> (adapter/, built against the reference by
+adapter/build_adapter.sh) running on the GPU through libls1b200.so, against the stock reference binary on the same XML.
+Compared: the reference's own per-step output (ResultWriter: U_pot, U_kin, p, beta_trans), tolerances of the north star.
+Skipped when the binaries are not in the snapshot (they are built in the build container only)."""
+import os
+import subprocess
+
+import numpy as np
+import pytest
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def run(exe, xml, cwd, steps):
+    p = subprocess.run([exe, "--steps", str(steps), "--final-checkpoint=0", xml], cwd=cwd, capture_output=True, text=True, timeout=600,
+                       env=dict(os.environ, OMP_NUM_THREADS="8"))
+    assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+    rows = [l.split() for l in open(os.path.join(cwd, "res.res")) if l.strip() and not l.lstrip().startswith("#")]
+    return np.array([[float(x) for x in r] for r in rows]), p.stdout + p.stderr
+
+
+@pytest.mark.parametrize("prec,tol", [("double", 1e-9), ("mixed", 1e-6)])
+def test_stock_simulation_loop_on_the_gpu(tmp_path, prec, tol):
+    ref = os.path.join(ROOT, "oracle", "_ref", prec, "MarDyn")
+    b200 = os.path.join(ROOT, "adapter", "_build", prec, "MarDyn_b200")
+    if not (os.path.exists(ref) and os.path.exists(b200)):
+        pytest.skip("reference / adapter binaries not built (oracle/build_ref.sh, adapter/build_adapter.sh)")
+    import bench
+    steps, n = 100, 16                                    # 8192 molecules
+    xml = bench.XML.replace("<output></output>", '<output><outputplugin name="ResultWriter"><writefrequency>1</writefrequency>'
+                            "<outputprefix>res</outputprefix><writeprecision>15</writeprecision></outputplugin></output>")
+    N = 2 * n ** 3; L = (N / bench.RHO) ** (1.0 / 3.0)
+    fmt = dict(dt=bench.DT, steps=steps, T=bench.TEMP, L=repr(L), rho=repr(N / L ** 3 * (1 + 1e-9)), rc=bench.RC)
+    out = {}
+    for name, exe, text in (("ref", ref, xml), ("b200", b200, xml.replace('type="LinkedCells"', 'type="LinkedCellsB200"').replace('integrator type="Leapfrog"', 'integrator type="LeapfrogB200"'))):
+        d = tmp_path / name; d.mkdir()
+        (d / "config.xml").write_text(text.format(**fmt))
+        out[name], log = run(exe, "config.xml", str(d), steps)
+        if name == "b200":
+            assert "molecules now live on the device" in log
+    a, b = out["b200"], out["ref"]
+    assert a.shape == b.shape and a.shape[0] >= steps
+    # columns: step time U_pot U_pot_avg U_kin U_kin_avg p p_avg beta_trans beta_rot c_v N
+    for name, col in (("U_pot", 2), ("U_kin", 4), ("beta_trans", 8)):
+        err = np.abs(a[:, col] - b[:, col]).max() / np.abs(b[:, col]).max()
+        assert err <= tol, (prec, name, err)
+    rhoT = (N / L ** 3) * (2.0 * b[:, 4] / (3.0 * N))      # p = rho T + rho W / 3N is a near cancellation: bound relative to its terms
+    err = np.abs(a[:, 6] - b[:, 6]).max() / max(np.abs(b[:, 6]).max(), rhoT.max())
+    assert err <= tol, (prec, "p", err)
+    assert np.array_equal(a[:, 11], b[:, 11])
