@@ -40,7 +40,7 @@ template <class C> struct TileCfg;
 // TPB threads, each owning RI molecules of ONE cell (RI > 1 is register blocking: one shared-memory load of a candidate
 // serves RI distance tests); W records per window row; LCAP list entries per molecule.
 template <> struct TileCfg<float> { static constexpr int RI = LS1_TILE_RI_F, TPB = LS1_TILE_TPB_F, W = LS1_TILE_W_F, LCAP = LS1_TILE_LCAP_F; };
-template <> struct TileCfg<double> { static constexpr int RI = 2, TPB = 32, W = 112, LCAP = 64; };
+template <> struct TileCfg<double> { static constexpr int RI = 1, TPB = 64, W = 112, LCAP = 64; };
 
 // ---------------------------------------------------------------------------------------------------------------------
 // chunk list
@@ -203,21 +203,23 @@ struct TArgs {
 	C eps24_0, sig2_0, shift6_0;
 };
 
-// LJ 12-6 of one pair, accumulated into FP32 partial sums (slot u)
+// LJ 12-6 of one pair, accumulated into FP32 partial sums (slot u). Force and virial are fused multiply-adds on the common
+// factor; with a single component 24 eps is pair independent and is applied once per list (scale1 omits it).
 #define LJ_PAIR_ACCUM(u, mj)                                                                   \
 	{                                                                                           \
 		const C dx = mi.x - (mj).x, dy = mi.y - (mj).y, dz = mi.z - (mj).z;                      \
-		const C r2 = dx * dx + dy * dy + dz * dz;                                                 \
+		const C dx2 = dx * dx, dy2 = dy * dy, dz2 = dz * dz;                                      \
+		const C r2 = dx2 + dy2 + dz2;                                                             \
 		if (!SINGLE) {                                                                            \
 			const size_t ti = (size_t) cid_i * a.n_lj + (wbits<C>((mj).w) & 0xFFFFu);              \
 			eps24 = a.eps24[ti]; sig2 = a.sig2[ti]; shift6 = a.shift6[ti];                          \
 		}                                                                                         \
 		const C r2inv = rcp_fast<C>(r2);                                                          \
 		const C lj2 = sig2 * r2inv, lj6 = lj2 * lj2 * lj2, lj12 = lj6 * lj6, lj12m6 = lj12 - lj6;  \
-		const C scale = eps24 * r2inv * (lj12 + lj12m6);                                          \
-		const C px = dx * scale, py = dy * scale, pz = dz * scale;                                \
-		fx[u] += px; fy[u] += py; fz[u] += pz;                                                    \
-		vx[u] += dx * px; vy[u] += dy * py; vz[u] += dz * pz;                                     \
+		C scale = r2inv * (lj12 + lj12m6);                                                        \
+		if (!SINGLE) scale *= eps24;                                                              \
+		fx[u] = fma(dx, scale, fx[u]); fy[u] = fma(dy, scale, fy[u]); fz[u] = fma(dz, scale, fz[u]); \
+		vx[u] = fma(dx2, scale, vx[u]); vy[u] = fma(dy2, scale, vy[u]); vz[u] = fma(dz2, scale, vz[u]); \
 		if (SINGLE) up[u] += lj12m6; else up[u] += eps24 * lj12m6 + shift6;                       \
 	}
 
@@ -231,6 +233,7 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 	uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw + (size_t) (9 * W + 1) * VB);   // [LCAP+1][RI][TPB]
 	uint32_t* cs = reinterpret_cast<uint32_t*>(list + (size_t) (LCAP + 1) * RI * TPB);   // [9][CH_MAXC+3]
 	__shared__ uint32_t s_tb[CH_MAXC + 1];
+	__shared__ uint32_t s_rowbase[9];
 	__shared__ __align__(8) unsigned long long s_bar;
 	__shared__ uint32_t s_chunk;
 	const uint32_t win_s = smem_u32(win), list_s = smem_u32(list) + threadIdx.x * 2, bar = smem_u32(&s_bar);
@@ -274,6 +277,7 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 							const C r2t = molpair_r2<C>(mi.x, mi.y, mi.z, mj.x, mj.y, mj.z);
 							if ((r2t < a.ljrc2) && (r2t != C(0))) { LJ_PAIR_ACCUM(0, mj); nh++; }
 						}
+						if (SINGLE) { fx[0] *= eps24; fy[0] *= eps24; fz[0] *= eps24; vx[0] *= eps24; vy[0] *= eps24; vz[0] *= eps24; }
 						Fd[0] += (double) fx[0]; Fd[1] += (double) fy[0]; Fd[2] += (double) fz[0];
 						Vd[0] += (double) vx[0]; Vd[1] += (double) vy[0]; Vd[2] += (double) vz[0];
 						Ud += SINGLE ? (double) (eps24 * up[0] + (C) nh * shift6) : (double) up[0];
@@ -293,17 +297,21 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 		for (int k = threadIdx.x; k < 9 * (nc + 3); k += TPB) {
 			const int r = k / (nc + 3), c = k % (nc + 3);
 			const uint32_t row = (uint32_t) ((int) R + (r / 3 - 1) * a.ny + (r % 3 - 1)) * a.nx;
-			cs[r * (CH_MAXC + 3) + c] = a.cell_start[row + xa - 1 + c];
+			// stored RELATIVE to the first record of the window (the absolute start goes to s_rowbase): the per-thread row
+			// set-up then needs two loads per row and no subtraction of a third one
+			const uint32_t b0 = a.cell_start[row + xa - 1];
+			cs[r * (CH_MAXC + 3) + c] = a.cell_start[row + xa - 1 + c] - b0;
+			if (c == 0) s_rowbase[r] = b0;
 		}
 		__syncthreads();
 		if (threadIdx.x == 0) {
 			uint32_t total = 0;
-			for (int r = 0; r < 9; r++) total += (cs[r * (CH_MAXC + 3) + nc + 2] - cs[r * (CH_MAXC + 3)]) * VB;
+			for (int r = 0; r < 9; r++) total += cs[r * (CH_MAXC + 3) + nc + 2] * VB;
 			if (total) {
 				fence_proxy_async();      // the previous chunk's generic-proxy reads of the windows precede these async-proxy writes
 				mbar_expect_tx(bar, total);
 				for (int r = 0; r < 9; r++) {
-					const uint32_t b = cs[r * (CH_MAXC + 3)], len = cs[r * (CH_MAXC + 3) + nc + 2] - b;
+					const uint32_t b = s_rowbase[r], len = cs[r * (CH_MAXC + 3) + nc + 2];
 					if (len) tma_bulk_g2s(win_s + (uint32_t) (r * W) * VB, a.mpos + b, len * VB, bar);
 				}
 			}
@@ -317,100 +325,106 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 		int kx = 0;
 		while (kx + 1 < nc && s_tb[kx + 1] <= threadIdx.x) kx++;
 		const bool have0 = threadIdx.x < s_tb[nc];
-		const uint32_t t0 = csc[kx + 1] + (uint32_t) RI * (threadIdx.x - s_tb[kx]);      // my first molecule (slot); the others follow
+		const uint32_t t0rel = csc[kx + 1] + (threadIdx.x - s_tb[kx]);      // my molecule: record index inside the centre window ...
+		const uint32_t t0 = s_rowbase[4] + t0rel;                           // ... and its slot
 		mbar_wait(bar, parity); parity ^= 1u;
-		// ---- 2. phase 1: distance tests from shared memory -> RI u16 lists of (row * W + k) ----
-		V4 mi[RI]; bool have[RI];
-		#pragma unroll
-		for (int l = 0; l < RI; l++) {
-			have[l] = have0 && (t0 + l < csc[kx + 2]);
-			mi[l] = make_c4<C>((C) 1e18, (C) 1e18, (C) 1e18, (C) 0);      // an absent molecule: no candidate is ever in range
-			if (have[l]) mi[l] = lds_v4<C>(win_s + (uint32_t) (4 * W + (int) (t0 + l - csc[0])) * VB);
+		// ---- 2. phase 1 + 3. phase 2, one molecule per thread -------------------------------------------------------------
+		// Phase 1 walks my 9 candidate rows (cells cx-1 .. cx+1 of each, one contiguous range of the row's window); every
+		// candidate is one LDS.128 and the reference's molecule-distance test (strict <, bit-identical to calcDistLookup; in my
+		// own row SingleCellPolicy_ additionally masks pairs at distance 0, i.e. the molecule itself). A hit appends the
+		// candidate's shared-memory ADDRESS (it fits 16 bits) to my list. When the list is nearly full, or after the last row,
+		// phase 2 evaluates the list densely (LJ 12-6; FP32 partial sums folded into FP64 like RealAccumVec) and empties it.
+		// There is exactly one instance of each loop in the code: the state machine below keeps the instruction footprint small.
+		const bool have = have0;
+		V4 mi = make_c4<C>((C) 1e18, (C) 1e18, (C) 1e18, (C) 0);      // an absent molecule: no candidate is ever in range
+		if (have) mi = lds_v4<C>(win_s + (uint32_t) (4 * W + (int) t0rel) * VB);
+		const uint32_t cid_i = wbits<C>(mi.w) & 0xFFFFu;
+		double Fd[3] = {0., 0., 0.}, Vd[3] = {0., 0., 0.}, Ud = 0.;
+		const uint32_t sentinel = win_s + (uint32_t) (9 * W) * VB;
+		const uint32_t wlimit = list_s + (uint32_t) (LCAP - 4) * LSTRIDE;
+		uint32_t w = list_s;                    // list write cursor
+		uint32_t src = 0, end = 0;              // shared-memory address of the next candidate / end of the row range
+		int r = -1;
+		for (;;) {
+			bool flush = true;
+			if (r < 9) {
+				if (r == 4) {
+					while (src + 4 * VB <= end && w <= wlimit) {
+						const V4 m0 = lds_v4<C>(src), m1 = lds_v4<C>(src + VB), m2 = lds_v4<C>(src + 2 * VB), m3 = lds_v4<C>(src + 3 * VB);
+						const C r0 = molpair_r2<C>(mi.x, mi.y, mi.z, m0.x, m0.y, m0.z), r1 = molpair_r2<C>(mi.x, mi.y, mi.z, m1.x, m1.y, m1.z);
+						const C r2 = molpair_r2<C>(mi.x, mi.y, mi.z, m2.x, m2.y, m2.z), r3 = molpair_r2<C>(mi.x, mi.y, mi.z, m3.x, m3.y, m3.z);
+						if (r0 < a.ljrc2 && r0 != C(0)) { sts16(w, src); w += LSTRIDE; }
+						if (r1 < a.ljrc2 && r1 != C(0)) { sts16(w, src + VB); w += LSTRIDE; }
+						if (r2 < a.ljrc2 && r2 != C(0)) { sts16(w, src + 2 * VB); w += LSTRIDE; }
+						if (r3 < a.ljrc2 && r3 != C(0)) { sts16(w, src + 3 * VB); w += LSTRIDE; }
+						src += 4 * VB;
+					}
+				} else {
+					while (src + 4 * VB <= end && w <= wlimit) {
+						const V4 m0 = lds_v4<C>(src), m1 = lds_v4<C>(src + VB), m2 = lds_v4<C>(src + 2 * VB), m3 = lds_v4<C>(src + 3 * VB);
+						const C r0 = molpair_r2<C>(mi.x, mi.y, mi.z, m0.x, m0.y, m0.z), r1 = molpair_r2<C>(mi.x, mi.y, mi.z, m1.x, m1.y, m1.z);
+						const C r2 = molpair_r2<C>(mi.x, mi.y, mi.z, m2.x, m2.y, m2.z), r3 = molpair_r2<C>(mi.x, mi.y, mi.z, m3.x, m3.y, m3.z);
+						if (r0 < a.ljrc2) { sts16(w, src); w += LSTRIDE; }
+						if (r1 < a.ljrc2) { sts16(w, src + VB); w += LSTRIDE; }
+						if (r2 < a.ljrc2) { sts16(w, src + 2 * VB); w += LSTRIDE; }
+						if (r3 < a.ljrc2) { sts16(w, src + 3 * VB); w += LSTRIDE; }
+						src += 4 * VB;
+					}
+				}
+				if (w <= wlimit) {                  // the row is down to < 4 candidates (the list is not the reason the loop stopped)
+					for (; src < end; src += VB) {
+						const V4 mj = lds_v4<C>(src);
+						const C rr = molpair_r2<C>(mi.x, mi.y, mi.z, mj.x, mj.y, mj.z);
+						if (rr < a.ljrc2 && (r != 4 || rr != C(0))) { sts16(w, src); w += LSTRIDE; }
+					}
+					r++;
+					if (r < 9) {
+						uint32_t kb = 0, ke = 0;
+						if (have) {
+							kb = cs[r * (CH_MAXC + 3) + kx]; ke = cs[r * (CH_MAXC + 3) + kx + 3];      // cells cx-1 .. cx+1 of this row
+						}
+						src = win_s + (uint32_t) (r * W + (int) kb) * VB; end = win_s + (uint32_t) (r * W + (int) ke) * VB;
+						flush = false;
+					}
+				}
+			}
+			if (flush) {
+				// ---- phase 2: dense LJ over the list; two interleaved FP32 accumulator sets ----
+				const int cnt = (int) ((w - list_s) / LSTRIDE);
+				C fx[2] = {C(0), C(0)}, fy[2] = {C(0), C(0)}, fz[2] = {C(0), C(0)}, vx[2] = {C(0), C(0)}, vy[2] = {C(0), C(0)}, vz[2] = {C(0), C(0)}, up[2] = {C(0), C(0)};
+				C eps24 = a.eps24_0, sig2 = a.sig2_0, shift6 = a.shift6_0;
+				if (cnt & 1) sts16(w, sentinel);      // pad odd lists with the far-away record (all LJ terms underflow to 0)
+				#pragma unroll 1
+				for (uint32_t e = list_s; e < w; e += 2 * LSTRIDE) {
+					const uint32_t i0 = lds16(e), i1 = lds16(e + LSTRIDE);
+					const V4 m0 = lds_v4<C>(i0), m1 = lds_v4<C>(i1);
+					LJ_PAIR_ACCUM(0, m0);
+					if (SINGLE || i1 != sentinel) LJ_PAIR_ACCUM(1, m1);
+				}
+				if (SINGLE) {
+					// eps24 and the shift are pair independent: applied once per list
+					const C f24 = eps24;
+					fx[0] = f24 * (fx[0] + fx[1]); fy[0] = f24 * (fy[0] + fy[1]); fz[0] = f24 * (fz[0] + fz[1]);
+					vx[0] = f24 * (vx[0] + vx[1]); vy[0] = f24 * (vy[0] + vy[1]); vz[0] = f24 * (vz[0] + vz[1]);
+					up[0] = f24 * (up[0] + up[1]) + (C) cnt * shift6;
+					fx[1] = fy[1] = fz[1] = vx[1] = vy[1] = vz[1] = up[1] = C(0);
+				}
+				Fd[0] += (double) fx[0] + (double) fx[1]; Fd[1] += (double) fy[0] + (double) fy[1]; Fd[2] += (double) fz[0] + (double) fz[1];
+				Vd[0] += (double) vx[0] + (double) vx[1]; Vd[1] += (double) vy[0] + (double) vy[1]; Vd[2] += (double) vz[0] + (double) vz[1];
+				Ud += (double) up[0] + (double) up[1];
+				w = list_s;
+				if (r >= 9) break;
+			}
 		}
-		double Fd[RI][3], Vd[RI][3], Ud[RI];
-		#pragma unroll
-		for (int l = 0; l < RI; l++) { Fd[l][0] = Fd[l][1] = Fd[l][2] = Vd[l][0] = Vd[l][1] = Vd[l][2] = Ud[l] = 0.; }
-		// dense LJ over list l (entries [0, cnt)); FP32 partial sums in two interleaved slots, folded into FP64
-		auto process_list = [&](const int l, const int cnt) {
-			const uint32_t cid_i = wbits<C>(mi[l].w) & 0xFFFFu;
-			const V4 mi_ = mi[l];
-			const uint32_t lbase = list_s + (uint32_t) l * (TPB * 2);
-			C fx[2] = {C(0), C(0)}, fy[2] = {C(0), C(0)}, fz[2] = {C(0), C(0)}, vx[2] = {C(0), C(0)}, vy[2] = {C(0), C(0)}, vz[2] = {C(0), C(0)}, up[2] = {C(0), C(0)};
-			C eps24 = a.eps24_0, sig2 = a.sig2_0, shift6 = a.shift6_0;
-			if (cnt & 1) sts16(lbase + (uint32_t) cnt * LSTRIDE, 9 * W);      // pad with the sentinel record
-			#pragma unroll 1
-			for (int e = 0; e < cnt; e += 2) {
-				const uint32_t i0 = lds16(lbase + (uint32_t) e * LSTRIDE), i1 = lds16(lbase + (uint32_t) (e + 1) * LSTRIDE);
-				const V4 m0 = lds_v4<C>(win_s + i0 * VB), m1 = lds_v4<C>(win_s + i1 * VB);
-				#define mi mi_
-				LJ_PAIR_ACCUM(0, m0);
-				if (SINGLE || i1 != 9 * W) LJ_PAIR_ACCUM(1, m1);
-				#undef mi
-			}
-			if (SINGLE) { up[0] = eps24 * (up[0] + up[1]) + (C) cnt * shift6; up[1] = C(0); }
-			Fd[l][0] += (double) fx[0] + (double) fx[1]; Fd[l][1] += (double) fy[0] + (double) fy[1]; Fd[l][2] += (double) fz[0] + (double) fz[1];
-			Vd[l][0] += (double) vx[0] + (double) vx[1]; Vd[l][1] += (double) vy[0] + (double) vy[1]; Vd[l][2] += (double) vz[0] + (double) vz[1];
-			Ud[l] += (double) up[0] + (double) up[1];
-		};
-		uint32_t w[RI];      // list write cursors (shared-window addresses)
-		#pragma unroll
-		for (int l = 0; l < RI; l++) w[l] = list_s + (uint32_t) l * (TPB * 2);
-		#pragma unroll 1
-		for (int r = 0; r < 9; r++) {
-			uint32_t kb = 0, ke = 0;
-			if (have0) {
-				const uint32_t base = cs[r * (CH_MAXC + 3)];
-				kb = cs[r * (CH_MAXC + 3) + kx] - base; ke = cs[r * (CH_MAXC + 3) + kx + 3] - base;      // cells cx-1 .. cx+1 of this row
-			}
-			const bool self_row = r == 4;
-			uint32_t src = win_s + (uint32_t) (r * W + (int) kb) * VB;
-			uint32_t idx = (uint32_t) (r * W) + kb;
-			// every candidate is loaded once (LDS.128) and tested against all of my molecules: strict <, bit-identical to
-			// calcDistLookup; in my own row SingleCellPolicy_ additionally masks pairs at distance 0 (the molecule itself).
-			// A list that could overflow during the next four candidates is evaluated and emptied first (lane-local, rare).
-			#define LJ_TESTS(m, off)                                                                                   \
-				_Pragma("unroll") for (int l = 0; l < RI; l++) {                                                        \
-					const C rr = molpair_r2<C>(mi[l].x, mi[l].y, mi[l].z, (m).x, (m).y, (m).z);                          \
-					if ((rr < a.ljrc2) && (!self_row || rr != C(0))) { sts16(w[l], idx + (off)); w[l] += LSTRIDE; }      \
-				}
-			#define LJ_ROOM()                                                                                          \
-				_Pragma("unroll") for (int l = 0; l < RI; l++) {                                                        \
-					if (w[l] > list_s + (uint32_t) l * (TPB * 2) + (uint32_t) (LCAP - 4) * LSTRIDE) {                    \
-						process_list(l, (int) ((w[l] - list_s - (uint32_t) l * (TPB * 2)) / LSTRIDE));                    \
-						w[l] = list_s + (uint32_t) l * (TPB * 2);                                                          \
-					}                                                                                                    \
-				}
-			uint32_t k = kb;
-			for (; k + 4 <= ke; k += 4, src += 4 * VB, idx += 4) {
-				const V4 m0 = lds_v4<C>(src), m1 = lds_v4<C>(src + VB), m2 = lds_v4<C>(src + 2 * VB), m3 = lds_v4<C>(src + 3 * VB);
-				LJ_ROOM();
-				LJ_TESTS(m0, 0); LJ_TESTS(m1, 1); LJ_TESTS(m2, 2); LJ_TESTS(m3, 3);
-			}
-			if (k < ke) {
-				LJ_ROOM();
-				for (; k < ke; k++, src += VB, idx++) {
-					const V4 mj = lds_v4<C>(src);
-					LJ_TESTS(mj, 0);
-				}
-			}
-			#undef LJ_TESTS
-			#undef LJ_ROOM
-		}
-		// ---- 3. phase 2 ----
-		#pragma unroll
-		for (int l = 0; l < RI; l++) process_list(l, (int) ((w[l] - list_s - (uint32_t) l * (TPB * 2)) / LSTRIDE));
 		// ---- 4. results ----
-		#pragma unroll
-		for (int l = 0; l < RI; l++) {
-			if (have[l]) {
-				const size_t cp = a.cap;
-				const uint32_t t = t0 + l;
-				acc[0] += 0.5 * Ud[l];                          // every pair is visited from both of its ends
-				acc[1] += 0.5 * (Vd[l][0] + Vd[l][1] + Vd[l][2]);
-				a.F[t] = Fd[l][0]; a.F[cp + t] = Fd[l][1]; a.F[2 * cp + t] = Fd[l][2];
-				a.Vi[t] = 0.5 * Vd[l][0]; a.Vi[cp + t] = 0.5 * Vd[l][1]; a.Vi[2 * cp + t] = 0.5 * Vd[l][2];
-				if (a.M) { a.M[t] = 0.; a.M[cp + t] = 0.; a.M[2 * cp + t] = 0.; }
-			}
+		if (have) {
+			const size_t cp = a.cap;
+			const uint32_t t = t0;
+			acc[0] += 0.5 * Ud;                          // every pair is visited from both of its ends
+			acc[1] += 0.5 * (Vd[0] + Vd[1] + Vd[2]);
+			a.F[t] = Fd[0]; a.F[cp + t] = Fd[1]; a.F[2 * cp + t] = Fd[2];
+			a.Vi[t] = 0.5 * Vd[0]; a.Vi[cp + t] = 0.5 * Vd[1]; a.Vi[2 * cp + t] = 0.5 * Vd[2];
+			if (a.M) { a.M[t] = 0.; a.M[cp + t] = 0.; a.M[2 * cp + t] = 0.; }
 		}
 		block_reduce_store<2>(acc, a.partials, ch);
 		__syncthreads();      // windows, lists and cs are reused by the next chunk
@@ -464,7 +478,8 @@ static int launch_tiled(ls1b200_ctx* c) {
 	const double rclj = c->cfg.cutoff_lj;
 	a.ljrc2 = (C) (rclj * rclj);
 	a.eps24_0 = (C) c->h_eps24[0]; a.sig2_0 = (C) c->h_sig2[0]; a.shift6_0 = (C) c->h_shift6[0];
-	const size_t smem = (size_t) (9 * W + 1) * sizeof(V4) + (size_t) (LCAP + 1) * RI * TPB * 2 + 9 * (CH_MAXC + 3) * 4;
+	// the cell_start cache is padded by three rows: the compiler hoists the (guarded) loads of the next row's entries
+	const size_t smem = (size_t) (9 * W + 1) * sizeof(V4) + (size_t) (LCAP + 1) * RI * TPB * 2 + 12 * (CH_MAXC + 3) * 4;
 	auto kern = c->comps.size() == 1 ? k_force_1clj_tiled<C, true> : k_force_1clj_tiled<C, false>;
 	LS1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int per_sm = 0;
