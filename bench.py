@@ -83,11 +83,14 @@ class ClockSampler:
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
 
 
-def make_system(n_per_dim, mixed=True, seed=0):
+def make_system(n_per_dim, mixed=True, seed=0, wl=None):
     """BCC lattice like the reference's CubicGridGenerator (generators.lattice), positions rounded through the calc type
     as ParticleCellBase::initCubicGrid does (ParticleCellBase.cpp:97-99)."""
     from ls1_mardyn_b200 import generators
-    ps = generators.lj_lattice(n_per_dim, rho=RHO, temperature=TEMP, rc=RC, seed=seed, jitter=0.0)
+    if wl is not None:
+        ps = generators.lattice(wl.ensemble, n_per_dim, wl.rho, wl.temperature, seed=seed, jitter=0.0, rc=wl.rc)
+    else:
+        ps = generators.lj_lattice(n_per_dim, rho=RHO, temperature=TEMP, rc=RC, seed=seed, jitter=0.0)
     if mixed:
         ps.r = ps.r.astype(np.float32).astype(np.float64)
     return ps
@@ -228,19 +231,20 @@ def our_arm(args):
     # weak scaling: the box grows with the number of GPUs; every rank owns one block of the 3D decomposition
     # with the same 2 n^3 molecules, generates only its own part of the lattice, and exchanges leaving molecules and halo
     # copies with its neighbours over NCCL inside the library every step
-    n = args.n_per_dim
-    from ls1_mardyn_b200 import generators
-    from ls1_mardyn_b200.components import lj_fluid
+    from ls1_mardyn_b200 import generators, workloads
     from ls1_mardyn_b200.decomposition import DomainDecomposition
+    wl = workloads.get(args.workload)
+    RHO, TEMP, RC, DT = wl.rho, wl.temperature, wl.rc, wl.dt
+    n = args.n_per_dim or wl.n_per_dim
     if world == 1:
-        ps = make_system(n, mixed=True, seed=rank)
+        ps = make_system(n, mixed=True, seed=rank, wl=wl)
         dd = None
         ctx = capi.Context([0, 0, 0], list(ps.length), RC, precision="mixed", geometry="xml", periodic=(1, 1, 1), device=local)
         ctx.set_components(ps.ensemble)
     else:
         grid = grid_for(world)
         dd0 = DomainDecomposition(rank, world, [1.0, 1.0, 1.0], grid)
-        ps = generators.lattice_block(lj_fluid(rc=RC), n, RHO, TEMP, dd0.coords, grid, seed=0)
+        ps = generators.lattice_block(wl.ensemble, n, RHO, TEMP, dd0.coords, grid, seed=0)
         ps.r = ps.r.astype(np.float32).astype(np.float64)
         dd = DomainDecomposition(rank, world, ps.length, grid)
         ctx = capi.Context(list(dd.box_min()), list(dd.box_max()), RC, precision="mixed", geometry="xml", periodic=dd.periodic(), device=local)
@@ -251,7 +255,8 @@ def our_arm(args):
     N = len(ps.id)
     N_global = world * N
     V_global = float(np.prod(ps.length))
-    ctx.upload(ps.id, ps.cid, ps.r, ps.v)
+    rot = any(c.Ipa()[1] for c in wl.ensemble.components)
+    ctx.upload(ps.id, ps.cid, ps.r, ps.v, ps.q if rot else None, ps.L if rot else None)
     if dd is not None:
         ctx.exchange()
     ctx.update(); ctx.traverse_cells()
@@ -329,7 +334,7 @@ def our_arm(args):
             "metric": "MMUPS", "value": round(value, 2), "unit": "MMUPS (1e6 molecule updates / s)", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1e3 * t_wall / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 pair arithmetic, f64 accumulation and state (MARDYN_SPDP)", "data": "synthetic (BCC lattice like CubicGridGenerator, equal-magnitude velocities)",
-            "config": {"workload": "BASELINE.json configs[1]: 1CLJ LJ liquid rho*=0.7 T*=0.85 rc=2.5 sigma dt=0.002, mixed precision, NVT velocity scaling",
+            "config": {"workload": wl.description,
                        "molecules_per_gpu": N, "molecules": world * N, "cells_per_dim": [int(x) for x in ctx.geometry()[0]],
                        "parallelism": "1 GPU" if world == 1 else "3D block decomposition %dx%dx%d, one process per GPU, leaving molecules + halo copies over NCCL send/recv every step, allreduce of 6 doubles" % grid_for(world),
                        "box": [float(x) for x in ps.length],
@@ -339,7 +344,7 @@ def our_arm(args):
             "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 2), "unit": "MMUPS", "h2d_bytes_per_step": int(h2d / e2e_steps), "d2h_bytes_per_step": int(d2h / e2e_steps), "steps": e2e_steps,
                     "path": "set_field(R,V) from pinned host -> leapfrog_pre -> update -> traverse_cells -> leapfrog_post -> download(R,V) + scalars"},
-            "roofline": {"kernel": "k_force_1clj<float>", "bound": "fp32", "achieved": round(achieved, 3), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
+            "roofline": {"kernel": "k_force_1clj_tiled<float>" if wl.name == "lj" else "k_force_general<float>", "bound": "fp32", "achieved": round(achieved, 3), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
                          "frac": round(achieved / fp32_peak, 4), "traffic": None,
                          "peak_source": "FP32 FMA micro-benchmark in this run (ls1b200_measure_fp32_peak); nominal 74.4",
                          "algorithmic_flops_per_launch": flops, "flops_per_molecule": round(flops / N, 1), "kernel_ms": round(force_ms, 4),
@@ -348,7 +353,7 @@ def our_arm(args):
             "clocks": clocks,
             "trace": {"T_first": rec[0, 4], "T_last": rec[-1, 4], "upot_last_per_molecule": rec[-1, 0] / N_global, "p_last": rec[-1, 5]},
         }
-        if world == 1 and not args.no_cpu_baseline:
+        if world == 1 and not args.no_cpu_baseline and wl.name == "lj":
             line["cpu_baseline"] = cpu_baseline()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
@@ -361,7 +366,8 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--n-per-dim", type=int, default=200, help="BCC lattice cells per dimension: N = 2 n^3 (200 -> 16 M molecules)")
+    ap.add_argument("--workload", default="lj", choices=["lj", "water", "co2"], help="lj = BASELINE.json configs[1] (the headline); water / co2 = configs[2] / [3]")
+    ap.add_argument("--n-per-dim", type=int, default=0, help="BCC lattice cells per dimension: N = 2 n^3 (default: the workload's single-GPU size, lj 200 -> 16 M molecules)")
     ap.add_argument("--ref-n-per-dim", type=int, default=80, help="size of the reference arm's bounded sample (80 -> 1.02 M molecules)")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -95,7 +95,7 @@ int ctx_alloc_molecules(ls1b200_ctx* c, uint64_t n_owned, uint64_t cap) {
 		LS1_TRY(dev_alloc(&c->sf, cap * c->smax * 9));
 	}
 	c->partial_blocks = (uint32_t) (((cap + 63) / 64) * std::max(c->smax, 1u) + 64);
-	if (c->all_1clj) c->partial_blocks = std::max<uint32_t>(c->partial_blocks, c->geom.ncells + 64);   // one partial per chunk
+	c->partial_blocks = std::max<uint32_t>(c->partial_blocks, c->geom.ncells + 64);   // tiled kernels: one partial per chunk
 	LS1_TRY(dev_alloc(&c->partials, (size_t) c->partial_blocks * 8));
 	if (c->dd.active) LS1_TRY(decomp_alloc(c));
 	LS1_CUDA(cudaMemsetAsync(c->F, 0, sizeof(double) * 3 * cap, c->stream));
@@ -234,6 +234,8 @@ int ls1b200_create(const ls1b200_config* cfg, ls1b200_ctx** out) {
 		cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
 		const char* k = getenv("LS1B200_LJ_KERNEL");
 		c->lj_kernel = (k && std::string(k) == "global") ? 1 : 0;
+		const char* m = getenv("LS1B200_MULTI_KERNEL");
+		c->multi_kernel = (m && std::string(m) == "general") ? 1 : (m && std::string(m) == "generic") ? 2 : 0;   // 2: tiled, but never specialised
 	}
 	if (dev_alloc(&c->d_scal, 1) || dev_alloc(&c->partials2, 1024 * 8)) return cleanup(1);
 	if (cudaMallocHost((void**) &c->h_scal, sizeof(DevScalars)) != cudaSuccess) return cleanup(fail("ls1b200_create: cudaMallocHost failed"));

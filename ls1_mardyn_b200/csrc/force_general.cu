@@ -248,6 +248,14 @@ static int launch_general(ls1b200_ctx* c) {
 	return reduce_force_partials(c, gx * c->smax);
 }
 
+// FullMolecule::calcFM for all slots from the per-site records (also used by force_multi_tiled.cu)
+int launch_calcfm(ls1b200_ctx* c) {
+	const uint32_t gx = (uint32_t) ((c->cap + 127) / 128);
+	LS1_LAUNCH(c, PH_FORCE, k_calcfm, gx, 128, 0, c->cur, (uint32_t) c->cap, c->smax, c->d_comps, c->d_sites, c->sf, (const uint32_t*) nullptr, (int) c->mixed,
+	           c->F, c->M, c->Vi, (const void*) c->mpos, c->d_scal, c->parity, (int) c->rotates);
+	return 0;
+}
+
 int force_general(ls1b200_ctx* c) { return c->mixed ? launch_general<float>(c) : launch_general<double>(c); }
 
 }  // namespace ls1b200

@@ -13,10 +13,15 @@
 namespace ls1b200 {
 
 template <class C> __device__ __forceinline__ C c_rcp(C x);
-template <> __device__ __forceinline__ float c_rcp<float>(float x) { return __frcp_rn(x); }
+// MUFU.RCP (1 ulp): the AVX2 reference itself uses rcp_ps + one Newton step (RealVecFloat.h:432-457), not a correctly rounded quotient
+template <> __device__ __forceinline__ float c_rcp<float>(float x) { float r; asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x)); return r; }
 template <> __device__ __forceinline__ double c_rcp<double>(double x) { return 1.0 / x; }
 template <class C> __device__ __forceinline__ C c_rsqrt(C x);
-template <> __device__ __forceinline__ float c_rsqrt<float>(float x) { return rsqrtf(x); }
+// MUFU.RSQ + one Newton step, like the reference's rsqrt_ps + NR (RealVecFloat.h:459-480)
+template <> __device__ __forceinline__ float c_rsqrt<float>(float x) {
+	float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(x));
+	return r * fmaf(-0.5f * x * r, r, 1.5f);
+}
 template <> __device__ __forceinline__ double c_rsqrt<double>(double x) { return 1.0 / sqrt(x); }
 template <class C> __device__ __forceinline__ C c_fma(C a, C b, C c);
 template <> __device__ __forceinline__ float c_fma<float>(float a, float b, float c) { return __fmaf_rn(a, b, c); }

@@ -76,7 +76,14 @@ def lattice_block(ens: Ensemble, n_per_dim: int, rho: float, temperature: float,
     v = d * np.sqrt(3.0 * temperature / mass)[:, None]
     v -= (mass[:, None] * v).sum(axis=0) / mass.sum()
     q = np.zeros((N, 4)); q[:, 0] = 1.0
+    Lang = np.zeros((N, 3))
+    inert = np.array([c.Ipa()[0] for c in ens.components])[cid]
+    rotating = inert.any(axis=1)
+    if rotating.any():
+        qq = rng.normal(size=(N, 4)); qq /= np.linalg.norm(qq, axis=1, keepdims=True)
+        q[rotating] = qq[rotating]
+        Lang = rng.normal(size=(N, 3)) * np.sqrt(temperature * inert)
     first = ((coords[0] * grid[1] + coords[1]) * grid[2] + coords[2]) * N
     ids = np.arange(first + 1, first + N + 1, dtype=np.uint64)
     perm = rng.permutation(N)
-    return PhaseSpace(L, float(temperature), 1e10, ens, ids, cid[perm], r[perm], v[perm], q[perm], np.zeros((N, 3)))
+    return PhaseSpace(L, float(temperature), 1e10, ens, ids, cid[perm], r[perm], v[perm], q[perm], Lang[perm])
