@@ -219,3 +219,48 @@ def test_edge_cases(capi):
 
 def test_kernels_were_launched(capi):
     assert capi.kernel_launch_count() > 0
+
+
+def _sig_ensembles():
+    """One single-component ensemble per compile-time site signature of force_multi_tiled.cu (plus one that has none)."""
+    from ls1_mardyn_b200 import workloads
+    from ls1_mardyn_b200.components import Charge, Component, Dipole, Ensemble, LJcenter, Quadrupole
+    lj = lambda z, m=1.0: LJcenter((0.0, 0.0, z), m, 1.0, 1.0, 0.0, False)
+    return {
+        "water_1lj3q": (workloads.water_like(), 4.935e-3, 9.437e-4, 14.9),
+        "co2_2cljq": (workloads.co2_2cljq(), 0.0137, 293.44, 14.9235 / 2),
+        "2cljd": (Ensemble([Component(ljcenters=[lj(-0.3), lj(0.3)], dipoles=[Dipole((0, 0, 0), (0, 0, 1), 1.2)])]), 0.5, 1.2, 2.5),
+        "stockmayer": (Ensemble([Component(ljcenters=[lj(0.0)], dipoles=[Dipole((0, 0, 0), (0, 0, 1), 1.5)], I_override=(0.1, 0.1, 0.1))]), 0.6, 1.2, 2.5),
+        "2clj": (Ensemble([Component(ljcenters=[lj(-0.25), lj(0.25)])]), 0.5, 1.2, 2.5),
+        "3lj3q": (Ensemble([Component(ljcenters=[lj(-0.4), lj(0.0, 2.0), lj(0.4)],
+                                       charges=[Charge((0, 0, -0.4), 0.0, -0.3), Charge((0, 0, 0.0), 0.0, 0.6), Charge((0, 0, 0.4), 0.0, -0.3)])]), 0.4, 1.5, 2.5),
+        "generic_1lj1q1d1quad": (Ensemble([Component(ljcenters=[lj(0.0)], charges=[Charge((0.2, 0, 0), 0.5, 0.4), Charge((-0.2, 0, 0), 0.5, -0.4)],
+                                                     dipoles=[Dipole((0, 0.1, 0), (0, 1, 0), 0.8)], quadrupoles=[Quadrupole((0, 0, 0.1), (0, 0, 1), 0.9)])]), 0.4, 1.5, 2.5),
+    }
+
+
+@pytest.mark.parametrize("name", ["water_1lj3q", "co2_2cljq", "2cljd", "stockmayer", "2clj", "3lj3q", "generic_1lj1q1d1quad"])
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_site_signature_kernels_vs_oracle(capi, name, prec):
+    """Every specialisation of the tiled multi-site kernel (and the generic one) against the CPU oracle: randomly oriented
+    molecules on a jittered periodic lattice; F, M, Vi per molecule, Upot, virial."""
+    import os
+    from oracle import oracle as orc
+    from ls1_mardyn_b200 import generators
+    ens, rho, T, rc = _sig_ensembles()[name]
+    ps = generators.lattice(ens, 6, rho, T, seed=17, jitter=0.12, rc=rc)      # 432 molecules
+    b = _mk(orc.OracleSim, ps, rc, prec); b.update(); mb = b.traverse_cells()
+    tol = TOL[prec]
+    for kernel in ("", "generic"):
+        os.environ["LS1B200_MULTI_KERNEL"] = kernel
+        try:
+            a = _mk(capi.Context, ps, rc, prec)
+        finally:
+            os.environ.pop("LS1B200_MULTI_KERNEL", None)
+        a.update(); ma = a.traverse_cells()
+        assert np.array_equal(a.download("CELL"), b.download("CELL"))
+        for f in ("F", "M", "VI"):
+            ok, worst = rel_close(a.download(f), b.download(f), tol)
+            assert ok, (name, prec, kernel or "specialised", f, worst)
+        terms = np.abs(b.download("VI")).sum()
+        assert abs(ma.upot - mb.upot) <= tol * max(abs(mb.upot), terms) and abs(ma.virial - mb.virial) <= tol * max(abs(mb.virial), terms)
