@@ -25,8 +25,11 @@
 namespace ls1b200 {
 
 template <class C> struct MultiCfg;
-template <> struct MultiCfg<float> { static constexpr int TPB = 96, W = 208, LCAP = 64; };
-template <> struct MultiCfg<double> { static constexpr int TPB = 64, W = 144, LCAP = 64; };
+// TPB threads (= molecules) per CTA pass, LCAP list entries per molecule; the window row length W = 2^LOGW records is chosen
+// per launch from the mean cell population (128 for liquids at rc = 2.5 sigma, 256 for 5 sigma), so that the tile leaves room
+// for more resident CTAs when cells are sparsely populated
+template <> struct MultiCfg<float> { static constexpr int TPB = 96, LCAP = 64; };
+template <> struct MultiCfg<double> { static constexpr int TPB = 64, LCAP = 64; };
 
 template <class C>
 struct MArgs {
@@ -179,10 +182,10 @@ template <int NLJ_, int NCH_, int NDI_, int NQU_> struct Sig {
 };
 struct SigGeneric { static constexpr int NLJ = 0, NCH = 0, NDI = 0, NQU = 0, NS = 1; static constexpr bool GENERIC = true; };
 
-template <class C, class SIG>
+template <class C, class SIG, int LOGW>
 __global__ void __launch_bounds__(MultiCfg<C>::TPB) k_force_multi_tiled(MArgs<C> a) {
 	typedef typename Vec4<C>::type V4;
-	constexpr int TPB = MultiCfg<C>::TPB, W = MultiCfg<C>::W, LCAP = MultiCfg<C>::LCAP;
+	constexpr int TPB = MultiCfg<C>::TPB, W = 1 << LOGW, LCAP = MultiCfg<C>::LCAP;
 	constexpr uint32_t VB = sizeof(V4), LSTRIDE = (uint32_t) TPB * 2u;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	V4* win = reinterpret_cast<V4*>(smem_raw);                                         // [9][W]
@@ -346,15 +349,24 @@ __global__ void __launch_bounds__(MultiCfg<C>::TPB) k_force_multi_tiled(MArgs<C>
 					C e24[NLJ * NLJ + 1], sg2[NLJ * NLJ + 1], sh6[NLJ * NLJ + 1];
 					#pragma unroll
 					for (int k = 0; k < NLJ * NLJ; k++) { e24[k] = a.eps24[k]; sg2[k] = a.sig2[k]; sh6[k] = a.shift6[k]; }
+					// software pipelined: the site records of the NEXT neighbour are requested (L1 / L2) before the current one is evaluated
+					V4 mj_n = mi; SiteC<C> oj_n[NS];
+					auto fetch = [&](uint32_t e) {
+						const uint32_t addr = lds16(e);
+						mj_n = lds_v4<C>(addr);
+						const uint32_t idx = (addr - win_s) / VB, rr = idx >> LOGW;
+						const size_t sj = ((size_t) s_rowbase[rr] + (idx & (uint32_t) (W - 1))) * a.smax;
+						#pragma unroll
+						for (int k = 0; k < NS; k++) oj_n[k] = m_load_site<C>(a, sj + k, k >= D0);
+					};
+					if (list_s < w) fetch(list_s);
 					#pragma unroll 1
 					for (uint32_t e = list_s; e < w; e += LSTRIDE) {
-						const uint32_t addr = lds16(e);
-						const V4 mj = lds_v4<C>(addr);
-						const uint32_t idx = (addr - win_s) / VB, rr = idx / (uint32_t) W;
-						const size_t sj = ((size_t) s_rowbase[rr] + (idx - rr * (uint32_t) W)) * a.smax;
+						const V4 mj = mj_n;
 						SiteC<C> oj[NS];
 						#pragma unroll
-						for (int k = 0; k < NS; k++) oj[k] = m_load_site<C>(a, sj + k, k >= D0);
+						for (int k = 0; k < NS; k++) oj[k] = oj_n[k];
+						if (e + LSTRIDE < w) fetch(e + LSTRIDE);
 						const C dmx = mi.x - mj.x, dmy = mi.y - mj.y, dmz = mi.z - mj.z;
 						bool ljin = true;
 						if (a.lj_shorter) ljin = molpair_r2<C>(mi.x, mi.y, mi.z, mj.x, mj.y, mj.z) < a.ljrc2;
@@ -454,10 +466,10 @@ __global__ void __launch_bounds__(MRED_BLOCKS) k_reduce_multi2(const double* __r
 
 int launch_calcfm(ls1b200_ctx* c);      // force_general.cu
 
-template <class C, class SIG>
+template <class C, class SIG, int LOGW>
 static int launch_multi(ls1b200_ctx* c) {
 	typedef typename Vec4<C>::type V4;
-	constexpr int TPB = MultiCfg<C>::TPB, W = MultiCfg<C>::W, LCAP = MultiCfg<C>::LCAP;
+	constexpr int TPB = MultiCfg<C>::TPB, W = 1 << LOGW, LCAP = MultiCfg<C>::LCAP;
 	const Geom& g = c->geom;
 	uint32_t nrows = 0;
 	LS1_TRY(build_chunks(c, TPB, W, 1, &nrows));
@@ -475,7 +487,7 @@ static int launch_multi(ls1b200_ctx* c) {
 	a.eps_rf_invrc3 = (C) (2. * (erf - 1.) / ((rc * rc * rc) * (2. * erf + 1.)));   // VectorizedCellProcessor.cpp:22
 	if ((uint64_t) c->geom.ncells + 64 > c->partial_blocks) return fail("force_multi_tiled: partials buffer too small");
 	const size_t smem = (size_t) (9 * W) * sizeof(V4) + (size_t) (LCAP + 1) * TPB * 2 + 12 * (CH_MAXC + 3) * 4;
-	auto kern = k_force_multi_tiled<C, SIG>;
+	auto kern = k_force_multi_tiled<C, SIG, LOGW>;
 	LS1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int per_sm = 0;
 	LS1_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, smem));
@@ -487,7 +499,14 @@ static int launch_multi(ls1b200_ctx* c) {
 	return 0;
 }
 
-template <class SIG> static int launch_sig(ls1b200_ctx* c) { return c->mixed ? launch_multi<float, SIG>(c) : launch_multi<double, SIG>(c); }
+template <class SIG> static int launch_sig(ls1b200_ctx* c) {
+	// mean population of a cell (halo layer included in both counts): short windows while a chunk's 9 candidate rows fit
+	const double nbar = (double) c->n_slots / (double) c->geom.ncells;
+	// W = 128 suffices while a chunk of about two thirds of the CTA's threads plus its two flanking cells fits (with 15 % head room)
+	const bool narrow = 0.67 * 1.15 * (c->mixed ? 96. : 64.) + 2.3 * nbar <= 128.;
+	if (c->mixed) return narrow ? launch_multi<float, SIG, 7>(c) : launch_multi<float, SIG, 8>(c);
+	return narrow ? launch_multi<double, SIG, 7>(c) : launch_multi<double, SIG, 8>(c);
+}
 
 int force_multi_tiled(ls1b200_ctx* c) {
 	// single-component ensembles with a known site signature take the register-resident specialisation
