@@ -348,7 +348,8 @@ int ls1b200_upload(ls1b200_ctx* c, uint64_t n, const uint64_t* id, const uint32_
 	double fac = 1.;
 	for (int d = 0; d < 3; d++) if (c->geom.periodic[d] || c->cfg.reserved[0] || c->dd.active) fac *= 1. + 2. * std::min(1., c->geom.cutoff / c->geom.lbox[d]);
 	// decomposed mode: + 10 % for molecules migrating in
-	const uint64_t cap = n + (uint64_t) ((fac - 1.) * 1.5 * (double) n) + (c->dd.active ? n / 10 + 16384 : 0) + 4096;
+	uint64_t cap = n + (uint64_t) ((fac - 1.) * 1.5 * (double) n) + (c->dd.active ? n / 10 + 16384 : 0) + 4096;
+	cap = (cap + 63) & ~63ull;      // even (the 16-byte streaming kernels handle two slots per thread); planes stay 512-byte aligned
 	LS1_TRY(ctx_alloc_molecules(c, n, cap));
 	c->rot_dof_total = 0;
 	for (uint64_t i = 0; i < n; i++) c->rot_dof_total += c->comps[cid[i]].rot_dof;

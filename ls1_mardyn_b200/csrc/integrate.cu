@@ -69,6 +69,60 @@ __global__ void __launch_bounds__(256) k_leapfrog_pre(State st, const double* __
 	}
 }
 
+// The same two kernels for ensembles without rotation, two slots per thread with 16-byte loads / stores (the slot planes are
+// 16-byte aligned and the capacity is even): more bytes in flight per thread, the streaming kernels get closer to the HBM roofline.
+__global__ void __launch_bounds__(256) k_leapfrog_pre_v2(State st, const double* __restrict__ F, uint32_t cap, const CompDev* __restrict__ comps, double dt,
+                                                          const DevScalars* __restrict__ scal, uint32_t parity, int use_beta) {
+	const uint32_t t = 2u * (blockIdx.x * blockDim.x + threadIdx.x);
+	const uint32_t n = min(scal->n_slots2[parity], cap);
+	if (t >= n) return;
+	const ulonglong2 m2 = *reinterpret_cast<const ulonglong2*>(st.meta + t);
+	const bool on0 = !meta_halo(m2.x), on1 = (t + 1 < n) && !meta_halo(m2.y);
+	if (!on0 && !on1) return;
+	const double bt = use_beta ? scal->beta_trans : 1.;
+	const double dth = .5 * dt;
+	const double a0 = on0 ? dth / comps[meta_cid(m2.x)].mass : 0., a1 = on1 ? dth / comps[meta_cid(m2.y)].mass : 0.;
+	const size_t c = cap;
+	#pragma unroll
+	for (int d = 0; d < 3; d++) {
+		double2 v = *reinterpret_cast<const double2*>(st.v + d * c + t);
+		const double2 f = *reinterpret_cast<const double2*>(F + d * c + t);
+		double2 r = *reinterpret_cast<const double2*>(st.r + d * c + t);
+		if (on0) { if (use_beta) v.x *= bt; v.x += a0 * f.x; r.x += dt * v.x; }
+		if (on1) { if (use_beta) v.y *= bt; v.y += a1 * f.y; r.y += dt * v.y; }
+		*reinterpret_cast<double2*>(st.v + d * c + t) = v;
+		*reinterpret_cast<double2*>(st.r + d * c + t) = r;
+	}
+}
+__global__ void __launch_bounds__(256) k_leapfrog_post_v2(State st, const double* __restrict__ F, uint32_t cap, const CompDev* __restrict__ comps, double dt,
+                                                           const DevScalars* __restrict__ scal, uint32_t parity, double* __restrict__ partials) {
+	const uint32_t t = 2u * (blockIdx.x * blockDim.x + threadIdx.x);
+	const uint32_t n = min(scal->n_slots2[parity], cap);
+	double acc[2] = {0., 0.};
+	if (t < n) {
+		const ulonglong2 m2 = *reinterpret_cast<const ulonglong2*>(st.meta + t);
+		const bool on0 = !meta_halo(m2.x), on1 = (t + 1 < n) && !meta_halo(m2.y);
+		if (on0 || on1) {
+			const double dth = .5 * dt;
+			const double mass0 = on0 ? comps[meta_cid(m2.x)].mass : 1., mass1 = on1 ? comps[meta_cid(m2.y)].mass : 1.;
+			const double a0 = dth / mass0, a1 = dth / mass1;
+			const size_t c = cap;
+			double v20 = 0., v21 = 0.;
+			#pragma unroll
+			for (int d = 0; d < 3; d++) {
+				double2 v = *reinterpret_cast<const double2*>(st.v + d * c + t);
+				const double2 f = *reinterpret_cast<const double2*>(F + d * c + t);
+				if (on0) { v.x += a0 * f.x; v20 += v.x * v.x; }
+				if (on1) { v.y += a1 * f.y; v21 += v.y * v.y; }
+				*reinterpret_cast<double2*>(st.v + d * c + t) = v;
+			}
+			// same summation order as one molecule per thread followed by the pairwise tree: (m0 v0^2) + (m1 v1^2)
+			acc[0] = (on0 ? mass0 * v20 : 0.) + (on1 ? mass1 * v21 : 0.);
+		}
+	}
+	block_reduce_store<2>(acc, partials, blockIdx.x);
+}
+
 // upd_postF + the sums of Leapfrog::transition2to3 (Leapfrog.cpp:113-143)
 __global__ void __launch_bounds__(256) k_leapfrog_post(State st, const double* __restrict__ F, const double* __restrict__ M, uint32_t cap,
                                                         const CompDev* __restrict__ comps, double dt, const DevScalars* __restrict__ scal,
@@ -156,6 +210,9 @@ int do_leapfrog_pre(ls1b200_ctx* c, double dt, bool use_beta) {
 	if (c->n_owned == 0 && !c->dd.active) return 0;
 	LS1_TRY(span_begin(c, PH_PRE));
 	const uint32_t g = (uint32_t) ((c->cap + 255) / 256);
+	if (!c->rotates && c->cap % 2 == 0)
+		LS1_LAUNCH(c, PH_PRE, k_leapfrog_pre_v2, (g + 1) / 2, 256, 0, c->cur, c->F, (uint32_t) c->cap, c->d_comps, dt, c->d_scal, c->parity, (int) use_beta);
+	else
 	LS1_LAUNCH(c, PH_PRE, k_leapfrog_pre, g, 256, 0, c->cur, c->F, c->M, (uint32_t) c->cap, c->d_comps, dt, c->d_scal, c->parity, (int) use_beta, (int) c->rotates);
 	LS1_TRY(span_end(c));
 	c->forces_valid = false;
@@ -167,8 +224,13 @@ int do_leapfrog_post(ls1b200_ctx* c, double dt) {
 	LS1_TRY(span_begin(c, PH_POST));
 	const uint32_t g = (uint32_t) ((c->cap + 255) / 256);
 	if (g > c->partial_blocks) return fail("leapfrog_post: partials buffer too small");
-	LS1_LAUNCH(c, PH_POST, k_leapfrog_post, g, 256, 0, c->cur, c->F, c->M, (uint32_t) c->cap, c->d_comps, dt, c->d_scal, c->parity, (int) c->rotates, c->partials);
-	LS1_LAUNCH(c, PH_POST, k_reduce_kinetic, 1, 1024, 0, c->partials, g, c->d_scal);
+	if (!c->rotates && c->cap % 2 == 0) {
+		LS1_LAUNCH(c, PH_POST, k_leapfrog_post_v2, (g + 1) / 2, 256, 0, c->cur, c->F, (uint32_t) c->cap, c->d_comps, dt, c->d_scal, c->parity, c->partials);
+		LS1_LAUNCH(c, PH_POST, k_reduce_kinetic, 1, 1024, 0, c->partials, (g + 1) / 2, c->d_scal);
+	} else {
+		LS1_LAUNCH(c, PH_POST, k_leapfrog_post, g, 256, 0, c->cur, c->F, c->M, (uint32_t) c->cap, c->d_comps, dt, c->d_scal, c->parity, (int) c->rotates, c->partials);
+		LS1_LAUNCH(c, PH_POST, k_reduce_kinetic, 1, 1024, 0, c->partials, g, c->d_scal);
+	}
 	LS1_TRY(span_end(c));
 	return 0;
 }
