@@ -24,8 +24,9 @@
 namespace ls1b200 {
 
 #ifndef LS1_TILE_RI_F
-// measured on B200, 16 M molecules (profiles/r01_tile_sweep.md): RI/TPB/W/LCAP = 1/128/176/64 -> 5.61 ms per traversal,
-// 2/64/176/64 -> 6.51, 1/64/112/64 -> 6.16, 2/32/112/64 -> 6.99, 2/64/176/80 -> 7.25
+// measured on B200, 16 M molecules (profiles/r01_tile_sweep.md): RI/TPB/W/LCAP = 1/128/176/64 -> 4.98 ms per traversal,
+// 2/64/176/64 -> 6.07 (register blocking over molecules halves the instructions per test but not the shared-memory
+// wavefronts -- a wavefront is spent per distinct cell range in the warp -- and leaves 10 warps per SM)
 #define LS1_TILE_RI_F 1
 #define LS1_TILE_TPB_F 128
 #define LS1_TILE_W_F 176
@@ -83,7 +84,6 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 	V4* win = reinterpret_cast<V4*>(smem_raw);                                         // [9][W] (+1 sentinel record at [9*W])
 	uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw + (size_t) (9 * W + 1) * VB);   // [LCAP+1][RI][TPB]
 	uint32_t* cs = reinterpret_cast<uint32_t*>(list + (size_t) (LCAP + 1) * RI * TPB);   // [9][CH_MAXC+3]
-	__shared__ uint32_t s_tb[CH_MAXC + 1];
 	__shared__ uint32_t s_rowbase[9];
 	__shared__ __align__(8) unsigned long long s_bar;
 	__shared__ uint32_t s_chunk;
@@ -166,116 +166,142 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 					if (len) tma_bulk_g2s(win_s + (uint32_t) (r * W) * VB, a.mpos + b, len * VB, bar);
 				}
 			}
-			// thread -> (cell, molecule pair): prefix of ceil(n_c / 2) over the cells of the chunk
-			uint32_t tb = 0;
-			for (int c = 0; c < nc; c++) { s_tb[c] = tb; tb += (cs[4 * (CH_MAXC + 3) + c + 2] - cs[4 * (CH_MAXC + 3) + c + 1] + (uint32_t) RI - 1u) / (uint32_t) RI; }
-			s_tb[nc] = tb;
 		}
 		__syncthreads();
-		const uint32_t* csc = cs + 4 * (CH_MAXC + 3);          // centre row
-		int kx = 0;
-		while (kx + 1 < nc && s_tb[kx + 1] <= threadIdx.x) kx++;
-		const bool have0 = threadIdx.x < s_tb[nc];
-		const uint32_t t0rel = csc[kx + 1] + (threadIdx.x - s_tb[kx]);      // my molecule: record index inside the centre window ...
-		const uint32_t t0 = s_rowbase[4] + t0rel;                           // ... and its slot
+		const uint32_t* csc = cs + 4 * (CH_MAXC + 3);          // centre row (relative record indices)
+		// thread -> RI consecutive molecules of the chunk (slot order); they may lie in two neighbouring cells
+		const uint32_t n_mol = csc[nc + 1] - csc[1];
+		uint32_t trel[RI]; bool have[RI];
+		#pragma unroll
+		for (int l = 0; l < RI; l++) { have[l] = (uint32_t) RI * threadIdx.x + l < n_mol; trel[l] = csc[1] + (uint32_t) RI * threadIdx.x + l; }
+		int kxa = 0;                                            // cell (inside the chunk) of my first molecule ...
+		while (kxa + 1 < nc && csc[kxa + 2] <= trel[0]) kxa++;
+		int kxb = kxa;                                          // ... and of my last one
+		if (RI > 1 && have[RI - 1]) { while (kxb + 1 < nc && csc[kxb + 2] <= trel[RI - 1]) kxb++; }
 		mbar_wait(bar, parity); parity ^= 1u;
-		// ---- 2. phase 1 + 3. phase 2, one molecule per thread -------------------------------------------------------------
-		// Phase 1 walks my 9 candidate rows (cells cx-1 .. cx+1 of each, one contiguous range of the row's window); every
-		// candidate is one LDS.128 and the reference's molecule-distance test (strict <, bit-identical to calcDistLookup; in my
-		// own row SingleCellPolicy_ additionally masks pairs at distance 0, i.e. the molecule itself). A hit appends the
-		// candidate's shared-memory ADDRESS (it fits 16 bits) to my list. When the list is nearly full, or after the last row,
-		// phase 2 evaluates the list densely (LJ 12-6; FP32 partial sums folded into FP64 like RealAccumVec) and empties it.
-		// There is exactly one instance of each loop in the code: the state machine below keeps the instruction footprint small.
-		const bool have = have0;
-		V4 mi = make_c4<C>((C) 1e18, (C) 1e18, (C) 1e18, (C) 0);      // an absent molecule: no candidate is ever in range
-		if (have) mi = lds_v4<C>(win_s + (uint32_t) (4 * W + (int) t0rel) * VB);
-		const uint32_t cid_i = wbits<C>(mi.w) & 0xFFFFu;
-		double Fd[3] = {0., 0., 0.}, Vd[3] = {0., 0., 0.}, Ud = 0.;
+		// ---- 2. phase 1 + 3. phase 2 -----------------------------------------------------------------------------------------
+		// Phase 1 walks my 9 candidate rows (cells cx-1 .. cx+1 of each -- one more cell if my molecules straddle two cells --
+		// one contiguous range of the row's window); every candidate is ONE LDS.128 that serves the reference's molecule-distance
+		// test (strict <, bit-identical to calcDistLookup; in my own row SingleCellPolicy_ additionally masks pairs at distance 0,
+		// i.e. the molecule itself) of all RI molecules of the thread (register blocking: shared-memory wavefronts per test
+		// halve, the kernel is shared-memory bound -- profiles/r01p_force_full.md). A hit appends the candidate's shared-memory
+		// ADDRESS (it fits 16 bits) to the molecule's list. When a list is nearly full, or after the last row, phase 2 evaluates
+		// the lists densely (LJ 12-6; FP32 partial sums folded into FP64 like RealAccumVec) and empties them.
+		V4 mi[RI]; uint32_t cid_i[RI];
+		#pragma unroll
+		for (int l = 0; l < RI; l++) {
+			mi[l] = make_c4<C>((C) 1e18, (C) 1e18, (C) 1e18, (C) 0);      // an absent molecule: no candidate is ever in range
+			if (have[l]) mi[l] = lds_v4<C>(win_s + (uint32_t) (4 * W + (int) trel[l]) * VB);
+			cid_i[l] = wbits<C>(mi[l].w) & 0xFFFFu;
+		}
+		double Fd[RI][3], Vd[RI][3], Ud[RI];
+		#pragma unroll
+		for (int l = 0; l < RI; l++) { Fd[l][0] = Fd[l][1] = Fd[l][2] = Vd[l][0] = Vd[l][1] = Vd[l][2] = Ud[l] = 0.; }
 		const uint32_t sentinel = win_s + (uint32_t) (9 * W) * VB;
-		const uint32_t wlimit = list_s + (uint32_t) (LCAP - 4) * LSTRIDE;
-		uint32_t w = list_s;                    // list write cursor
+		uint32_t w[RI], wlimit[RI], lbase[RI];
+		#pragma unroll
+		for (int l = 0; l < RI; l++) { lbase[l] = list_s + (uint32_t) l * (TPB * 2); w[l] = lbase[l]; wlimit[l] = lbase[l] + (uint32_t) (LCAP - 4) * LSTRIDE; }
 		uint32_t src = 0, end = 0;              // shared-memory address of the next candidate / end of the row range
 		int r = -1;
+		auto room = [&]() -> bool { bool ok = true; _Pragma("unroll") for (int l = 0; l < RI; l++) ok = ok && (w[l] <= wlimit[l]); return ok; };
 		for (;;) {
 			bool flush = true;
 			if (r < 9) {
 				if (r == 4) {
-					while (src + 4 * VB <= end && w <= wlimit) {
+					while (src + 4 * VB <= end && room()) {
 						const V4 m0 = lds_v4<C>(src), m1 = lds_v4<C>(src + VB), m2 = lds_v4<C>(src + 2 * VB), m3 = lds_v4<C>(src + 3 * VB);
-						const C r0 = molpair_r2<C>(mi.x, mi.y, mi.z, m0.x, m0.y, m0.z), r1 = molpair_r2<C>(mi.x, mi.y, mi.z, m1.x, m1.y, m1.z);
-						const C r2 = molpair_r2<C>(mi.x, mi.y, mi.z, m2.x, m2.y, m2.z), r3 = molpair_r2<C>(mi.x, mi.y, mi.z, m3.x, m3.y, m3.z);
-						if (r0 < a.ljrc2 && r0 != C(0)) { sts16(w, src); w += LSTRIDE; }
-						if (r1 < a.ljrc2 && r1 != C(0)) { sts16(w, src + VB); w += LSTRIDE; }
-						if (r2 < a.ljrc2 && r2 != C(0)) { sts16(w, src + 2 * VB); w += LSTRIDE; }
-						if (r3 < a.ljrc2 && r3 != C(0)) { sts16(w, src + 3 * VB); w += LSTRIDE; }
+						#pragma unroll
+						for (int l = 0; l < RI; l++) {
+							const C r0 = molpair_r2<C>(mi[l].x, mi[l].y, mi[l].z, m0.x, m0.y, m0.z), r1 = molpair_r2<C>(mi[l].x, mi[l].y, mi[l].z, m1.x, m1.y, m1.z);
+							const C r2 = molpair_r2<C>(mi[l].x, mi[l].y, mi[l].z, m2.x, m2.y, m2.z), r3 = molpair_r2<C>(mi[l].x, mi[l].y, mi[l].z, m3.x, m3.y, m3.z);
+							if (r0 < a.ljrc2 && r0 != C(0)) { sts16(w[l], src); w[l] += LSTRIDE; }
+							if (r1 < a.ljrc2 && r1 != C(0)) { sts16(w[l], src + VB); w[l] += LSTRIDE; }
+							if (r2 < a.ljrc2 && r2 != C(0)) { sts16(w[l], src + 2 * VB); w[l] += LSTRIDE; }
+							if (r3 < a.ljrc2 && r3 != C(0)) { sts16(w[l], src + 3 * VB); w[l] += LSTRIDE; }
+						}
 						src += 4 * VB;
 					}
 				} else {
-					while (src + 4 * VB <= end && w <= wlimit) {
+					while (src + 4 * VB <= end && room()) {
 						const V4 m0 = lds_v4<C>(src), m1 = lds_v4<C>(src + VB), m2 = lds_v4<C>(src + 2 * VB), m3 = lds_v4<C>(src + 3 * VB);
-						const C r0 = molpair_r2<C>(mi.x, mi.y, mi.z, m0.x, m0.y, m0.z), r1 = molpair_r2<C>(mi.x, mi.y, mi.z, m1.x, m1.y, m1.z);
-						const C r2 = molpair_r2<C>(mi.x, mi.y, mi.z, m2.x, m2.y, m2.z), r3 = molpair_r2<C>(mi.x, mi.y, mi.z, m3.x, m3.y, m3.z);
-						if (r0 < a.ljrc2) { sts16(w, src); w += LSTRIDE; }
-						if (r1 < a.ljrc2) { sts16(w, src + VB); w += LSTRIDE; }
-						if (r2 < a.ljrc2) { sts16(w, src + 2 * VB); w += LSTRIDE; }
-						if (r3 < a.ljrc2) { sts16(w, src + 3 * VB); w += LSTRIDE; }
+						#pragma unroll
+						for (int l = 0; l < RI; l++) {
+							const C r0 = molpair_r2<C>(mi[l].x, mi[l].y, mi[l].z, m0.x, m0.y, m0.z), r1 = molpair_r2<C>(mi[l].x, mi[l].y, mi[l].z, m1.x, m1.y, m1.z);
+							const C r2 = molpair_r2<C>(mi[l].x, mi[l].y, mi[l].z, m2.x, m2.y, m2.z), r3 = molpair_r2<C>(mi[l].x, mi[l].y, mi[l].z, m3.x, m3.y, m3.z);
+							if (r0 < a.ljrc2) { sts16(w[l], src); w[l] += LSTRIDE; }
+							if (r1 < a.ljrc2) { sts16(w[l], src + VB); w[l] += LSTRIDE; }
+							if (r2 < a.ljrc2) { sts16(w[l], src + 2 * VB); w[l] += LSTRIDE; }
+							if (r3 < a.ljrc2) { sts16(w[l], src + 3 * VB); w[l] += LSTRIDE; }
+						}
 						src += 4 * VB;
 					}
 				}
-				if (w <= wlimit) {                  // the row is down to < 4 candidates (the list is not the reason the loop stopped)
+				if (room()) {                        // the row is down to < 4 candidates (the lists are not the reason the loop stopped)
 					for (; src < end; src += VB) {
 						const V4 mj = lds_v4<C>(src);
-						const C rr = molpair_r2<C>(mi.x, mi.y, mi.z, mj.x, mj.y, mj.z);
-						if (rr < a.ljrc2 && (r != 4 || rr != C(0))) { sts16(w, src); w += LSTRIDE; }
+						#pragma unroll
+						for (int l = 0; l < RI; l++) {
+							const C rr = molpair_r2<C>(mi[l].x, mi[l].y, mi[l].z, mj.x, mj.y, mj.z);
+							if (rr < a.ljrc2 && (r != 4 || rr != C(0))) { sts16(w[l], src); w[l] += LSTRIDE; }
+						}
 					}
 					r++;
 					if (r < 9) {
 						uint32_t kb = 0, ke = 0;
-						if (have) {
-							kb = cs[r * (CH_MAXC + 3) + kx]; ke = cs[r * (CH_MAXC + 3) + kx + 3];      // cells cx-1 .. cx+1 of this row
-						}
+						if (have[0]) { kb = cs[r * (CH_MAXC + 3) + kxa]; ke = cs[r * (CH_MAXC + 3) + kxb + 3]; }      // cells cxa-1 .. cxb+1 of this row
 						src = win_s + (uint32_t) (r * W + (int) kb) * VB; end = win_s + (uint32_t) (r * W + (int) ke) * VB;
 						flush = false;
 					}
 				}
 			}
 			if (flush) {
-				// ---- phase 2: dense LJ over the list; two interleaved FP32 accumulator sets ----
-				const int cnt = (int) ((w - list_s) / LSTRIDE);
-				C fx[2] = {C(0), C(0)}, fy[2] = {C(0), C(0)}, fz[2] = {C(0), C(0)}, vx[2] = {C(0), C(0)}, vy[2] = {C(0), C(0)}, vz[2] = {C(0), C(0)}, up[2] = {C(0), C(0)};
-				C eps24 = a.eps24_0, sig2 = a.sig2_0, shift6 = a.shift6_0;
-				if (cnt & 1) sts16(w, sentinel);      // pad odd lists with the far-away record (all LJ terms underflow to 0)
-				#pragma unroll 1
-				for (uint32_t e = list_s; e < w; e += 2 * LSTRIDE) {
-					const uint32_t i0 = lds16(e), i1 = lds16(e + LSTRIDE);
-					const V4 m0 = lds_v4<C>(i0), m1 = lds_v4<C>(i1);
-					LJ_PAIR_ACCUM(0, m0);
-					if (SINGLE || i1 != sentinel) LJ_PAIR_ACCUM(1, m1);
+				// ---- phase 2: dense LJ over the lists; two interleaved FP32 accumulator sets per list ----
+				#pragma unroll
+				for (int l = 0; l < RI; l++) {
+					const int cnt = (int) ((w[l] - lbase[l]) / LSTRIDE);
+					C fx[2] = {C(0), C(0)}, fy[2] = {C(0), C(0)}, fz[2] = {C(0), C(0)}, vx[2] = {C(0), C(0)}, vy[2] = {C(0), C(0)}, vz[2] = {C(0), C(0)}, up[2] = {C(0), C(0)};
+					C eps24 = a.eps24_0, sig2 = a.sig2_0, shift6 = a.shift6_0;
+					if (cnt & 1) sts16(w[l], sentinel);      // pad odd lists with the far-away record (all LJ terms underflow to 0)
+					const V4 mi_ = mi[l]; const uint32_t cid_i_ = cid_i[l];
+					#pragma unroll 1
+					for (uint32_t e = lbase[l]; e < w[l]; e += 2 * LSTRIDE) {
+						const uint32_t i0 = lds16(e), i1 = lds16(e + LSTRIDE);
+						const V4 m0 = lds_v4<C>(i0), m1 = lds_v4<C>(i1);
+						#define mi mi_
+						#define cid_i cid_i_
+						LJ_PAIR_ACCUM(0, m0);
+						if (SINGLE || i1 != sentinel) LJ_PAIR_ACCUM(1, m1);
+						#undef mi
+						#undef cid_i
+					}
+					if (SINGLE) {
+						// eps24 and the shift are pair independent: applied once per list
+						const C f24 = eps24;
+						fx[0] = f24 * (fx[0] + fx[1]); fy[0] = f24 * (fy[0] + fy[1]); fz[0] = f24 * (fz[0] + fz[1]);
+						vx[0] = f24 * (vx[0] + vx[1]); vy[0] = f24 * (vy[0] + vy[1]); vz[0] = f24 * (vz[0] + vz[1]);
+						up[0] = f24 * (up[0] + up[1]) + (C) cnt * shift6;
+						fx[1] = fy[1] = fz[1] = vx[1] = vy[1] = vz[1] = up[1] = C(0);
+					}
+					Fd[l][0] += (double) fx[0] + (double) fx[1]; Fd[l][1] += (double) fy[0] + (double) fy[1]; Fd[l][2] += (double) fz[0] + (double) fz[1];
+					Vd[l][0] += (double) vx[0] + (double) vx[1]; Vd[l][1] += (double) vy[0] + (double) vy[1]; Vd[l][2] += (double) vz[0] + (double) vz[1];
+					Ud[l] += (double) up[0] + (double) up[1];
+					w[l] = lbase[l];
 				}
-				if (SINGLE) {
-					// eps24 and the shift are pair independent: applied once per list
-					const C f24 = eps24;
-					fx[0] = f24 * (fx[0] + fx[1]); fy[0] = f24 * (fy[0] + fy[1]); fz[0] = f24 * (fz[0] + fz[1]);
-					vx[0] = f24 * (vx[0] + vx[1]); vy[0] = f24 * (vy[0] + vy[1]); vz[0] = f24 * (vz[0] + vz[1]);
-					up[0] = f24 * (up[0] + up[1]) + (C) cnt * shift6;
-					fx[1] = fy[1] = fz[1] = vx[1] = vy[1] = vz[1] = up[1] = C(0);
-				}
-				Fd[0] += (double) fx[0] + (double) fx[1]; Fd[1] += (double) fy[0] + (double) fy[1]; Fd[2] += (double) fz[0] + (double) fz[1];
-				Vd[0] += (double) vx[0] + (double) vx[1]; Vd[1] += (double) vy[0] + (double) vy[1]; Vd[2] += (double) vz[0] + (double) vz[1];
-				Ud += (double) up[0] + (double) up[1];
-				w = list_s;
 				if (r >= 9) break;
 			}
 		}
 		// ---- 4. results ----
-		if (have) {
-			const size_t cp = a.cap;
-			const uint32_t t = t0;
-			acc[0] += 0.5 * Ud;                          // every pair is visited from both of its ends
-			acc[1] += 0.5 * (Vd[0] + Vd[1] + Vd[2]);
-			a.F[t] = Fd[0]; a.F[cp + t] = Fd[1]; a.F[2 * cp + t] = Fd[2];
-			a.Vi[t] = 0.5 * Vd[0]; a.Vi[cp + t] = 0.5 * Vd[1]; a.Vi[2 * cp + t] = 0.5 * Vd[2];
-			if (a.M) { a.M[t] = 0.; a.M[cp + t] = 0.; a.M[2 * cp + t] = 0.; }
+		#pragma unroll
+		for (int l = 0; l < RI; l++) {
+			if (have[l]) {
+				const size_t cp = a.cap;
+				const uint32_t t = s_rowbase[4] + trel[l];
+				acc[0] += 0.5 * Ud[l];                          // every pair is visited from both of its ends
+				acc[1] += 0.5 * (Vd[l][0] + Vd[l][1] + Vd[l][2]);
+				a.F[t] = Fd[l][0]; a.F[cp + t] = Fd[l][1]; a.F[2 * cp + t] = Fd[l][2];
+				a.Vi[t] = 0.5 * Vd[l][0]; a.Vi[cp + t] = 0.5 * Vd[l][1]; a.Vi[2 * cp + t] = 0.5 * Vd[l][2];
+				if (a.M) { a.M[t] = 0.; a.M[cp + t] = 0.; a.M[2 * cp + t] = 0.; }
+			}
 		}
 		block_reduce_store<2>(acc, a.partials, ch);
 		__syncthreads();      // windows, lists and cs are reused by the next chunk
@@ -307,7 +333,7 @@ static int launch_tiled(ls1b200_ctx* c) {
 	constexpr int TPB = TileCfg<C>::TPB, W = TileCfg<C>::W, LCAP = TileCfg<C>::LCAP, RI = TileCfg<C>::RI;
 	const Geom& g = c->geom;
 	uint32_t nrows = 0;
-	LS1_TRY(build_chunks(c, TPB, W, RI, &nrows));
+	LS1_TRY(build_chunks(c, TPB * RI, W, 1, &nrows));      // a chunk holds at most TPB * RI molecules
 	Chunk* chunks = (Chunk*) c->chunks;
 	TArgs<C> a;
 	a.mpos = (const V4*) c->mpos; a.cell_start = c->cell_start; a.cell_of = c->cell_of2;
