@@ -171,7 +171,7 @@ struct ls1b200_ctx {
 	// chunk list of the tiled 1CLJ kernel (force_1clj_tiled.cu)
 	void* chunks = nullptr; uint32_t* chunk_row_count = nullptr; uint32_t* chunk_row_start = nullptr; uint32_t* work_counter = nullptr;
 	int sm_count = 148;
-	int lj_kernel = 0;                // 0: tiled (shared-memory windows, TMA), 1: global-memory variant (force_1clj.cu)
+	int lj_kernel = 0;                // LS1B200_LJ_KERNEL: 0 tiled (default; shared-memory windows, TMA), 1 "global" (force_1clj.cu), 3 "mma" / 4 "tc": tensor-core prefilter experiments (force_1clj_mma.cu, force_1clj_tc.cu; measured slower, profiles/r01_tensor_prefilter.md)
 	int multi_kernel = 0;             // 0: tiled thread-per-molecule (force_multi_tiled.cu), 1: v1 thread-per-site (force_general.cu)
 
 	// reductions
@@ -226,6 +226,8 @@ int do_globals(ls1b200_ctx* c, double target_T, uint64_t global_n, double global
 int force_general(ls1b200_ctx* c);
 int force_1clj(ls1b200_ctx* c);
 int force_1clj_tiled(ls1b200_ctx* c);
+int force_1clj_mma(ls1b200_ctx* c);
+int force_1clj_tc(ls1b200_ctx* c);
 int force_multi_tiled(ls1b200_ctx* c);
 int reduce_force_partials(ls1b200_ctx* c, uint32_t nblocks);
 int do_exchange(ls1b200_ctx* c);                    // NCCL halo + leaving-molecule exchange of one step (no-op if not decomposed)

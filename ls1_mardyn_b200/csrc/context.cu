@@ -233,7 +233,7 @@ int ls1b200_create(const ls1b200_config* cfg, ls1b200_ctx** out) {
 		if (dev_alloc(&c->chunk_row_count, nrows) || dev_alloc(&c->chunk_row_start, nrows) || dev_alloc(&c->work_counter, 4)) return cleanup(1);
 		cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
 		const char* k = getenv("LS1B200_LJ_KERNEL");
-		c->lj_kernel = (k && std::string(k) == "global") ? 1 : 0;
+		c->lj_kernel = (k && std::string(k) == "global") ? 1 : (k && std::string(k) == "mma") ? 3 : (k && std::string(k) == "tc") ? 4 : 0;
 		const char* m = getenv("LS1B200_MULTI_KERNEL");
 		c->multi_kernel = (m && std::string(m) == "general") ? 1 : (m && std::string(m) == "generic") ? 2 : 0;   // 2: tiled, but never specialised
 	}

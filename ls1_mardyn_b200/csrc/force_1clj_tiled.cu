@@ -327,6 +327,13 @@ __global__ void __launch_bounds__(RED_BLOCKS) k_reduce_force_chunks2(const doubl
 	if (threadIdx.x == 0) { scal->upot6lj = out[0]; scal->upot_xpoles = 0.; scal->virial = out[1]; scal->my_rf = 0.; }
 }
 
+// sums the per-chunk partials of a chunked force kernel into DevScalars (also used by force_1clj_mma.cu)
+int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows) {
+	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks1, RED_BLOCKS, 256, 0, c->partials, c->chunk_row_start + nrows, c->partials2);
+	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks2, 1, RED_BLOCKS, 0, c->partials2, c->d_scal);
+	return 0;
+}
+
 template <class C>
 static int launch_tiled(ls1b200_ctx* c) {
 	typedef typename Vec4<C>::type V4;
@@ -354,9 +361,7 @@ static int launch_tiled(ls1b200_ctx* c) {
 	if (per_sm < 1) return fail("force_1clj_tiled: kernel does not fit on an SM");
 	const uint32_t grid = (uint32_t) (c->sm_count * per_sm);
 	LS1_LAUNCH(c, PH_FORCE, kern, grid, TPB, smem, a);
-	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks1, RED_BLOCKS, 256, 0, c->partials, c->chunk_row_start + nrows, c->partials2);
-	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks2, 1, RED_BLOCKS, 0, c->partials2, c->d_scal);
-	return 0;
+	return reduce_force_chunks(c, nrows);
 }
 
 int force_1clj_tiled(ls1b200_ctx* c) { return c->mixed ? launch_tiled<float>(c) : launch_tiled<double>(c); }

@@ -107,6 +107,34 @@ def test_multicomponent_1clj_fast_path(capi):
         assert abs(ma.upot - mb.upot) <= TOL[prec] * abs(mb.upot)
 
 
+@pytest.mark.parametrize("kernel", ["tiled", "global", "mma", "tc"])
+def test_1clj_kernel_variants_vs_oracle(capi, kernel):
+    """The alternative 1CLJ force kernels (LS1B200_LJ_KERNEL): the global-memory v1 kernel and the two tensor-core prefilter
+    experiments (mma.sync TF32 / tcgen05 FP16 with TMEM; both fall back to the tiled kernel in the double build). Same bar as
+    the production kernel: forces, virial, energy against the CPU oracle, single- and multi-component."""
+    import os
+    from oracle import oracle as orc
+    from ls1_mardyn_b200.components import Component, Ensemble, LJcenter
+    two = Ensemble([Component(ljcenters=[LJcenter((0, 0, 0), 1.0, 1.0, 1.0, 2.5, False)]),
+                    Component(ljcenters=[LJcenter((0, 0, 0), 2.0, 0.7, 1.15, 2.5, True)])],
+                   xi=np.array([[1, 0.9], [1, 1]]), eta=np.array([[1, 1.05], [1, 1]]))
+    for case, ps in enumerate((_lattice_case(20, seed=11), _lattice_case(8, seed=5, ens=two, rho=0.6), _lattice_case(14, seed=3, jitter=0.15))):
+        for prec in ("mixed", "double"):
+            os.environ["LS1B200_LJ_KERNEL"] = kernel
+            try:
+                a = _mk(capi.Context, ps, 2.5, prec)
+            finally:
+                os.environ.pop("LS1B200_LJ_KERNEL", None)
+            b = _mk(orc.OracleSim, ps, 2.5, prec)
+            a.update(); b.update(); ma, mb = a.traverse_cells(), b.traverse_cells()
+            tol = TOL[prec]
+            for f in ("F", "VI"):
+                ok, worst = rel_close(a.download(f), b.download(f), tol)
+                assert ok, (kernel, case, prec, f, worst)
+            assert abs(ma.upot - mb.upot) <= tol * abs(mb.upot), (kernel, case, prec, ma.upot, mb.upot)
+            assert abs(ma.virial - mb.virial) <= tol * max(abs(mb.virial), np.abs(b.download("VI")).sum()), (kernel, case, prec)
+
+
 @pytest.mark.parametrize("prec", ["double", "mixed"])
 def test_leapfrog_and_thermostat_steps_vs_oracle(capi, prec):
     """Phase-by-phase: pre -> update -> traverse -> post -> scale, 5 steps, state compared after every phase."""
