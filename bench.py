@@ -257,7 +257,13 @@ def our_arm(args):
     V_global = float(np.prod(ps.length))
     rot = any(c.Ipa()[1] for c in wl.ensemble.components)
     ctx.upload(ps.id, ps.cid, ps.r, ps.v, ps.q if rot else None, ps.L if rot else None)
+    transport = "none"
     if dd is not None:
+        # molecule exchange: NVLink stores into the neighbours' receive buffers (CUDA IPC); LS1B200_TRANSPORT=nccl keeps ncclSend / Recv
+        transport = "nccl"
+        if os.environ.get("LS1B200_TRANSPORT", "peer") != "nccl":
+            ctx.peer_attach_collective(dist, device=torch.device("cuda", local))
+            transport = "peer-memory"
         ctx.exchange()
     ctx.update(); ctx.traverse_cells()
     fc0 = ctx.count_flops()
@@ -336,7 +342,7 @@ def our_arm(args):
             "dtype": "f32 pair arithmetic, f64 accumulation and state (MARDYN_SPDP)", "data": "synthetic (BCC lattice like CubicGridGenerator, equal-magnitude velocities)",
             "config": {"workload": wl.description,
                        "molecules_per_gpu": N, "molecules": world * N, "cells_per_dim": [int(x) for x in ctx.geometry()[0]],
-                       "parallelism": "1 GPU" if world == 1 else "3D block decomposition %dx%dx%d, one process per GPU, leaving molecules + halo copies over NCCL send/recv every step, allreduce of 6 doubles" % grid_for(world),
+                       "parallelism": "1 GPU" if world == 1 else ("3D block decomposition %dx%dx%d, one process per GPU, leaving molecules + halo copies every step " % grid_for(world)) + ("stored by the packing kernel straight into the neighbours' memory over NVLink (CUDA IPC)" if transport == "peer-memory" else "over NCCL send/recv") + ", NCCL allreduce of 6 doubles",
                        "box": [float(x) for x in ps.length],
                        "l2_policy": "inputs larger than L2: state %.1f GB per GPU" % (N * 150 / 1e9)},
             "ms_per_step_device_events": round(1e3 * t_dev / args.steps, 4),
@@ -357,6 +363,14 @@ def our_arm(args):
             line["cpu_baseline"] = cpu_baseline()
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
+        # orderly teardown: nobody frees receive buffers a neighbour still has mapped
+        torch.cuda.synchronize()
+        if transport == "peer-memory":
+            ctx.peer_detach_collective(dist)
+        else:
+            dist.barrier()
+        ctx.close()
+        dist.barrier()
         dist.destroy_process_group()
 
 

@@ -218,8 +218,23 @@ int ls1b200_nccl_unique_id(uint8_t out[128]);
  * molecules, and ls1b200_download returns the molecules this rank owns NOW, in slot order (download LS1B200_F_ID
  * to match them; ls1b200_num_molecules gives the count). */
 int ls1b200_decomp_attach(ls1b200_ctx* ctx, const ls1b200_decomp* dd);
-/* One exchange (all stages) over NCCL on the context's stream; collective. ls1b200_simulate calls it every step;
- * phase-by-phase drivers call it between ls1b200_leapfrog_pre and ls1b200_update (and once before the first update). */
+/* Peer-memory transport (the GPUs of one NVLink / NVSwitch domain, one process per GPU): after ls1b200_upload every rank
+ * publishes the CUDA IPC handle of its receive buffers (ls1b200_peer_handle), the caller gathers the n_ranks handles with
+ * whatever it has (MPI_Allgather, torch.distributed.all_gather) and hands the table to ls1b200_peer_attach, which maps the
+ * buffers of the (at most six) neighbours. From then on ls1b200_exchange / ls1b200_simulate do not call NCCL for the
+ * molecule exchange: the packing kernel stores the records straight into the neighbour's receive buffer over NVLink and
+ * publishes {sequence number, count} when the last record is out; the import kernel of the neighbour waits for that
+ * sequence number (bounded wait: a vanished peer is reported as an error, not a hang). Replaces DomainDecompMPIBase::exchangeMoleculesMPI's MPI_Isend / Irecv
+ * (parallel/CommunicationPartner.cpp:140-330) for the ranks of one box; a new ls1b200_upload invalidates the mapping. */
+#define LS1B200_PEER_HANDLE_BYTES 96
+int ls1b200_peer_handle(ls1b200_ctx* ctx, uint8_t out[LS1B200_PEER_HANDLE_BYTES]);
+int ls1b200_peer_attach(ls1b200_ctx* ctx, const uint8_t* handles /* [n_ranks][LS1B200_PEER_HANDLE_BYTES] */, int32_t n_ranks);
+/* Unmaps the neighbours' buffers (back to the NCCL transport, if any). Every rank calls it -- followed by a barrier of the
+ * caller's -- BEFORE any rank destroys its context or uploads again: memory must not be freed while a peer has it mapped. */
+int ls1b200_peer_detach(ls1b200_ctx* ctx);
+/* One exchange (all stages) on the context's stream -- peer-memory transport if attached, else NCCL send / recv; collective.
+ * ls1b200_simulate calls it every step; phase-by-phase drivers call it between ls1b200_leapfrog_pre and ls1b200_update
+ * (and once before the first update). */
 int ls1b200_exchange(ls1b200_ctx* ctx);
 /* Sums the macroscopic values of the last traversal / leapfrog_post over all ranks (ncclAllReduce; replaces the
  * collective communication of Domain::calculateGlobalValues, Domain.cpp:176-182, :220-230); collective. */

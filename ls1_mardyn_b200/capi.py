@@ -30,7 +30,7 @@ EXPORTS = ["ls1b200_last_error", "ls1b200_abi_version", "ls1b200_kernel_launch_c
            "ls1b200_geometry", "ls1b200_update", "ls1b200_traverse_cells", "ls1b200_leapfrog_pre", "ls1b200_leapfrog_post",
            "ls1b200_scale_velocities", "ls1b200_simulate", "ls1b200_halo_export", "ls1b200_halo_import",
            "ls1b200_halo_import_host", "ls1b200_phase_times", "ls1b200_count_flops", "ls1b200_measure_fp32_peak",
-           "ls1b200_measure_hbm_copy", "ls1b200_stream", "ls1b200_nccl_unique_id", "ls1b200_decomp_attach", "ls1b200_exchange",
+           "ls1b200_measure_hbm_copy", "ls1b200_stream", "ls1b200_nccl_unique_id", "ls1b200_decomp_attach", "ls1b200_peer_handle", "ls1b200_peer_attach", "ls1b200_peer_detach", "ls1b200_exchange",
            "ls1b200_allreduce_macro", "ls1b200_halo_export_host"]
 
 
@@ -57,6 +57,9 @@ class StepRecord(C.Structure):
 
 
 RECORD_FIELDS = [k for k, _ in StepRecord._fields_]
+
+
+PEER_HANDLE_BYTES = 96      # LS1B200_PEER_HANDLE_BYTES
 
 
 class Decomp(C.Structure):
@@ -111,6 +114,9 @@ def lib():
         L.ls1b200_nccl_unique_id.argtypes = [C.c_void_p]
         L.ls1b200_decomp_attach.argtypes = [C.c_void_p, C.c_void_p]
         L.ls1b200_exchange.argtypes = [C.c_void_p]
+        L.ls1b200_peer_handle.argtypes = [C.c_void_p, C.c_void_p]
+        L.ls1b200_peer_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
+        L.ls1b200_peer_detach.argtypes = [C.c_void_p]
         L.ls1b200_allreduce_macro.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p]
         L.ls1b200_halo_export_host.argtypes = [C.c_void_p, C.c_int32, C.c_int32, C.c_void_p, C.c_uint64, C.c_void_p]
         L.ls1b200_halo_import_host.argtypes = [C.c_void_p, C.c_void_p, C.c_uint64]
@@ -208,6 +214,38 @@ class Context:
                 d.nccl_unique_id[k] = unique_id[k]
         _check(lib().ls1b200_decomp_attach(self.h, C.byref(d)))
         self.decomposed = True
+
+    def peer_handle(self) -> bytes:
+        """ls1b200_peer_handle: the CUDA IPC handle of this rank's receive buffers (after upload)."""
+        buf = (C.c_uint8 * PEER_HANDLE_BYTES)()
+        _check(lib().ls1b200_peer_handle(self.h, buf))
+        return bytes(buf)
+
+    def peer_attach(self, handles) -> None:
+        """ls1b200_peer_attach: `handles` = the peer_handle() of every rank, in rank order. From here on exchange / simulate
+        store the molecule records straight into the neighbours' memory over NVLink instead of calling NCCL send / recv."""
+        blob = b"".join(handles)
+        assert len(blob) % PEER_HANDLE_BYTES == 0
+        arr = (C.c_uint8 * len(blob)).from_buffer_copy(blob)
+        _check(lib().ls1b200_peer_attach(self.h, arr, len(blob) // PEER_HANDLE_BYTES))
+
+    def peer_detach(self) -> None:
+        """ls1b200_peer_detach; every rank calls it, then a barrier, before any context is closed."""
+        _check(lib().ls1b200_peer_detach(self.h))
+
+    def peer_detach_collective(self, dist) -> None:
+        self.peer_detach()
+        dist.barrier()
+
+    def peer_attach_collective(self, dist, device=None) -> None:
+        """Gathers the handles of all ranks over torch.distributed (any backend) and attaches them."""
+        import torch
+        mine = torch.frombuffer(bytearray(self.peer_handle()), dtype=torch.uint8)
+        if device is not None:
+            mine = mine.to(device)
+        out = [torch.empty_like(mine) for _ in range(dist.get_world_size())]
+        dist.all_gather(out, mine)
+        self.peer_attach([bytes(t.cpu().numpy().tobytes()) for t in out])
 
     def num_molecules(self) -> int:
         return int(lib().ls1b200_num_molecules(self.h))

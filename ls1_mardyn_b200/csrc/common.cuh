@@ -114,6 +114,8 @@ struct DevScalars {
 	uint32_t n_slots2[2];                         // slots in use (owned + halo), ping-pong: [ctx->parity] is current
 	uint32_t overflow;                            // 1: an update needed more than cap slots, 2: a halo message buffer was too small
 	uint32_t n_owned_dev;                         // owned molecules counted by the last count_owned() (decomposed mode)
+	uint32_t n_sorted;                            // slots in cell order (count of the last update); imports of the exchange follow behind
+	uint32_t pad0;
 };
 
 }  // namespace ls1b200
@@ -150,6 +152,7 @@ struct ls1b200_ctx {
 	ls1b200::State cur, nxt;
 	double* F = nullptr; double* M = nullptr; double* Vi = nullptr;   // [3][cap] each, slot order
 	bool sorted = false;          // update() has run since the last upload
+	bool ever_sorted = false;     // some update() has run since the last upload (cell_of2 / DevScalars::n_sorted describe it)
 	bool forces_valid = false;
 
 	// cells
@@ -208,6 +211,14 @@ struct ls1b200_ctx {
 	unsigned char* msg_in[2] = {nullptr, nullptr};
 	uint64_t msg_cap = 0;                               // records per message
 	ls1b200_particle* import_stage = nullptr; uint64_t import_stage_cap = 0;   // host-staged imports (ls1b200_halo_import_host)
+	// peer-memory transport (NVLink stores straight into the neighbour's receive buffers; CUDA IPC): [step parity][stage][side]
+	unsigned char* pin_base = nullptr; size_t pin_stride = 0;      // my 12 receive buffers, one allocation
+	unsigned char* peer_base[3][2] = {{nullptr, nullptr}, {nullptr, nullptr}, {nullptr, nullptr}};      // the neighbours' pin_base, mapped
+	size_t peer_stride[3][2] = {{0, 0}, {0, 0}, {0, 0}}; uint64_t peer_cap[3][2] = {{0, 0}, {0, 0}, {0, 0}};      // the neighbours' buffer stride / record capacity
+	void* peer_opened[6] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr}; int peer_opened_rank[6] = {-1, -1, -1, -1, -1, -1};
+	bool peer_ok = false;
+	uint32_t xseq = 0;                                  // exchange calls so far (the sequence number published with every message)
+	uint32_t* xcnt = nullptr;                           // device: {count low, count high, pad, pad}
 	uint64_t* ekey = nullptr;                           // [cap] (id << 5 | shift code) per provisional slot: content-based in-cell order
 	uint64_t n_owned_local = 0;                         // owned molecules of this rank (host copy, decomposed mode)
 };

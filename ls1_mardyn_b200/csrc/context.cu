@@ -381,7 +381,7 @@ int ls1b200_upload(ls1b200_ctx* c, uint64_t n, const uint64_t* id, const uint32_
 	c->h_scal->n_slots2[0] = (uint32_t) n; c->h_scal->n_slots2[1] = 0; c->h_scal->overflow = 0;
 	c->h_scal->beta_trans = 1.; c->h_scal->beta_rot = 1.;
 	LS1_CUDA(cudaMemcpy(c->d_scal, c->h_scal, sizeof(DevScalars), cudaMemcpyHostToDevice));
-	c->sorted = false; c->forces_valid = false;
+	c->sorted = false; c->ever_sorted = false; c->forces_valid = false;
 	return 0;
 }
 
@@ -490,7 +490,7 @@ int ls1b200_set_field(ls1b200_ctx* c, int field, const void* src, uint64_t n) {
 	const uint32_t* oi = c->dd.active ? c->entry : nullptr;
 	double* planes = nullptr; int dim = 3;
 	switch (field) {
-		case LS1B200_F_R: planes = c->cur.r; c->forces_valid = false; break;
+		case LS1B200_F_R: planes = c->cur.r; c->forces_valid = false; c->ever_sorted = false; break;      // arbitrary new positions: the exchange scans every slot
 		case LS1B200_F_V: planes = c->cur.v; break;
 		case LS1B200_F_Q: planes = c->cur.q; dim = 4; break;
 		case LS1B200_F_L: planes = c->cur.L; break;

@@ -22,6 +22,8 @@
 
 #include <algorithm>
 
+#include <stdio.h>
+#include <stdlib.h>
 #include "common.cuh"
 
 namespace ls1b200 {
@@ -82,17 +84,19 @@ struct XArgs {
 	int lo_wrap, hi_wrap;                  // the low / high neighbour lies across the global periodic boundary
 	uint32_t cap, parity, msg_cap;
 	int rotates;
+	// slots [0, n_sorted) are in the cell order of the last update: only cells within `layers` of a face of dimension dim can hold
+	// a molecule that leaves or needs a halo copy (a molecule moves less than a cell per step); cell_of == nullptr: scan everything
+	const uint32_t* cell_of;
+	uint32_t cstride, ncd, ncells;         // cell coordinate in dim = (cell / cstride) % ncd
 };
 
+// writes one record (local message buffer or, peer transport, the neighbour's receive buffer over NVLink)
 template <bool FULL>
-__device__ __forceinline__ void pack(unsigned char* msg, uint32_t msg_cap, DevScalars* scal, const State& st, size_t cap, uint32_t s, uint64_t meta,
+__device__ __forceinline__ void pack(unsigned char* rec, uint32_t k, const State& st, size_t cap, uint32_t s, uint64_t meta,
                                      int dim, double xd, uint32_t flags, int rotates) {
-	const uint32_t k = atomicAdd(reinterpret_cast<uint32_t*>(msg), 1u);
-	if (k >= msg_cap) { scal->overflow = 2; return; }
-	double r[3] = {st.r[s], st.r[cap + s], st.r[2 * cap + s]};
-	r[dim] = xd;
+	const double r[3] = {dim == 0 ? xd : st.r[s], dim == 1 ? xd : st.r[cap + s], dim == 2 ? xd : st.r[2 * cap + s]};
 	if (FULL) {
-		ls1b200_particle* p = reinterpret_cast<ls1b200_particle*>(msg + MSG_HEADER) + k;
+		ls1b200_particle* p = reinterpret_cast<ls1b200_particle*>(rec) + k;
 		p->id = st.id[s]; p->cid = meta_cid(meta); p->flags = flags;
 		for (int d = 0; d < 3; d++) { p->r[d] = r[d]; p->v[d] = st.v[d * cap + s]; }
 		if (rotates) {
@@ -102,70 +106,155 @@ __device__ __forceinline__ void pack(unsigned char* msg, uint32_t msg_cap, DevSc
 			p->q[0] = 1.; p->q[1] = p->q[2] = p->q[3] = 0.; p->L[0] = p->L[1] = p->L[2] = 0.;
 		}
 	} else {
-		RecCompact* p = reinterpret_cast<RecCompact*>(msg + MSG_HEADER) + k;
-		p->id = st.id[s]; p->cid = meta_cid(meta); p->flags = flags;
-		for (int d = 0; d < 3; d++) { p->r[d] = r[d]; p->v[d] = st.v[d * cap + s]; }
+		// 64 bytes as four 16-byte stores
+		const double v0 = st.v[s], v1 = st.v[cap + s], v2 = st.v[2 * cap + s];
+		uint4* p = reinterpret_cast<uint4*>(reinterpret_cast<RecCompact*>(rec) + k);
+		const uint64_t id = st.id[s];
+		p[0] = make_uint4((uint32_t) id, (uint32_t) (id >> 32), meta_cid(meta), flags);
+		double2* q = reinterpret_cast<double2*>(p + 1);
+		q[0] = make_double2(r[0], r[1]); q[1] = make_double2(r[2], v0); q[2] = make_double2(v1, v2);
 	}
 }
 
-// which == 3: both sides (the NCCL path), 1: low side only, 2: high side only (the staged C ABI exports one side per call;
-// a leaving molecule is converted by the call for ITS side, so low + high together equal one which == 3 pass)
+struct XOut {
+	unsigned char* rec[2];        // record arrays of the low / high message (local, or mapped peer memory)
+	uint32_t* cnt[2];             // record counters (always local)
+	unsigned long long* hdr[2];   // peer transport: the receive buffers' headers (k_publish)
+	uint32_t seq;
+	uint32_t cap[2];              // record capacity of the two targets
+};
+
+// which == 3: both sides (the transports inside the library), 1: low side only, 2: high side only (the staged C ABI exports one
+// side per call; a leaving molecule is converted by the call for ITS side, so low + high together equal one which == 3 pass)
 template <bool FULL>
-__global__ void __launch_bounds__(256) k_export(XArgs a, State st, unsigned char* __restrict__ out_lo, unsigned char* __restrict__ out_hi, DevScalars* scal, int which) {
-	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= min(scal->n_slots2[a.parity], a.cap)) return;
-	const uint64_t meta = st.meta[s];
-	const bool halo = meta_halo(meta);
-	if (halo && !meta_fresh(meta)) return;                       // stale halo slot of the previous sort
+__global__ void __launch_bounds__(256) k_export(XArgs a, State st, XOut o, DevScalars* scal, int which) {
+	// persistent blocks striding over the slots: 68 000 blocks of a few hundred nanoseconds each cost more than the scan itself
 	const size_t cap = a.cap;
-	const double x = st.r[(size_t) a.dim * cap + s];
-	if (!halo && x < a.bmin) {
-		if (!(which & 1)) return;
-		// leaving through the low face: LEAVING shift + clamp (CommunicationPartner.cpp:550-562) ...
-		double xn = x;
-		if (a.lo_wrap) { xn = __dadd_rn(x, a.glen); if (xn >= a.gmax) xn = a.wrap_hi; }
-		pack<FULL>(out_lo, a.msg_cap, scal, st, cap, s, meta, a.dim, xn, 0u, a.rotates);
-		// ... and it stays behind as my halo copy of the molecule its new owner now holds (HALO shift + clamp, :533-547)
-		double xh = xn;
-		if (a.lo_wrap) { xh = __dsub_rn(xn, a.glen); if (xh >= a.gmin) xh = a.halo_lo; }
-		st.r[(size_t) a.dim * cap + s] = xh;
-		st.meta[s] = meta | META_HALO | META_FRESH;
-		return;
+	const uint32_t n_slots = min(scal->n_slots2[a.parity], a.cap), n_sorted = scal->n_sorted;
+	constexpr int REC = FULL ? (int) sizeof(ls1b200_particle) : (int) sizeof(RecCompact);
+	__shared__ __align__(16) unsigned char stage[8][32 * REC];
+	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+	for (uint32_t s0 = blockIdx.x * blockDim.x; s0 < n_slots; s0 += gridDim.x * blockDim.x) {
+	const uint32_t s = s0 + threadIdx.x;
+	bool want[2] = {false, false}; double xn[2] = {0., 0.}; uint32_t fl[2] = {0u, 0u};
+	uint64_t meta = 0;
+	bool candidate = s < n_slots;
+	if (candidate && a.cell_of && s < n_sorted) {
+		const uint32_t cell = a.cell_of[s];
+		if (cell < a.ncells) { const uint32_t k = (cell / a.cstride) % a.ncd; candidate = k <= 3u || k + 4u >= a.ncd; }
 	}
-	if (!halo && x >= a.bmax) {
-		if (!(which & 2)) return;
-		double xn = x;
-		if (a.hi_wrap) { xn = __dsub_rn(x, a.glen); if (xn < a.gmin) xn = a.gmin; }
-		pack<FULL>(out_hi, a.msg_cap, scal, st, cap, s, meta, a.dim, xn, 0u, a.rotates);
-		double xh = xn;
-		if (a.hi_wrap) { xh = __dadd_rn(xn, a.glen); if (xh < a.gmax) xh = a.halo_hi; }
-		st.r[(size_t) a.dim * cap + s] = xh;
-		st.meta[s] = meta | META_HALO | META_FRESH;
-		return;
+	if (candidate) {
+		meta = st.meta[s];
+		const bool halo = meta_halo(meta);
+		if (!(halo && !meta_fresh(meta))) {                       // not a stale halo slot of the previous sort
+			const double x = st.r[(size_t) a.dim * cap + s];
+			if (!halo && x < a.bmin) {
+				if (which & 1) {
+					// leaving through the low face: LEAVING shift + clamp (CommunicationPartner.cpp:550-562) ...
+					double xl = x;
+					if (a.lo_wrap) { xl = __dadd_rn(x, a.glen); if (xl >= a.gmax) xl = a.wrap_hi; }
+					want[0] = true; xn[0] = xl; fl[0] = 0u;
+					// ... and it stays behind as my halo copy of the molecule its new owner now holds (HALO shift + clamp, :533-547)
+					double xh = xl;
+					if (a.lo_wrap) { xh = __dsub_rn(xl, a.glen); if (xh >= a.gmin) xh = a.halo_lo; }
+					st.r[(size_t) a.dim * cap + s] = xh;
+					st.meta[s] = meta | META_HALO | META_FRESH;
+				}
+			} else if (!halo && x >= a.bmax) {
+				if (which & 2) {
+					double xl = x;
+					if (a.hi_wrap) { xl = __dsub_rn(x, a.glen); if (xl < a.gmin) xl = a.gmin; }
+					want[1] = true; xn[1] = xl; fl[1] = 0u;
+					double xh = xl;
+					if (a.hi_wrap) { xh = __dadd_rn(xl, a.glen); if (xh < a.gmax) xh = a.halo_hi; }
+					st.r[(size_t) a.dim * cap + s] = xh;
+					st.meta[s] = meta | META_HALO | META_FRESH;
+				}
+			} else {
+				// halo copies: an owned molecule inside the boundary layer, or a fresh halo copy of an earlier stage (forwarded to the
+				// edge / corner neighbours; it may lie outside [bmin, bmax) in this dimension if its owner is about to hand it over)
+				if ((which & 1) && x < __dadd_rn(a.bmin, a.rc)) {
+					double xl = x;
+					if (a.lo_wrap) { xl = __dadd_rn(x, a.glen); if (x >= a.bmin && xl < a.gmax) xl = a.halo_hi; }
+					want[0] = true; xn[0] = xl; fl[0] = 1u;
+				}
+				if ((which & 2) && x >= __dsub_rn(a.bmax, a.rc)) {
+					double xl = x;
+					if (a.hi_wrap) { xl = __dsub_rn(x, a.glen); if (x < a.bmax && xl >= a.gmin) xl = a.halo_lo; }
+					want[1] = true; xn[1] = xl; fl[1] = 1u;
+				}
+			}
+		}
 	}
-	// halo copies: an owned molecule inside the boundary layer, or a fresh halo copy of an earlier stage (forwarded to the
-	// edge / corner neighbours; it may lie outside [bmin, bmax) in this dimension if its owner is about to hand it over)
-	if ((which & 1) && x < __dadd_rn(a.bmin, a.rc)) {
-		double xn = x;
-		if (a.lo_wrap) { xn = __dadd_rn(x, a.glen); if (x >= a.bmin && xn < a.gmax) xn = a.halo_hi; }
-		pack<FULL>(out_lo, a.msg_cap, scal, st, cap, s, meta, a.dim, xn, 1u, a.rotates);
+	// One counter update per warp and side (the boundary layer is a few hundred thousand records on ONE counter). The records of
+	// a warp are consecutive in the message: they are staged in shared memory and leave as whole 16-byte (8-byte for the 120-byte
+	// records) lanes-contiguous stores -- over NVLink a 64-byte record written as four scattered stores costs ten times as much.
+	#pragma unroll
+	for (int side = 0; side < 2; side++) {
+		const uint32_t b = __ballot_sync(0xffffffffu, want[side]);
+		if (b == 0u) continue;
+		const int leader = __ffs(b) - 1;
+		const uint32_t cnt = (uint32_t) __popc(b);
+		uint32_t base = 0;
+		if (lane == leader) base = atomicAdd(o.cnt[side], cnt);
+		base = __shfl_sync(0xffffffffu, base, leader);
+		if (want[side]) pack<FULL>(stage[wid], (uint32_t) __popc(b & ((1u << lane) - 1u)), st, cap, s, meta, a.dim, xn[side], fl[side], a.rotates);
+		__syncwarp();
+		uint32_t n_copy = cnt;
+		if (base + cnt > o.cap[side]) { n_copy = base < o.cap[side] ? o.cap[side] - base : 0u; if (lane == 0) scal->overflow = 2; }
+		if (FULL) {
+			const unsigned long long* src = reinterpret_cast<const unsigned long long*>(stage[wid]);
+			unsigned long long* dst = reinterpret_cast<unsigned long long*>(o.rec[side] + (size_t) base * REC);
+			for (uint32_t i = lane; i < n_copy * (REC / 8); i += 32) dst[i] = src[i];
+		} else {
+			const uint4* src = reinterpret_cast<const uint4*>(stage[wid]);
+			uint4* dst = reinterpret_cast<uint4*>(o.rec[side] + (size_t) base * REC);
+			for (uint32_t i = lane; i < n_copy * (REC / 16); i += 32) dst[i] = src[i];
+		}
+		__syncwarp();
 	}
-	if ((which & 2) && x >= __dsub_rn(a.bmax, a.rc)) {
-		double xn = x;
-		if (a.hi_wrap) { xn = __dsub_rn(x, a.glen); if (x < a.bmax && xn >= a.gmin) xn = a.halo_lo; }
-		pack<FULL>(out_hi, a.msg_cap, scal, st, cap, s, meta, a.dim, xn, 1u, a.rotates);
 	}
+}
+
+// peer transport: publishes {sequence number, count} in the receivers' headers. A kernel of its own behind k_export: the
+// kernel boundary orders every record store before it, where a system-scope fence per block of k_export cost 0.8 ms.
+__global__ void k_publish(XOut o) {
+	if (blockIdx.x || threadIdx.x > 1) return;
+	const bool hi = threadIdx.x == 1;      // (no dynamic indexing of the parameter struct: it would be copied to local memory)
+	__threadfence_system();
+	const uint32_t n = min(*reinterpret_cast<volatile uint32_t*>(hi ? o.cnt[1] : o.cnt[0]), hi ? o.cap[1] : o.cap[0]);
+	*reinterpret_cast<volatile unsigned long long*>(hi ? o.hdr[1] : o.hdr[0]) = ((unsigned long long) o.seq << 32) | n;
+	__threadfence_system();
+}
+
+// peer transport: wait until the neighbour has published sequence number seq in this receive buffer (every thread of k_import
+// and k_import_bump calls it; bounded: a peer that died must not hang the GPU -- overflow = 4 reports it)
+__device__ __forceinline__ uint32_t msg_count(const unsigned char* msg, uint32_t seq, uint32_t msg_cap, DevScalars* scal) {
+	const volatile unsigned long long* h = reinterpret_cast<const volatile unsigned long long*>(msg);
+	unsigned long long v = *h;
+	if (seq) {
+		const long long t0 = clock64();
+		while ((uint32_t) (v >> 32) != seq) {
+			if (clock64() - t0 > 8000000000ll) { scal->overflow = 4; return 0u; }      // ~4 s
+			__nanosleep(200);
+			v = *h;
+		}
+		__threadfence_system();
+	}
+	return min((uint32_t) v, msg_cap);
 }
 
 // appends the records of one message behind the slots in use (+ the records of the message imported just before)
 template <bool FULL>
 __global__ void __launch_bounds__(256) k_import(const unsigned char* __restrict__ msg, const unsigned char* __restrict__ prev_msg, State st, uint32_t cap, uint32_t parity,
-                                                 uint32_t msg_cap, int rotates, DevScalars* scal) {
+                                                 uint32_t msg_cap, int rotates, DevScalars* scal, uint32_t seq) {
 	const uint32_t i = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t n = min(*reinterpret_cast<const uint32_t*>(msg), msg_cap);
+	__shared__ uint32_t s_n, s_prev;
+	if (threadIdx.x == 0) { s_n = msg_count(msg, seq, msg_cap, scal); s_prev = prev_msg ? msg_count(prev_msg, seq, msg_cap, scal) : 0u; }
+	__syncthreads();
+	const uint32_t n = s_n;
 	if (i >= n) return;
-	uint32_t base = scal->n_slots2[parity];
-	if (prev_msg) base += min(*reinterpret_cast<const uint32_t*>(prev_msg), msg_cap);
+	const uint32_t base = scal->n_slots2[parity] + s_prev;
 	const uint32_t t = base + i;
 	if (t >= cap) { scal->overflow = 1; return; }
 	const size_t c = cap;
@@ -185,10 +274,10 @@ __global__ void __launch_bounds__(256) k_import(const unsigned char* __restrict_
 	st.id[t] = id;
 	st.meta[t] = make_meta(0u, cid, false) | ((flags & 1u) ? (META_HALO | META_FRESH) : 0ull);
 }
-__global__ void k_import_bump(const unsigned char* __restrict__ m0, const unsigned char* __restrict__ m1, uint32_t cap, uint32_t parity, uint32_t msg_cap, DevScalars* scal) {
+__global__ void k_import_bump(const unsigned char* __restrict__ m0, const unsigned char* __restrict__ m1, uint32_t cap, uint32_t parity, uint32_t msg_cap, DevScalars* scal, uint32_t seq) {
 	if (threadIdx.x || blockIdx.x) return;
-	uint32_t n = scal->n_slots2[parity] + min(*reinterpret_cast<const uint32_t*>(m0), msg_cap);
-	if (m1) n += min(*reinterpret_cast<const uint32_t*>(m1), msg_cap);
+	uint32_t n = scal->n_slots2[parity] + msg_count(m0, seq, msg_cap, scal);
+	if (m1) n += msg_count(m1, seq, msg_cap, scal);
 	if (n > cap) { scal->overflow = 1; n = cap; }
 	scal->n_slots2[parity] = n;
 }
@@ -273,6 +362,10 @@ static XArgs stage_args(const ls1b200_ctx* c, int d) {
 	a.wrap_hi = dd.wrap_hi[d]; a.halo_hi = dd.halo_hi[d]; a.halo_lo = dd.halo_lo[d];
 	a.lo_wrap = dd.coords[d] == 0; a.hi_wrap = dd.coords[d] == dd.grid[d] - 1;
 	a.cap = (uint32_t) c->cap; a.parity = c->parity; a.msg_cap = (uint32_t) c->msg_cap; a.rotates = c->rotates;
+	// the cell filter needs the cell of every sorted slot: valid once an update has run (cell_of2 and n_sorted are of that update)
+	a.cell_of = c->ever_sorted ? c->cell_of2 : nullptr;
+	a.cstride = d == 0 ? 1u : d == 1 ? (uint32_t) c->geom.cells[0] : (uint32_t) (c->geom.cells[0] * c->geom.cells[1]);
+	a.ncd = (uint32_t) c->geom.cells[d]; a.ncells = c->geom.ncells;
 	return a;
 }
 
@@ -292,6 +385,13 @@ int decomp_alloc(ls1b200_ctx* c) {
 		LS1_CUDA(cudaMemsetAsync(c->msg_in[k], 0, MSG_HEADER, c->stream));
 	}
 	LS1_CUDA(cudaMalloc((void**) &c->ekey, sizeof(uint64_t) * c->cap));
+	// receive buffers of the peer-memory transport: [step parity][stage][side], one allocation (one IPC handle)
+	c->pin_stride = (bytes + 255) & ~(size_t) 255;
+	LS1_CUDA(cudaMalloc((void**) &c->pin_base, 12 * c->pin_stride));
+	LS1_CUDA(cudaMemsetAsync(c->pin_base, 0, 12 * c->pin_stride, c->stream));
+	LS1_CUDA(cudaMalloc((void**) &c->xcnt, 16));
+	LS1_CUDA(cudaStreamSynchronize(c->stream));
+	c->xseq = 0; c->peer_ok = false;
 	return 0;
 }
 void decomp_free(ls1b200_ctx* c) {
@@ -300,42 +400,96 @@ void decomp_free(ls1b200_ctx* c) {
 		if (c->msg_in[k]) cudaFree(c->msg_in[k]); c->msg_in[k] = nullptr;
 	}
 	if (c->ekey) cudaFree(c->ekey); c->ekey = nullptr;
+	for (int k = 0; k < 6; k++) { if (c->peer_opened[k]) cudaIpcCloseMemHandle(c->peer_opened[k]); c->peer_opened[k] = nullptr; c->peer_opened_rank[k] = -1; }
+	for (int d = 0; d < 3; d++) c->peer_base[d][0] = c->peer_base[d][1] = nullptr;
+	c->peer_ok = false;
+	if (c->pin_base) cudaFree(c->pin_base); c->pin_base = nullptr;
+	if (c->xcnt) cudaFree(c->xcnt); c->xcnt = nullptr;
 	if (c->import_stage) cudaFree(c->import_stage); c->import_stage = nullptr; c->import_stage_cap = 0;
 	c->msg_cap = 0;
 }
 
+// message buffers of this rank as the target of k_export (NCCL transport, staged C ABI): the count lives in the header
+static XOut local_out(ls1b200_ctx* c) {
+	XOut o;
+	for (int k = 0; k < 2; k++) { o.rec[k] = c->msg_out[k] + MSG_HEADER; o.cnt[k] = reinterpret_cast<uint32_t*>(c->msg_out[k]); o.hdr[k] = nullptr; o.cap[k] = (uint32_t) c->msg_cap; }
+	o.seq = 0;
+	return o;
+}
+
 int do_exchange(ls1b200_ctx* c) {
 	if (!c->dd.active) return 0;
-	if (!c->dd.comm) return fail("ls1b200_exchange: this context was attached with use_nccl = 0 (move the messages with ls1b200_halo_export / import)");
+	if (!c->dd.comm && !c->peer_ok) return fail("ls1b200_exchange: this context has no transport (use_nccl = 0 and no ls1b200_peer_attach): move the messages with ls1b200_halo_export / import");
 	if (!c->msg_out[0]) return fail("ls1b200_exchange: call ls1b200_upload first");
 	LS1_TRY(span_begin(c, PH_UPDATE));
 	const bool full = c->rotates;
 	const size_t rec = full ? sizeof(ls1b200_particle) : sizeof(RecCompact);
 	const size_t bytes = MSG_HEADER + c->msg_cap * rec;
-	const uint32_t g = (uint32_t) ((c->cap + 255) / 256), gi = (uint32_t) ((c->msg_cap + 255) / 256);
+	const uint32_t g = std::min<uint32_t>((uint32_t) ((c->cap + 255) / 256), (uint32_t) c->sm_count * 8u), gi = (uint32_t) ((c->msg_cap + 255) / 256);
+	// LS1B200_EXCHANGE_PROFILE=1: CUDA-event breakdown of the stages (export / transport / import), printed by rank 0 every 32 calls
+	static const bool prof = getenv("LS1B200_EXCHANGE_PROFILE") != nullptr;
+	static cudaEvent_t pe[4]; static double pacc[3] = {0., 0., 0.}; static int pcalls = 0;
+	if (prof && pcalls == 0) for (int k = 0; k < 4; k++) cudaEventCreate(&pe[k]);
+	const bool peer = c->peer_ok;
+	const uint32_t par = c->xseq & 1u;
 	for (int d = 0; d < 3; d++) {
 		if (c->dd.grid[d] == 1) continue;
 		const XArgs a = stage_args(c, d);
-		LS1_CUDA(cudaMemsetAsync(c->msg_out[0], 0, MSG_HEADER, c->stream));
-		LS1_CUDA(cudaMemsetAsync(c->msg_out[1], 0, MSG_HEADER, c->stream));
-		if (full) LS1_LAUNCH(c, PH_UPDATE, k_export<true>, g, 256, 0, a, c->cur, c->msg_out[0], c->msg_out[1], c->d_scal, 3);
-		else LS1_LAUNCH(c, PH_UPDATE, k_export<false>, g, 256, 0, a, c->cur, c->msg_out[0], c->msg_out[1], c->d_scal, 3);
-		// fixed-size messages (the count travels in the header): no host round trip, the whole step stays asynchronous
-		LS1_NCCL(g_nccl.GroupStart());
-		LS1_NCCL(g_nccl.Send(c->msg_out[0], bytes, NCCL_UINT8, c->dd.nbr[d][0], c->dd.comm, c->stream));
-		LS1_NCCL(g_nccl.Send(c->msg_out[1], bytes, NCCL_UINT8, c->dd.nbr[d][1], c->dd.comm, c->stream));
-		LS1_NCCL(g_nccl.Recv(c->msg_in[0], bytes, NCCL_UINT8, c->dd.nbr[d][1], c->dd.comm, c->stream));      // the high neighbour's low message
-		LS1_NCCL(g_nccl.Recv(c->msg_in[1], bytes, NCCL_UINT8, c->dd.nbr[d][0], c->dd.comm, c->stream));      // the low neighbour's high message
-		LS1_NCCL(g_nccl.GroupEnd());
-		if (full) {
-			LS1_LAUNCH(c, PH_UPDATE, k_import<true>, gi, 256, 0, c->msg_in[0], (const unsigned char*) nullptr, c->cur, (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, (int) c->rotates, c->d_scal);
-			LS1_LAUNCH(c, PH_UPDATE, k_import<true>, gi, 256, 0, c->msg_in[1], c->msg_in[0], c->cur, (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, (int) c->rotates, c->d_scal);
+		if (prof) cudaEventRecord(pe[0], c->stream);
+		XOut o = local_out(c);
+		const unsigned char* in[2] = {c->msg_in[0], c->msg_in[1]};
+		uint32_t seq = 0;
+		if (peer) {
+			// ---- peer transport: k_export stores the records straight into the neighbours' receive buffers (NVLink), the last
+			// block publishes {sequence number, count}; k_import waits for the sequence number in MY receive buffers ----
+			seq = c->xseq * 4u + (uint32_t) d + 1u;
+			LS1_CUDA(cudaMemsetAsync(c->xcnt, 0, 16, c->stream));
+			const size_t slot_lo = ((size_t) par * 3 + d) * 2 + 0, slot_hi = ((size_t) par * 3 + d) * 2 + 1;
+			// my low message is what the low neighbour receives "from its high side" (its slot 0), my high message goes to slot 1
+			unsigned char* dst_lo = c->peer_base[d][0] + slot_lo * c->peer_stride[d][0];
+			unsigned char* dst_hi = c->peer_base[d][1] + slot_hi * c->peer_stride[d][1];
+			o.cap[0] = (uint32_t) c->peer_cap[d][0]; o.cap[1] = (uint32_t) c->peer_cap[d][1];
+			o.rec[0] = dst_lo + MSG_HEADER; o.rec[1] = dst_hi + MSG_HEADER;
+			o.cnt[0] = c->xcnt; o.cnt[1] = c->xcnt + 1;
+			o.hdr[0] = reinterpret_cast<unsigned long long*>(dst_lo); o.hdr[1] = reinterpret_cast<unsigned long long*>(dst_hi);
+			o.seq = seq;
+			in[0] = c->pin_base + slot_lo * c->pin_stride; in[1] = c->pin_base + slot_hi * c->pin_stride;
 		} else {
-			LS1_LAUNCH(c, PH_UPDATE, k_import<false>, gi, 256, 0, c->msg_in[0], (const unsigned char*) nullptr, c->cur, (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, (int) c->rotates, c->d_scal);
-			LS1_LAUNCH(c, PH_UPDATE, k_import<false>, gi, 256, 0, c->msg_in[1], c->msg_in[0], c->cur, (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, (int) c->rotates, c->d_scal);
+			LS1_CUDA(cudaMemsetAsync(c->msg_out[0], 0, MSG_HEADER, c->stream));
+			LS1_CUDA(cudaMemsetAsync(c->msg_out[1], 0, MSG_HEADER, c->stream));
 		}
-		LS1_LAUNCH(c, PH_UPDATE, k_import_bump, 1, 32, 0, c->msg_in[0], c->msg_in[1], (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, c->d_scal);
+		if (full) LS1_LAUNCH(c, PH_UPDATE, k_export<true>, g, 256, 0, a, c->cur, o, c->d_scal, 3);
+		else LS1_LAUNCH(c, PH_UPDATE, k_export<false>, g, 256, 0, a, c->cur, o, c->d_scal, 3);
+		if (peer) LS1_LAUNCH(c, PH_UPDATE, k_publish, 1, 32, 0, o);
+		if (prof) cudaEventRecord(pe[1], c->stream);
+		if (!peer) {
+			// NCCL transport: fixed-size messages (the count travels in the header): no host round trip, the whole step stays asynchronous
+			LS1_NCCL(g_nccl.GroupStart());
+			LS1_NCCL(g_nccl.Send(c->msg_out[0], bytes, NCCL_UINT8, c->dd.nbr[d][0], c->dd.comm, c->stream));
+			LS1_NCCL(g_nccl.Send(c->msg_out[1], bytes, NCCL_UINT8, c->dd.nbr[d][1], c->dd.comm, c->stream));
+			LS1_NCCL(g_nccl.Recv(c->msg_in[0], bytes, NCCL_UINT8, c->dd.nbr[d][1], c->dd.comm, c->stream));      // the high neighbour's low message
+			LS1_NCCL(g_nccl.Recv(c->msg_in[1], bytes, NCCL_UINT8, c->dd.nbr[d][0], c->dd.comm, c->stream));      // the low neighbour's high message
+			LS1_NCCL(g_nccl.GroupEnd());
+		}
+		if (prof) cudaEventRecord(pe[2], c->stream);
+		if (full) {
+			LS1_LAUNCH(c, PH_UPDATE, k_import<true>, gi, 256, 0, in[0], (const unsigned char*) nullptr, c->cur, (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, (int) c->rotates, c->d_scal, seq);
+			LS1_LAUNCH(c, PH_UPDATE, k_import<true>, gi, 256, 0, in[1], in[0], c->cur, (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, (int) c->rotates, c->d_scal, seq);
+		} else {
+			LS1_LAUNCH(c, PH_UPDATE, k_import<false>, gi, 256, 0, in[0], (const unsigned char*) nullptr, c->cur, (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, (int) c->rotates, c->d_scal, seq);
+			LS1_LAUNCH(c, PH_UPDATE, k_import<false>, gi, 256, 0, in[1], in[0], c->cur, (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, (int) c->rotates, c->d_scal, seq);
+		}
+		LS1_LAUNCH(c, PH_UPDATE, k_import_bump, 1, 32, 0, in[0], in[1], (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, c->d_scal, seq);
+		if (prof) {
+			cudaEventRecord(pe[3], c->stream); cudaEventSynchronize(pe[3]);
+			++pcalls;
+			if (pcalls > 16) for (int k = 0; k < 3; k++) { float ms = 0.f; cudaEventElapsedTime(&ms, pe[k], pe[k + 1]); pacc[k] += ms; }      // the first calls set up the connections
+			if (pcalls > 16 && pcalls % 32 == 0 && c->dd.rank == 0)
+				fprintf(stderr, "[ls1b200 exchange] %s transport, per stage: export %.3f ms, transport %.3f ms, import %.3f ms (message capacity %zu bytes)\n", peer ? "peer-memory" : "NCCL",
+				        pacc[0] / (pcalls - 16), pacc[1] / (pcalls - 16), pacc[2] / (pcalls - 16), bytes);
+		}
 	}
+	c->xseq++;
 	LS1_TRY(span_end(c));
 	c->sorted = false;
 	return 0;
@@ -411,6 +565,60 @@ int ls1b200_decomp_attach(ls1b200_ctx* c, const ls1b200_decomp* dd) {
 	return 0;
 }
 
+int ls1b200_peer_handle(ls1b200_ctx* c, uint8_t out[LS1B200_PEER_HANDLE_BYTES]) {
+	if (!c || !out) return fail("ls1b200_peer_handle: null argument");
+	if (!c->dd.active || !c->pin_base) return fail("ls1b200_peer_handle: call ls1b200_decomp_attach and ls1b200_upload first");
+	LS1_CUDA(cudaSetDevice(c->device));
+	static_assert(sizeof(cudaIpcMemHandle_t) + 16 <= LS1B200_PEER_HANDLE_BYTES, "handle size");
+	memset(out, 0, LS1B200_PEER_HANDLE_BYTES);
+	cudaIpcMemHandle_t h;
+	LS1_CUDA(cudaIpcGetMemHandle(&h, c->pin_base));
+	memcpy(out, &h, sizeof(h));
+	const uint64_t stride = c->pin_stride, cap = c->msg_cap;
+	memcpy(out + sizeof(h), &stride, 8); memcpy(out + sizeof(h) + 8, &cap, 8);
+	return 0;
+}
+
+int ls1b200_peer_attach(ls1b200_ctx* c, const uint8_t* handles, int32_t n_ranks) {
+	if (!c || !handles) return fail("ls1b200_peer_attach: null argument");
+	if (!c->dd.active || !c->pin_base) return fail("ls1b200_peer_attach: call ls1b200_decomp_attach and ls1b200_upload first");
+	if (n_ranks != c->dd.n_ranks) return fail("ls1b200_peer_attach: one handle per rank of the decomposition is expected");
+	LS1_CUDA(cudaSetDevice(c->device));
+	int n_open = 0;
+	for (int d = 0; d < 3; d++) for (int side = 0; side < 2; side++) {
+		c->peer_base[d][side] = nullptr;
+		if (c->dd.grid[d] == 1) continue;
+		const int r = c->dd.nbr[d][side];
+		const uint8_t* hp = handles + (size_t) r * LS1B200_PEER_HANDLE_BYTES;
+		uint64_t stride = 0, cap = 0;
+		memcpy(&stride, hp + sizeof(cudaIpcMemHandle_t), 8); memcpy(&cap, hp + sizeof(cudaIpcMemHandle_t) + 8, 8);
+		// the sender addresses the receiver's slots and honours the receiver's capacity
+		if (stride == 0 || cap == 0) return fail("ls1b200_peer_attach: empty handle (did every rank call ls1b200_peer_handle after its upload?)");
+		c->peer_stride[d][side] = (size_t) stride; c->peer_cap[d][side] = cap;
+		if (r == c->dd.rank) { c->peer_base[d][side] = c->pin_base; continue; }
+		void* base = nullptr;
+		for (int k = 0; k < n_open; k++) if (c->peer_opened_rank[k] == r) base = c->peer_opened[k];
+		if (!base) {
+			cudaIpcMemHandle_t h; memcpy(&h, hp, sizeof(h));
+			LS1_CUDA(cudaIpcOpenMemHandle(&base, h, cudaIpcMemLazyEnablePeerAccess));
+			c->peer_opened[n_open] = base; c->peer_opened_rank[n_open] = r; n_open++;
+		}
+		c->peer_base[d][side] = (unsigned char*) base;
+	}
+	c->peer_ok = true;
+	return 0;
+}
+
+int ls1b200_peer_detach(ls1b200_ctx* c) {
+	if (!c) return fail("ls1b200_peer_detach: null context");
+	LS1_CUDA(cudaSetDevice(c->device));
+	if (c->stream) LS1_CUDA(cudaStreamSynchronize(c->stream));
+	for (int k = 0; k < 6; k++) { if (c->peer_opened[k]) cudaIpcCloseMemHandle(c->peer_opened[k]); c->peer_opened[k] = nullptr; c->peer_opened_rank[k] = -1; }
+	for (int d = 0; d < 3; d++) c->peer_base[d][0] = c->peer_base[d][1] = nullptr;
+	c->peer_ok = false;
+	return 0;
+}
+
 int ls1b200_exchange(ls1b200_ctx* c) {
 	if (!c) return fail("ls1b200_exchange: null context");
 	LS1_CUDA(cudaSetDevice(c->device));
@@ -440,7 +648,7 @@ int ls1b200_halo_export(ls1b200_ctx* c, int32_t dim, int32_t side, void** device
 	LS1_CUDA(cudaSetDevice(c->device));
 	const XArgs a = stage_args(c, dim);
 	LS1_CUDA(cudaMemsetAsync(c->msg_out[side], 0, MSG_HEADER, c->stream));
-	LS1_LAUNCH(c, PH_UPDATE, k_export<true>, (uint32_t) ((c->cap + 255) / 256), 256, 0, a, c->cur, c->msg_out[0], c->msg_out[1], c->d_scal, side ? 2 : 1);
+	LS1_LAUNCH(c, PH_UPDATE, k_export<true>, std::min<uint32_t>((uint32_t) ((c->cap + 255) / 256), (uint32_t) c->sm_count * 8u), 256, 0, a, c->cur, local_out(c), c->d_scal, side ? 2 : 1);
 	uint32_t n = 0;
 	LS1_CUDA(cudaMemcpyAsync(&n, c->msg_out[side], 4, cudaMemcpyDeviceToHost, c->stream));
 	LS1_CUDA(cudaStreamSynchronize(c->stream));
@@ -481,8 +689,8 @@ static int import_records(ls1b200_ctx* c, const void* buf, uint64_t count, cudaM
 	LS1_CUDA(cudaMemcpyAsync(c->msg_in[0], &n, 4, cudaMemcpyHostToDevice, c->stream));
 	LS1_CUDA(cudaMemcpyAsync(c->msg_in[0] + MSG_HEADER, buf, count * sizeof(ls1b200_particle), kind, c->stream));
 	LS1_LAUNCH(c, PH_UPDATE, k_import<true>, (uint32_t) ((count + 255) / 256), 256, 0, c->msg_in[0], (const unsigned char*) nullptr, c->cur, (uint32_t) c->cap, c->parity,
-	           (uint32_t) c->msg_cap, (int) c->rotates, c->d_scal);
-	LS1_LAUNCH(c, PH_UPDATE, k_import_bump, 1, 32, 0, c->msg_in[0], (const unsigned char*) nullptr, (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, c->d_scal);
+	           (uint32_t) c->msg_cap, (int) c->rotates, c->d_scal, 0u);
+	LS1_LAUNCH(c, PH_UPDATE, k_import_bump, 1, 32, 0, c->msg_in[0], (const unsigned char*) nullptr, (uint32_t) c->cap, c->parity, (uint32_t) c->msg_cap, c->d_scal, 0u);
 	LS1_CUDA(cudaStreamSynchronize(c->stream));      // n and a pageable host buffer are read by the copies above
 	c->sorted = false;
 	return 0;

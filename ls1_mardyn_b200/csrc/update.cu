@@ -34,25 +34,34 @@ __device__ __forceinline__ bool code_valid(uint32_t mask, int a, int b, int c) {
 
 __global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __restrict__ key, uint32_t* __restrict__ count, const DevScalars* __restrict__ scal) {
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= min(scal->n_slots2[a.parity], a.cap)) return;
-	const uint64_t meta = cur.meta[s];
-	if (meta_halo(meta) && !meta_fresh(meta)) { key[s] = KEY_NONE; return; }      // stale halo slot; fresh halo copies (halo.cu) are binned
+	const bool in_range = s < min(scal->n_slots2[a.parity], a.cap);
 	const Geom& g = a.g;
-	double x = cur.r[s], y = cur.r[(size_t) a.cap + s], z = cur.r[2 * (size_t) a.cap + s];
-	if (g.periodic[0]) { double w = wrap_coord<0>(g, x); if (w != x) { x = w; cur.r[s] = w; } }
-	if (g.periodic[1]) { double w = wrap_coord<1>(g, y); if (w != y) { y = w; cur.r[(size_t) a.cap + s] = w; } }
-	if (g.periodic[2]) { double w = wrap_coord<2>(g, z); if (w != z) { z = w; cur.r[2 * (size_t) a.cap + s] = w; } }
-	const int cx = cell1d<0>(g, x), cy = cell1d<1>(g, y), cz = cell1d<2>(g, z);
-	const bool out = cx < 0 || cy < 0 || cz < 0 || cx >= g.cells[0] || cy >= g.cells[1] || cz >= g.cells[2];
-	if (out) {
-		key[s] = g.ncells;
-		atomicAdd(&count[g.ncells], 1u);
-		return;
+	uint32_t bin = KEY_NONE, mask = 0;
+	double x = 0., y = 0., z = 0.;
+	if (in_range) {
+		const uint64_t meta = cur.meta[s];
+		if (meta_halo(meta) && !meta_fresh(meta)) key[s] = KEY_NONE;      // stale halo slot; fresh halo copies (halo.cu) are binned
+		else {
+			x = cur.r[s]; y = cur.r[(size_t) a.cap + s]; z = cur.r[2 * (size_t) a.cap + s];
+			if (g.periodic[0]) { double w = wrap_coord<0>(g, x); if (w != x) { x = w; cur.r[s] = w; } }
+			if (g.periodic[1]) { double w = wrap_coord<1>(g, y); if (w != y) { y = w; cur.r[(size_t) a.cap + s] = w; } }
+			if (g.periodic[2]) { double w = wrap_coord<2>(g, z); if (w != z) { z = w; cur.r[2 * (size_t) a.cap + s] = w; } }
+			const int cx = cell1d<0>(g, x), cy = cell1d<1>(g, y), cz = cell1d<2>(g, z);
+			const bool out = cx < 0 || cy < 0 || cz < 0 || cx >= g.cells[0] || cy >= g.cells[1] || cz >= g.cells[2];
+			if (out) { bin = g.ncells; key[s] = bin; }
+			else {
+				bin = cell_index(g, cx, cy, cz);
+				mask = shift_mask<0>(g, x) | (shift_mask<1>(g, y) << 2) | (shift_mask<2>(g, z) << 4);
+				key[s] = bin | (mask << SHIFT_BITS);
+			}
+		}
 	}
-	const uint32_t bin = cell_index(g, cx, cy, cz);
-	const uint32_t mask = shift_mask<0>(g, x) | (shift_mask<1>(g, y) << 2) | (shift_mask<2>(g, z) << 4);
-	key[s] = bin | (mask << SHIFT_BITS);
-	atomicAdd(&count[bin], 1u);
+	// histogram: slots are in the cell order of the previous step, so the lanes of a warp fall into a handful of bins --
+	// one atomic per distinct bin and warp instead of one per molecule
+	{
+		const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+		if (bin != KEY_NONE && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&count[bin], (uint32_t) __popc(peers));
+	}
 	if (mask) {
 		for (int c3 = 0; c3 < 3; c3++) for (int b3 = 0; b3 < 3; b3++) for (int a3 = 0; a3 < 3; a3++) {
 			if ((a3 | b3 | c3) == 0 || !code_valid(mask, a3, b3, c3)) continue;
@@ -120,6 +129,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict__ star
 		const uint32_t total = *grand_total;
 		start[n] = total;
 		scal->n_slots2[parity ^ 1u] = total;
+		scal->n_sorted = min(total, cap);
 		if (total > cap) scal->overflow = 1;
 	}
 }
@@ -128,12 +138,18 @@ __global__ void __launch_bounds__(256) k_scatter(UpdArgs a, State cur, const uin
                                                   uint32_t* __restrict__ entry, uint32_t* __restrict__ cell_of, const DevScalars* __restrict__ scal,
                                                   uint64_t* __restrict__ ekey) {
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= min(scal->n_slots2[a.parity], a.cap)) return;
-	const uint32_t k = key[s];
-	if (k == KEY_NONE) return;
+	const bool in_range = s < min(scal->n_slots2[a.parity], a.cap);
+	const uint32_t k = in_range ? key[s] : KEY_NONE;
 	const Geom& g = a.g;
-	const uint32_t bin = k & ((1u << SHIFT_BITS) - 1u), mask = k >> SHIFT_BITS;
-	uint32_t p = atomicAdd(&cursor[bin], 1u);
+	const uint32_t bin = (k == KEY_NONE) ? KEY_NONE : (k & ((1u << SHIFT_BITS) - 1u)), mask = (k == KEY_NONE) ? 0u : (k >> SHIFT_BITS);
+	// provisional slot: one atomic per distinct bin and warp (the in-cell order is made deterministic by k_gather)
+	const uint32_t peers = __match_any_sync(0xffffffffu, bin);
+	const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
+	uint32_t base = 0;
+	if (bin != KEY_NONE && lane == leader) base = atomicAdd(&cursor[bin], (uint32_t) __popc(peers));
+	base = __shfl_sync(0xffffffffu, base, leader);
+	if (bin == KEY_NONE) return;
+	uint32_t p = base + (uint32_t) __popc(peers & ((1u << lane) - 1u));
 	const uint64_t idk = ekey ? (cur.id[s] << 5) : 0ull;      // decomposed mode: in-cell order by (molecule id, shift code)
 	if (p < a.cap) { entry[p] = s << 5; cell_of[p] = bin; if (ekey) ekey[p] = idk; }
 	if (mask) {
@@ -262,7 +278,7 @@ int do_update(ls1b200_ctx* c) {
 			LS1_LAUNCH(c, PH_UPDATE, k_sites<double>, g2, 128, 0, c->cur, (uint32_t) c->cap, c->smax, c->d_comps, c->d_sites, (double4*) c->spos, (double4*) c->sori, c->d_scal, c->parity, (int) c->rotates);
 	}
 	LS1_TRY(span_end(c));
-	c->sorted = true;
+	c->sorted = true; c->ever_sorted = true;
 	c->forces_valid = false;
 	return 0;
 }

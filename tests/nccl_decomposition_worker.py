@@ -33,6 +33,8 @@ def main():
         c.decomp_attach(dd, uid[0])
         m = dd.owner_of(ps.r) == rank
         c.upload(ps.id[m], ps.cid[m], ps.r[m], ps.v[m])
+        if os.environ.get("LS1B200_TRANSPORT", "peer") != "nccl":      # NVLink stores into the neighbours' buffers instead of ncclSend / Recv
+            c.peer_attach_collective(dist)
         c.exchange(); c.update(); c.traverse_cells()
         rec = c.simulate(steps, dt, T, global_n=N, global_volume=V)
         cnt = torch.tensor([c.num_molecules()]); dist.all_reduce(cnt)
@@ -48,9 +50,10 @@ def main():
             rho = N / V
             err = np.abs(rec[:, 5] - ref[:, 5]).max() / max(np.abs(ref[:, 5]).max(), rho * np.abs(ref[:, 4]).max())
             assert err <= tol, (prec, "pressure", err)
-            print(f"{prec}: {world} ranks vs 1 GPU over {steps} steps ok (N={N}, owned by rank 0 now: {c.num_molecules()})")
-        dist.barrier()
+            print(f"{prec} ({os.environ.get('LS1B200_TRANSPORT', 'peer')} transport): {world} ranks vs 1 GPU over {steps} steps ok (N={N}, owned by rank 0 now: {c.num_molecules()})")
+        c.peer_detach_collective(dist)      # (a barrier inside) nobody frees receive buffers a neighbour still has mapped
         c.close()
+        dist.barrier()
     if rank == 0:
         print("NCCL-DECOMP-OK")
     dist.destroy_process_group()

@@ -148,12 +148,14 @@ def test_multisite_blocks(capi):
         one.leapfrog_post(dt)
 
 
-def test_nccl_two_gpus(capi, tmp_path):
-    """The NCCL transport (ls1b200_exchange inside ls1b200_simulate), one process per GPU."""
+@pytest.mark.parametrize("transport", ["peer", "nccl"])
+def test_nccl_two_gpus(capi, tmp_path, transport):
+    """The transports inside the library (ls1b200_exchange inside ls1b200_simulate), one process per GPU: records stored
+    straight into the neighbour's memory over NVLink (CUDA IPC, ls1b200_peer_attach), and NCCL send / recv."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29641",
            os.path.join(ROOT, "tests", "nccl_decomposition_worker.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PYTHONPATH=ROOT))
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PYTHONPATH=ROOT, LS1B200_TRANSPORT=transport))
     assert p.returncode == 0 and "NCCL-DECOMP-OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
