@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(M_TPB, 3) k_force_1clj_mma(MArgs a) {
 
 }  // namespace
 
-int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows);      // force_1clj_tiled.cu
+int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows, int per_warp);      // force_1clj_tiled.cu
 
 // mixed-precision ensembles of 1CLJ components whose cells are wider than the cutoff by more than FP32 rounding (otherwise a
 // molecule two cells away could pass the FP32 test although the reference never pairs those cells): everything else takes
@@ -362,7 +362,7 @@ int force_1clj_mma(ls1b200_ctx* c) {
 	if (per_sm < 1) return fail("force_1clj_mma: kernel does not fit on an SM");
 	const uint32_t grid = (uint32_t) (c->sm_count * per_sm);
 	LS1_LAUNCH(c, PH_FORCE, kern, grid, M_TPB, M_SMEM, a);
-	return reduce_force_chunks(c, nrows);
+	return reduce_force_chunks(c, nrows, 0);
 }
 
 }  // namespace ls1b200

@@ -412,7 +412,7 @@ __global__ void __launch_bounds__(T_TPB, 2) k_force_1clj_tc(TcArgs a) {
 
 }  // namespace
 
-int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows);      // force_1clj_tiled.cu
+int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows, int per_warp);      // force_1clj_tiled.cu
 
 // mixed-precision ensembles of 1CLJ components whose cells are wider than the cutoff by more than FP32 rounding (otherwise a
 // molecule two cells away could pass the FP32 test although the reference never pairs those cells): everything else takes
@@ -445,7 +445,7 @@ int force_1clj_tc(ls1b200_ctx* c) {
 	// so the grid size is not a correctness matter)
 	const uint32_t grid = (uint32_t) (c->sm_count * (int) (512 / T_TMEM_COLS));
 	LS1_LAUNCH(c, PH_FORCE, kern, grid, T_TPB, T_SMEM, a);
-	return reduce_force_chunks(c, nrows);
+	return reduce_force_chunks(c, nrows, 0);
 }
 
 }  // namespace ls1b200

@@ -83,32 +83,73 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	V4* win = reinterpret_cast<V4*>(smem_raw);                                         // [9][W] (+1 sentinel record at [9*W])
 	uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw + (size_t) (9 * W + 1) * VB);   // [LCAP+1][RI][TPB]
-	uint32_t* cs = reinterpret_cast<uint32_t*>(list + (size_t) (LCAP + 1) * RI * TPB);   // [9][CH_MAXC+3]
-	__shared__ uint32_t s_rowbase[9];
+	uint32_t* cs_all = reinterpret_cast<uint32_t*>(list + (size_t) (LCAP + 1) * RI * TPB);   // [2][12][CH_MAXC+3]: this chunk's and the next one's
+	constexpr int CSB = 12 * (CH_MAXC + 3);
+	__shared__ uint32_t s_rowbase_all[2][9];
 	__shared__ __align__(8) unsigned long long s_bar;
-	__shared__ uint32_t s_chunk;
+	__shared__ uint32_t s_next;
 	const uint32_t win_s = smem_u32(win), list_s = smem_u32(list) + threadIdx.x * 2, bar = smem_u32(&s_bar);
 	const uint32_t n_chunks = *a.n_chunks;
 	if (threadIdx.x == 0) {
 		mbar_init(bar, 1);
 		// sentinel record: a point far away from everything, pads odd lists (all LJ terms underflow to 0)
 		win[9 * W] = make_c4<C>((C) 1e18, (C) 1e18, (C) 1e18, (C) 0);
+		s_next = atomicAdd(a.work_counter, 1u);
 	}
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
 	fence_proxy_async();
 	__syncthreads();
+	// cell_start cache of the 9 rows of a chunk (cells xa-1 .. xb+2 -> nc+3 entries each), stored RELATIVE to the first record of
+	// the window (the absolute start goes to rowbase): the per-thread row set-up then needs two loads per row and no subtraction
+	auto fill_cs = [&](const Chunk& q, uint32_t* csq, uint32_t* rbq) {
+		const int qn = q.ncells;
+		const uint32_t qR = q.cell0 / (uint32_t) a.nx;
+		const int qxa = (int) (q.cell0 % (uint32_t) a.nx);
+		for (int k = threadIdx.x; k < 9 * (qn + 3); k += TPB) {
+			const int r = k / (qn + 3), c = k % (qn + 3);
+			const uint32_t row = (uint32_t) ((int) qR + (r / 3 - 1) * a.ny + (r % 3 - 1)) * a.nx;
+			const uint32_t b0 = a.cell_start[row + qxa - 1];
+			csq[r * (CH_MAXC + 3) + c] = a.cell_start[row + qxa - 1 + c] - b0;
+			if (c == 0) rbq[r] = b0;
+		}
+	};
+	// The chunk loop is software pipelined: while chunk n is computed, the id of chunk n + 1 is claimed from the work counter,
+	// its descriptor is loaded and its cell_start cache is filled (second buffer), so that at the chunk boundary only the TMA
+	// load of the windows is exposed -- two barriers per chunk, and no dependent chain of four global round trips.
+	uint32_t ch = s_next;
+	Chunk cd; cd.cell0 = 0; cd.ncells = 0; cd.flags = 0;
+	int cur = 0;
+	if (ch < n_chunks) { cd = a.chunks[ch]; if (!(cd.flags & CHUNK_BIG)) fill_cs(cd, cs_all, s_rowbase_all[0]); }
+	__syncthreads();
 	uint32_t parity = 0;
-	for (;;) {
-		if (threadIdx.x == 0) s_chunk = atomicAdd(a.work_counter, 1u);
-		__syncthreads();
-		const uint32_t ch = s_chunk;
-		if (ch >= n_chunks) break;
-		const Chunk cd = a.chunks[ch];
+	while (ch < n_chunks) {
+		uint32_t* cs = cs_all + cur * CSB;
+		uint32_t* s_rowbase = s_rowbase_all[cur];
+		const bool big = (cd.flags & CHUNK_BIG) != 0;
 		const int nc = cd.ncells;
 		const uint32_t R = cd.cell0 / (uint32_t) a.nx;                 // row index cz*ny + cy
 		const int xa = (int) (cd.cell0 % (uint32_t) a.nx);
+		if (threadIdx.x == 0) {
+			if (!big) {
+				uint32_t total = 0;
+				for (int r = 0; r < 9; r++) total += cs[r * (CH_MAXC + 3) + nc + 2] * VB;
+				if (total) {
+					fence_proxy_async();      // the previous chunk's generic-proxy reads of the windows precede these async-proxy writes
+					mbar_expect_tx(bar, total);
+					for (int r = 0; r < 9; r++) {
+						const uint32_t b = s_rowbase[r], len = cs[r * (CH_MAXC + 3) + nc + 2];
+						if (len) tma_bulk_g2s(win_s + (uint32_t) (r * W) * VB, a.mpos + b, len * VB, bar);
+					}
+				}
+			}
+			s_next = atomicAdd(a.work_counter, 1u);      // the NEXT chunk of this CTA
+		}
+		__syncthreads();
+		const uint32_t nch = s_next;
+		Chunk ncd; ncd.cell0 = 0; ncd.ncells = 0; ncd.flags = 0;
+		if (nch < n_chunks) { ncd = a.chunks[nch]; if (!(ncd.flags & CHUNK_BIG)) fill_cs(ncd, cs_all + (cur ^ 1) * CSB, s_rowbase_all[cur ^ 1]); }
 		double acc[2] = {0., 0.};
-		if (cd.flags & CHUNK_BIG) {
+		if (big) {
 			// ---- slow generic path: a cell denser than the tile. Global loads, pair evaluated as soon as it is found. ----
 			const uint32_t ib = a.cell_start[cd.cell0], ie = a.cell_start[cd.cell0 + nc];
 			for (uint32_t t = ib + threadIdx.x; t < ie; t += TPB) {
@@ -140,34 +181,7 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 				a.Vi[t] = 0.5 * Vd[0]; a.Vi[cp + t] = 0.5 * Vd[1]; a.Vi[2 * cp + t] = 0.5 * Vd[2];
 				if (a.M) { a.M[t] = 0.; a.M[cp + t] = 0.; a.M[2 * cp + t] = 0.; }
 			}
-			block_reduce_store<2>(acc, a.partials, ch);
-			__syncthreads();
-			continue;
-		}
-		// ---- 1. cell_start cache of the 9 rows (cells xa-1 .. xb+2 -> nc+3 entries each) and the TMA loads ----
-		for (int k = threadIdx.x; k < 9 * (nc + 3); k += TPB) {
-			const int r = k / (nc + 3), c = k % (nc + 3);
-			const uint32_t row = (uint32_t) ((int) R + (r / 3 - 1) * a.ny + (r % 3 - 1)) * a.nx;
-			// stored RELATIVE to the first record of the window (the absolute start goes to s_rowbase): the per-thread row
-			// set-up then needs two loads per row and no subtraction of a third one
-			const uint32_t b0 = a.cell_start[row + xa - 1];
-			cs[r * (CH_MAXC + 3) + c] = a.cell_start[row + xa - 1 + c] - b0;
-			if (c == 0) s_rowbase[r] = b0;
-		}
-		__syncthreads();
-		if (threadIdx.x == 0) {
-			uint32_t total = 0;
-			for (int r = 0; r < 9; r++) total += cs[r * (CH_MAXC + 3) + nc + 2] * VB;
-			if (total) {
-				fence_proxy_async();      // the previous chunk's generic-proxy reads of the windows precede these async-proxy writes
-				mbar_expect_tx(bar, total);
-				for (int r = 0; r < 9; r++) {
-					const uint32_t b = s_rowbase[r], len = cs[r * (CH_MAXC + 3) + nc + 2];
-					if (len) tma_bulk_g2s(win_s + (uint32_t) (r * W) * VB, a.mpos + b, len * VB, bar);
-				}
-			}
-		}
-		__syncthreads();
+		} else {
 		const uint32_t* csc = cs + 4 * (CH_MAXC + 3);          // centre row (relative record indices)
 		// thread -> RI consecutive molecules of the chunk (slot order); they may lie in two neighbouring cells
 		const uint32_t n_mol = csc[nc + 1] - csc[1];
@@ -303,19 +317,29 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 				if (a.M) { a.M[t] = 0.; a.M[cp + t] = 0.; a.M[2 * cp + t] = 0.; }
 			}
 		}
-		block_reduce_store<2>(acc, a.partials, ch);
-		__syncthreads();      // windows, lists and cs are reused by the next chunk
+		}
+		// per-warp partial sums of the chunk (slot 2 * warp of its 8 doubles; unused slots are zeroed): no block-wide reduction
+		#pragma unroll
+		for (int k = 0; k < 2; k++) {
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
+		}
+		if ((threadIdx.x & 31) == 0) *reinterpret_cast<double2*>(a.partials + (size_t) ch * 8 + 2 * (threadIdx.x >> 5)) = make_double2(acc[0], acc[1]);
+		if (TPB < 128 && threadIdx.x >= TPB / 32 && threadIdx.x < 4) *reinterpret_cast<double2*>(a.partials + (size_t) ch * 8 + 2 * threadIdx.x) = make_double2(0., 0.);
+		__syncthreads();      // windows and lists are reused by the next chunk; its cell_start cache is complete
+		ch = nch; cd = ncd; cur ^= 1;
 	}
 }
 
 // deterministic two-level reduction of the per-chunk partial sums (fixed assignment chunk -> block -> thread, fixed order)
 constexpr int RED_BLOCKS = 128;
-__global__ void __launch_bounds__(256) k_reduce_force_chunks1(const double* __restrict__ partials, const uint32_t* __restrict__ n_chunks, double* __restrict__ partials2) {
+__global__ void __launch_bounds__(256) k_reduce_force_chunks1(const double* __restrict__ partials, const uint32_t* __restrict__ n_chunks, double* __restrict__ partials2, int per_warp) {
 	double v[2] = {0., 0.};
 	const uint32_t n = *n_chunks;
 	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
-		const double2 p = *reinterpret_cast<const double2*>(partials + (size_t) b * 8);
-		v[0] += p.x; v[1] += p.y;
+		const double2* q = reinterpret_cast<const double2*>(partials + (size_t) b * 8);
+		if (per_warp) { const double2 p0 = q[0], p1 = q[1], p2 = q[2], p3 = q[3]; v[0] += (p0.x + p1.x) + (p2.x + p3.x); v[1] += (p0.y + p1.y) + (p2.y + p3.y); }
+		else { const double2 p = q[0]; v[0] += p.x; v[1] += p.y; }
 	}
 	block_reduce_store<2>(v, partials2, blockIdx.x);
 }
@@ -328,8 +352,8 @@ __global__ void __launch_bounds__(RED_BLOCKS) k_reduce_force_chunks2(const doubl
 }
 
 // sums the per-chunk partials of a chunked force kernel into DevScalars (also used by force_1clj_mma.cu)
-int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows) {
-	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks1, RED_BLOCKS, 256, 0, c->partials, c->chunk_row_start + nrows, c->partials2);
+int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows, int per_warp) {
+	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks1, RED_BLOCKS, 256, 0, c->partials, c->chunk_row_start + nrows, c->partials2, per_warp);
 	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks2, 1, RED_BLOCKS, 0, c->partials2, c->d_scal);
 	return 0;
 }
@@ -353,7 +377,7 @@ static int launch_tiled(ls1b200_ctx* c) {
 	a.ljrc2 = (C) (rclj * rclj);
 	a.eps24_0 = (C) c->h_eps24[0]; a.sig2_0 = (C) c->h_sig2[0]; a.shift6_0 = (C) c->h_shift6[0];
 	// the cell_start cache is padded by three rows: the compiler hoists the (guarded) loads of the next row's entries
-	const size_t smem = (size_t) (9 * W + 1) * sizeof(V4) + (size_t) (LCAP + 1) * RI * TPB * 2 + 12 * (CH_MAXC + 3) * 4;
+	const size_t smem = (size_t) (9 * W + 1) * sizeof(V4) + (size_t) (LCAP + 1) * RI * TPB * 2 + 2 * 12 * (CH_MAXC + 3) * 4;
 	auto kern = c->comps.size() == 1 ? k_force_1clj_tiled<C, true> : k_force_1clj_tiled<C, false>;
 	LS1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int per_sm = 0;
@@ -361,7 +385,7 @@ static int launch_tiled(ls1b200_ctx* c) {
 	if (per_sm < 1) return fail("force_1clj_tiled: kernel does not fit on an SM");
 	const uint32_t grid = (uint32_t) (c->sm_count * per_sm);
 	LS1_LAUNCH(c, PH_FORCE, kern, grid, TPB, smem, a);
-	return reduce_force_chunks(c, nrows);
+	return reduce_force_chunks(c, nrows, 1);
 }
 
 int force_1clj_tiled(ls1b200_ctx* c) { return c->mixed ? launch_tiled<float>(c) : launch_tiled<double>(c); }

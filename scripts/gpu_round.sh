@@ -14,7 +14,7 @@ timeout 300 python bench.py --impl reference --steps 3 --warmup 1 > "$OUT/bench_
 # launch list of the same command (shares, not absolutes), reduced steps
 timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file "$OUT/launches.csv" \
     python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > "$OUT/bench_under_ncu.log" 2>&1
-# full capture of the force kernel on a 2 M molecule system (keeps the ~40 replays short)
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_force -s 2 -c 2 -o "$OUT/force_full" -f \
-    python bench.py --steps 3 --warmup 3 --n-per-dim 100 --no-cpu-baseline --e2e-steps 1 > "$OUT/ncu_full.log" 2>&1
+# full capture of the force kernel at the bench size (16 M molecules: dram bytes per launch = roofline.traffic)
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:k_force_1clj_tiled -s 2 -c 1 -o "$OUT/force_full" -f \
+    python bench.py --steps 3 --warmup 3 --no-cpu-baseline --e2e-steps 1 > "$OUT/ncu_full.log" 2>&1
 ls -la "$OUT"
