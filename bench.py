@@ -351,7 +351,9 @@ def our_arm(args):
             "e2e": {"value": round(e2e_value, 2), "unit": "MMUPS", "h2d_bytes_per_step": int(h2d / e2e_steps), "d2h_bytes_per_step": int(d2h / e2e_steps), "steps": e2e_steps,
                     "path": "set_field(R,V) from pinned host -> leapfrog_pre -> update -> traverse_cells -> leapfrog_post -> download(R,V) + scalars"},
             "roofline": {"kernel": "k_force_1clj_tiled<float>" if wl.name == "lj" else "k_force_general<float>", "bound": "fp32", "achieved": round(achieved, 3), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
-                         "frac": round(achieved / fp32_peak, 4), "traffic": None,
+                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size, `ncu --set full` (profiles/r01r_force_full.md):
+                         # 285 MB + 723 MB, against 272 MB of mpos read + 768 MB of F / Vi written algorithmically
+                         "frac": round(achieved / fp32_peak, 4), "traffic": 1007574272 if (wl.name == "lj" and N == 16000000) else None,
                          "peak_source": "FP32 FMA micro-benchmark in this run (ls1b200_measure_fp32_peak); nominal 74.4",
                          "algorithmic_flops_per_launch": flops, "flops_per_molecule": round(flops / N, 1), "kernel_ms": round(force_ms, 4),
                          "pair_interactions_per_s": round(0.5 * (fc0.lj + fc1.lj) / (force_ms * 1e-3), 1),
