@@ -219,6 +219,7 @@ struct ls1b200_ctx {
 	bool peer_ok = false;
 	uint32_t xseq = 0;                                  // exchange calls so far (the sequence number published with every message)
 	uint32_t* xcnt = nullptr;                           // device: {count low, count high, pad, pad}
+	cudaEvent_t xprof_ev[4] = {nullptr, nullptr, nullptr, nullptr}; double xprof_acc[3] = {0., 0., 0.}; int xprof_calls = 0;      // LS1B200_EXCHANGE_PROFILE
 	uint64_t* ekey = nullptr;                           // [cap] (id << 5 | shift code) per provisional slot: content-based in-cell order
 	uint64_t n_owned_local = 0;                         // owned molecules of this rank (host copy, decomposed mode)
 };

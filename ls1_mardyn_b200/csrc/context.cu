@@ -259,6 +259,7 @@ int ls1b200_destroy(ls1b200_ctx* c) {
 	dev_free(c->chunk_row_count); dev_free(c->chunk_row_start); dev_free(c->work_counter);
 	if (c->h_scal) cudaFreeHost(c->h_scal);
 	for (auto e : c->ev_pool) cudaEventDestroy(e);
+	for (auto e : c->xprof_ev) if (e) cudaEventDestroy(e);
 	decomp_free(c);
 	if (c->stage) cudaFree(c->stage);
 	if (c->stream) cudaStreamDestroy(c->stream);

@@ -428,8 +428,8 @@ int do_exchange(ls1b200_ctx* c) {
 	const uint32_t g = std::min<uint32_t>((uint32_t) ((c->cap + 255) / 256), (uint32_t) c->sm_count * 8u), gi = (uint32_t) ((c->msg_cap + 255) / 256);
 	// LS1B200_EXCHANGE_PROFILE=1: CUDA-event breakdown of the stages (export / transport / import), printed by rank 0 every 32 calls
 	static const bool prof = getenv("LS1B200_EXCHANGE_PROFILE") != nullptr;
-	static cudaEvent_t pe[4]; static double pacc[3] = {0., 0., 0.}; static int pcalls = 0;
-	if (prof && pcalls == 0) for (int k = 0; k < 4; k++) cudaEventCreate(&pe[k]);
+	cudaEvent_t* pe = c->xprof_ev; double* pacc = c->xprof_acc; int& pcalls = c->xprof_calls;
+	if (prof && pcalls == 0 && !pe[0]) for (int k = 0; k < 4; k++) cudaEventCreate(&pe[k]);
 	const bool peer = c->peer_ok;
 	const uint32_t par = c->xseq & 1u;
 	for (int d = 0; d < 3; d++) {
