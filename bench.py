@@ -237,9 +237,9 @@ def our_arm(args):
     RHO, TEMP, RC, DT = wl.rho, wl.temperature, wl.rc, wl.dt
     n = args.n_per_dim or wl.n_per_dim
     if world == 1:
-        ps = make_system(n, mixed=True, seed=rank, wl=wl)
+        ps = make_system(n, mixed=(args.precision == "mixed"), seed=rank, wl=wl)
         dd = None
-        ctx = capi.Context([0, 0, 0], list(ps.length), RC, precision="mixed", geometry="xml", periodic=(1, 1, 1), device=local)
+        ctx = capi.Context([0, 0, 0], list(ps.length), RC, precision=args.precision, geometry="xml", periodic=(1, 1, 1), device=local)
         ctx.set_components(ps.ensemble)
     else:
         grid = grid_for(world)
@@ -247,7 +247,7 @@ def our_arm(args):
         ps = generators.lattice_block(wl.ensemble, n, RHO, TEMP, dd0.coords, grid, seed=0)
         ps.r = ps.r.astype(np.float32).astype(np.float64)
         dd = DomainDecomposition(rank, world, ps.length, grid)
-        ctx = capi.Context(list(dd.box_min()), list(dd.box_max()), RC, precision="mixed", geometry="xml", periodic=dd.periodic(), device=local)
+        ctx = capi.Context(list(dd.box_min()), list(dd.box_max()), RC, precision=args.precision, geometry="xml", periodic=dd.periodic(), device=local)
         ctx.set_components(ps.ensemble)
         uid = [capi.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0, device=torch.device("cuda", local))
@@ -262,8 +262,19 @@ def our_arm(args):
         # molecule exchange: NVLink stores into the neighbours' receive buffers (CUDA IPC); LS1B200_TRANSPORT=nccl keeps ncclSend / Recv
         transport = "nccl"
         if os.environ.get("LS1B200_TRANSPORT", "peer") != "nccl":
-            ctx.peer_attach_collective(dist, device=torch.device("cuda", local))
-            transport = "peer-memory"
+            # every rank must end up on the same transport: if mapping a neighbour's buffers fails anywhere (no P2P / IPC between
+            # two of the GPUs), all ranks detach and the exchange goes over NCCL
+            ok = torch.ones(1, device=torch.device("cuda", local))
+            try:
+                ctx.peer_attach_collective(dist, device=torch.device("cuda", local))
+            except Exception as e:      # noqa: BLE001
+                sys.stderr.write("rank %d: peer-memory transport unavailable (%s), falling back to NCCL send/recv\n" % (rank, e))
+                ok.zero_()
+            dist.all_reduce(ok, op=dist.ReduceOp.MIN)
+            if float(ok.item()) > 0:
+                transport = "peer-memory"
+            else:
+                ctx.peer_detach_collective(dist)
         ctx.exchange()
     ctx.update(); ctx.traverse_cells()
     fc0 = ctx.count_flops()
@@ -339,7 +350,8 @@ def our_arm(args):
         line = {
             "metric": "MMUPS", "value": round(value, 2), "unit": "MMUPS (1e6 molecule updates / s)", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1e3 * t_wall / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
-            "dtype": "f32 pair arithmetic, f64 accumulation and state (MARDYN_SPDP)", "data": "synthetic (BCC lattice like CubicGridGenerator, equal-magnitude velocities)",
+            "dtype": "f32 pair arithmetic, f64 accumulation and state (MARDYN_SPDP)" if args.precision == "mixed" else "f64 throughout (MARDYN_DPDP, the reference's double build)",
+            "data": "synthetic (BCC lattice like CubicGridGenerator, equal-magnitude velocities)",
             "config": {"workload": wl.description,
                        "molecules_per_gpu": N, "molecules": world * N, "cells_per_dim": [int(x) for x in ctx.geometry()[0]],
                        "parallelism": "1 GPU" if world == 1 else ("3D block decomposition %dx%dx%d, one process per GPU, leaving molecules + halo copies every step " % grid_for(world)) + ("stored by the packing kernel straight into the neighbours' memory over NVLink (CUDA IPC)" if transport == "peer-memory" else "over NCCL send/recv") + ", NCCL allreduce of 6 doubles",
@@ -350,7 +362,8 @@ def our_arm(args):
             "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 2), "unit": "MMUPS", "h2d_bytes_per_step": int(h2d / e2e_steps), "d2h_bytes_per_step": int(d2h / e2e_steps), "steps": e2e_steps,
                     "path": "set_field(R,V) from pinned host -> leapfrog_pre -> update -> traverse_cells -> leapfrog_post -> download(R,V) + scalars"},
-            "roofline": {"kernel": "k_force_1clj_tiled<float>" if wl.name == "lj" else "k_force_general<float>", "bound": "fp32", "achieved": round(achieved, 3), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
+            "roofline": {"kernel": ("k_force_1clj_tiled<%s, true>" if wl.name == "lj" else "k_force_multi_tiled<%s> (site-signature specialisation)") % ("float" if args.precision == "mixed" else "double"),
+                         "bound": "fp32" if args.precision == "mixed" else "fp64 (against the FP32 peak: MEASURED_PEAKS.json has no FP64 figure)", "achieved": round(achieved, 3), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size, `ncu --set full` (profiles/r01r_force_full.md):
                          # 285 MB + 723 MB, against 272 MB of mpos read + 768 MB of F / Vi written algorithmically
                          "frac": round(achieved / fp32_peak, 4), "traffic": 1007574272 if (wl.name == "lj" and N == 16000000) else None,
@@ -386,6 +399,7 @@ def main():
     ap.add_argument("--n-per-dim", type=int, default=0, help="BCC lattice cells per dimension: N = 2 n^3 (default: the workload's single-GPU size, lj 200 -> 16 M molecules)")
     ap.add_argument("--ref-n-per-dim", type=int, default=80, help="size of the reference arm's bounded sample (80 -> 1.02 M molecules)")
     ap.add_argument("--e2e-steps", type=int, default=3)
+    ap.add_argument("--precision", default="mixed", choices=["mixed", "double"], help="mixed = the headline (BASELINE.json configs[1]); double = the full-FP64 variant of the reference's double build")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     args = ap.parse_args()
     if args.impl == "reference":
