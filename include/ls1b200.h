@@ -143,6 +143,13 @@ int ls1b200_upload(ls1b200_ctx* ctx, uint64_t n, const uint64_t* id, const uint3
                    const double* r, const double* v, const double* q, const double* L);
 uint64_t ls1b200_num_molecules(const ls1b200_ctx* ctx);
 int ls1b200_download(ls1b200_ctx* ctx, int field, void* dst, uint64_t n);
+/* Asynchronous variant for per-step consumers (the host-coherence layer of plugins / writers, FullMolecule fields as in
+ * io/CheckpointWriter): _begin enqueues the gather behind the kernels already submitted and starts the copy to `dst`
+ * (pinned memory for real overlap) on a side stream, so that e.g. the positions of this step travel to the host while the
+ * force traversal runs; `dst` is borrowed until _end returns. One download in flight per context; R, V, Q, L, F, M, VI;
+ * not on decomposed contexts. */
+int ls1b200_download_begin(ls1b200_ctx* ctx, int field, void* dst, uint64_t n);
+int ls1b200_download_end(ls1b200_ctx* ctx);
 /* Overwrite one per-molecule field (R, V, Q, L or F, M) from host memory: the lazy host->device sync the adapter
  * needs when a plugin modified molecules on the host. */
 int ls1b200_set_field(ls1b200_ctx* ctx, int field, const void* src, uint64_t n);

@@ -30,7 +30,7 @@ EXPORTS = ["ls1b200_last_error", "ls1b200_abi_version", "ls1b200_kernel_launch_c
            "ls1b200_geometry", "ls1b200_update", "ls1b200_traverse_cells", "ls1b200_leapfrog_pre", "ls1b200_leapfrog_post",
            "ls1b200_scale_velocities", "ls1b200_simulate", "ls1b200_halo_export", "ls1b200_halo_import",
            "ls1b200_halo_import_host", "ls1b200_phase_times", "ls1b200_count_flops", "ls1b200_measure_fp32_peak",
-           "ls1b200_measure_hbm_copy", "ls1b200_stream", "ls1b200_nccl_unique_id", "ls1b200_decomp_attach", "ls1b200_peer_handle", "ls1b200_peer_attach", "ls1b200_peer_detach", "ls1b200_exchange",
+           "ls1b200_measure_hbm_copy", "ls1b200_stream", "ls1b200_nccl_unique_id", "ls1b200_decomp_attach", "ls1b200_download_begin", "ls1b200_download_end", "ls1b200_peer_handle", "ls1b200_peer_attach", "ls1b200_peer_detach", "ls1b200_exchange",
            "ls1b200_allreduce_macro", "ls1b200_halo_export_host"]
 
 
@@ -114,6 +114,8 @@ def lib():
         L.ls1b200_nccl_unique_id.argtypes = [C.c_void_p]
         L.ls1b200_decomp_attach.argtypes = [C.c_void_p, C.c_void_p]
         L.ls1b200_exchange.argtypes = [C.c_void_p]
+        L.ls1b200_download_begin.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
+        L.ls1b200_download_end.argtypes = [C.c_void_p]
         L.ls1b200_peer_handle.argtypes = [C.c_void_p, C.c_void_p]
         L.ls1b200_peer_attach.argtypes = [C.c_void_p, C.c_void_p, C.c_int32]
         L.ls1b200_peer_detach.argtypes = [C.c_void_p]
@@ -302,6 +304,18 @@ class Context:
             out = np.zeros((self.n,) + shp, dtype=dt)
         _check(lib().ls1b200_download(self.h, f, _vp(out), self.n))
         return out
+
+    def download_begin(self, field, out):
+        """ls1b200_download_begin: starts the copy of a field to `out` (keep it alive, ideally pinned) on a side stream; call
+        download_end() before reading it. Overlaps with whatever is enqueued next (e.g. traverse_cells)."""
+        f = FIELDS[field] if isinstance(field, str) else field
+        assert out.dtype == _FIELD_SHAPE[f][0] and out.flags["C_CONTIGUOUS"] and len(out) == self.n
+        self._dl_keep = out
+        _check(lib().ls1b200_download_begin(self.h, f, _vp(out), self.n))
+
+    def download_end(self):
+        _check(lib().ls1b200_download_end(self.h))
+        self._dl_keep = None
 
     def set_field(self, field, a):
         f = FIELDS[field] if isinstance(field, str) else field

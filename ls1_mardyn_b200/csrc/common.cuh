@@ -187,6 +187,8 @@ struct ls1b200_ctx {
 
 	// staging buffer of download / set_field (grow-only: no cudaMalloc / cudaFree per call on the host-coherent path)
 	void* stage = nullptr; size_t stage_bytes = 0;
+	// ls1b200_download_begin / _end: one download in flight on a side stream while the main stream keeps computing
+	cudaStream_t stream2 = nullptr; cudaEvent_t ev_dl = nullptr; void* stage2 = nullptr; size_t stage2_bytes = 0; bool dl_pending = false;
 
 	// timing
 	std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;

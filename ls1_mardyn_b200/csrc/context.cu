@@ -261,6 +261,9 @@ int ls1b200_destroy(ls1b200_ctx* c) {
 	for (auto e : c->ev_pool) cudaEventDestroy(e);
 	for (auto e : c->xprof_ev) if (e) cudaEventDestroy(e);
 	decomp_free(c);
+	if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+	if (c->ev_dl) cudaEventDestroy(c->ev_dl);
+	if (c->stage2) cudaFree(c->stage2);
 	if (c->stage) cudaFree(c->stage);
 	if (c->stream) cudaStreamDestroy(c->stream);
 	delete c;
@@ -476,6 +479,58 @@ int ls1b200_download(ls1b200_ctx* c, int field, void* dst, uint64_t n) {
 	LS1_CUDA(cudaGetLastError());
 	LS1_CUDA(cudaMemcpyAsync(dst, tmp, sizeof(double) * dim * n, cudaMemcpyDeviceToHost, c->stream));
 	LS1_CUDA(cudaStreamSynchronize(c->stream));
+	return 0;
+}
+
+int ls1b200_download_begin(ls1b200_ctx* c, int field, void* dst, uint64_t n) {
+	if (!c || !dst) return fail("ls1b200_download_begin: null argument");
+	if (c->dd.active) return fail("ls1b200_download_begin: not available on a decomposed context (use ls1b200_download)");
+	if (c->dl_pending) return fail("ls1b200_download_begin: a download is already in flight (call ls1b200_download_end)");
+	if (n != c->n_owned) return fail("ls1b200_download_begin: n does not match the number of molecules");
+	LS1_CUDA(cudaSetDevice(c->device));
+	const double* planes = nullptr; int dim = 3;
+	switch (field) {
+		case LS1B200_F_R: planes = c->cur.r; break;
+		case LS1B200_F_V: planes = c->cur.v; break;
+		case LS1B200_F_Q: planes = c->cur.q; dim = 4; break;
+		case LS1B200_F_L: planes = c->cur.L; break;
+		case LS1B200_F_F: planes = c->F; break;
+		case LS1B200_F_M: planes = c->M; break;
+		case LS1B200_F_VI: planes = c->Vi; break;
+		default: return fail("ls1b200_download_begin: field must be one of R, V, Q, L, F, M, VI");
+	}
+	if (!planes) return fail("ls1b200_download_begin: this ensemble does not store the field (use ls1b200_download)");
+	if (n == 0) return 0;
+	LS1_TRY(sync_scalars(c));      // the slot count of the current sort
+	if (!c->stream2) {
+		LS1_CUDA(cudaStreamCreateWithFlags(&c->stream2, cudaStreamNonBlocking));
+		LS1_CUDA(cudaEventCreateWithFlags(&c->ev_dl, cudaEventDisableTiming));
+	}
+	const size_t bytes = sizeof(double) * dim * n;
+	if (bytes > c->stage2_bytes) {
+		if (c->stage2) { LS1_CUDA(cudaStreamSynchronize(c->stream2)); cudaFree(c->stage2); c->stage2 = nullptr; c->stage2_bytes = 0; }
+		LS1_CUDA(cudaMalloc(&c->stage2, bytes));
+		c->stage2_bytes = bytes;
+	}
+	const uint32_t ns = c->n_slots;
+	// the gather into upload order runs on the main stream (ordered with the kernels that wrote the field), the copy to the host
+	// on the side stream: it overlaps whatever the caller enqueues next
+	k_download_planes<<<(ns + 255) / 256, 256, 0, c->stream>>>(planes, c->cur.meta, (double*) c->stage2, ns, c->cap, dim, (const uint32_t*) nullptr);
+	g_launches++;
+	LS1_CUDA(cudaGetLastError());
+	LS1_CUDA(cudaEventRecord(c->ev_dl, c->stream));
+	LS1_CUDA(cudaStreamWaitEvent(c->stream2, c->ev_dl, 0));
+	LS1_CUDA(cudaMemcpyAsync(dst, c->stage2, bytes, cudaMemcpyDeviceToHost, c->stream2));
+	c->dl_pending = true;
+	return 0;
+}
+
+int ls1b200_download_end(ls1b200_ctx* c) {
+	if (!c) return fail("ls1b200_download_end: null context");
+	if (!c->dl_pending) return 0;
+	LS1_CUDA(cudaSetDevice(c->device));
+	LS1_CUDA(cudaStreamSynchronize(c->stream2));
+	c->dl_pending = false;
 	return 0;
 }
 

@@ -208,6 +208,24 @@ def test_simulate_equals_phase_calls(capi):
     assert np.allclose(a.download("R"), b.download("R"), rtol=1e-13, atol=1e-13)
 
 
+def test_async_download_matches_download(capi):
+    """ls1b200_download_begin / _end (side-stream copy overlapping the next kernels) returns what ls1b200_download returns."""
+    ps = _lattice_case(12, seed=4, jitter=0.1)
+    a = _mk(capi.Context, ps, 2.5, "mixed")
+    a.update()
+    r_async = np.empty((len(ps.id), 3))
+    a.download_begin("R", r_async)              # positions while the forces are computed
+    a.traverse_cells()
+    a.download_end()
+    assert np.array_equal(r_async, a.download("R"))
+    f_async = np.empty((len(ps.id), 3))
+    a.download_begin("F", f_async); a.download_end()
+    assert np.array_equal(f_async, a.download("F"))
+    with pytest.raises(capi.Ls1B200Error):
+        a.download_begin("F", f_async); a.download_begin("V", f_async)      # one download in flight
+    a.download_end()
+
+
 def test_update_is_deterministic_and_idempotent(capi):
     ps = _lattice_case(12, seed=3, jitter=0.2)
     a = _mk(capi.Context, ps, 2.5, "mixed"); b = _mk(capi.Context, ps, 2.5, "mixed")
