@@ -318,12 +318,7 @@ def our_arm(args):
     barrier()
     t0 = time.perf_counter()
     for _ in range(e2e_steps):
-        # host -> device: this step's inputs. On one GPU the loop is pipelined the way a host-resident consumer would drive it:
-        # the velocities of the previous step are still travelling to the host (PCIe is full duplex) while the positions go up.
-        ctx.set_field("R", r_h.numpy()[:n_now])
-        if dd is None:
-            ctx.download_end()                                  # v_h of the previous step is complete
-        ctx.set_field("V", v_h.numpy()[:n_now])
+        ctx.set_field("R", r_h.numpy()[:n_now]); ctx.set_field("V", v_h.numpy()[:n_now])        # host -> device: this step's inputs
         h2d += 48 * n_now
         ctx.leapfrog_pre(DT)
         if dd is not None:
@@ -335,14 +330,12 @@ def our_arm(args):
         if dd is not None:
             m, k = ctx.allreduce_macro()
             n_now = ctx.num_molecules()
-            ctx.download("R", out=r_h.numpy()[:n_now]); ctx.download("V", out=v_h.numpy()[:n_now])
-        else:
-            ctx.download_end()                                  # r_h complete
-            ctx.download_begin("V", v_h.numpy()[:n_now])        # device -> host: the step's results
+            ctx.download("R", out=r_h.numpy()[:n_now])
+        ctx.download("V", out=v_h.numpy()[:n_now])              # device -> host: the step's results
+        if dd is None:
+            ctx.download_end()
         d2h += 48 * n_now + 24
         _ = (m.upot, m.virial, k.summv2)
-    if dd is None:
-        ctx.download_end()
     barrier()
     t_e2e = time.perf_counter() - t0
     t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
@@ -374,7 +367,7 @@ def our_arm(args):
             "phases_ms_per_step": {k: round(v / args.steps, 4) for k, v in ph_ms.items()},
             "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 2), "unit": "MMUPS", "h2d_bytes_per_step": int(h2d / e2e_steps), "d2h_bytes_per_step": int(d2h / e2e_steps), "steps": e2e_steps,
-                    "path": "set_field(R,V) from pinned host -> leapfrog_pre -> update -> traverse_cells -> leapfrog_post -> R,V + scalars back to the host every step; the device->host copies are asynchronous (ls1b200_download_begin/_end): R overlaps the force traversal, V overlaps the next step's upload of R"},
+                    "path": "set_field(R,V) from pinned host -> leapfrog_pre -> update -> [ls1b200_download_begin(R): the positions travel while the forces run] traverse_cells -> leapfrog_post -> download(V), download_end + scalars"},
             "roofline": {"kernel": ("k_force_1clj_tiled<%s, true>" if wl.name == "lj" else "k_force_multi_tiled<%s> (site-signature specialisation)") % ("float" if args.precision == "mixed" else "double"),
                          "bound": "fp32" if args.precision == "mixed" else "fp64 (against the FP32 peak: MEASURED_PEAKS.json has no FP64 figure)", "achieved": round(achieved, 3), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
                          # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size, `ncu --set full` (profiles/r01r_force_full.md):
