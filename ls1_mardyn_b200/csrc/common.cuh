@@ -246,7 +246,8 @@ int force_multi_tiled(ls1b200_ctx* c);
 int reduce_force_partials(ls1b200_ctx* c, uint32_t nblocks);
 int do_exchange(ls1b200_ctx* c);                    // NCCL halo + leaving-molecule exchange of one step (no-op if not decomposed)
 int do_allreduce_scalars(ls1b200_ctx* c);           // sums the 6 leading doubles of DevScalars over the ranks
-int count_owned(ls1b200_ctx* c, bool want_index);   // decomposed mode: n_owned_local (+ entry[slot] = index among owned slots)
+int count_owned(ls1b200_ctx* c, bool want_index);
+const char* overflow_message(uint32_t code);        // DevScalars::overflow -> text   // decomposed mode: n_owned_local (+ entry[slot] = index among owned slots)
 int decomp_alloc(ls1b200_ctx* c);
 void decomp_free(ls1b200_ctx* c);
 }  // namespace ls1b200

@@ -397,13 +397,25 @@ static int stage_reserve(ls1b200_ctx* c, size_t bytes) {
 	return 0;
 }
 
+}  // extern "C"
+namespace ls1b200 {
+const char* overflow_message(uint32_t code) {
+	switch (code) {
+		case 2: return "a halo message buffer was too small (more boundary molecules than the message capacity)";
+		case 4: return "a neighbour's message did not arrive within the time limit (peer-memory transport: did a rank fail or skip ls1b200_exchange?)";
+		default: return "slot capacity exceeded (more halo copies than reserved)";
+	}
+}
+}  // namespace ls1b200
+extern "C" {
+
 // brings n_slots / overflow to the host (synchronises the stream)
 static int sync_scalars(ls1b200_ctx* c, bool owned_index = false) {
 	if (c->dd.active && c->cap) LS1_TRY(count_owned(c, owned_index));
 	LS1_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
 	LS1_CUDA(cudaStreamSynchronize(c->stream));
 	c->n_slots = std::min<uint64_t>(c->h_scal->n_slots2[c->parity], c->cap);
-	if (c->h_scal->overflow) return fail("ls1b200: slot capacity exceeded (more halo copies than reserved)");
+	if (c->h_scal->overflow) return fail(std::string("ls1b200: ") + overflow_message(c->h_scal->overflow));
 	return 0;
 }
 

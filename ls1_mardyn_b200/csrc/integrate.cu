@@ -325,7 +325,7 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 	LS1_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
 	LS1_CUDA(cudaStreamSynchronize(c->stream));
 	c->n_slots = std::min<uint64_t>(c->h_scal->n_slots2[c->parity], c->cap);
-	if (c->h_scal->overflow) return fail(c->h_scal->overflow == 2 ? "ls1b200_simulate: a halo message buffer was too small" : "ls1b200_simulate: slot capacity exceeded (more halo copies than reserved)");
+	if (c->h_scal->overflow) return fail(std::string("ls1b200_simulate: ") + overflow_message(c->h_scal->overflow));
 	if (c->dd.active) LS1_TRY(count_owned(c, false));
 	return 0;
 }

@@ -38,6 +38,35 @@ def test_library_exports_every_declared_symbol(libpath):
     assert lib.ls1b200_abi_version() == 2
 
 
+def declared_arity():
+    """{symbol: number of parameters} parsed from the prototypes of include/ls1b200.h"""
+    hdr = open(os.path.join(ROOT, "include", "ls1b200.h")).read()
+    hdr = re.sub(r"/\*.*?\*/", "", hdr, flags=re.S)
+    out = {}
+    for name, params in re.findall(r"\b(ls1b200_[a-z0-9_]+)\s*\(([^;{]*?)\)\s*;", hdr, flags=re.S):
+        params = params.strip()
+        out[name] = 0 if params in ("", "void") else params.count(",") + 1
+    return out
+
+
+def test_ctypes_bindings_match_the_prototypes(libpath):
+    """Every argtypes list of the ctypes mirror has as many entries as the C prototype has parameters (binding drift shows
+    up here, not as a corrupted stack on the GPU box)."""
+    from ls1_mardyn_b200 import capi
+    lib = capi.lib()
+    arity = declared_arity()
+    assert set(arity) == set(declared_symbols())
+    bad = []
+    for name, n in arity.items():
+        at = getattr(lib, name).argtypes
+        if at is not None and len(at) != n:
+            bad.append((name, n, len(at)))
+    assert not bad, bad
+    # the entry points added in round 1 are bound
+    for name in ("ls1b200_peer_handle", "ls1b200_peer_attach", "ls1b200_peer_detach", "ls1b200_download_begin", "ls1b200_download_end"):
+        assert getattr(lib, name).argtypes is not None, name
+
+
 def test_struct_layouts_match_header(libpath):
     from ls1_mardyn_b200 import capi
     from ls1_mardyn_b200.components import CComponent, CSite
