@@ -63,6 +63,7 @@ struct Geom {
 	double halo_hi[3];           // value for a +L halo copy that landed < bmax   (DomainDecompBase.cpp:364-368)
 	double halo_lo[3];           // value for a -L halo copy that landed >= bmin  (DomainDecompBase.cpp:358-362)
 	double cutoff;
+	double lo_band[3], hi_band[3];   // bmin + cutoff, bmax - cutoff: the layers that need periodic halo copies (DomainDecompBase.cpp:329)
 	int cells[3];                // cells per dimension incl. the halo layer
 	int periodic[3];
 	uint32_t ncells;             // cells[0]*cells[1]*cells[2]; bin ncells is the "limbo" bin (outside the halo box)
@@ -158,7 +159,11 @@ struct ls1b200_ctx {
 	// cells
 	uint32_t* cell_count = nullptr;   // [ncells+2]
 	uint32_t* cell_start = nullptr;   // [ncells+2] exclusive scan
-	uint32_t* cursor = nullptr;       // [ncells+2]
+	uint32_t* cursor = nullptr;       // [ncells+2] next free slot of the halo-copy part of every bin (k_scatter)
+	uint32_t* cell_count_halo = nullptr;   // [ncells+2] periodic halo copies per bin (cell_count holds the non-copies, whose rank k_key already knows)
+	uint32_t* rank = nullptr;         // [cap] provisional rank of a slot's molecule inside its bin (returned by the histogram atomic)
+	double* d_border = nullptr;       // [3][border_stride] cell borders (bit-identical to CellBorderAndFlagManager::getBorder)
+	uint32_t border_stride = 0;
 	uint32_t* scan_tmp = nullptr;
 	uint32_t* key = nullptr;          // [cap] cell | shiftmask << 26 per source slot
 	uint32_t* entry = nullptr;        // [cap] src << 5 | shift code, per provisional slot

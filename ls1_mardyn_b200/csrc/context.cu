@@ -61,6 +61,7 @@ static void free_state(State& s) { dev_free(s.r); dev_free(s.v); dev_free(s.q); 
 void ctx_free_molecules(ls1b200_ctx* c) {
 	free_state(c->cur); free_state(c->nxt);
 	dev_free(c->d_id); dev_free(c->F); dev_free(c->M); dev_free(c->Vi);
+	dev_free(c->rank);
 	dev_free(c->key); dev_free(c->entry); dev_free(c->cell_of); dev_free(c->cell_of2);
 	if (c->mpos) cudaFree(c->mpos); c->mpos = nullptr;
 	if (c->spos) cudaFree(c->spos); c->spos = nullptr;
@@ -79,6 +80,7 @@ int ctx_alloc_molecules(ls1b200_ctx* c, uint64_t n_owned, uint64_t cap) {
 	LS1_TRY(dev_alloc(&c->d_id, n_owned));
 	LS1_TRY(dev_alloc(&c->F, 3 * cap)); LS1_TRY(dev_alloc(&c->Vi, 3 * cap));
 	if (rot) LS1_TRY(dev_alloc(&c->M, 3 * cap));
+	LS1_TRY(dev_alloc(&c->rank, cap));
 	LS1_TRY(dev_alloc(&c->key, cap)); LS1_TRY(dev_alloc(&c->entry, cap)); LS1_TRY(dev_alloc(&c->cell_of, cap)); LS1_TRY(dev_alloc(&c->cell_of2, cap));
 	const size_t v4 = c->mixed ? 16 : 32;
 	// + 64 padding records; mpos[cap] is the far-away sentinel the 1CLJ kernel pads odd neighbour lists with
@@ -129,6 +131,7 @@ static int init_geometry(ls1b200_ctx* c) {
 		g.cells[d] = box_cells + 2;
 		g.lbox[d] = diff;
 		g.periodic[d] = f.periodic[d] ? 1 : 0;
+		g.lo_band[d] = g.bmin[d] + f.cutoff; g.hi_band[d] = g.bmax[d] - f.cutoff;      // one rounding each, like __dadd_rn / __dsub_rn on the device
 		// clamp values of DomainDecompBase.cpp:236-240, :358-368 -- nexttoward in vcp_real_calc (float: mixed, double: double build)
 		if (c->mixed) {
 			const float rmax = (float) g.bmax[d], rmin = (float) g.bmin[d];
@@ -226,7 +229,22 @@ int ls1b200_create(const ls1b200_config* cfg, ls1b200_ctx** out) {
 	if (cudaSetDevice(c->device) != cudaSuccess) return cleanup(fail("ls1b200_create: cudaSetDevice failed"));
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail("ls1b200_create: cannot create stream"));
 	const size_t nb = (size_t) c->geom.ncells + 4;
-	if (dev_alloc(&c->cell_count, nb) || dev_alloc(&c->cell_start, nb) || dev_alloc(&c->cursor, nb) || dev_alloc(&c->scan_tmp, nb / 2048 + 16)) return cleanup(1);
+	if (dev_alloc(&c->cell_count, 2 * nb) || dev_alloc(&c->cell_start, nb) || dev_alloc(&c->cursor, nb) || dev_alloc(&c->scan_tmp, nb / 2048 + 16)) return cleanup(1);
+	c->cell_count_halo = c->cell_count + nb;      // one allocation, one memset per update
+	{
+		// border table, evaluated exactly like cell_border<D> (one fused multiply-add; the first / last two are the stored constants)
+		int maxc = std::max(c->geom.cells[0], std::max(c->geom.cells[1], c->geom.cells[2]));
+		c->border_stride = (uint32_t) maxc + 2;
+		std::vector<double> tab(3 * (size_t) c->border_stride, 0.);
+		for (int d = 0; d < 3; d++) for (int i = 0; i <= c->geom.cells[d]; i++) {
+			double b;
+			if (i == 0) b = c->geom.hmin[d]; else if (i == 1) b = c->geom.bmin[d]; else if (i == c->geom.cells[d] - 1) b = c->geom.bmax[d];
+			else if (i == c->geom.cells[d]) b = c->geom.hmax[d]; else b = fma((double) i, c->geom.clen[d], c->geom.hmin[d]);
+			tab[(size_t) d * c->border_stride + i] = b;
+		}
+		if (dev_alloc(&c->d_border, tab.size())) return cleanup(1);
+		if (cudaMemcpy(c->d_border, tab.data(), sizeof(double) * tab.size(), cudaMemcpyHostToDevice) != cudaSuccess) return cleanup(fail("ls1b200_create: memcpy failed"));
+	}
 	{
 		const size_t nrows = (size_t) c->geom.cells[1] * c->geom.cells[2] + 8;
 		if (cudaMalloc(&c->chunks, ((size_t) c->geom.ncells + 8) * 8) != cudaSuccess) return cleanup(fail("ls1b200_create: out of device memory"));
@@ -253,7 +271,7 @@ int ls1b200_destroy(ls1b200_ctx* c) {
 	ctx_free_molecules(c);
 	dev_free(c->d_comps); dev_free(c->d_sites);
 	dev_free(c->d_eps24); dev_free(c->d_sig2); dev_free(c->d_shift6); dev_free(c->d_eps24f); dev_free(c->d_sig2f); dev_free(c->d_shift6f);
-	dev_free(c->cell_count); dev_free(c->cell_start); dev_free(c->cursor); dev_free(c->scan_tmp);
+	dev_free(c->cell_count); dev_free(c->cell_start); dev_free(c->cursor); dev_free(c->scan_tmp); dev_free(c->d_border);
 	dev_free(c->d_scal); dev_free(c->d_records); dev_free(c->partials2);
 	if (c->chunks) cudaFree(c->chunks);
 	dev_free(c->chunk_row_count); dev_free(c->chunk_row_start); dev_free(c->work_counter);

@@ -29,6 +29,18 @@ __device__ __forceinline__ int cell1d(const Geom& g, double x) {
 	if (x >= g.hmax[D]) return g.cells[D];
 	return c;
 }
+// The same with the borders read from a table (`tab[i]` == cell_border<D>(g, i), filled once by k_borders): the binning
+// kernel is bound by FP64 conversions (int -> double per border evaluation), not by HBM -- profiles/r01u_hbm_kernels.md.
+template <int D>
+__device__ __forceinline__ int cell1d_tab(const Geom& g, const double* __restrict__ tab, double x) {
+	int c = __double2int_rd(__dmul_rn(__dsub_rn(x, g.bmin[D]), g.crecip[D])) + 1;
+	c = min(max(c, 0), g.cells[D] - 1);
+	while (c > 0 && x < __ldg(tab + c)) c--;
+	while (c < g.cells[D] - 1 && x >= __ldg(tab + c + 1)) c++;
+	if (x < g.hmin[D]) return -1;
+	if (x >= g.hmax[D]) return g.cells[D];
+	return c;
+}
 
 __device__ __forceinline__ uint32_t cell_index(const Geom& g, int cx, int cy, int cz) {
 	return (uint32_t) ((cz * g.cells[1] + cy) * g.cells[0] + cx);
@@ -73,8 +85,8 @@ template <int D>
 __device__ __forceinline__ uint32_t shift_mask(const Geom& g, double x) {
 	uint32_t m = 0;
 	if (g.periodic[D]) {
-		if (x >= g.bmin[D] && x < __dadd_rn(g.bmin[D], g.cutoff)) m |= 1u;
-		if (x >= __dsub_rn(g.bmax[D], g.cutoff) && x < g.bmax[D]) m |= 2u;
+		if (x >= g.bmin[D] && x < g.lo_band[D]) m |= 1u;
+		if (x >= g.hi_band[D] && x < g.bmax[D]) m |= 2u;
 	}
 	return m;
 }

@@ -26,13 +26,15 @@ struct UpdArgs {
 	Geom g;
 	uint32_t cap;
 	uint32_t parity;     // DevScalars::n_slots2[parity] = source slots of this update, [parity^1] receives the new count
+	const double* bx; const double* by; const double* bz;      // cell border tables (context.cu)
 };
 
 __device__ __forceinline__ bool code_valid(uint32_t mask, int a, int b, int c) {
 	return (a == 0 || ((mask >> (a - 1)) & 1u)) && (b == 0 || ((mask >> (2 + b - 1)) & 1u)) && (c == 0 || ((mask >> (4 + c - 1)) & 1u));
 }
 
-__global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __restrict__ key, uint32_t* __restrict__ count, const DevScalars* __restrict__ scal) {
+__global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __restrict__ key, uint32_t* __restrict__ count, uint32_t* __restrict__ count_halo,
+                                              uint32_t* __restrict__ rank, const DevScalars* __restrict__ scal) {
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool in_range = s < min(scal->n_slots2[a.parity], a.cap);
 	const Geom& g = a.g;
@@ -46,7 +48,7 @@ __global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __r
 			if (g.periodic[0]) { double w = wrap_coord<0>(g, x); if (w != x) { x = w; cur.r[s] = w; } }
 			if (g.periodic[1]) { double w = wrap_coord<1>(g, y); if (w != y) { y = w; cur.r[(size_t) a.cap + s] = w; } }
 			if (g.periodic[2]) { double w = wrap_coord<2>(g, z); if (w != z) { z = w; cur.r[2 * (size_t) a.cap + s] = w; } }
-			const int cx = cell1d<0>(g, x), cy = cell1d<1>(g, y), cz = cell1d<2>(g, z);
+			const int cx = cell1d_tab<0>(g, a.bx, x), cy = cell1d_tab<1>(g, a.by, y), cz = cell1d_tab<2>(g, a.bz, z);
 			const bool out = cx < 0 || cy < 0 || cz < 0 || cx >= g.cells[0] || cy >= g.cells[1] || cz >= g.cells[2];
 			if (out) { bin = g.ncells; key[s] = bin; }
 			else {
@@ -56,17 +58,29 @@ __global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __r
 			}
 		}
 	}
-	// histogram: slots are in the cell order of the previous step, so the lanes of a warp fall into a handful of bins --
-	// one atomic per distinct bin and warp instead of one per molecule
+	// Histogram: slots are in the cell order of the previous step, so the lanes of a warp fall into a handful of bins -- one
+	// atomic per distinct bin and warp instead of one per molecule. The value the atomic returns is the provisional rank of the
+	// molecule inside its bin: k_scatter needs no second round of atomics for it.
 	{
-		const uint32_t peers = __match_any_sync(0xffffffffu, bin);
-		if (bin != KEY_NONE && (threadIdx.x & 31) == __ffs(peers) - 1) atomicAdd(&count[bin], (uint32_t) __popc(peers));
+		// runs of equal bins among consecutive lanes (a shuffle, a ballot and bit arithmetic; __match_any_sync is far more expensive)
+		const int lane = threadIdx.x & 31;
+		const uint32_t prev = __shfl_up_sync(0xffffffffu, bin, 1);
+		const bool head = lane == 0 || prev != bin;
+		const uint32_t heads = __ballot_sync(0xffffffffu, head);
+		const uint32_t upto = 0xFFFFFFFFu >> (31 - lane);                 // lanes <= mine
+		const int start = 31 - __clz(heads & upto);                        // head of my run
+		const uint32_t above = heads & ~upto;
+		const int end = above ? __ffs(above) - 1 : 32;                     // one past its last lane
+		uint32_t base = 0;
+		if (head && bin != KEY_NONE) base = atomicAdd(&count[bin], (uint32_t) (end - start));
+		base = __shfl_sync(0xffffffffu, base, start);
+		if (bin != KEY_NONE) rank[s] = base + (uint32_t) (lane - start);
 	}
 	if (mask) {
 		for (int c3 = 0; c3 < 3; c3++) for (int b3 = 0; b3 < 3; b3++) for (int a3 = 0; a3 < 3; a3++) {
 			if ((a3 | b3 | c3) == 0 || !code_valid(mask, a3, b3, c3)) continue;
-			const int hx = cell1d<0>(g, halo_coord<0>(g, x, a3)), hy = cell1d<1>(g, halo_coord<1>(g, y, b3)), hz = cell1d<2>(g, halo_coord<2>(g, z, c3));
-			atomicAdd(&count[cell_index(g, hx, hy, hz)], 1u);
+			const int hx = cell1d_tab<0>(g, a.bx, halo_coord<0>(g, x, a3)), hy = cell1d_tab<1>(g, a.by, halo_coord<1>(g, y, b3)), hz = cell1d_tab<2>(g, a.bz, halo_coord<2>(g, z, c3));
+			atomicAdd(&count_halo[cell_index(g, hx, hy, hz)], 1u);
 		}
 	}
 }
@@ -94,12 +108,12 @@ __device__ __forceinline__ uint32_t block_exclusive_scan(uint32_t v, uint32_t* t
 	return r;
 }
 
-__global__ void __launch_bounds__(SCAN_T) k_scan_block(const uint32_t* __restrict__ in, uint32_t* __restrict__ out, uint32_t* __restrict__ bsum, uint32_t n) {
+__global__ void __launch_bounds__(SCAN_T) k_scan_block(const uint32_t* __restrict__ in, const uint32_t* __restrict__ in2, uint32_t* __restrict__ out, uint32_t* __restrict__ bsum, uint32_t n) {
 	__shared__ uint32_t sh[32]; __shared__ uint32_t tot;
 	const uint32_t base = blockIdx.x * SCAN_B + threadIdx.x * SCAN_V;
 	uint32_t v[SCAN_V], sum = 0;
 	#pragma unroll
-	for (int k = 0; k < SCAN_V; k++) { v[k] = (base + k < n) ? in[base + k] : 0u; sum += v[k]; }
+	for (int k = 0; k < SCAN_V; k++) { v[k] = (base + k < n) ? in[base + k] + in2[base + k] : 0u; sum += v[k]; }
 	uint32_t off = block_exclusive_scan(sum, &tot, sh);
 	#pragma unroll
 	for (int k = 0; k < SCAN_V; k++) { if (base + k < n) out[base + k] = off; off += v[k]; }
@@ -119,12 +133,12 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_top(uint32_t* __restrict__ bsum
 	if (threadIdx.x == 0) *grand_total = carry;
 }
 // adds the block offsets; writes cell_start[0..n] (cell_start[n] = total), the scatter cursor, and the slot count
-__global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict__ start, uint32_t* __restrict__ cursor, const uint32_t* __restrict__ bsum,
+__global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict__ start, uint32_t* __restrict__ cursor, const uint32_t* __restrict__ count, const uint32_t* __restrict__ bsum,
                                                       const uint32_t* __restrict__ grand_total, uint32_t n, uint32_t cap, uint32_t parity, DevScalars* scal) {
 	const uint32_t base = blockIdx.x * SCAN_B + threadIdx.x * SCAN_V;
 	const uint32_t off = bsum[blockIdx.x];
 	#pragma unroll
-	for (int k = 0; k < SCAN_V; k++) if (base + k < n) { uint32_t v = start[base + k] + off; start[base + k] = v; cursor[base + k] = v; }
+	for (int k = 0; k < SCAN_V; k++) if (base + k < n) { uint32_t v = start[base + k] + off; start[base + k] = v; cursor[base + k] = v + count[base + k]; }      // halo copies follow the ranked entries
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		const uint32_t total = *grand_total;
 		start[n] = total;
@@ -134,31 +148,27 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict__ star
 	}
 }
 
-__global__ void __launch_bounds__(256) k_scatter(UpdArgs a, State cur, const uint32_t* __restrict__ key, uint32_t* __restrict__ cursor,
-                                                  uint32_t* __restrict__ entry, uint32_t* __restrict__ cell_of, const DevScalars* __restrict__ scal,
+__global__ void __launch_bounds__(256) k_scatter(UpdArgs a, State cur, const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ cell_start,
+                                                  uint32_t* __restrict__ cursor, uint32_t* __restrict__ entry, uint32_t* __restrict__ cell_of, const DevScalars* __restrict__ scal,
                                                   uint64_t* __restrict__ ekey) {
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	const bool in_range = s < min(scal->n_slots2[a.parity], a.cap);
-	const uint32_t k = in_range ? key[s] : KEY_NONE;
+	if (s >= min(scal->n_slots2[a.parity], a.cap)) return;
+	const uint32_t k = key[s];
+	if (k == KEY_NONE) return;
 	const Geom& g = a.g;
-	const uint32_t bin = (k == KEY_NONE) ? KEY_NONE : (k & ((1u << SHIFT_BITS) - 1u)), mask = (k == KEY_NONE) ? 0u : (k >> SHIFT_BITS);
-	// provisional slot: one atomic per distinct bin and warp (the in-cell order is made deterministic by k_gather)
-	const uint32_t peers = __match_any_sync(0xffffffffu, bin);
-	const int lane = threadIdx.x & 31, leader = __ffs(peers) - 1;
-	uint32_t base = 0;
-	if (bin != KEY_NONE && lane == leader) base = atomicAdd(&cursor[bin], (uint32_t) __popc(peers));
-	base = __shfl_sync(0xffffffffu, base, leader);
-	if (bin == KEY_NONE) return;
-	uint32_t p = base + (uint32_t) __popc(peers & ((1u << lane) - 1u));
+	const uint32_t bin = k & ((1u << SHIFT_BITS) - 1u), mask = k >> SHIFT_BITS;
+	// provisional slot: start of the bin + the rank k_key obtained from the histogram atomic (the in-cell order is made
+	// deterministic by k_gather)
+	uint32_t p = cell_start[bin] + rank[s];
 	const uint64_t idk = ekey ? (cur.id[s] << 5) : 0ull;      // decomposed mode: in-cell order by (molecule id, shift code)
 	if (p < a.cap) { entry[p] = s << 5; cell_of[p] = bin; if (ekey) ekey[p] = idk; }
 	if (mask) {
 		const double x = cur.r[s], y = cur.r[(size_t) a.cap + s], z = cur.r[2 * (size_t) a.cap + s];
 		for (int c3 = 0; c3 < 3; c3++) for (int b3 = 0; b3 < 3; b3++) for (int a3 = 0; a3 < 3; a3++) {
 			if ((a3 | b3 | c3) == 0 || !code_valid(mask, a3, b3, c3)) continue;
-			const int hx = cell1d<0>(g, halo_coord<0>(g, x, a3)), hy = cell1d<1>(g, halo_coord<1>(g, y, b3)), hz = cell1d<2>(g, halo_coord<2>(g, z, c3));
+			const int hx = cell1d_tab<0>(g, a.bx, halo_coord<0>(g, x, a3)), hy = cell1d_tab<1>(g, a.by, halo_coord<1>(g, y, b3)), hz = cell1d_tab<2>(g, a.bz, halo_coord<2>(g, z, c3));
 			const uint32_t hb = cell_index(g, hx, hy, hz);
-			p = atomicAdd(&cursor[hb], 1u);
+			p = atomicAdd(&cursor[hb], 1u);      // the periodic copies of a bin follow its ranked entries
 			if (p < a.cap) { entry[p] = (s << 5) | (uint32_t) (a3 + 3 * b3 + 9 * c3); cell_of[p] = hb; if (ekey) ekey[p] = idk | (uint64_t) (a3 + 3 * b3 + 9 * c3); }
 		}
 	}
@@ -253,16 +263,17 @@ int do_update(ls1b200_ctx* c) {
 	if (c->cap == 0) return fail("ls1b200_update: call ls1b200_upload first");
 	LS1_TRY(span_begin(c, PH_UPDATE));
 	UpdArgs a; a.g = c->geom; a.cap = (uint32_t) c->cap; a.parity = c->parity;
+	a.bx = c->d_border; a.by = c->d_border + c->border_stride; a.bz = c->d_border + 2 * (size_t) c->border_stride;
 	const uint32_t nb = c->geom.ncells + 1;   // + limbo bin
-	LS1_CUDA(cudaMemsetAsync(c->cell_count, 0, sizeof(uint32_t) * (nb + 1), c->stream));
+	LS1_CUDA(cudaMemsetAsync(c->cell_count, 0, sizeof(uint32_t) * 2 * ((size_t) c->geom.ncells + 4), c->stream));      // cell_count and cell_count_halo
 	// slot counts are only known on the device: every per-slot kernel is launched over the capacity, threads beyond exit
 	const uint32_t gs = (uint32_t) ((c->cap + 255) / 256);
-	LS1_LAUNCH(c, PH_UPDATE, k_key, gs, 256, 0, a, c->cur, c->key, c->cell_count, c->d_scal);
+	LS1_LAUNCH(c, PH_UPDATE, k_key, gs, 256, 0, a, c->cur, c->key, c->cell_count, c->cell_count_halo, c->rank, c->d_scal);
 	const uint32_t sb = (nb + SCAN_B - 1) / SCAN_B;
-	LS1_LAUNCH(c, PH_UPDATE, k_scan_block, sb, SCAN_T, 0, c->cell_count, c->cell_start, c->scan_tmp, nb);
+	LS1_LAUNCH(c, PH_UPDATE, k_scan_block, sb, SCAN_T, 0, c->cell_count, c->cell_count_halo, c->cell_start, c->scan_tmp, nb);
 	LS1_LAUNCH(c, PH_UPDATE, k_scan_top, 1, SCAN_T, 0, c->scan_tmp, sb, c->scan_tmp + sb);
-	LS1_LAUNCH(c, PH_UPDATE, k_scan_add, sb, SCAN_T, 0, c->cell_start, c->cursor, c->scan_tmp, c->scan_tmp + sb, nb, (uint32_t) c->cap, a.parity, c->d_scal);
-	LS1_LAUNCH(c, PH_UPDATE, k_scatter, gs, 256, 0, a, c->cur, c->key, c->cursor, c->entry, c->cell_of, c->d_scal, c->dd.active ? c->ekey : (uint64_t*) nullptr);
+	LS1_LAUNCH(c, PH_UPDATE, k_scan_add, sb, SCAN_T, 0, c->cell_start, c->cursor, c->cell_count, c->scan_tmp, c->scan_tmp + sb, nb, (uint32_t) c->cap, a.parity, c->d_scal);
+	LS1_LAUNCH(c, PH_UPDATE, k_scatter, gs, 256, 0, a, c->cur, c->key, c->rank, c->cell_start, c->cursor, c->entry, c->cell_of, c->d_scal, c->dd.active ? c->ekey : (uint64_t*) nullptr);
 	const uint32_t gc = gs;
 	if (c->mixed)
 		LS1_LAUNCH(c, PH_UPDATE, k_gather<float>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, c->cell_start, c->cell_of2, (float4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr);
