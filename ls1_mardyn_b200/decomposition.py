@@ -26,16 +26,50 @@ def dims_create(n: int):
     return best
 
 
-class DomainDecomposition:
-    """Equal blocks of a periodic box of size global_length (origin 0): getBoundingBoxMin/Max as
-    DomainDecomposition.cpp:130-139 (coords * L / grid, the last block ends exactly at L)."""
+def balanced_cuts(r, global_length, grid, min_width):
+    """Cut positions of a tensor-product decomposition that balances the molecule count per slab of every dimension
+    (the marginal quantiles of the coordinates), for inhomogeneous systems (droplets, films: SURVEY.md 8f-4; the reference's
+    answer is the k-d tree of parallel/KDDecomposition.cpp). Every slab is at least `min_width` (two cutoff radii) wide.
+    Returns three arrays of grid[d] + 1 cut positions, the first 0 and the last global_length[d]. Deterministic: every rank
+    computes the same cuts from the same (gathered) coordinates."""
+    r = np.asarray(r, dtype=np.float64)
+    cuts = []
+    for d in range(3):
+        g, L = int(grid[d]), float(global_length[d])
+        if g * min_width > L * (1.0 + 1e-12):
+            raise ValueError("balanced_cuts: %d slabs of width >= %g do not fit into %g" % (g, min_width, L))
+        c = np.empty(g + 1); c[0] = 0.0; c[g] = L
+        x = np.sort(r[:, d])
+        for k in range(1, g):
+            c[k] = x[min(len(x) - 1, (k * len(x)) // g)] if len(x) else k * L / g
+        # enforce the minimum width from the left, then from the right
+        for k in range(1, g):
+            c[k] = max(c[k], c[k - 1] + min_width)
+        for k in range(g - 1, 0, -1):
+            c[k] = min(c[k], c[k + 1] - min_width)
+        cuts.append(c)
+    return cuts
 
-    def __init__(self, rank: int, n_ranks: int, global_length, grid=None):
+
+class DomainDecomposition:
+    """Blocks of a periodic box of size global_length (origin 0). Default: equal blocks, getBoundingBoxMin/Max as
+    DomainDecomposition.cpp:130-139 (coords * L / grid, the last block ends exactly at L). With `cuts` (three arrays of
+    grid[d] + 1 positions, e.g. from balanced_cuts) the blocks are the cells of that tensor-product grid: neighbour relations,
+    the staged exchange and the library side are unchanged -- every rank's context simply gets its own box."""
+
+    def __init__(self, rank: int, n_ranks: int, global_length, grid=None, cuts=None):
         self.rank, self.n_ranks = int(rank), int(n_ranks)
         self.global_length = np.asarray(global_length, dtype=np.float64)
         self.grid = tuple(int(g) for g in (grid if grid is not None else dims_create(n_ranks)))
         if self.grid[0] * self.grid[1] * self.grid[2] != n_ranks:
             raise ValueError("DomainDecomposition: Wrong grid size given!")
+        self.cuts = None
+        if cuts is not None:
+            self.cuts = [np.asarray(c, dtype=np.float64) for c in cuts]
+            for d in range(3):
+                c = self.cuts[d]
+                if len(c) != self.grid[d] + 1 or c[0] != 0.0 or c[-1] != self.global_length[d] or np.any(np.diff(c) <= 0.0):
+                    raise ValueError("DomainDecomposition: cuts[%d] must be %d increasing positions from 0 to the box length" % (d, self.grid[d] + 1))
         self.coords = self.coords_of(rank)
 
     def coords_of(self, rank):
@@ -49,10 +83,14 @@ class DomainDecomposition:
 
     def box_min(self, coords=None):
         c = self.coords if coords is None else coords
+        if self.cuts is not None:
+            return np.array([self.cuts[d][c[d]] for d in range(3)])
         return np.array([c[d] * self.global_length[d] / self.grid[d] for d in range(3)])
 
     def box_max(self, coords=None):
         c = self.coords if coords is None else coords
+        if self.cuts is not None:
+            return np.array([self.cuts[d][c[d] + 1] for d in range(3)])
         return np.array([self.global_length[d] if c[d] + 1 == self.grid[d] else (c[d] + 1) * self.global_length[d] / self.grid[d] for d in range(3)])
 
     def periodic(self):

@@ -12,7 +12,7 @@ import pytest
 from ls1_mardyn_b200 import generators
 from ls1_mardyn_b200.capi import PARTICLE
 from ls1_mardyn_b200.components import lj_fluid
-from ls1_mardyn_b200.decomposition import DomainDecomposition, dims_create, exchange_local
+from ls1_mardyn_b200.decomposition import DomainDecomposition, balanced_cuts, dims_create, exchange_local
 from oracle import oracle as orc
 from oracle.decomposed import OracleRank
 
@@ -123,6 +123,50 @@ def test_decomposed_oracle_equals_single_domain(n_ranks, grid, prec):
     ids, R = gather(ranks, "R")
     R1 = one.download("R")[o1]
     assert np.abs(R - R1).max() <= (1e-9 if prec == "double" else 1e-4)
+
+
+def test_balanced_cuts_and_inhomogeneous_system():
+    """Load-balanced tensor-product decomposition (host logic only; the library side is the same per-rank box): the cuts follow
+    the molecule distribution, respect the minimum width, and the union of the blocks still reproduces the single domain."""
+    rc = 2.0
+    ps = generators.lj_lattice(9, seed=8, jitter=0.1)           # 1458 molecules, L = 12.77
+    L = ps.length
+    # an inhomogeneous system: keep all molecules of the lower 45 % of x, every fourth one elsewhere (a film with vapour)
+    keep = (ps.r[:, 0] < 0.45 * L[0]) | (np.arange(len(ps.id)) % 4 == 0)
+    for f in ("id", "cid", "r", "v", "q", "L"):
+        setattr(ps, f, getattr(ps, f)[keep])
+    n = len(ps.id)
+    grid = (2, 1, 1)
+    cuts = balanced_cuts(ps.r, L, grid, 2 * rc)
+    assert cuts[0][0] == 0.0 and cuts[0][2] == L[0] and len(cuts[1]) == 2
+    assert cuts[0][1] < 0.45 * L[0] and cuts[0][1] >= 2 * rc and L[0] - cuts[0][1] >= 2 * rc      # the cut moved into the dense part
+    dds = [DomainDecomposition(r, 2, L, grid, cuts=cuts) for r in range(2)]
+    owner = dds[0].owner_of(ps.r)
+    counts = np.bincount(owner, minlength=2)
+    equal = np.bincount(DomainDecomposition(0, 2, L, grid).owner_of(ps.r), minlength=2)
+    assert abs(int(counts[0]) - int(counts[1])) < abs(int(equal[0]) - int(equal[1])), (counts, equal)
+    with pytest.raises(ValueError):
+        balanced_cuts(ps.r, L, (4, 1, 1), 2 * rc)               # four slabs of width 4 do not fit into 12.77
+    with pytest.raises(ValueError):
+        DomainDecomposition(0, 2, L, grid, cuts=[np.array([0.0, 3.0]), cuts[1], cuts[2]])
+    # physics: blocks of unequal width == the single periodic domain, with migration over a few steps
+    ps.v *= 5.0
+    ranks = make_ranks(ps, dds, owner, "double", rc)
+    one = orc.OracleSim([0, 0, 0], list(L), rc, epsilon_rf=ps.epsilon_rf, precision="double", geometry="xml", periodic=(1, 1, 1))
+    one.set_components(ps.ensemble); one.upload(ps.id, ps.cid, ps.r, ps.v, ps.q, ps.L)
+    exchange_local(ranks, dds)
+    for k in ranks:
+        k.update()
+    ms = [k.traverse_cells() for k in ranks]
+    one.update(); m1 = one.traverse_cells()
+    ids, F = gather(ranks, "F")
+    o1 = np.argsort(one.download("ID")); F1 = one.download("F")[o1]
+    assert np.abs(F - F1).max() <= 1e-11 * max(np.sqrt((F1 ** 2).mean()), np.abs(F1).max())
+    assert abs(sum(m.upot for m in ms) - m1.upot) <= 1e-11 * abs(m1.upot)
+    for step in range(6):
+        up, vir, mv2, nn = step_all(ranks, dds, 0.005)
+        one.leapfrog_pre(0.005); one.update(); m1 = one.traverse_cells(); k1 = one.leapfrog_post(0.005)
+        assert nn == n and abs(up - m1.upot) <= 1e-10 * abs(m1.upot) and abs(mv2 - k1.summv2) <= 1e-10 * k1.summv2
 
 
 def test_two_processes_gloo(tmp_path):
