@@ -240,6 +240,9 @@ int ls1b200_peer_attach(ls1b200_ctx* ctx, const uint8_t* handles /* [n_ranks][LS
  * caller's -- BEFORE any rank destroys its context or uploads again: memory must not be freed while a peer has it mapped. */
 int ls1b200_peer_detach(ls1b200_ctx* ctx);
 /* One exchange (all stages) on the context's stream -- peer-memory transport if attached, else NCCL send / recv; collective.
+ * The NCCL transport sends fixed-capacity messages whose capacity derives from the number of molecules a rank uploaded: use
+ * it with (nearly) equal molecule counts per rank, as the equal-volume decomposition of a homogeneous system gives; the
+ * peer-memory transport honours the capacity of every receiver and has no such restriction.
  * ls1b200_simulate calls it every step; phase-by-phase drivers call it between ls1b200_leapfrog_pre and ls1b200_update
  * (and once before the first update). */
 int ls1b200_exchange(ls1b200_ctx* ctx);
