@@ -584,6 +584,10 @@ int ls1b200_peer_attach(ls1b200_ctx* c, const uint8_t* handles, int32_t n_ranks)
 	if (!c->dd.active || !c->pin_base) return fail("ls1b200_peer_attach: call ls1b200_decomp_attach and ls1b200_upload first");
 	if (n_ranks != c->dd.n_ranks) return fail("ls1b200_peer_attach: one handle per rank of the decomposition is expected");
 	LS1_CUDA(cudaSetDevice(c->device));
+	// a second attach replaces the first: unmap what is mapped
+	if (c->stream) LS1_CUDA(cudaStreamSynchronize(c->stream));
+	for (int k = 0; k < 6; k++) { if (c->peer_opened[k]) cudaIpcCloseMemHandle(c->peer_opened[k]); c->peer_opened[k] = nullptr; c->peer_opened_rank[k] = -1; }
+	c->peer_ok = false;
 	int n_open = 0;
 	for (int d = 0; d < 3; d++) for (int side = 0; side < 2; side++) {
 		c->peer_base[d][side] = nullptr;
