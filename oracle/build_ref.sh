@@ -5,6 +5,11 @@
 #
 #   oracle/_ref/mixed/MarDyn    PRECISION=MIXED  (-DMARDYN_SPDP), AVX2+FMA, OpenMP
 #   oracle/_ref/double/MarDyn   PRECISION=DOUBLE (-DMARDYN_DPDP), AVX2+FMA, OpenMP
+#   oracle/_ref/rmm/MarDyn      PRECISION=SINGLE + REDUCED_MEMORY_MODE (only on request: build_ref.sh rmm). STATUS: the unmodified
+#                               reference does NOT compile in this configuration with g++ 13.3 (-std=c++17 or c++23):
+#                               particleContainer/ParticleIterator.h:78 and RegionParticleIterator.h:75 default a constexpr copy
+#                               constructor whose implicit version is not constexpr once Molecule = MoleculeRMM. An oracle for the
+#                               RMM path therefore needs a patched build-time copy (drop the two `constexpr`).
 #   oracle/_ref/<prec>/refdump  our dump driver (oracle/refdump.cpp) linked against the same objects
 #
 # The source list mirrors what the reference's CMakeLists select for ENABLE_MPI=OFF, ENABLE_ADIOS2=OFF,
@@ -38,6 +43,7 @@ for prec in $PRECS; do
   case "$prec" in
     mixed)  PDEF=-DMARDYN_SPDP;;
     double) PDEF=-DMARDYN_DPDP;;
+    rmm)    PDEF="-DMARDYN_SPSP -DENABLE_REDUCED_MEMORY_MODE=1";;      # the reference's reduced-memory mode: all FP32, 1CLJ only (VCP1CLJRMM)
     *) echo "unknown precision $prec"; exit 2;;
   esac
   OUT="$HERE/_ref/$prec"; OBJ="$OUT/obj"; mkdir -p "$OBJ" "$OUT/gen"
@@ -47,7 +53,8 @@ for prec in $PRECS; do
 #include <string>
 const std::string MARDYN_VERSION = "1.2.0_oracle_ref_$prec";
 H
-  FLAGS="-std=c++17 -O3 -DNDEBUG -fopenmp -DENABLE_OPENMP -fopenmp-simd -mavx2 -mfma -DENABLE_VECTORIZED_CODE=1 \
+  STD=c++17; [ "$prec" = rmm ] && STD=c++23      # the RMM configuration declares constexpr copy constructors g++ only accepts from C++23 on (P2448)
+  FLAGS="-std=$STD -O3 -DNDEBUG -fopenmp -DENABLE_OPENMP -fopenmp-simd -mavx2 -mfma -DENABLE_VECTORIZED_CODE=1 \
 $PDEF -DTIMERS -w -I$OUT/gen -I$REF/src -I$REF/libs/rapidxml -I$REF/libs"
   MK="$OUT/Makefile.gen"
   { echo "CXX=$CXX"; echo "FLAGS=$FLAGS"; echo "OBJS="; } > "$MK"
