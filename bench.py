@@ -180,6 +180,9 @@ def cpu_baseline(sample_n=60, steps=3):
             "sample": f"oracle/liboracle.so scalar port: 1CLJ lattice N={n}, 2 steps, {t:.2f} s"}
 
 
+WL_LJ_DESCRIPTION = "BASELINE.json configs[1]: 1CLJ LJ liquid rho*=0.7 T*=0.85 rc=2.5 sigma dt=0.002, mixed precision, NVT velocity scaling"
+
+
 def reference_arm(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -196,7 +199,8 @@ def reference_arm(args):
     line = {"metric": "MMUPS", "value": round(v, 4), "unit": "MMUPS (1e6 molecule updates / s)", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1e3 * t / max(args.steps, 1), 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 pair arithmetic, f64 accumulation and state (MARDYN_SPDP)", "data": "synthetic (BCC lattice, CubicGridGenerator)", "impl": "reference",
-            "config": {"workload": "1CLJ LJ liquid rho*=0.7 T*=0.85 rc=2.5 sigma dt=0.002, mixed precision, NVT", "molecules": nmol,
+            # the same workload as our arm (same `workload` string); the reference is timed on a bounded sample of it
+            "config": {"workload": WL_LJ_DESCRIPTION, "molecules": nmol, "molecules_of_the_workload": 16000000,
                        "note": "bounded sample of the 16M-molecule workload (MMUPS is size independent to first order)"},
             "cpu_baseline": {"value": round(v, 4), "unit": "MMUPS", "cores": cores, "kind": kind,
                              "sample": f"N={nmol}, {args.steps} steps, main loop {t:.2f} s, total wall {time.perf_counter() - t0:.1f} s"},
