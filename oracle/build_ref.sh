@@ -8,8 +8,9 @@
 #   oracle/_ref/rmm/MarDyn      PRECISION=SINGLE + REDUCED_MEMORY_MODE (only on request: build_ref.sh rmm). STATUS: the unmodified
 #                               reference does NOT compile in this configuration with g++ 13.3 (-std=c++17 or c++23):
 #                               particleContainer/ParticleIterator.h:78 and RegionParticleIterator.h:75 default a constexpr copy
-#                               constructor whose implicit version is not constexpr once Molecule = MoleculeRMM. An oracle for the
-#                               RMM path therefore needs a patched build-time copy (drop the two `constexpr`).
+#                               constructor whose implicit version is not constexpr once Molecule = MoleculeRMM. The rmm build
+#                               therefore compiles from a shadow tree of symbolic links under _ref/rmm/shadow with that keyword
+#                               removed from those two declarations (generated at build time, never copied into the repo).
 #   oracle/_ref/<prec>/refdump  our dump driver (oracle/refdump.cpp) linked against the same objects
 #
 # The source list mirrors what the reference's CMakeLists select for ENABLE_MPI=OFF, ENABLE_ADIOS2=OFF,
@@ -53,15 +54,26 @@ for prec in $PRECS; do
 #include <string>
 const std::string MARDYN_VERSION = "1.2.0_oracle_ref_$prec";
 H
-  STD=c++17; [ "$prec" = rmm ] && STD=c++23      # the RMM configuration declares constexpr copy constructors g++ only accepts from C++23 on (P2448)
-  FLAGS="-std=$STD -O3 -DNDEBUG -fopenmp -DENABLE_OPENMP -fopenmp-simd -mavx2 -mfma -DENABLE_VECTORIZED_CODE=1 \
-$PDEF -DTIMERS -w -I$OUT/gen -I$REF/src -I$REF/libs/rapidxml -I$REF/libs"
+  SRC="$REF/src"
+  if [ "$prec" = rmm ]; then
+    # g++ 13.3 rejects two `constexpr ... = default` copy constructors once Molecule = MoleculeRMM (see the header of this file).
+    # The sources are compiled from a shadow tree under _ref/ (git-ignored, generated here): symbolic links to every reference
+    # file, except the two headers, which are written by sed with that one keyword removed. Nothing is copied into the repo.
+    SRC="$OUT/shadow"; rm -rf "$SRC"; mkdir -p "$SRC"
+    ( cd "$REF/src" && find . -type d ) | while read -r d; do mkdir -p "$SRC/$d"; done
+    ( cd "$REF/src" && find . -type f ) | while read -r f; do ln -s "$REF/src/$f" "$SRC/$f"; done
+    for h in particleContainer/ParticleIterator.h particleContainer/RegionParticleIterator.h; do
+      rm "$SRC/$h"; sed 's/^\(\s*\)constexpr \(\(Region\)\?ParticleIterator\s*(const\)/\1\2/' "$REF/src/$h" > "$SRC/$h"
+    done
+  fi
+  FLAGS="-std=c++17 -O3 -DNDEBUG -fopenmp -DENABLE_OPENMP -fopenmp-simd -mavx2 -mfma -DENABLE_VECTORIZED_CODE=1 \
+$PDEF -DTIMERS -w -I$OUT/gen -I$SRC -I$REF/libs/rapidxml -I$REF/libs"
   MK="$OUT/Makefile.gen"
   { echo "CXX=$CXX"; echo "FLAGS=$FLAGS"; echo "OBJS="; } > "$MK"
   for f in $(list_sources); do
     o="$OBJ/$(echo "$f" | tr '/' '_' | sed 's/\.cpp$/.o/')"
     echo "OBJS+=$o" >> "$MK"
-    printf '%s: %s\n\t@$(CXX) $(FLAGS) -c $< -o $@\n' "$o" "$REF/src/$f" >> "$MK"
+    printf '%s: %s\n\t@$(CXX) $(FLAGS) -c $< -o $@\n' "$o" "$SRC/$f" >> "$MK"
   done
   cat >> "$MK" <<M
 LIBOBJS=\$(filter-out %/MarDyn.o,\$(OBJS))
@@ -73,6 +85,6 @@ $OUT/refdump.o: $HERE/refdump.cpp
 $OUT/refdump: \$(LIBOBJS) $OUT/refdump.o
 	@\$(CXX) -fopenmp \$(LIBOBJS) $OUT/refdump.o -o \$@
 M
-  if [ -f "$HERE/refdump.cpp" ]; then make -f "$MK" -j"$JOBS" all; else make -f "$MK" -j"$JOBS" "$OUT/MarDyn"; fi
+  if [ -f "$HERE/refdump.cpp" ] && [ "$prec" != rmm ]; then make -f "$MK" -j"$JOBS" all; else make -f "$MK" -j"$JOBS" "$OUT/MarDyn"; fi      # refdump reads F / M / Vi, which MoleculeRMM does not store
   echo "build_ref: built $OUT/MarDyn"
 done
