@@ -5,6 +5,7 @@
 #
 #   oracle/_ref/mixed/MarDyn    PRECISION=MIXED  (-DMARDYN_SPDP), AVX2+FMA, OpenMP
 #   oracle/_ref/double/MarDyn   PRECISION=DOUBLE (-DMARDYN_DPDP), AVX2+FMA, OpenMP
+#   oracle/_ref/mixed512/MarDyn PRECISION=MIXED with AVX-512 (only on request: build_ref.sh mixed512; bench.py's CPU legs prefer it on AVX-512 hosts)
 #   oracle/_ref/rmm/MarDyn      PRECISION=SINGLE + REDUCED_MEMORY_MODE (only on request: build_ref.sh rmm). STATUS: the unmodified
 #                               reference does NOT compile in this configuration with g++ 13.3 (-std=c++17 or c++23):
 #                               particleContainer/ParticleIterator.h:78 and RegionParticleIterator.h:75 default a constexpr copy
@@ -41,9 +42,11 @@ list_sources() {
 }
 
 for prec in $PRECS; do
+  VEC="-mavx2 -mfma"
   case "$prec" in
     mixed)  PDEF=-DMARDYN_SPDP;;
     double) PDEF=-DMARDYN_DPDP;;
+    mixed512) PDEF=-DMARDYN_SPDP; VEC="-mavx512f -mavx512cd -mavx512vl -mavx512bw -mavx512dq -mavx2 -mfma";;      # VCP_VEC_AVX512F (SIMD_TYPES.h:70-75): the CPU baseline on AVX-512 hosts
     rmm)    PDEF="-DMARDYN_SPSP -DENABLE_REDUCED_MEMORY_MODE=1";;      # the reference's reduced-memory mode: all FP32, 1CLJ only (VCP1CLJRMM)
     *) echo "unknown precision $prec"; exit 2;;
   esac
@@ -66,7 +69,7 @@ H
       rm "$SRC/$h"; sed 's/^\(\s*\)constexpr \(\(Region\)\?ParticleIterator\s*(const\)/\1\2/' "$REF/src/$h" > "$SRC/$h"
     done
   fi
-  FLAGS="-std=c++17 -O3 -DNDEBUG -fopenmp -DENABLE_OPENMP -fopenmp-simd -mavx2 -mfma -DENABLE_VECTORIZED_CODE=1 \
+  FLAGS="-std=c++17 -O3 -DNDEBUG -fopenmp -DENABLE_OPENMP -fopenmp-simd $VEC -DENABLE_VECTORIZED_CODE=1 \
 $PDEF -DTIMERS -w -I$OUT/gen -I$SRC -I$REF/libs/rapidxml -I$REF/libs"
   MK="$OUT/Makefile.gen"
   { echo "CXX=$CXX"; echo "FLAGS=$FLAGS"; echo "OBJS="; } > "$MK"
@@ -85,6 +88,6 @@ $OUT/refdump.o: $HERE/refdump.cpp
 $OUT/refdump: \$(LIBOBJS) $OUT/refdump.o
 	@\$(CXX) -fopenmp \$(LIBOBJS) $OUT/refdump.o -o \$@
 M
-  if [ -f "$HERE/refdump.cpp" ] && [ "$prec" != rmm ]; then make -f "$MK" -j"$JOBS" all; else make -f "$MK" -j"$JOBS" "$OUT/MarDyn"; fi      # refdump reads F / M / Vi, which MoleculeRMM does not store
+  if [ -f "$HERE/refdump.cpp" ] && [ "$prec" != rmm ] && [ "$prec" != mixed512 ]; then make -f "$MK" -j"$JOBS" all; else make -f "$MK" -j"$JOBS" "$OUT/MarDyn"; fi      # refdump reads F / M / Vi, which MoleculeRMM does not store
   echo "build_ref: built $OUT/MarDyn"
 done
