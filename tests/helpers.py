@@ -78,3 +78,43 @@ def macro_close(m, g, tag, ref, abs_scale=None, tol=None):
             print("macro mismatch", mine, theirs, bound)
             return False
     return True
+
+
+# ---- 100-step traces of the reference binary (tests/golden/make_traces.py) ------------------------------------------
+TRACE_TOL = {"double": 1e-9, "mixed": 1e-6}     # north_star: T and p over 100 steps within 1e-6 relative
+
+
+def check_trace_vs_reference(cls, name, prec, report=None):
+    """Runs `cls` (OracleSim or the CUDA Context: same interface) from the fixture's phase space for the trace's number of
+    steps and compares every step with the reference binary's ResultWriter line: U_pot, U_kin = (sum m v^2 + sum I w^2) / 2,
+    p, beta_trans, beta_rot. Row 0 of the reference file is the initial force calculation, row k the state after step k.
+    U_pot, U_kin and the betas are held to the STRICT relative error (|a-b| / max|b|); p = rho T + rho W / 3N is a
+    cancellation of two terms, its bound is relative to max(|p|, rho T) -- the strict figure is returned beside it."""
+    t = dict(np.load(os.path.join(GOLD, "trace_" + name + ".npz")))
+    g = load("periodic_" + name)
+    ref = t[prec]
+    steps, dt, temperature = int(t["steps"]), float(t["dt"]), float(t["temperature"])
+    s = make_sim(cls, g, prec)
+    s.update()
+    m0 = s.traverse_cells()
+    rec = s.simulate(steps, dt, temperature)
+    tol = TRACE_TOL[prec]
+    n = len(g["in_id"]); vol = float(np.prod(g["length"]))
+    out = {}
+    b = ref[1:steps + 1]
+    ukin = 0.5 * (rec[:, 2] + rec[:, 3])
+    # row 0 (the initial force calculation) is part of the U_pot series; normalised, like every row, by max |U_pot| of the trace
+    upot = np.concatenate([[m0.upot], rec[:, 0]])
+    out["U_pot"] = float(np.abs(upot - ref[:steps + 1, 2]).max() / np.abs(ref[:steps + 1, 2]).max())
+    out["U_kin"] = float(np.abs(ukin - b[:, 4]).max() / np.abs(b[:, 4]).max())
+    out["beta_trans"] = float(np.abs(rec[:, 6] - b[:, 8]).max())
+    out["beta_rot"] = float(np.abs(rec[:, 7] - b[:, 9]).max())
+    rho_t = (n / vol) * rec[:, 4]
+    out["p"] = float(np.abs(rec[:, 5] - b[:, 6]).max() / max(np.abs(b[:, 6]).max(), rho_t.max()))
+    out["p_strict"] = float(np.abs(rec[:, 5] - b[:, 6]).max() / np.abs(b[:, 6]).max())
+    # T = 2 U_kin / (3N + rotDOF): same relative error as U_kin
+    if report is not None:
+        report.append((name, prec, out))
+    for k in ("U_pot", "U_kin", "beta_trans", "beta_rot", "p"):
+        assert out[k] <= tol, (name, prec, k, out)
+    return out

@@ -7,7 +7,7 @@ Tolerances (north_star): bit-exact cell binning; F, M, Vi, Upot, Virial within 1
 import numpy as np
 import pytest
 
-from helpers import ABS_SCALE, TOL, macro_close, golden_names, load, make_sim, ref_by_id, rel_close
+from helpers import ABS_SCALE, TOL, check_trace_vs_reference, macro_close, golden_names, load, make_sim, ref_by_id, rel_close
 
 pytestmark = pytest.mark.gpu
 
@@ -310,3 +310,14 @@ def test_site_signature_kernels_vs_oracle(capi, name, prec):
             assert ok, (name, prec, kernel or "specialised", f, worst)
         terms = np.abs(b.download("VI")).sum()
         assert abs(ma.upot - mb.upot) <= tol * max(abs(mb.upot), terms) and abs(ma.virial - mb.virial) <= tol * max(abs(mb.virial), terms)
+
+
+@pytest.mark.parametrize("name", ["1clj_1458", "water_432", "multi_250"])
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_trace_vs_reference_binary(capi, name, prec):
+    """ls1b200_simulate (k_leapfrog_pre / _post with quaternions, k_globals, thermostat on load) against 100 steps of the
+    UNMODIFIED reference binary's ResultWriter output (tests/golden/trace_*.npz, made by tests/golden/make_traces.py):
+    U_pot, U_kin, p, beta_trans, beta_rot at 1e-9 (double) / 1e-6 (mixed). water_432 and multi_250 are rotating multi-site
+    ensembles with beta_rot != 1."""
+    out = check_trace_vs_reference(capi.Context, name, prec)
+    print(name, prec, {k: "%.2e" % v for k, v in out.items()})

@@ -4,7 +4,7 @@
 import numpy as np
 import pytest
 
-from helpers import ABS_SCALE, TOL, macro_close, golden_names, load, make_sim, ref_by_id, rel_close
+from helpers import ABS_SCALE, TOL, check_trace_vs_reference, macro_close, golden_names, load, make_sim, ref_by_id, rel_close
 from oracle import oracle as orc
 
 FORCE = golden_names("force_")
@@ -84,3 +84,13 @@ def test_halo_copies_vs_reference(name, prec):
     theirs = sorted(zip(g[f"{prec}_mol_id"][h].tolist(), g[f"{prec}_mol_cell"][h].tolist(), map(tuple, g[f"{prec}_mol_r"][h].tolist())))
     assert len(mine) == len(theirs)
     assert mine == theirs
+
+
+@pytest.mark.parametrize("name", ["1clj_1458", "water_432", "multi_250"])
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_trace_vs_reference_binary(name, prec):
+    """The integrator and the global values, pinned against the UNMODIFIED reference binary (stock Simulation loop, Leapfrog
+    with rigid-body rotation, Domain::calculateGlobalValues, velocity scaling; tests/golden/make_traces.py): 100 steps of
+    U_pot, U_kin (sum m v^2 + sum I w^2), p, beta_trans, beta_rot. water_432 and multi_250 rotate (beta_rot != 1)."""
+    out = check_trace_vs_reference(orc.OracleSim, name, prec)
+    print(name, prec, {k: "%.2e" % v for k, v in out.items()})
