@@ -240,9 +240,13 @@ int ls1b200_peer_attach(ls1b200_ctx* ctx, const uint8_t* handles /* [n_ranks][LS
  * caller's -- BEFORE any rank destroys its context or uploads again: memory must not be freed while a peer has it mapped. */
 int ls1b200_peer_detach(ls1b200_ctx* ctx);
 /* One exchange (all stages) on the context's stream -- peer-memory transport if attached, else NCCL send / recv; collective.
- * The NCCL transport sends fixed-capacity messages whose capacity derives from the number of molecules a rank uploaded: use
- * it with (nearly) equal molecule counts per rank, as the equal-volume decomposition of a homogeneous system gives; the
- * peer-memory transport honours the capacity of every receiver and has no such restriction.
+ * The NCCL transport sends fixed-capacity messages; the capacity is agreed over all ranks (the maximum of what each rank
+ * derives from its own upload: one ncclAllReduce inside ls1b200_upload, which is therefore collective on contexts with
+ * use_nccl = 1), so blocks of different population are fine; the peer-memory transport honours the capacity of every receiver.
+ * Failure handling: a message that does not fit, a slot overflow or a neighbour that does not publish its message within
+ * LS1B200_PEER_TIMEOUT_S seconds (environment, default 60) marks the step as failed ON THE DEVICE: from then on the
+ * integration and export kernels leave the state untouched, the flag travels to every rank with the allreduce of the
+ * macroscopic sums, and ls1b200_simulate / the next synchronising call returns the error on all ranks.
  * ls1b200_simulate calls it every step; phase-by-phase drivers call it between ls1b200_leapfrog_pre and ls1b200_update
  * (and once before the first update). */
 int ls1b200_exchange(ls1b200_ctx* ctx);

@@ -110,10 +110,12 @@ struct State {
 struct DevScalars {
 	double upot6lj, upot_xpoles, virial, my_rf;   // force traversal
 	double summv2, sum_iw2;                       // leapfrog post
+	double fault;                                 // != 0: some rank reported overflow (summed over the ranks with the six doubles above)
 	unsigned long long n_mol, rot_dof;
 	double beta_trans, beta_rot;                  // thermostat factors applied by the next leapfrog_pre
 	uint32_t n_slots2[2];                         // slots in use (owned + halo), ping-pong: [ctx->parity] is current
-	uint32_t overflow;                            // 1: an update needed more than cap slots, 2: a halo message buffer was too small
+	uint32_t overflow;                            // 1: an update needed more than cap slots, 2: a halo message buffer was too small, 4: a peer timed out, 5: another rank failed.
+	                                              // Once set, the integration kernels leave the state untouched (the step loop is frozen) until the host reports it
 	uint32_t n_owned_dev;                         // owned molecules counted by the last count_owned() (decomposed mode)
 	uint32_t n_sorted;                            // slots in cell order (count of the last update); imports of the exchange follow behind
 	uint32_t pad0;
@@ -229,6 +231,7 @@ struct ls1b200_ctx {
 	cudaEvent_t xprof_ev[4] = {nullptr, nullptr, nullptr, nullptr}; double xprof_acc[3] = {0., 0., 0.}; int xprof_calls = 0;      // LS1B200_EXCHANGE_PROFILE
 	uint64_t* ekey = nullptr;                           // [cap] (id << 5 | shift code) per provisional slot: content-based in-cell order
 	uint64_t n_owned_local = 0;                         // owned molecules of this rank (host copy, decomposed mode)
+	uint64_t rot_dof_local = 0;                         // their rotational degrees of freedom (count_owned)
 };
 
 namespace ls1b200 {

@@ -398,7 +398,7 @@ int ls1b200_upload(ls1b200_ctx* c, uint64_t n, const uint64_t* id, const uint32_
 		LS1_CUDA(cudaStreamSynchronize(c->stream));
 		cudaFree(stage); cudaFree(cstage);
 	}
-	c->n_owned_local = n; c->dd.rot_dof_valid = false;
+	c->n_owned_local = n; c->rot_dof_local = c->rot_dof_total; c->dd.rot_dof_valid = false;
 	c->parity = 0; c->n_slots = (uint32_t) n;
 	c->h_scal->n_slots2[0] = (uint32_t) n; c->h_scal->n_slots2[1] = 0; c->h_scal->overflow = 0;
 	c->h_scal->beta_trans = 1.; c->h_scal->beta_rot = 1.;
@@ -420,7 +420,8 @@ namespace ls1b200 {
 const char* overflow_message(uint32_t code) {
 	switch (code) {
 		case 2: return "a halo message buffer was too small (more boundary molecules than the message capacity)";
-		case 4: return "a neighbour's message did not arrive within the time limit (peer-memory transport: did a rank fail or skip ls1b200_exchange?)";
+		case 4: return "a neighbour's message did not arrive within the time limit (peer-memory transport, LS1B200_PEER_TIMEOUT_S: did a rank fail or skip ls1b200_exchange?); the state was frozen at the failed step";
+		case 5: return "another rank of the decomposition reported a failed step (overflow or time-out); the state was frozen at that step";
 		default: return "slot capacity exceeded (more halo copies than reserved)";
 	}
 }
@@ -576,9 +577,11 @@ int ls1b200_set_field(ls1b200_ctx* c, int field, const void* src, uint64_t n) {
 	const uint32_t* oi = c->dd.active ? c->entry : nullptr;
 	double* planes = nullptr; int dim = 3;
 	switch (field) {
-		case LS1B200_F_R: planes = c->cur.r; c->forces_valid = false; c->ever_sorted = false; break;      // arbitrary new positions: the exchange scans every slot
+		// new positions / orientations: the cell order, the halo copies and the calc-precision records (mpos, spos, sori) are stale --
+		// ls1b200_traverse_cells must not run before the next ls1b200_update
+		case LS1B200_F_R: planes = c->cur.r; c->forces_valid = false; c->ever_sorted = false; c->sorted = false; break;      // arbitrary new positions: the exchange scans every slot
 		case LS1B200_F_V: planes = c->cur.v; break;
-		case LS1B200_F_Q: planes = c->cur.q; dim = 4; break;
+		case LS1B200_F_Q: planes = c->cur.q; dim = 4; if (c->cur.q) { c->forces_valid = false; c->sorted = false; } break;
 		case LS1B200_F_L: planes = c->cur.L; break;
 		case LS1B200_F_F: planes = c->F; break;
 		case LS1B200_F_M: planes = c->M; break;

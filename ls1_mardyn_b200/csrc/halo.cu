@@ -46,7 +46,7 @@ struct Nccl {
 	const char* (*GetErrorString)(int) = nullptr;
 };
 Nccl g_nccl;
-constexpr int NCCL_UINT8 = 1, NCCL_FLOAT64 = 8, NCCL_SUM = 0;   // ncclDataType_t / ncclRedOp_t values of nccl.h (stable since 2.0)
+constexpr int NCCL_UINT8 = 1, NCCL_FLOAT64 = 8, NCCL_SUM = 0, NCCL_MAX = 2;   // ncclDataType_t / ncclRedOp_t values of nccl.h (stable since 2.0)
 
 int nccl_load() {
 	if (g_nccl.h) return 0;
@@ -130,7 +130,7 @@ template <bool FULL>
 __global__ void __launch_bounds__(256) k_export(XArgs a, State st, XOut o, DevScalars* scal, int which) {
 	// persistent blocks striding over the slots: 68 000 blocks of a few hundred nanoseconds each cost more than the scan itself
 	const size_t cap = a.cap;
-	const uint32_t n_slots = min(scal->n_slots2[a.parity], a.cap), n_sorted = scal->n_sorted;
+	const uint32_t n_slots = scal->overflow ? 0u : min(scal->n_slots2[a.parity], a.cap), n_sorted = scal->n_sorted;      // a failed step exports nothing (the step loop is frozen)
 	constexpr int REC = FULL ? (int) sizeof(ls1b200_particle) : (int) sizeof(RecCompact);
 	__shared__ __align__(16) unsigned char stage[8][32 * REC];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -227,6 +227,9 @@ __global__ void k_publish(XOut o) {
 	__threadfence_system();
 }
 
+// ticks of clock64() a receiver waits for its neighbour (set from LS1B200_PEER_TIMEOUT_S at ls1b200_peer_attach)
+__device__ long long g_peer_timeout_ticks = 120000000000ll;
+
 // peer transport: wait until the neighbour has published sequence number seq in this receive buffer (every thread of k_import
 // and k_import_bump calls it; bounded: a peer that died must not hang the GPU -- overflow = 4 reports it)
 __device__ __forceinline__ uint32_t msg_count(const unsigned char* msg, uint32_t seq, uint32_t msg_cap, DevScalars* scal) {
@@ -235,7 +238,7 @@ __device__ __forceinline__ uint32_t msg_count(const unsigned char* msg, uint32_t
 	if (seq) {
 		const long long t0 = clock64();
 		while ((uint32_t) (v >> 32) != seq) {
-			if (clock64() - t0 > 8000000000ll) { scal->overflow = 4; return 0u; }      // ~4 s
+			if (clock64() - t0 > g_peer_timeout_ticks) { scal->overflow = 4; return 0u; }      // LS1B200_PEER_TIMEOUT_S (default 60 s)
 			__nanosleep(200);
 			v = *h;
 		}
@@ -283,10 +286,20 @@ __global__ void k_import_bump(const unsigned char* __restrict__ m0, const unsign
 }
 
 // ---- owned-molecule count / compaction index (decomposed mode: the set a rank owns changes every step) ----------------
-__global__ void __launch_bounds__(256) k_flag_owned(const uint64_t* __restrict__ meta, uint32_t* __restrict__ flag, uint32_t cap, uint32_t parity, const DevScalars* __restrict__ scal) {
+__global__ void __launch_bounds__(256) k_flag_owned(const uint64_t* __restrict__ meta, uint32_t* __restrict__ flag, uint32_t cap, uint32_t parity, DevScalars* __restrict__ scal,
+                                                     const CompDev* __restrict__ comps) {
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= cap) return;
-	flag[s] = (s < min(scal->n_slots2[parity], cap) && !meta_halo(meta[s])) ? 1u : 0u;
+	uint32_t rd = 0;
+	if (s < cap) {
+		const uint64_t m = meta[s];
+		const bool own = s < min(scal->n_slots2[parity], cap) && !meta_halo(m);
+		flag[s] = own ? 1u : 0u;
+		if (own) rd = comps[meta_cid(m)].rot_dof;
+	}
+	// rotational degrees of freedom of the molecules owned NOW (Domain::setLocalNrotDOF of a phase-by-phase driver)
+	#pragma unroll
+	for (int o = 16; o > 0; o >>= 1) rd += __shfl_xor_sync(0xffffffffu, rd, o);
+	if ((threadIdx.x & 31) == 0 && rd) atomicAdd(&scal->rot_dof, (unsigned long long) rd);
 }
 constexpr int CS_T = 256, CS_V = 8, CS_B = CS_T * CS_V;
 __device__ __forceinline__ uint32_t cs_block_scan(uint32_t v, uint32_t* total, uint32_t* sh) {
@@ -343,13 +356,15 @@ int count_owned(ls1b200_ctx* c, bool want_index) {
 	const uint32_t cap = (uint32_t) c->cap, g = (cap + 255) / 256, sb = (cap + CS_B - 1) / CS_B;
 	uint32_t* bsum = reinterpret_cast<uint32_t*>(c->msg_out[0] + MSG_HEADER);      // scratch: the message buffers are idle here
 	if ((uint64_t) sb * 4 > c->msg_cap * sizeof(RecCompact)) return fail("count_owned: scratch too small");
-	LS1_LAUNCH(c, PH_UPDATE, k_flag_owned, g, 256, 0, c->cur.meta, c->key, cap, c->parity, c->d_scal);
+	LS1_CUDA(cudaMemsetAsync(&c->d_scal->rot_dof, 0, sizeof(unsigned long long), c->stream));
+	LS1_LAUNCH(c, PH_UPDATE, k_flag_owned, g, 256, 0, c->cur.meta, c->key, cap, c->parity, c->d_scal, (const CompDev*) c->d_comps);
 	LS1_LAUNCH(c, PH_UPDATE, k_cs_block, sb, CS_T, 0, c->key, c->entry, bsum, cap);
 	LS1_LAUNCH(c, PH_UPDATE, k_cs_top, 1, CS_T, 0, bsum, sb, c->d_scal);
 	if (want_index) LS1_LAUNCH(c, PH_UPDATE, k_cs_add, sb, CS_T, 0, c->entry, bsum, cap);
 	LS1_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
 	LS1_CUDA(cudaStreamSynchronize(c->stream));
 	c->n_owned_local = c->h_scal->n_owned_dev;
+	c->rot_dof_local = c->h_scal->rot_dof;
 	return 0;
 }
 
@@ -377,6 +392,18 @@ int decomp_alloc(ls1b200_ctx* c) {
 	double ring = 1.;
 	for (int d = 0; d < 3; d++) ring *= 1. + 2. * std::min(1., c->geom.cutoff / c->geom.lbox[d]);
 	c->msg_cap = (uint64_t) (1.6 * frac * ring * (double) std::max<uint64_t>(c->n_owned, 1)) + 8192;
+	if (c->dd.comm) {
+		// NCCL transport: Send and Recv of a pair must carry the same byte count, so all ranks agree on ONE capacity (the
+		// largest): blocks of different population (balanced_cuts, uneven uploads) would otherwise size their messages differently
+		double h = (double) c->msg_cap, *dcap = nullptr;
+		LS1_CUDA(cudaMalloc((void**) &dcap, sizeof(double)));
+		LS1_CUDA(cudaMemcpyAsync(dcap, &h, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+		LS1_NCCL(g_nccl.AllReduce(dcap, dcap, 1, NCCL_FLOAT64, NCCL_MAX, c->dd.comm, c->stream));
+		LS1_CUDA(cudaMemcpyAsync(&h, dcap, sizeof(double), cudaMemcpyDeviceToHost, c->stream));
+		LS1_CUDA(cudaStreamSynchronize(c->stream));
+		cudaFree(dcap);
+		c->msg_cap = (uint64_t) h;
+	}
 	const size_t bytes = MSG_HEADER + c->msg_cap * sizeof(ls1b200_particle);
 	for (int k = 0; k < 2; k++) {
 		LS1_CUDA(cudaMalloc((void**) &c->msg_out[k], bytes));
@@ -497,8 +524,8 @@ int do_exchange(ls1b200_ctx* c) {
 
 int do_allreduce_scalars(ls1b200_ctx* c) {
 	if (!c->dd.active || !c->dd.comm) return 0;
-	// upot6lj, upot_xpoles, virial, my_rf, summv2, sum_iw2: the six leading doubles of DevScalars
-	LS1_NCCL(g_nccl.AllReduce(c->d_scal, c->d_scal, 6, NCCL_FLOAT64, NCCL_SUM, c->dd.comm, c->stream));
+	// upot6lj, upot_xpoles, virial, my_rf, summv2, sum_iw2 + the fault flag: the seven leading doubles of DevScalars
+	LS1_NCCL(g_nccl.AllReduce(c->d_scal, c->d_scal, 7, NCCL_FLOAT64, NCCL_SUM, c->dd.comm, c->stream));
 	return 0;
 }
 
@@ -608,6 +635,15 @@ int ls1b200_peer_attach(ls1b200_ctx* c, const uint8_t* handles, int32_t n_ranks)
 			c->peer_opened[n_open] = base; c->peer_opened_rank[n_open] = r; n_open++;
 		}
 		c->peer_base[d][side] = (unsigned char*) base;
+	}
+	{
+		// how long k_import waits for a neighbour's message: generous by default (a neighbour may be busy with I/O between two
+		// ls1b200_simulate calls); LS1B200_PEER_TIMEOUT_S overrides. Ticks of clock64() at the SM clock.
+		double sec = 60.;
+		if (const char* e = getenv("LS1B200_PEER_TIMEOUT_S")) { const double v = atof(e); if (v > 0.) sec = v; }
+		int khz = 1965000; cudaDeviceGetAttribute(&khz, cudaDevAttrClockRate, c->device);
+		const long long ticks = (long long) (sec * 1e3 * (double) khz);
+		LS1_CUDA(cudaMemcpyToSymbol(g_peer_timeout_ticks, &ticks, sizeof(ticks)));
 	}
 	c->peer_ok = true;
 	return 0;

@@ -33,6 +33,7 @@ __global__ void __launch_bounds__(256) k_leapfrog_pre(State st, const double* __
                                                        const CompDev* __restrict__ comps, double dt, const DevScalars* __restrict__ scal,
                                                        uint32_t parity, int use_beta, int rotates) {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
+	if (scal->overflow) return;      // a failed step (lost message, peer time-out, another rank's fault): the state stays as it is
 	if (t >= min(scal->n_slots2[parity], cap)) return;
 	const uint64_t meta = st.meta[t];
 	if (meta_halo(meta)) return;
@@ -75,7 +76,7 @@ __global__ void __launch_bounds__(256) k_leapfrog_pre_v2(State st, const double*
                                                           const DevScalars* __restrict__ scal, uint32_t parity, int use_beta) {
 	const uint32_t t = 2u * (blockIdx.x * blockDim.x + threadIdx.x);
 	const uint32_t n = min(scal->n_slots2[parity], cap);
-	if (t >= n) return;
+	if (t >= n || scal->overflow) return;      // overflow: see k_leapfrog_pre
 	const ulonglong2 m2 = *reinterpret_cast<const ulonglong2*>(st.meta + t);
 	const bool on0 = !meta_halo(m2.x), on1 = (t + 1 < n) && !meta_halo(m2.y);
 	if (!on0 && !on1) return;
@@ -99,7 +100,7 @@ __global__ void __launch_bounds__(256) k_leapfrog_post_v2(State st, const double
 	const uint32_t t = 2u * (blockIdx.x * blockDim.x + threadIdx.x);
 	const uint32_t n = min(scal->n_slots2[parity], cap);
 	double acc[2] = {0., 0.};
-	if (t < n) {
+	if (t < n && !scal->overflow) {
 		const ulonglong2 m2 = *reinterpret_cast<const ulonglong2*>(st.meta + t);
 		const bool on0 = !meta_halo(m2.x), on1 = (t + 1 < n) && !meta_halo(m2.y);
 		if (on0 || on1) {
@@ -129,7 +130,7 @@ __global__ void __launch_bounds__(256) k_leapfrog_post(State st, const double* _
                                                         uint32_t parity, int rotates, double* __restrict__ partials) {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	double acc[2] = {0., 0.};
-	if (t < min(scal->n_slots2[parity], cap)) {
+	if (t < min(scal->n_slots2[parity], cap) && !scal->overflow) {
 		const uint64_t meta = st.meta[t];
 		if (!meta_halo(meta)) {
 			const CompDev& cp = comps[meta_cid(meta)];
@@ -163,7 +164,7 @@ __global__ void __launch_bounds__(1024) k_reduce_kinetic(const double* __restric
 	__shared__ double out[8];
 	block_reduce_store<2>(v, out, 0);
 	__syncthreads();
-	if (threadIdx.x == 0) { scal->summv2 = out[0]; scal->sum_iw2 = out[1]; }
+	if (threadIdx.x == 0) { scal->summv2 = out[0]; scal->sum_iw2 = out[1]; scal->fault = scal->overflow ? 1. : 0.; }      // fault travels with the allreduce of the sums
 }
 
 __global__ void __launch_bounds__(256) k_scale(State st, uint32_t cap, double bt, double br, const DevScalars* __restrict__ scal, uint32_t parity,
@@ -181,6 +182,7 @@ __global__ void __launch_bounds__(256) k_scale(State st, uint32_t cap, double bt
 // Domain::calculateGlobalValues + getGlobalPressure for one rank (Domain.cpp:157-252, :142-146)
 __global__ void k_globals(DevScalars* scal, double target_T, unsigned long long N, unsigned long long rot_dof, double volume, ls1b200_step_record* rec) {
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
+	if (scal->fault != 0. && !scal->overflow) scal->overflow = 5;      // another rank failed: every rank freezes in the same step
 	const double upot = scal->upot6lj / 6.0 + scal->upot_xpoles + scal->my_rf;
 	const double virial = scal->virial + 3.0 * scal->my_rf;
 	const double summv2 = scal->summv2;
@@ -264,7 +266,8 @@ int ls1b200_leapfrog_post(ls1b200_ctx* c, double dt, ls1b200_kinetic* out) {
 		LS1_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));
 		LS1_CUDA(cudaStreamSynchronize(c->stream));
 		out->summv2 = c->h_scal->summv2; out->sum_iw2 = c->h_scal->sum_iw2;
-		out->n_molecules = c->dd.active ? c->n_owned_local : c->n_owned; out->rot_dof = c->rot_dof_total;
+		out->n_molecules = c->dd.active ? c->n_owned_local : c->n_owned;
+		out->rot_dof = c->dd.active ? c->rot_dof_local : c->rot_dof_total;      // decomposed: over the slots owned NOW (count_owned)
 	}
 	return 0;
 }

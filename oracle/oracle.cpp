@@ -5,7 +5,9 @@
 // Parity status: PINNED. tests/test_oracle_golden.py checks this restatement against golden vectors produced by
 // the unmodified reference built from /root/reference by oracle/build_ref.sh (oracle/_ref/{mixed,double}/refdump and
 // MarDyn): the reference's own known-answer fixtures (ForceCalculationTestU0/F0), all 11 Vectorization*.inp
-// differential fixtures, periodic-halo dumps, the Comp2Param tables and 100-step T/U/p traces.
+// differential fixtures, periodic-halo dumps, the Comp2Param tables and 100-step U_pot / U_kin / p / beta traces of the reference
+// binary on a 1CLJ, a rotating water-like and a rotating multi-potential two-component system (tests/golden/make_traces.py ->
+// tests/golden/trace_*.npz; test_trace_vs_reference_binary).
 //
 // Every function cites the reference file:line (relative to /root/reference/src) it restates.
 //

@@ -114,38 +114,64 @@ def test_blocks_on_one_device_vs_oracle(capi, n_ranks, grid, prec):
     assert np.abs(Rg - one.download("R")[o1]).max() <= (1e-9 if prec == "double" else 1e-4)
 
 
-def test_multisite_blocks(capi):
-    """Rotating multi-site molecules (water-like golden fixture): orientation and angular momentum travel with the molecule."""
+def _water_lattice(n_per_dim=10, seed=7):
+    """Water-like component of the reference's VectorizationWater fixture (1 LJ + 3 charges, rotating) on a lattice whose box
+    (L = 74.0 for n = 10, rc = 14.9) is wide enough for two blocks of two cutoff radii per dimension."""
     from helpers import load
-    from ls1_mardyn_b200.ascii_reader import PhaseSpace
-    from ls1_mardyn_b200.decomposition import DomainDecomposition, exchange_local
+    from ls1_mardyn_b200 import generators
     g = load("periodic_water_432")
-    L = np.asarray(g["length"], dtype=float); rc = float(g["cutoff"])
-    if L.min() < 4 * rc:
-        pytest.skip("fixture box too small for two blocks of two cutoff radii")
-    ps = PhaseSpace(L, float(g["temperature"]), float(g["epsilon_rf"]), g["ensemble"], g["in_id"], g["in_cid"], g["in_r"], g["in_v"], g["in_q"], g["in_L"])
-    dds, owner = split(ps, 2)
-    G = make_gpu_ranks(capi, ps, dds, owner, "double", rc)
-    one = capi.Context([0, 0, 0], list(L), rc, epsilon_rf=ps.epsilon_rf, precision="double", geometry="xml", periodic=(1, 1, 1))
+    ps = generators.lattice(g["ensemble"], n_per_dim, 250.0 / 37.0 ** 3, 9.437e-4, seed=seed, jitter=0.1, rc=14.9)
+    return ps, 14.9
+
+
+@pytest.mark.parametrize("n_ranks", [2, 8])
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_multisite_blocks(capi, n_ranks, prec):
+    """Rotating multi-site molecules through the device-side export / import (120-byte records: orientation and angular
+    momentum travel with the molecule), several blocks on one device: every exported record against the decomposed CPU
+    oracle, forces and torques against the oracle ranks and against the single-domain CUDA path, over 4 steps."""
+    from ls1_mardyn_b200.decomposition import exchange_local
+    ps, rc = _water_lattice()
+    assert ps.length.min() >= 4 * rc
+    dds, owner = split(ps, n_ranks)
+    G = [Recorder(k) for k in make_gpu_ranks(capi, ps, dds, owner, prec, rc)]
+    O = [Recorder(k) for k in make_ranks(ps, dds, owner, prec, rc)]
+    one = capi.Context([0, 0, 0], list(ps.length), rc, epsilon_rf=ps.epsilon_rf, precision=prec, geometry="xml", periodic=(1, 1, 1))
     one.set_components(ps.ensemble); one.upload(ps.id, ps.cid, ps.r, ps.v, ps.q, ps.L)
     one.update(); one.traverse_cells(); o1 = np.argsort(one.download("ID"))
-    dt = 0.0667516
+    dt = 0.0166879
+    n_leaving = 0
     for step in range(4):
+        tol = TOL[prec] * (1 if step == 0 else 50)      # see test_blocks_on_one_device_vs_oracle
         if step:
-            for k in G:
+            for k in G + O:
                 k.leapfrog_pre(dt)
             one.leapfrog_pre(dt); one.update(); one.traverse_cells()
-        exchange_local(G, dds)
-        for k in G:
+        exchange_local(G, dds); exchange_local(O, dds)
+        for g, o in zip(G, O):
+            assert len(g.log) == len(o.log)
+            for (d, sd, a), (_, _, b) in zip(g.log, o.log):
+                assert same_records(a, b, exact=(step == 0)), (step, d, sd, len(a), len(b))
+                if step == 0:      # the rotational state of the leaving molecules is bit-identical on both sides
+                    a2 = np.sort(a, order=["flags", "id", "r"]); b2 = np.sort(b, order=["flags", "id", "r"]); lv = a2["flags"] == 0
+                    assert np.array_equal(a2["q"][lv], b2["q"][lv]) and np.array_equal(a2["L"][lv], b2["L"][lv])
+                n_leaving += int((a["flags"] == 0).sum())
+            g.log.clear(); o.log.clear()
+        for k in G + O:
             k.update()
-        for k in G:
+        for k in G + O:
             k.traverse_cells()
+        for g, o in zip(G, O):
+            assert np.array_equal(np.sort(g.download("ID")), np.sort(o.download("ID")))
         for f in ("F", "M"):
-            _, a = gather(G, f)
-            ok, worst = rel_close(a, one.download(f)[o1], 1e-9); assert ok, (step, f, worst)
-        for k in G:
-            k.leapfrog_post(dt)
-        one.leapfrog_post(dt)
+            _, a = gather(G, f); _, b = gather(O, f)
+            ok, worst = rel_close(a, b, tol); assert ok, (step, f, "vs oracle ranks", worst)
+            ok, worst = rel_close(a, one.download(f)[o1], 3 * tol); assert ok, (step, f, "vs single domain", worst)
+        kg = [k.leapfrog_post(dt) for k in G]; [k.leapfrog_post(dt) for k in O]; k1 = one.leapfrog_post(dt)
+        assert sum(k.n_molecules for k in kg) == len(ps.id)
+        assert abs(sum(k.sum_iw2 for k in kg) - k1.sum_iw2) <= 10 * tol * max(k1.sum_iw2, 1e-300)
+    _, qg = gather(G, "Q")
+    assert np.abs(qg - one.download("Q")[o1]).max() <= (1e-9 if prec == "double" else 1e-4)
 
 
 @pytest.mark.parametrize("transport", ["peer", "nccl"])
