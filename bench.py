@@ -62,16 +62,24 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.rows.append([x.strip() for x in line.split(",")])
+            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
 
-    def stop(self):
+    def stop(self, t_begin=None, t_end=None):
+        """Summary of the rows received inside [t_begin, t_end] (the timed region). nvidia-smi needs a few hundred ms to start, so
+        the sampler is started before the warm-up steps; if the timed region is shorter than the sampling period the rows from the
+        warm-up on (the GPU is under the same load) are used and `window` says so."""
         if not self.proc:
-            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
+        rows = [r for (t, r) in self.rows if t_begin is None or (t_begin <= t <= t_end + 0.05)]
+        window = "timed region"
+        if not rows:
+            rows = [r for (t, r) in self.rows]; window = "warm-up + timed region (timed region shorter than the sampling period)"
+        all_rows = self.rows; self.rows = rows
         sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
         mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         reasons = set()
@@ -80,7 +88,7 @@ class ClockSampler:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "window": window}
 
 
 def make_system(n_per_dim, mixed=True, seed=0, wl=None):
@@ -155,19 +163,26 @@ def reference_build():
     return _REF_BUILD
 
 
-def run_reference_binary(n_per_dim, steps, threads=None, prec=None):
-    """Runs oracle/_ref/<prec>/MarDyn (the unmodified reference, built by oracle/build_ref.sh) on a lattice of 2*n^3 molecules.
-    Returns (MMUPS from the reference's own main-loop timer, N, threads) or None if the binary is not there."""
+def run_reference_binary(n_per_dim, steps, threads=None, prec=None, wl=None):
+    """Runs oracle/_ref/<prec>/MarDyn (the unmodified reference, built by oracle/build_ref.sh) on a lattice of 2*n^3 molecules of
+    workload `wl` (default: the 1CLJ liquid), generated by the reference's own CubicGridGenerator.
+    Returns (MMUPS from the reference's own main-loop timer, N, threads, main-loop seconds) or None if the binary is not there."""
     prec = prec or reference_build()[0]
     exe = os.path.join(ROOT, "oracle", "_ref", prec, "MarDyn")
     if not os.path.exists(exe):
         return None
+    rho, temp, rc, dt = (RHO, TEMP, RC, DT) if wl is None else (wl.rho, wl.temperature, wl.rc, wl.dt)
     N = 2 * n_per_dim ** 3
-    L = (N / RHO) ** (1.0 / 3.0)
+    L = (N / rho) ** (1.0 / 3.0)
     threads = threads or os.cpu_count() or 1
     with tempfile.TemporaryDirectory() as td:
         cfg = os.path.join(td, "config.xml")
-        open(cfg, "w").write(XML.format(dt=DT, steps=steps, T=TEMP, L=repr(L), rho=repr(N / L ** 3 * (1 + 1e-9)), rc=RC))
+        if wl is None or wl.name == "lj":
+            text = XML.format(dt=dt, steps=steps, T=temp, L=repr(L), rho=repr(N / L ** 3 * (1 + 1e-9)), rc=rc)
+        else:
+            from ls1_mardyn_b200.xml_config import simulation_xml
+            text = simulation_xml(wl.ensemble, [L, L, L], temp, dt, steps, rc, generator_density=N / L ** 3 * (1 + 1e-9), longrange="homogeneous", result_prefix=None)
+        open(cfg, "w").write(text)
         env = dict(os.environ, OMP_NUM_THREADS=str(threads))
         p = subprocess.run([exe, "--steps", str(steps), "--final-checkpoint=0", cfg], cwd=td, env=env, capture_output=True, text=True, timeout=3000)
         out = p.stdout + p.stderr
@@ -193,41 +208,64 @@ def run_port(n_per_dim, steps):
     return len(ps.id) * steps / t / 1e6, len(ps.id), 1, t
 
 
-def cpu_baseline(sample_n=60, steps=3):
-    r = run_reference_binary(sample_n, steps)
+# bounded samples of the CPU legs inside the default run: molecules-per-dimension and steps chosen for a few seconds of main loop on
+# the GPU box's host cores (1CLJ: 4 M molecules x 5 steps = 20 M updates at ~12 MMUPS; the multi-site models are 10 - 40 x slower per update)
+CPU_SAMPLE = {"lj": (126, 5), "water": (40, 3), "co2": (30, 3), "argon": (37, 10)}
+
+
+def cpu_baseline(wl=None):
+    name = "lj" if wl is None else wl.name
+    sample_n, steps = CPU_SAMPLE[name]
+    r = run_reference_binary(sample_n, steps, wl=wl)
     if r is not None:
         v, n, cores, t = r
         return {"value": round(v, 3), "unit": "MMUPS", "cores": cores, "kind": "reference",
-                "sample": f"oracle/_ref/{reference_build()[0]}/MarDyn (unmodified reference, {reference_build()[1]}, OpenMP): 1CLJ lattice N={n}, {steps} steps, main loop {t:.2f} s"}
+                "sample": f"oracle/_ref/{reference_build()[0]}/MarDyn (unmodified reference, {reference_build()[1]}, OpenMP): {name} lattice N={n}, {steps} steps, main loop {t:.2f} s"}
+    if name != "lj":
+        return None
     v, n, cores, t = run_port(24, 2)
     return {"value": round(v, 3), "unit": "MMUPS", "cores": cores, "kind": "port",
             "sample": f"oracle/liboracle.so scalar port: 1CLJ lattice N={n}, 2 steps, {t:.2f} s"}
+
+
+def workload_config(wl, n_per_dim, world):
+    """The `config` object of the JSON line: the workload only (identical for our arm and the reference arm); how each arm executes
+    it is reported under `execution`."""
+    N = 2 * n_per_dim ** 3
+    L = (world * N / wl.rho) ** (1.0 / 3.0)
+    return {"workload": wl.description, "molecules_per_gpu": N, "molecules": world * N, "box": [L, L, L], "steps_size": "dt=%g" % wl.dt}
 
 
 WL_LJ_DESCRIPTION = "BASELINE.json configs[1]: 1CLJ LJ liquid rho*=0.7 T*=0.85 rc=2.5 sigma dt=0.002, mixed precision, NVT velocity scaling"
 
 
 def reference_arm(args):
+    """--impl reference: the unmodified reference on the host cores, on THE benchmark configuration (16 M molecules at N = 1; for
+    N > 1 the single-GPU size, MMUPS being size independent to first order -- 128 M molecules do not fit a few minutes of CPU time).
+    Two processes of the reference binary: W warm-up steps (discarded), then exactly K steps timed by its own main-loop timer."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
-    n = args.ref_n_per_dim
+    from ls1_mardyn_b200 import workloads
+    wl = workloads.get(args.workload)
+    n = args.ref_n_per_dim or args.n_per_dim or wl.n_per_dim
     t0 = time.perf_counter()
-    # warm-up and timed run are separate processes of the reference binary; the value comes from its own main-loop timer
-    r = run_reference_binary(n, args.steps + args.warmup) if args.warmup else None
-    r = run_reference_binary(n, args.steps)
+    if args.warmup:
+        run_reference_binary(n, args.warmup, wl=wl)
+    r = run_reference_binary(n, args.steps, wl=wl)
     kind = "reference"
     if r is None:
         r = run_port(24, max(1, min(args.steps, 3))); kind = "port"
     v, nmol, cores, t = r
+    cfg = workload_config(wl, args.n_per_dim or wl.n_per_dim, args.gpus)
+    sample = "the whole workload" if nmol == cfg["molecules"] else "bounded sample: %d of the workload's %d molecules (MMUPS is size independent to first order)" % (nmol, cfg["molecules"])
     line = {"metric": "MMUPS", "value": round(v, 4), "unit": "MMUPS (1e6 molecule updates / s)", "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1e3 * t / max(args.steps, 1), 3), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 pair arithmetic, f64 accumulation and state (MARDYN_SPDP)", "data": "synthetic (BCC lattice, CubicGridGenerator)", "impl": "reference",
-            # the same workload as our arm (same `workload` string); the reference is timed on a bounded sample of it
-            "config": {"workload": WL_LJ_DESCRIPTION, "molecules": nmol, "molecules_of_the_workload": 16000000,
-                       "note": "bounded sample of the 16M-molecule workload (MMUPS is size independent to first order)"},
+            "config": cfg,
+            "execution": {"molecules_run": nmol, "sample": sample, "host_threads": cores, "build": "oracle/_ref/%s/MarDyn (%s, OpenMP)" % reference_build()},
             "cpu_baseline": {"value": round(v, 4), "unit": "MMUPS", "cores": cores, "kind": kind,
-                             "sample": f"oracle/_ref/{reference_build()[0]}/MarDyn ({reference_build()[1]}, OpenMP), N={nmol}, {args.steps} steps, main loop {t:.2f} s, total wall {time.perf_counter() - t0:.1f} s"},
+                             "sample": f"oracle/_ref/{reference_build()[0]}/MarDyn ({reference_build()[1]}, OpenMP), N={nmol} ({sample}), {args.steps} steps, main loop {t:.2f} s, total wall {time.perf_counter() - t0:.1f} s"},
             "e2e": {"value": round(v, 4), "unit": "MMUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     print(json.dumps(line), flush=True)
 
@@ -235,6 +273,46 @@ def reference_arm(args):
 # ----------------------------------------------------------------------------------------------------------------------
 # our arm
 # ----------------------------------------------------------------------------------------------------------------------
+# dram__bytes_read.sum + dram__bytes_write.sum per launch of the force kernel, from the `ncu --set full` captures under profiles/
+# (keyed by workload, precision, molecules): reported, with its source, as roofline.traffic
+FORCE_TRAFFIC = {}
+
+
+def run_secondary(name, local, fp32_peak, capi, with_cpu=True, steps=10, warmup=3):
+    """One of the other single-GPU configurations of BASELINE.json, device-resident loop only: MMUPS, force-kernel time and its
+    fraction of the FP32 peak (FlopCounter flops of the state), CPU baseline on a bounded sample."""
+    from ls1_mardyn_b200 import workloads
+    wl = workloads.get(name)
+    ps = make_system(wl.n_per_dim, mixed=True, seed=0, wl=wl)
+    ctx = capi.Context([0, 0, 0], list(ps.length), wl.rc, precision="mixed", geometry="xml", periodic=(1, 1, 1), device=local)
+    ctx.set_components(ps.ensemble)
+    rot = any(c.Ipa()[1] for c in wl.ensemble.components)
+    ctx.upload(ps.id, ps.cid, ps.r, ps.v, ps.q if rot else None, ps.L if rot else None)
+    N = len(ps.id)
+    ctx.update(); ctx.traverse_cells()
+    fc0 = ctx.count_flops()
+    ctx.simulate(warmup, wl.dt, wl.temperature, records=False)
+    ctx.phase_times(reset=True)
+    import torch
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rec = ctx.simulate(steps, wl.dt, wl.temperature)
+    torch.cuda.synchronize()
+    t = time.perf_counter() - t0
+    ph_ms, _ = ctx.phase_times(reset=True)
+    fc1 = ctx.count_flops()
+    force_ms = ph_ms["force"] / steps
+    flops = 0.5 * (fc0.flops + fc1.flops)
+    out = {"workload": wl.description, "molecules": N, "steps": steps, "warmup": warmup, "MMUPS": round(N * steps / t / 1e6, 2), "ms_per_step": round(1e3 * t / steps, 4),
+           "phases_ms_per_step": {k: round(v / steps, 4) for k, v in ph_ms.items()},
+           "kernel_ms": round(force_ms, 4), "flops_per_molecule": round(flops / N, 1), "achieved_tflops": round(flops / (force_ms * 1e-3) / 1e12, 3),
+           "frac": round(flops / (force_ms * 1e-3) / 1e12 / fp32_peak, 4), "T_last": rec[-1, 4], "upot_last_per_molecule": rec[-1, 0] / N}
+    ctx.close()
+    if with_cpu:
+        out["cpu_baseline"] = cpu_baseline(wl)
+    return out
+
+
 def our_arm(args):
     # exactly ONE line on stdout: libraries that chat on fd 1 (NCCL prints its version there) are sent to stderr
     real_stdout = os.dup(1)
@@ -308,15 +386,16 @@ def our_arm(args):
     fc0 = ctx.count_flops()
 
     fp32_peak = capi.measure_fp32_peak(local)
+    fp64_peak = capi.measure_fp64_peak(local) if args.precision == "double" else None
     hbm_peak, hbm_src = peaks()
 
     # ---- HBM-resident: K steps inside the library, no host round trip ----
+    sampler = ClockSampler(local); sampler.start()      # before the warm-up: nvidia-smi takes a few hundred ms to deliver its first row
     ctx.simulate(args.warmup, DT, TEMP, global_n=N_global, global_volume=V_global, records=False)
     ctx.phase_times(reset=True)
     launches0 = capi.kernel_launch_count()
     ext = torch.cuda.ExternalStream(ctx.stream(), device=local)
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
-    sampler = ClockSampler(local); sampler.start()
     barrier()
     t0 = time.perf_counter()
     e0.record(ext)
@@ -324,7 +403,7 @@ def our_arm(args):
     e1.record(ext)
     barrier()
     t_wall = time.perf_counter() - t0
-    clocks = sampler.stop()
+    clocks = sampler.stop(t0, t0 + t_wall)
     t_dev = e0.elapsed_time(e1) * 1e-3
     launches = capi.kernel_launch_count() - launches0
     ph_ms, ph_launch = ctx.phase_times(reset=True)
@@ -375,41 +454,50 @@ def our_arm(args):
         force_ms = ph_ms["force"] / max(args.steps, 1)
         flops = 0.5 * (fc0.flops + fc1.flops)          # algorithmic flops / force launch (state drifts slowly off the lattice)
         achieved = flops / (force_ms * 1e-3) / 1e12
-        # algorithmic bytes of the HBM-bound phases per molecule: update 236 B, leapfrog pre 120 B, post 72 B
+        # algorithmic bytes of the HBM-bound phases per molecule, SURVEY.md 8(d): update = read r 24 + key 4 + permute r, v, id, cid
+        # 2 x 60 = 148 B, + 16 B for the calc-precision record the force kernel reads; leapfrog pre 120 B, post 72 B (FP64 state)
         hbm = {}
-        for name, bpm in (("update", 236.0), ("leapfrog_pre", 120.0), ("leapfrog_post", 72.0)):
+        for name, bpm in (("update", 164.0), ("leapfrog_pre", 120.0), ("leapfrog_post", 72.0)):
             ms = ph_ms[name] / max(args.steps, 1)
             hbm[name] = {"ms": round(ms, 4), "algorithmic_bytes_per_molecule": bpm, "achieved_gbs": round(bpm * N / (ms * 1e-3) / 1e9, 1) if ms > 0 else None,
                          "frac": round(bpm * N / (ms * 1e-3) / 1e9 / hbm_peak, 4) if ms > 0 else None}
+        double = args.precision == "double"
+        peak = fp64_peak if double else fp32_peak
+        traffic, traffic_src = FORCE_TRAFFIC.get((wl.name, args.precision, N), (None, None))
+        roofline = {"kernel": ("k_force_1clj_v3<%s>" if wl.name in ("lj", "argon") else "k_force_multi_tiled<%s> (site-signature specialisation)") % ("double" if double else "float"),
+                    "bound": "fp64" if double else "fp32", "achieved": round(achieved, 3), "peak": round(peak, 2), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
+                    # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at this size from an `ncu --set full` capture (not measured in this run)
+                    "traffic": traffic, "traffic_source": traffic_src,
+                    "peak_source": ("FP64" if double else "FP32") + " FMA micro-benchmark in this run (ls1b200_measure_fp%s_peak); MEASURED_PEAKS.json holds no CUDA-core figure; nominal FP32 74.4" % ("64" if double else "32"),
+                    "algorithmic_flops_per_launch": flops, "flops_per_molecule": round(flops / N, 1), "kernel_ms": round(force_ms, 4),
+                    "pair_interactions_per_s": round(0.5 * (fc0.lj + fc1.lj) / (force_ms * 1e-3), 1),
+                    "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src, "hbm": hbm}
         line = {
             "metric": "MMUPS", "value": round(value, 2), "unit": "MMUPS (1e6 molecule updates / s)", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1e3 * t_wall / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 pair arithmetic, f64 accumulation and state (MARDYN_SPDP)" if args.precision == "mixed" else "f64 throughout (MARDYN_DPDP, the reference's double build)",
             "data": "synthetic (BCC lattice like CubicGridGenerator, equal-magnitude velocities)",
-            "config": {"workload": wl.description,
-                       "molecules_per_gpu": N, "molecules": world * N, "cells_per_dim": [int(x) for x in ctx.geometry()[0]],
-                       "parallelism": "1 GPU" if world == 1 else ("3D block decomposition %dx%dx%d, one process per GPU, leaving molecules + halo copies every step " % grid_for(world)) + ("stored by the packing kernel straight into the neighbours' memory over NVLink (CUDA IPC)" if transport == "peer-memory" else "over NCCL send/recv") + ", NCCL allreduce of 6 doubles",
-                       "box": [float(x) for x in ps.length],
-                       "l2_policy": "inputs larger than L2: state %.1f GB per GPU" % (N * 150 / 1e9)},
+            "config": workload_config(wl, n, world),
+            "execution": {"cells_per_dim": [int(x) for x in ctx.geometry()[0]],
+                          "parallelism": "1 GPU" if world == 1 else ("3D block decomposition %dx%dx%d, one process per GPU, leaving molecules + halo copies every step " % grid_for(world)) + ("stored by the packing kernel straight into the neighbours' memory over NVLink (CUDA IPC)" if transport == "peer-memory" else "over NCCL send/recv") + ", NCCL allreduce of 7 doubles",
+                          "l2_policy": "inputs larger than L2: state %.1f GB per GPU" % (N * 150 / 1e9)},
             "ms_per_step_device_events": round(1e3 * t_dev / args.steps, 4),
             "phases_ms_per_step": {k: round(v / args.steps, 4) for k, v in ph_ms.items()},
             "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 2), "unit": "MMUPS", "h2d_bytes_per_step": int(h2d / e2e_steps), "d2h_bytes_per_step": int(d2h / e2e_steps), "steps": e2e_steps,
                     "path": "set_field(R,V) from pinned host -> leapfrog_pre -> update -> [ls1b200_download_begin(R): the positions travel while the forces run] traverse_cells -> leapfrog_post -> download(V), download_end + scalars"},
-            "roofline": {"kernel": ("k_force_1clj_tiled<%s, true>" if wl.name == "lj" else "k_force_multi_tiled<%s> (site-signature specialisation)") % ("float" if args.precision == "mixed" else "double"),
-                         "bound": "fp32" if args.precision == "mixed" else "fp64 (against the FP32 peak: MEASURED_PEAKS.json has no FP64 figure)", "achieved": round(achieved, 3), "peak": round(fp32_peak, 2), "unit": "TFLOP/s",
-                         # dram__bytes_read.sum + dram__bytes_write.sum of one launch at this size, `ncu --set full` (profiles/r01r_force_full.md):
-                         # 285 MB + 723 MB, against 272 MB of mpos read + 768 MB of F / Vi written algorithmically
-                         "frac": round(achieved / fp32_peak, 4), "traffic": 1007574272 if (wl.name == "lj" and N == 16000000) else None,
-                         "peak_source": "FP32 FMA micro-benchmark in this run (ls1b200_measure_fp32_peak); nominal 74.4",
-                         "algorithmic_flops_per_launch": flops, "flops_per_molecule": round(flops / N, 1), "kernel_ms": round(force_ms, 4),
-                         "pair_interactions_per_s": round(0.5 * (fc0.lj + fc1.lj) / (force_ms * 1e-3), 1),
-                         "hbm_peak_gbs": hbm_peak, "hbm_peak_source": hbm_src, "hbm": hbm},
+            "roofline": roofline,
             "clocks": clocks,
             "trace": {"T_first": rec[0, 4], "T_last": rec[-1, 4], "upot_last_per_molecule": rec[-1, 0] / N_global, "p_last": rec[-1, 5]},
         }
-        if world == 1 and not args.no_cpu_baseline and wl.name == "lj":
-            line["cpu_baseline"] = cpu_baseline()
+        if world == 1 and not args.no_cpu_baseline:
+            cb = cpu_baseline(wl)
+            if cb is not None:
+                line["cpu_baseline"] = cb
+        if world == 1 and wl.name == "lj" and args.precision == "mixed" and not args.no_secondary and not args.n_per_dim:
+            # BASELINE.json configs[0], [2], [3] at their single-GPU sizes, measured in the same run (device-resident loop only)
+            ctx.close()
+            line["secondary"] = {k: run_secondary(k, local, fp32_peak, capi, with_cpu=not args.no_cpu_baseline) for k in ("argon", "water", "co2")}
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         # orderly teardown: nobody frees receive buffers a neighbour still has mapped
@@ -431,7 +519,8 @@ def main():
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
     ap.add_argument("--workload", default="lj", choices=["lj", "water", "co2"], help="lj = BASELINE.json configs[1] (the headline); water / co2 = configs[2] / [3]")
     ap.add_argument("--n-per-dim", type=int, default=0, help="BCC lattice cells per dimension: N = 2 n^3 (default: the workload's single-GPU size, lj 200 -> 16 M molecules)")
-    ap.add_argument("--ref-n-per-dim", type=int, default=80, help="size of the reference arm's bounded sample (80 -> 1.02 M molecules)")
+    ap.add_argument("--ref-n-per-dim", type=int, default=0, help="size of the reference arm's run (default: the workload's single-GPU size, 200 -> 16 M molecules)")
+    ap.add_argument("--no-secondary", action="store_true", help="skip the water-like 4 M and CO2 8 M runs reported under `secondary`")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--precision", default="mixed", choices=["mixed", "double"], help="mixed = the headline (BASELINE.json configs[1]); double = the full-FP64 variant of the reference's double build")
     ap.add_argument("--no-cpu-baseline", action="store_true")

@@ -287,6 +287,8 @@ int ls1b200_count_flops(ls1b200_ctx* ctx, ls1b200_flopcount* out);
 /* FP32 FMA micro-benchmark on this device: returns TFLOP/s (2 flops per FMA), the denominator of the
  * "% of FP32 pair-rate peak" metric (MEASURED_PEAKS.json has no FP32 figure). */
 int ls1b200_measure_fp32_peak(int device, double* tflops);
+/* The same with FP64 fused multiply-adds: the denominator for the full-FP64 variant (the reference's double build). */
+int ls1b200_measure_fp64_peak(int device, double* tflops);
 int ls1b200_measure_hbm_copy(int device, double* gbs);
 
 #ifdef __cplusplus

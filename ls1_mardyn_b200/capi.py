@@ -29,7 +29,7 @@ EXPORTS = ["ls1b200_last_error", "ls1b200_abi_version", "ls1b200_kernel_launch_c
            "ls1b200_set_components", "ls1b200_upload", "ls1b200_num_molecules", "ls1b200_download", "ls1b200_set_field",
            "ls1b200_geometry", "ls1b200_update", "ls1b200_traverse_cells", "ls1b200_leapfrog_pre", "ls1b200_leapfrog_post",
            "ls1b200_scale_velocities", "ls1b200_simulate", "ls1b200_halo_export", "ls1b200_halo_import",
-           "ls1b200_halo_import_host", "ls1b200_phase_times", "ls1b200_count_flops", "ls1b200_measure_fp32_peak",
+           "ls1b200_halo_import_host", "ls1b200_phase_times", "ls1b200_count_flops", "ls1b200_measure_fp32_peak", "ls1b200_measure_fp64_peak",
            "ls1b200_measure_hbm_copy", "ls1b200_stream", "ls1b200_nccl_unique_id", "ls1b200_decomp_attach", "ls1b200_download_begin", "ls1b200_download_end", "ls1b200_peer_handle", "ls1b200_peer_attach", "ls1b200_peer_detach", "ls1b200_exchange",
            "ls1b200_allreduce_macro", "ls1b200_halo_export_host"]
 
@@ -110,6 +110,7 @@ def lib():
         L.ls1b200_phase_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.ls1b200_count_flops.argtypes = [C.c_void_p, C.c_void_p]
         L.ls1b200_measure_fp32_peak.argtypes = [C.c_int, C.c_void_p]
+        L.ls1b200_measure_fp64_peak.argtypes = [C.c_int, C.c_void_p]
         L.ls1b200_measure_hbm_copy.argtypes = [C.c_int, C.c_void_p]
         L.ls1b200_nccl_unique_id.argtypes = [C.c_void_p]
         L.ls1b200_decomp_attach.argtypes = [C.c_void_p, C.c_void_p]
@@ -148,6 +149,10 @@ def nccl_unique_id() -> bytes:
 
 def measure_fp32_peak(device: int = 0) -> float:
     v = C.c_double(); _check(lib().ls1b200_measure_fp32_peak(device, C.byref(v))); return v.value
+
+
+def measure_fp64_peak(device: int = 0) -> float:
+    v = C.c_double(); _check(lib().ls1b200_measure_fp64_peak(device, C.byref(v))); return v.value
 
 
 def measure_hbm_copy(device: int = 0) -> float:

@@ -160,7 +160,10 @@ struct ls1b200_ctx {
 
 	// cells
 	uint32_t* cell_count = nullptr;   // [ncells+2]
-	uint32_t* cell_start = nullptr;   // [ncells+2] exclusive scan
+	uint32_t* cell_start = nullptr;   // [ncells+2] exclusive scan (reference cells)
+	uint32_t* cell_start_fine = nullptr;   // [ncells*fine_s+2] exclusive scan over the fine x-bins (fine_s > 1)
+	uint32_t fine_s = 1;              // fine x-bins per reference cell: the in-cell order of the slots is by x sub-bin
+	double fine_inv = 0.;             // fine_s / cell length in x
 	uint32_t* cursor = nullptr;       // [ncells+2] next free slot of the halo-copy part of every bin (k_scatter)
 	uint32_t* cell_count_halo = nullptr;   // [ncells+2] periodic halo copies per bin (cell_count holds the non-copies, whose rank k_key already knows)
 	uint32_t* rank = nullptr;         // [cap] provisional rank of a slot's molecule inside its bin (returned by the histogram atomic)
@@ -181,7 +184,8 @@ struct ls1b200_ctx {
 	// chunk list of the tiled 1CLJ kernel (force_1clj_tiled.cu)
 	void* chunks = nullptr; uint32_t* chunk_row_count = nullptr; uint32_t* chunk_row_start = nullptr; uint32_t* work_counter = nullptr;
 	int sm_count = 148;
-	int lj_kernel = 0;                // LS1B200_LJ_KERNEL: 0 tiled (default; shared-memory windows, TMA), 1 "global" (force_1clj.cu), 3 "mma" / 4 "tc": tensor-core prefilter experiments (force_1clj_mma.cu, force_1clj_tc.cu; measured slower, profiles/r01_tensor_prefilter.md)
+	void* chunks2 = nullptr; size_t chunks2_bytes = 0;      // molecule-granular chunk list of force_1clj_v3.cu
+	int lj_kernel = 0;                // LS1B200_LJ_KERNEL: 0 tiled (default; shared-memory windows, TMA), 1 "global" (force_1clj.cu), 3 "mma" / 4 "tc": tensor-core prefilter experiments (force_1clj_mma.cu, force_1clj_tc.cu; measured slower, profiles/r01_tensor_prefilter.md), 5 "v3": molecule-granular chunks + x-trimmed ranges over fine bins (force_1clj_v3.cu; measured slower, profiles/r02_force_kernel_experiments.md)
 	int multi_kernel = 0;             // 0: tiled thread-per-molecule (force_multi_tiled.cu), 1: v1 thread-per-site (force_general.cu)
 
 	// reductions
@@ -248,6 +252,7 @@ int do_globals(ls1b200_ctx* c, double target_T, uint64_t global_n, double global
 int force_general(ls1b200_ctx* c);
 int force_1clj(ls1b200_ctx* c);
 int force_1clj_tiled(ls1b200_ctx* c);
+int force_1clj_v3(ls1b200_ctx* c);          // round-2 production kernel (force_1clj_v3.cu)
 int force_1clj_mma(ls1b200_ctx* c);
 int force_1clj_tc(ls1b200_ctx* c);
 int force_multi_tiled(ls1b200_ctx* c);

@@ -98,6 +98,10 @@ int ctx_alloc_molecules(ls1b200_ctx* c, uint64_t n_owned, uint64_t cap) {
 	}
 	c->partial_blocks = (uint32_t) (((cap + 63) / 64) * std::max(c->smax, 1u) + 64);
 	c->partial_blocks = std::max<uint32_t>(c->partial_blocks, c->geom.ncells + 64);   // tiled kernels: one partial per chunk
+	{	// force_1clj_v3.cu: molecule-granular chunks (at most one per inner cell, or per 32 slots, plus one per row)
+		const uint64_t nrows = (uint64_t) std::max(c->geom.cells[1] - 2, 0) * (uint64_t) std::max(c->geom.cells[2] - 2, 0);
+		c->partial_blocks = (uint32_t) std::max<uint64_t>(c->partial_blocks, (uint64_t) c->geom.ncells + cap / 32 + nrows + 64);
+	}
 	LS1_TRY(dev_alloc(&c->partials, (size_t) c->partial_blocks * 8));
 	if (c->dd.active) LS1_TRY(decomp_alloc(c));
 	LS1_CUDA(cudaMemsetAsync(c->F, 0, sizeof(double) * 3 * cap, c->stream));
@@ -228,8 +232,14 @@ int ls1b200_create(const ls1b200_config* cfg, ls1b200_ctx** out) {
 	auto cleanup = [&](int code) { ls1b200_destroy(c); return code; };
 	if (cudaSetDevice(c->device) != cudaSuccess) return cleanup(fail("ls1b200_create: cudaSetDevice failed"));
 	if (cudaStreamCreateWithFlags(&c->stream, cudaStreamNonBlocking) != cudaSuccess) return cleanup(fail("ls1b200_create: cannot create stream"));
-	const size_t nb = (size_t) c->geom.ncells + 4;
-	if (dev_alloc(&c->cell_count, 2 * nb) || dev_alloc(&c->cell_start, nb) || dev_alloc(&c->cursor, nb) || dev_alloc(&c->scan_tmp, nb / 2048 + 16)) return cleanup(1);
+	// fine x-bins per reference cell (the sort key inside a cell; the force kernels trim their candidate ranges with it)
+	c->fine_s = 1;      // default off: measured +0.08 ms in the sort and no gain in the force kernel (profiles/r02_force_kernel_experiments.md)
+	if (const char* e = getenv("LS1B200_FINE_S")) { const int v = atoi(e); if (v == 1 || v == 2 || v == 4 || v == 8) c->fine_s = (uint32_t) v; }
+	if ((uint64_t) c->geom.ncells * c->fine_s + 2 >= (1ull << 28)) c->fine_s = 1;
+	c->fine_inv = (double) c->fine_s * c->geom.crecip[0];
+	const size_t nb = (size_t) c->geom.ncells * c->fine_s + 4;
+	if (dev_alloc(&c->cell_count, 2 * nb) || dev_alloc(&c->cell_start, (size_t) c->geom.ncells + 4) || dev_alloc(&c->cursor, nb) || dev_alloc(&c->scan_tmp, nb / 2048 + 16)) return cleanup(1);
+	if (c->fine_s > 1 && dev_alloc(&c->cell_start_fine, nb)) return cleanup(1);
 	c->cell_count_halo = c->cell_count + nb;      // one allocation, one memset per update
 	{
 		// border table, evaluated exactly like cell_border<D> (one fused multiply-add; the first / last two are the stored constants)
@@ -251,7 +261,7 @@ int ls1b200_create(const ls1b200_config* cfg, ls1b200_ctx** out) {
 		if (dev_alloc(&c->chunk_row_count, nrows) || dev_alloc(&c->chunk_row_start, nrows) || dev_alloc(&c->work_counter, 4)) return cleanup(1);
 		cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
 		const char* k = getenv("LS1B200_LJ_KERNEL");
-		c->lj_kernel = (k && std::string(k) == "global") ? 1 : (k && std::string(k) == "mma") ? 3 : (k && std::string(k) == "tc") ? 4 : 0;
+		c->lj_kernel = (k && std::string(k) == "global") ? 1 : (k && std::string(k) == "mma") ? 3 : (k && std::string(k) == "tc") ? 4 : (k && std::string(k) == "v3") ? 5 : 0;      // default: the tiled kernel (v3 measured slower, profiles/r02_force_kernel_experiments.md)
 		const char* m = getenv("LS1B200_MULTI_KERNEL");
 		c->multi_kernel = (m && std::string(m) == "general") ? 1 : (m && std::string(m) == "generic") ? 2 : 0;   // 2: tiled, but never specialised
 	}
@@ -271,9 +281,10 @@ int ls1b200_destroy(ls1b200_ctx* c) {
 	ctx_free_molecules(c);
 	dev_free(c->d_comps); dev_free(c->d_sites);
 	dev_free(c->d_eps24); dev_free(c->d_sig2); dev_free(c->d_shift6); dev_free(c->d_eps24f); dev_free(c->d_sig2f); dev_free(c->d_shift6f);
-	dev_free(c->cell_count); dev_free(c->cell_start); dev_free(c->cursor); dev_free(c->scan_tmp); dev_free(c->d_border);
+	dev_free(c->cell_count); dev_free(c->cell_start); dev_free(c->cell_start_fine); dev_free(c->cursor); dev_free(c->scan_tmp); dev_free(c->d_border);
 	dev_free(c->d_scal); dev_free(c->d_records); dev_free(c->partials2);
 	if (c->chunks) cudaFree(c->chunks);
+	if (c->chunks2) cudaFree(c->chunks2);
 	dev_free(c->chunk_row_count); dev_free(c->chunk_row_start); dev_free(c->work_counter);
 	if (c->h_scal) cudaFreeHost(c->h_scal);
 	for (auto e : c->ev_pool) cudaEventDestroy(e);

@@ -42,6 +42,16 @@ __device__ __forceinline__ int cell1d_tab(const Geom& g, const double* __restric
 	return c;
 }
 
+// Fine x-bin of a coordinate inside ITS reference cell (lower border `border` from the same table the cell assignment uses):
+// the counting sort orders the molecules of a cell by this key, so a row of cells is (coarsely) sorted by x and the force
+// kernels can trim their candidate ranges to [x - rc, x + rc]. Not part of the reference's semantics -- the reference cell
+// (and everything reported as CELL) is unchanged; the SAME FP64 expression is evaluated by the sort and by the force kernel,
+// which makes the trim rigorous (floating-point operations are monotone).
+__device__ __forceinline__ int fine_sub(double x, double border, double finv, int S) {
+	const int s = __double2int_rd(__dmul_rn(__dsub_rn(x, border), finv));
+	return min(max(s, 0), S - 1);
+}
+
 __device__ __forceinline__ uint32_t cell_index(const Geom& g, int cx, int cy, int cz) {
 	return (uint32_t) ((cz * g.cells[1] + cy) * g.cells[0] + cx);
 }

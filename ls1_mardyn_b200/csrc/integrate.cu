@@ -202,7 +202,7 @@ __global__ void k_globals(DevScalars* scal, double target_T, unsigned long long 
 int do_forces(ls1b200_ctx* c) {
 	if (c->n_owned == 0 && !c->dd.active) { c->forces_valid = true; return 0; }
 	LS1_TRY(span_begin(c, PH_FORCE));
-	LS1_TRY(c->all_1clj ? (c->lj_kernel == 0 ? force_1clj_tiled(c) : c->lj_kernel == 1 ? force_1clj(c) : c->lj_kernel == 3 ? force_1clj_mma(c) : force_1clj_tc(c)) : (c->multi_kernel != 1 ? force_multi_tiled(c) : force_general(c)));
+	LS1_TRY(c->all_1clj ? (c->lj_kernel == 5 ? force_1clj_v3(c) : c->lj_kernel == 0 ? force_1clj_tiled(c) : c->lj_kernel == 1 ? force_1clj(c) : c->lj_kernel == 3 ? force_1clj_mma(c) : force_1clj_tc(c)) : (c->multi_kernel != 1 ? force_multi_tiled(c) : force_general(c)));
 	LS1_TRY(span_end(c));
 	c->forces_valid = true;
 	return 0;

@@ -75,6 +75,20 @@ __global__ void __launch_bounds__(256) k_fma_peak(float* out, int iters, float a
 	if (s == 123.456f) out[0] = s;
 }
 
+// FP64 FMA peak (the roofline denominator of the double build): same structure with DFMA
+__global__ void __launch_bounds__(256) k_dfma_peak(double* out, int iters, double a, double b) {
+	double x0 = threadIdx.x * 1e-3, x1 = x0 + 1., x2 = x0 + 2., x3 = x0 + 3., x4 = x0 + 4., x5 = x0 + 5., x6 = x0 + 6., x7 = x0 + 7.;
+	for (int i = 0; i < iters; i++) {
+		#pragma unroll
+		for (int u = 0; u < 8; u++) {
+			x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+			x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+		}
+	}
+	const double s = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+	if (s == 123.456) out[0] = s;
+}
+
 __global__ void __launch_bounds__(256) k_copy16(const int4* __restrict__ src, int4* __restrict__ dst, size_t n) {
 	const size_t stride = (size_t) gridDim.x * blockDim.x;
 	for (size_t i = (size_t) blockIdx.x * blockDim.x + threadIdx.x; i < n; i += stride) dst[i] = src[i];
@@ -133,6 +147,29 @@ int ls1b200_measure_fp32_peak(int device, double* tflops) {
 	for (int rep = 0; rep < 6; rep++) {
 		LS1_CUDA(cudaEventRecord(a));
 		k_fma_peak<<<blocks, 256>>>(d, iters, 0.999f, 1e-3f);
+		g_launches++;
+		LS1_CUDA(cudaEventRecord(b));
+		LS1_CUDA(cudaEventSynchronize(b));
+		float ms = 0.f; LS1_CUDA(cudaEventElapsedTime(&ms, a, b));
+		const double fl = 2.0 * 64.0 * (double) iters * 256.0 * (double) blocks;
+		if (rep > 0) best = std::max(best, fl / (ms * 1e-3) / 1e12);
+	}
+	cudaEventDestroy(a); cudaEventDestroy(b); cudaFree(d);
+	*tflops = best;
+	return 0;
+}
+
+int ls1b200_measure_fp64_peak(int device, double* tflops) {
+	if (!tflops) return fail("ls1b200_measure_fp64_peak: null argument");
+	LS1_CUDA(cudaSetDevice(device));
+	cudaDeviceProp prop; LS1_CUDA(cudaGetDeviceProperties(&prop, device));
+	double* d = nullptr; LS1_CUDA(cudaMalloc((void**) &d, 64));
+	cudaEvent_t a, b; LS1_CUDA(cudaEventCreate(&a)); LS1_CUDA(cudaEventCreate(&b));
+	const int blocks = prop.multiProcessorCount * 8, iters = 1024;
+	double best = 0.;
+	for (int rep = 0; rep < 6; rep++) {
+		LS1_CUDA(cudaEventRecord(a));
+		k_dfma_peak<<<blocks, 256>>>(d, iters, 0.999, 1e-3);
 		g_launches++;
 		LS1_CUDA(cudaEventRecord(b));
 		LS1_CUDA(cudaEventSynchronize(b));

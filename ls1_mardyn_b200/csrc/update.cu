@@ -22,13 +22,18 @@ namespace ls1b200 {
 
 constexpr int SHIFT_BITS = 26;   // key = bin | shiftmask << 26  (bin <= ncells < 2^26)
 
+constexpr uint32_t RANK_BITS = 28, RANK_MASK = (1u << RANK_BITS) - 1u;      // rank[] = in-bin rank | fine x-bin << 28
+
 struct UpdArgs {
 	Geom g;
 	uint32_t cap;
+	uint32_t S;          // fine x-bins per reference cell (1, 2, 4 or 8); histogram bin = cell * S + fine_sub (limbo: ncells * S)
+	double finv;         // S / cell length in x
 	uint32_t parity;     // DevScalars::n_slots2[parity] = source slots of this update, [parity^1] receives the new count
 	const double* bx; const double* by; const double* bz;      // cell border tables (context.cu)
 };
 
+__device__ __forceinline__ uint32_t g_ncells(const UpdArgs& a) { return a.g.ncells; }
 __device__ __forceinline__ bool code_valid(uint32_t mask, int a, int b, int c) {
 	return (a == 0 || ((mask >> (a - 1)) & 1u)) && (b == 0 || ((mask >> (2 + b - 1)) & 1u)) && (c == 0 || ((mask >> (4 + c - 1)) & 1u));
 }
@@ -38,7 +43,7 @@ __global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __r
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool in_range = s < min(scal->n_slots2[a.parity], a.cap);
 	const Geom& g = a.g;
-	uint32_t bin = KEY_NONE, mask = 0;
+	uint32_t bin = KEY_NONE, mask = 0, sub = 0;      // bin: FINE bin (reference cell * S + x sub-bin)
 	double x = 0., y = 0., z = 0.;
 	if (in_range) {
 		const uint64_t meta = cur.meta[s];
@@ -50,11 +55,13 @@ __global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __r
 			if (g.periodic[2]) { double w = wrap_coord<2>(g, z); if (w != z) { z = w; cur.r[2 * (size_t) a.cap + s] = w; } }
 			const int cx = cell1d_tab<0>(g, a.bx, x), cy = cell1d_tab<1>(g, a.by, y), cz = cell1d_tab<2>(g, a.bz, z);
 			const bool out = cx < 0 || cy < 0 || cz < 0 || cx >= g.cells[0] || cy >= g.cells[1] || cz >= g.cells[2];
-			if (out) { bin = g.ncells; key[s] = bin; }
+			if (out) { key[s] = g.ncells; bin = g.ncells * a.S; }
 			else {
-				bin = cell_index(g, cx, cy, cz);
+				const uint32_t cell = cell_index(g, cx, cy, cz);
 				mask = shift_mask<0>(g, x) | (shift_mask<1>(g, y) << 2) | (shift_mask<2>(g, z) << 4);
-				key[s] = bin | (mask << SHIFT_BITS);
+				key[s] = cell | (mask << SHIFT_BITS);
+				sub = (uint32_t) fine_sub(x, __ldg(a.bx + cx), a.finv, (int) a.S);
+				bin = cell * a.S + sub;
 			}
 		}
 	}
@@ -74,13 +81,14 @@ __global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __r
 		uint32_t base = 0;
 		if (head && bin != KEY_NONE) base = atomicAdd(&count[bin], (uint32_t) (end - start));
 		base = __shfl_sync(0xffffffffu, base, start);
-		if (bin != KEY_NONE) rank[s] = base + (uint32_t) (lane - start);
+		if (bin != KEY_NONE) rank[s] = ((base + (uint32_t) (lane - start)) & RANK_MASK) | (sub << RANK_BITS);
 	}
 	if (mask) {
 		for (int c3 = 0; c3 < 3; c3++) for (int b3 = 0; b3 < 3; b3++) for (int a3 = 0; a3 < 3; a3++) {
 			if ((a3 | b3 | c3) == 0 || !code_valid(mask, a3, b3, c3)) continue;
-			const int hx = cell1d_tab<0>(g, a.bx, halo_coord<0>(g, x, a3)), hy = cell1d_tab<1>(g, a.by, halo_coord<1>(g, y, b3)), hz = cell1d_tab<2>(g, a.bz, halo_coord<2>(g, z, c3));
-			atomicAdd(&count_halo[cell_index(g, hx, hy, hz)], 1u);
+			const double xh = halo_coord<0>(g, x, a3);
+			const int hx = cell1d_tab<0>(g, a.bx, xh), hy = cell1d_tab<1>(g, a.by, halo_coord<1>(g, y, b3)), hz = cell1d_tab<2>(g, a.bz, halo_coord<2>(g, z, c3));
+			atomicAdd(&count_halo[cell_index(g, hx, hy, hz) * a.S + (uint32_t) fine_sub(xh, __ldg(a.bx + hx), a.finv, (int) a.S)], 1u);
 		}
 	}
 }
@@ -133,15 +141,21 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_top(uint32_t* __restrict__ bsum
 	if (threadIdx.x == 0) *grand_total = carry;
 }
 // adds the block offsets; writes cell_start[0..n] (cell_start[n] = total), the scatter cursor, and the slot count
+// (n = ncells * S + 1 FINE bins; `coarse` = the reference cells' cell_start: entry c is the start of fine bin c * S)
 __global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict__ start, uint32_t* __restrict__ cursor, const uint32_t* __restrict__ count, const uint32_t* __restrict__ bsum,
-                                                      const uint32_t* __restrict__ grand_total, uint32_t n, uint32_t cap, uint32_t parity, DevScalars* scal) {
+                                                      const uint32_t* __restrict__ grand_total, uint32_t n, uint32_t cap, uint32_t parity, DevScalars* scal,
+                                                      uint32_t* __restrict__ coarse, uint32_t S) {
 	const uint32_t base = blockIdx.x * SCAN_B + threadIdx.x * SCAN_V;
 	const uint32_t off = bsum[blockIdx.x];
 	#pragma unroll
-	for (int k = 0; k < SCAN_V; k++) if (base + k < n) { uint32_t v = start[base + k] + off; start[base + k] = v; cursor[base + k] = v + count[base + k]; }      // halo copies follow the ranked entries
+	for (int k = 0; k < SCAN_V; k++) if (base + k < n) {
+		uint32_t v = start[base + k] + off; start[base + k] = v; cursor[base + k] = v + count[base + k];      // halo copies follow the ranked entries
+		if (coarse != start && (base + k) % S == 0) coarse[(base + k) / S] = v;
+	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		const uint32_t total = *grand_total;
 		start[n] = total;
+		if (coarse != start) coarse[(n - 1) / S + 1] = total;
 		scal->n_slots2[parity ^ 1u] = total;
 		scal->n_sorted = min(total, cap);
 		if (total > cap) scal->overflow = 1;
@@ -156,18 +170,21 @@ __global__ void __launch_bounds__(256) k_scatter(UpdArgs a, State cur, const uin
 	const uint32_t k = key[s];
 	if (k == KEY_NONE) return;
 	const Geom& g = a.g;
-	const uint32_t bin = k & ((1u << SHIFT_BITS) - 1u), mask = k >> SHIFT_BITS;
-	// provisional slot: start of the bin + the rank k_key obtained from the histogram atomic (the in-cell order is made
+	const uint32_t cell = k & ((1u << SHIFT_BITS) - 1u), mask = k >> SHIFT_BITS;
+	const uint32_t rk = rank[s];
+	const uint32_t bin = cell >= g_ncells(a) ? g_ncells(a) * a.S : cell * a.S + (rk >> RANK_BITS);      // fine bin (cell_start is the FINE array here)
+	// provisional slot: start of the bin + the rank k_key obtained from the histogram atomic (the in-bin order is made
 	// deterministic by k_gather)
-	uint32_t p = cell_start[bin] + rank[s];
+	uint32_t p = cell_start[bin] + (rk & RANK_MASK);
 	const uint64_t idk = ekey ? (cur.id[s] << 5) : 0ull;      // decomposed mode: in-cell order by (molecule id, shift code)
 	if (p < a.cap) { entry[p] = s << 5; cell_of[p] = bin; if (ekey) ekey[p] = idk; }
 	if (mask) {
 		const double x = cur.r[s], y = cur.r[(size_t) a.cap + s], z = cur.r[2 * (size_t) a.cap + s];
 		for (int c3 = 0; c3 < 3; c3++) for (int b3 = 0; b3 < 3; b3++) for (int a3 = 0; a3 < 3; a3++) {
 			if ((a3 | b3 | c3) == 0 || !code_valid(mask, a3, b3, c3)) continue;
-			const int hx = cell1d_tab<0>(g, a.bx, halo_coord<0>(g, x, a3)), hy = cell1d_tab<1>(g, a.by, halo_coord<1>(g, y, b3)), hz = cell1d_tab<2>(g, a.bz, halo_coord<2>(g, z, c3));
-			const uint32_t hb = cell_index(g, hx, hy, hz);
+			const double xh = halo_coord<0>(g, x, a3);
+			const int hx = cell1d_tab<0>(g, a.bx, xh), hy = cell1d_tab<1>(g, a.by, halo_coord<1>(g, y, b3)), hz = cell1d_tab<2>(g, a.bz, halo_coord<2>(g, z, c3));
+			const uint32_t hb = cell_index(g, hx, hy, hz) * a.S + (uint32_t) fine_sub(xh, __ldg(a.bx + hx), a.finv, (int) a.S);
 			p = atomicAdd(&cursor[hb], 1u);      // the periodic copies of a bin follow its ranked entries
 			if (p < a.cap) { entry[p] = (s << 5) | (uint32_t) (a3 + 3 * b3 + 9 * c3); cell_of[p] = hb; if (ekey) ekey[p] = idk | (uint64_t) (a3 + 3 * b3 + 9 * c3); }
 		}
@@ -183,8 +200,9 @@ __global__ void __launch_bounds__(256) k_gather(UpdArgs a, State cur, State nxt,
 	const uint32_t n_slots = min(scal->n_slots2[a.parity ^ 1u], a.cap);
 	if (p >= n_slots) return;
 	const Geom& g = a.g;
-	const uint32_t e = entry[p], c = cell_of[p];
-	const uint32_t b = cell_start[c], en = min(cell_start[c + 1], a.cap);
+	const uint32_t e = entry[p], fb = cell_of[p];              // fine bin; cell_start is the FINE array
+	const uint32_t c = min(fb / a.S, g.ncells);                // reference cell (limbo: ncells)
+	const uint32_t b = cell_start[fb], en = min(cell_start[fb + 1], a.cap);
 	uint32_t rank = 0;
 	if (ekey) { const uint64_t ek = ekey[p]; for (uint32_t u = b; u < en; u++) rank += (ekey[u] < ek) ? 1u : 0u; }
 	else for (uint32_t u = b; u < en; u++) rank += (entry[u] < e) ? 1u : 0u;
@@ -262,23 +280,25 @@ int do_update(ls1b200_ctx* c) {
 	if (c->n_owned == 0 && !c->dd.active) { c->sorted = true; return 0; }
 	if (c->cap == 0) return fail("ls1b200_update: call ls1b200_upload first");
 	LS1_TRY(span_begin(c, PH_UPDATE));
-	UpdArgs a; a.g = c->geom; a.cap = (uint32_t) c->cap; a.parity = c->parity;
+	UpdArgs a; a.g = c->geom; a.cap = (uint32_t) c->cap; a.parity = c->parity; a.S = c->fine_s; a.finv = c->fine_inv;
 	a.bx = c->d_border; a.by = c->d_border + c->border_stride; a.bz = c->d_border + 2 * (size_t) c->border_stride;
-	const uint32_t nb = c->geom.ncells + 1;   // + limbo bin
-	LS1_CUDA(cudaMemsetAsync(c->cell_count, 0, sizeof(uint32_t) * 2 * ((size_t) c->geom.ncells + 4), c->stream));      // cell_count and cell_count_halo
+	const uint32_t nb = c->geom.ncells * c->fine_s + 1;   // fine bins + limbo bin
+	LS1_CUDA(cudaMemsetAsync(c->cell_count, 0, sizeof(uint32_t) * 2 * ((size_t) c->geom.ncells * c->fine_s + 4), c->stream));      // cell_count and cell_count_halo
 	// slot counts are only known on the device: every per-slot kernel is launched over the capacity, threads beyond exit
 	const uint32_t gs = (uint32_t) ((c->cap + 255) / 256);
 	LS1_LAUNCH(c, PH_UPDATE, k_key, gs, 256, 0, a, c->cur, c->key, c->cell_count, c->cell_count_halo, c->rank, c->d_scal);
 	const uint32_t sb = (nb + SCAN_B - 1) / SCAN_B;
-	LS1_LAUNCH(c, PH_UPDATE, k_scan_block, sb, SCAN_T, 0, c->cell_count, c->cell_count_halo, c->cell_start, c->scan_tmp, nb);
+	// cell_start_fine: exclusive scan over the fine bins; cell_start (the reference cells) is every S-th entry of it
+	uint32_t* fstart = c->fine_s > 1 ? c->cell_start_fine : c->cell_start;
+	LS1_LAUNCH(c, PH_UPDATE, k_scan_block, sb, SCAN_T, 0, c->cell_count, c->cell_count_halo, fstart, c->scan_tmp, nb);
 	LS1_LAUNCH(c, PH_UPDATE, k_scan_top, 1, SCAN_T, 0, c->scan_tmp, sb, c->scan_tmp + sb);
-	LS1_LAUNCH(c, PH_UPDATE, k_scan_add, sb, SCAN_T, 0, c->cell_start, c->cursor, c->cell_count, c->scan_tmp, c->scan_tmp + sb, nb, (uint32_t) c->cap, a.parity, c->d_scal);
-	LS1_LAUNCH(c, PH_UPDATE, k_scatter, gs, 256, 0, a, c->cur, c->key, c->rank, c->cell_start, c->cursor, c->entry, c->cell_of, c->d_scal, c->dd.active ? c->ekey : (uint64_t*) nullptr);
+	LS1_LAUNCH(c, PH_UPDATE, k_scan_add, sb, SCAN_T, 0, fstart, c->cursor, c->cell_count, c->scan_tmp, c->scan_tmp + sb, nb, (uint32_t) c->cap, a.parity, c->d_scal, c->cell_start, c->fine_s);
+	LS1_LAUNCH(c, PH_UPDATE, k_scatter, gs, 256, 0, a, c->cur, c->key, c->rank, (const uint32_t*) fstart, c->cursor, c->entry, c->cell_of, c->d_scal, c->dd.active ? c->ekey : (uint64_t*) nullptr);
 	const uint32_t gc = gs;
 	if (c->mixed)
-		LS1_LAUNCH(c, PH_UPDATE, k_gather<float>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, c->cell_start, c->cell_of2, (float4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr);
+		LS1_LAUNCH(c, PH_UPDATE, k_gather<float>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, (const uint32_t*) fstart, c->cell_of2, (float4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr);
 	else
-		LS1_LAUNCH(c, PH_UPDATE, k_gather<double>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, c->cell_start, c->cell_of2, (double4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr);
+		LS1_LAUNCH(c, PH_UPDATE, k_gather<double>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, (const uint32_t*) fstart, c->cell_of2, (double4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr);
 	std::swap(c->cur, c->nxt);
 	c->parity ^= 1u;
 	if (!c->all_1clj) {

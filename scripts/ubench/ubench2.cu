@@ -23,10 +23,11 @@ __global__ void __launch_bounds__(1024) k_lds(float* out, int iters, Pattern pat
 		#pragma unroll
 		for (int u = 0; u < 8; u++) {
 			const uint32_t ad = base + (uint32_t) u * WB * (MODE == 1 ? 16 : 1);
-			if (WB == 4) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ad)); acc0 += v; }
-			if (WB == 8) { float v, w; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v), "=f"(w) : "r"(ad)); acc0 += v; acc1 += w; }
-			if (WB == 16) { float v, w, x, y; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v), "=f"(w), "=f"(x), "=f"(y) : "r"(ad)); acc0 += v; acc1 += w; acc2 += x; acc3 += y; }
+			if (WB == 4) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(ad) : "memory"); acc0 += v; }
+			if (WB == 8) { float v, w; asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(v), "=f"(w) : "r"(ad) : "memory"); acc0 += v; acc1 += w; }
+			if (WB == 16) { float v, w, x, y; asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(v), "=f"(w), "=f"(x), "=f"(y) : "r"(ad) : "memory"); acc0 += v; acc1 += w; acc2 += x; acc3 += y; }
 		}
+		base += 16; if ((it & 15) == 15) base -= 16 * 16;
 	}
 	long long t1 = clock64();
 	float s = acc0 + acc1 + acc2 + acc3;
@@ -73,7 +74,7 @@ int main() {
 	CK(cudaFuncSetAttribute(k_lds<16, 0>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
 	CK(cudaFuncSetAttribute(k_lds<8, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
 	CK(cudaFuncSetAttribute(k_lds<16, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, 64 * 1024));
-	for (int mode = 0; mode < 2; mode++) for (int wb = (mode ? 8 : 4); wb <= 16; wb *= 2) for (int pi = 0; pi < 16; pi++) for (int stride = 176; stride <= 1072; stride += 896) {
+	for (int mode = 0; mode < 2; mode++) for (int wb = (mode ? 8 : 4); wb <= 16; wb *= 2) for (int pi = 0; pi < 16; pi++) for (int stride = 176; stride <= 208; stride += 32) {
 		const int iters = 2048, warps = 16;
 		Pattern pt = make(pats[pi], npat[pi]);
 		void (*k)(float*, int, Pattern, int, long long*) = mode == 0 ? (wb == 4 ? k_lds<4, 0> : wb == 8 ? k_lds<8, 0> : k_lds<16, 0>) : (wb == 8 ? k_lds<8, 1> : k_lds<16, 1>);

@@ -107,10 +107,12 @@ def test_multicomponent_1clj_fast_path(capi):
         assert abs(ma.upot - mb.upot) <= TOL[prec] * abs(mb.upot)
 
 
-@pytest.mark.parametrize("kernel", ["tiled", "global", "mma", "tc"])
+@pytest.mark.parametrize("kernel", ["tiled", "global", "mma", "tc", "v3", "v3:4", "v3:8:2"])
 def test_1clj_kernel_variants_vs_oracle(capi, kernel):
-    """The alternative 1CLJ force kernels (LS1B200_LJ_KERNEL): the global-memory v1 kernel and the two tensor-core prefilter
-    experiments (mma.sync TF32 / tcgen05 FP16 with TMEM; both fall back to the tiled kernel in the double build). Same bar as
+    """The alternative 1CLJ force kernels (LS1B200_LJ_KERNEL): the global-memory v1 kernel, the two tensor-core prefilter
+    experiments (mma.sync TF32 / tcgen05 FP16 with TMEM; both fall back to the tiled kernel in the double build) and the round-2
+    experiment v3 (molecule-granular chunks; "v3:S[:A]" = sorted by S fine x-bins per cell with x-trimmed candidate ranges, lane
+    groups padded to A). Same bar as
     the production kernel: forces, virial, energy against the CPU oracle, single- and multi-component."""
     import os
     from oracle import oracle as orc
@@ -120,11 +122,17 @@ def test_1clj_kernel_variants_vs_oracle(capi, kernel):
                    xi=np.array([[1, 0.9], [1, 1]]), eta=np.array([[1, 1.05], [1, 1]]))
     for case, ps in enumerate((_lattice_case(20, seed=11), _lattice_case(8, seed=5, ens=two, rho=0.6), _lattice_case(14, seed=3, jitter=0.15))):
         for prec in ("mixed", "double"):
-            os.environ["LS1B200_LJ_KERNEL"] = kernel
+            parts = kernel.split(":")
+            os.environ["LS1B200_LJ_KERNEL"] = parts[0]
+            if len(parts) > 1:
+                os.environ["LS1B200_FINE_S"] = parts[1]
+            if len(parts) > 2:
+                os.environ["LS1B200_V3_ALIGN"] = parts[2]
             try:
                 a = _mk(capi.Context, ps, 2.5, prec)
             finally:
-                os.environ.pop("LS1B200_LJ_KERNEL", None)
+                for k in ("LS1B200_LJ_KERNEL", "LS1B200_FINE_S", "LS1B200_V3_ALIGN"):
+                    os.environ.pop(k, None)
             b = _mk(orc.OracleSim, ps, 2.5, prec)
             a.update(); b.update(); ma, mb = a.traverse_cells(), b.traverse_cells()
             tol = TOL[prec]
@@ -165,7 +173,7 @@ def test_leapfrog_and_thermostat_steps_vs_oracle(capi, prec):
             ok, worst = rel_close(a.download(f), b.download(f), tol); assert ok, (step, "scale", f, worst)
 
 
-@pytest.mark.parametrize("name,dt,nsteps", [("periodic_1clj_1458", 0.002, 100), ("periodic_water_432", 0.0667516, 40), ("periodic_multi_250", 0.0667516, 40)])
+@pytest.mark.parametrize("name,dt,nsteps", [("periodic_1clj_1458", 0.002, 100), ("periodic_water_432", 0.0166879, 40), ("periodic_multi_250", 0.0667516, 40)])      # water: the time step of tests/golden/make_traces.py (at the full step this lattice start heats by a factor 3 within 10 steps: the reference itself then switches to its "explosion" heuristics, Domain.cpp:260-306, and FP32 summation order decides the 7th digit)
 @pytest.mark.parametrize("prec", ["double", "mixed"])
 def test_simulate_trace_vs_oracle(capi, name, dt, nsteps, prec):
     """Fused multi-step loop (NVT velocity scaling): T, U_pot, p per step against the oracle's loop."""
