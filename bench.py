@@ -210,7 +210,7 @@ def run_port(n_per_dim, steps):
 
 # bounded samples of the CPU legs inside the default run: molecules-per-dimension and steps chosen for a few seconds of main loop on
 # the GPU box's host cores (1CLJ: 4 M molecules x 5 steps = 20 M updates at ~12 MMUPS; the multi-site models are 10 - 40 x slower per update)
-CPU_SAMPLE = {"lj": (126, 5), "water": (40, 3), "co2": (30, 3), "argon": (37, 10)}
+CPU_SAMPLE = {"lj": (126, 5), "water": (50, 25), "co2": (40, 30), "argon": (37, 150)}
 
 
 def cpu_baseline(wl=None):
@@ -232,8 +232,9 @@ def workload_config(wl, n_per_dim, world):
     """The `config` object of the JSON line: the workload only (identical for our arm and the reference arm); how each arm executes
     it is reported under `execution`."""
     N = 2 * n_per_dim ** 3
-    L = (world * N / wl.rho) ** (1.0 / 3.0)
-    return {"workload": wl.description, "molecules_per_gpu": N, "molecules": world * N, "box": [L, L, L], "steps_size": "dt=%g" % wl.dt}
+    L1 = (N / wl.rho) ** (1.0 / 3.0)
+    g = grid_for(world)
+    return {"workload": wl.description, "molecules_per_gpu": N, "molecules": world * N, "box": [L1 * g[0], L1 * g[1], L1 * g[2]], "steps_size": "dt=%g" % wl.dt}
 
 
 WL_LJ_DESCRIPTION = "BASELINE.json configs[1]: 1CLJ LJ liquid rho*=0.7 T*=0.85 rc=2.5 sigma dt=0.002, mixed precision, NVT velocity scaling"
@@ -342,27 +343,36 @@ def our_arm(args):
     wl = workloads.get(args.workload)
     RHO, TEMP, RC, DT = wl.rho, wl.temperature, wl.rc, wl.dt
     n = args.n_per_dim or wl.n_per_dim
+    rot = any(c.Ipa()[1] for c in wl.ensemble.components)
+    device_gen = not rot and not args.host_gen      # 1CLJ systems are generated ON the device (ls1b200_generate_cubic_grid): no host array of the system exists
+    grid = grid_for(world)
+    L1 = (2 * n ** 3 / RHO) ** (1.0 / 3.0)             # box of one block
+    box = np.array([L1 * grid[0], L1 * grid[1], L1 * grid[2]])
     if world == 1:
-        ps = make_system(n, mixed=(args.precision == "mixed"), seed=rank, wl=wl)
         dd = None
-        ctx = capi.Context([0, 0, 0], list(ps.length), RC, precision=args.precision, geometry="xml", periodic=(1, 1, 1), device=local)
-        ctx.set_components(ps.ensemble)
+        ctx = capi.Context([0, 0, 0], list(box), RC, precision=args.precision, geometry="xml", periodic=(1, 1, 1), device=local)
+        ctx.set_components(wl.ensemble)
     else:
-        grid = grid_for(world)
-        dd0 = DomainDecomposition(rank, world, [1.0, 1.0, 1.0], grid)
-        ps = generators.lattice_block(wl.ensemble, n, RHO, TEMP, dd0.coords, grid, seed=0)
-        ps.r = ps.r.astype(np.float32).astype(np.float64)
-        dd = DomainDecomposition(rank, world, ps.length, grid)
+        dd = DomainDecomposition(rank, world, box, grid)
         ctx = capi.Context(list(dd.box_min()), list(dd.box_max()), RC, precision=args.precision, geometry="xml", periodic=dd.periodic(), device=local)
-        ctx.set_components(ps.ensemble)
+        ctx.set_components(wl.ensemble)
         uid = [capi.nccl_unique_id() if rank == 0 else None]
         dist.broadcast_object_list(uid, src=0, device=torch.device("cuda", local))
         ctx.decomp_attach(dd, uid[0])
-    N = len(ps.id)
+    if device_gen:
+        N = ctx.generate_cubic_grid([n * grid[0], n * grid[1], n * grid[2]], box, TEMP, seed=0, remove_momentum=True)
+    else:
+        if world == 1:
+            ps = make_system(n, mixed=(args.precision == "mixed"), seed=rank, wl=wl)
+        else:
+            ps = generators.lattice_block(wl.ensemble, n, RHO, TEMP, dd.coords, grid, seed=0)
+            ps.r = ps.r.astype(np.float32).astype(np.float64)
+        ctx.upload(ps.id, ps.cid, ps.r, ps.v, ps.q if rot else None, ps.L if rot else None)
+        N = len(ps.id)
     N_global = world * N
-    V_global = float(np.prod(ps.length))
-    rot = any(c.Ipa()[1] for c in wl.ensemble.components)
-    ctx.upload(ps.id, ps.cid, ps.r, ps.v, ps.q if rot else None, ps.L if rot else None)
+    if world > 1 and device_gen:
+        tn = torch.tensor([N], dtype=torch.int64, device="cuda"); dist.all_reduce(tn); N_global = int(tn.item())
+    V_global = float(np.prod(box))
     transport = "none"
     if dd is not None:
         # molecule exchange: NVLink stores into the neighbours' receive buffers (CUDA IPC); LS1B200_TRANSPORT=nccl keeps ncclSend / Recv
@@ -412,7 +422,7 @@ def our_arm(args):
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     t_wall, t_dev = float(t[0]), float(t[1])
-    value = world * N * args.steps / t_wall / 1e6
+    value = N_global * args.steps / t_wall / 1e6
 
     # ---- end to end through the C ABI with host buffers ----
     e2e_steps = max(1, min(args.steps, args.e2e_steps))
@@ -448,7 +458,7 @@ def our_arm(args):
     t = torch.tensor([t_e2e], dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    e2e_value = world * N * e2e_steps / float(t[0]) / 1e6
+    e2e_value = N_global * e2e_steps / float(t[0]) / 1e6
 
     if rank == 0:
         force_ms = ph_ms["force"] / max(args.steps, 1)
@@ -476,7 +486,7 @@ def our_arm(args):
             "metric": "MMUPS", "value": round(value, 2), "unit": "MMUPS (1e6 molecule updates / s)", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
             "ms_per_step": round(1e3 * t_wall / args.steps, 4), "higher_is_better": True, "scaling": "weak", "vs_baseline": None,
             "dtype": "f32 pair arithmetic, f64 accumulation and state (MARDYN_SPDP)" if args.precision == "mixed" else "f64 throughout (MARDYN_DPDP, the reference's double build)",
-            "data": "synthetic (BCC lattice like CubicGridGenerator, equal-magnitude velocities)",
+            "data": "synthetic (BCC lattice like CubicGridGenerator, equal-magnitude velocities" + (", generated on the device by ls1b200_generate_cubic_grid)" if device_gen else ", host arrays uploaded)"),
             "config": workload_config(wl, n, world),
             "execution": {"cells_per_dim": [int(x) for x in ctx.geometry()[0]],
                           "parallelism": "1 GPU" if world == 1 else ("3D block decomposition %dx%dx%d, one process per GPU, leaving molecules + halo copies every step " % grid_for(world)) + ("stored by the packing kernel straight into the neighbours' memory over NVLink (CUDA IPC)" if transport == "peer-memory" else "over NCCL send/recv") + ", NCCL allreduce of 7 doubles",
@@ -517,13 +527,14 @@ def main():
     ap.add_argument("--steps", type=int, default=100)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
-    ap.add_argument("--workload", default="lj", choices=["lj", "water", "co2"], help="lj = BASELINE.json configs[1] (the headline); water / co2 = configs[2] / [3]")
+    ap.add_argument("--workload", default="lj", choices=["lj", "water", "co2", "argon"], help="lj = BASELINE.json configs[1] (the headline); argon / water / co2 = configs[0] / [2] / [3]")
     ap.add_argument("--n-per-dim", type=int, default=0, help="BCC lattice cells per dimension: N = 2 n^3 (default: the workload's single-GPU size, lj 200 -> 16 M molecules)")
     ap.add_argument("--ref-n-per-dim", type=int, default=0, help="size of the reference arm's run (default: the workload's single-GPU size, 200 -> 16 M molecules)")
     ap.add_argument("--no-secondary", action="store_true", help="skip the water-like 4 M and CO2 8 M runs reported under `secondary`")
     ap.add_argument("--e2e-steps", type=int, default=3)
     ap.add_argument("--precision", default="mixed", choices=["mixed", "double"], help="mixed = the headline (BASELINE.json configs[1]); double = the full-FP64 variant of the reference's double build")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--host-gen", action="store_true", help="build the lattice in numpy and upload it instead of generating it on the device")
     args = ap.parse_args()
     if args.impl == "reference":
         reference_arm(args)

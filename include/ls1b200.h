@@ -271,6 +271,18 @@ int ls1b200_halo_import(ls1b200_ctx* ctx, const void* device_buf, uint64_t count
 int ls1b200_halo_import_host(ls1b200_ctx* ctx, const ls1b200_particle* host_buf, uint64_t count);
 
 /* ---- measurement helpers (bench.py) ---- */
+/* The reference's CubicGridGenerator on the device (io/CubicGridGeneratorInternal.cpp:125-187, ParticleCellBase::initCubicGrid,
+ * particleContainer/ParticleCellBase.cpp:51-159): a body-centred cubic lattice of 2 * nx * ny * nz molecules of component 0 over
+ * the whole simulation box [0, sim_box) -- two sub-lattices at 1/4 and 3/4 of the spacing, coordinates created in the calc type --
+ * of which this context keeps those inside ITS box (min <= r < max): every rank of a decomposition generates its own block, no
+ * host array of the system ever exists. Velocities: |v| = sqrt((3 + rotDOF) T / m), direction from two uniform numbers
+ * (EqualVelocityAssigner.h:16-29) drawn from a counter-based generator keyed by `seed` and the molecule's global lattice index
+ * (the state does not depend on the decomposition); q = (1, 0, 0, 0), L = 0; id = lattice index + 1. remove_momentum != 0
+ * subtracts sum(m v) / sum(m) over all ranks (IOHelpers::removeMomentum; collective on contexts with a communicator).
+ * Replaces ls1b200_upload: afterwards the context is in the same state as after an upload of these molecules. */
+int ls1b200_generate_cubic_grid(ls1b200_ctx* ctx, const uint64_t mols_per_dim[3], const double sim_box[3], double temperature,
+                                uint64_t seed, int32_t remove_momentum);
+
 /* Device time (ms) spent in each phase since the last reset, measured with CUDA events on the library's stream:
  * [0] update (binning+halo+SoA), [1] force kernels, [2] leapfrog pre, [3] leapfrog post + reductions. */
 int ls1b200_phase_times(ls1b200_ctx* ctx, double ms[4], uint64_t launches[4], int reset);

@@ -31,7 +31,7 @@ EXPORTS = ["ls1b200_last_error", "ls1b200_abi_version", "ls1b200_kernel_launch_c
            "ls1b200_scale_velocities", "ls1b200_simulate", "ls1b200_halo_export", "ls1b200_halo_import",
            "ls1b200_halo_import_host", "ls1b200_phase_times", "ls1b200_count_flops", "ls1b200_measure_fp32_peak", "ls1b200_measure_fp64_peak",
            "ls1b200_measure_hbm_copy", "ls1b200_stream", "ls1b200_nccl_unique_id", "ls1b200_decomp_attach", "ls1b200_download_begin", "ls1b200_download_end", "ls1b200_peer_handle", "ls1b200_peer_attach", "ls1b200_peer_detach", "ls1b200_exchange",
-           "ls1b200_allreduce_macro", "ls1b200_halo_export_host"]
+           "ls1b200_allreduce_macro", "ls1b200_halo_export_host", "ls1b200_generate_cubic_grid"]
 
 
 class Ls1B200Error(RuntimeError):
@@ -98,6 +98,7 @@ def lib():
         L.ls1b200_destroy.argtypes = [C.c_void_p]
         L.ls1b200_set_components.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ls1b200_upload.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 6
+        L.ls1b200_generate_cubic_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_uint64, C.c_int32]
         L.ls1b200_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
         L.ls1b200_set_field.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
         L.ls1b200_geometry.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p]
@@ -206,6 +207,15 @@ class Context:
         L = None if L is None else np.ascontiguousarray(L, dtype=np.float64)
         _check(lib().ls1b200_upload(self.h, n, _vp(id), _vp(cid), _vp(r), _vp(v), _vp(q), _vp(L)))
         self.n = n
+
+    def generate_cubic_grid(self, mols_per_dim, sim_box, temperature, seed=0, remove_momentum=True):
+        """ls1b200_generate_cubic_grid: the reference's CubicGridGenerator on the device (replaces upload). Returns the number of
+        molecules this context generated (those of the global lattice that lie inside its box)."""
+        m = np.ascontiguousarray(np.broadcast_to(np.asarray(mols_per_dim, dtype=np.uint64), (3,)))
+        b = np.ascontiguousarray(sim_box, dtype=np.float64)
+        _check(lib().ls1b200_generate_cubic_grid(self.h, _vp(m), _vp(b), float(temperature), int(seed), int(bool(remove_momentum))))
+        self.n = int(lib().ls1b200_num_molecules(self.h))
+        return self.n
 
     # ---- multi-GPU block decomposition (ls1_mardyn_b200.decomposition.DomainDecomposition) ----
     def decomp_attach(self, dd, unique_id: bytes | None = None):

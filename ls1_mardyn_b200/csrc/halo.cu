@@ -522,6 +522,13 @@ int do_exchange(ls1b200_ctx* c) {
 	return 0;
 }
 
+// sum of n doubles in device memory over the ranks of a decomposed context that has a communicator (no-op otherwise); collective
+int allreduce_doubles(ls1b200_ctx* c, double* dev, int n) {
+	if (!c->dd.active || !c->dd.comm) return 0;
+	LS1_NCCL(g_nccl.AllReduce(dev, dev, (size_t) n, NCCL_FLOAT64, NCCL_SUM, c->dd.comm, c->stream));
+	return 0;
+}
+
 int do_allreduce_scalars(ls1b200_ctx* c) {
 	if (!c->dd.active || !c->dd.comm) return 0;
 	// upot6lj, upot_xpoles, virial, my_rf, summv2, sum_iw2 + the fault flag: the seven leading doubles of DevScalars

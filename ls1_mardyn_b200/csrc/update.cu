@@ -27,7 +27,7 @@ constexpr uint32_t RANK_BITS = 28, RANK_MASK = (1u << RANK_BITS) - 1u;      // r
 struct UpdArgs {
 	Geom g;
 	uint32_t cap;
-	uint32_t S;          // fine x-bins per reference cell (1, 2, 4 or 8); histogram bin = cell * S + fine_sub (limbo: ncells * S)
+	uint32_t S, logS;    // fine x-bins per reference cell (1, 2, 4 or 8 = 1 << logS); histogram bin = cell * S + fine_sub (limbo: ncells * S)
 	double finv;         // S / cell length in x
 	uint32_t parity;     // DevScalars::n_slots2[parity] = source slots of this update, [parity^1] receives the new count
 	const double* bx; const double* by; const double* bz;      // cell border tables (context.cu)
@@ -60,8 +60,8 @@ __global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __r
 				const uint32_t cell = cell_index(g, cx, cy, cz);
 				mask = shift_mask<0>(g, x) | (shift_mask<1>(g, y) << 2) | (shift_mask<2>(g, z) << 4);
 				key[s] = cell | (mask << SHIFT_BITS);
-				sub = (uint32_t) fine_sub(x, __ldg(a.bx + cx), a.finv, (int) a.S);
-				bin = cell * a.S + sub;
+				if (a.S > 1) sub = (uint32_t) fine_sub(x, __ldg(a.bx + cx), a.finv, (int) a.S);      // S == 1: the reference cell is the bin
+				bin = (cell << a.logS) + sub;
 			}
 		}
 	}
@@ -88,7 +88,7 @@ __global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __r
 			if ((a3 | b3 | c3) == 0 || !code_valid(mask, a3, b3, c3)) continue;
 			const double xh = halo_coord<0>(g, x, a3);
 			const int hx = cell1d_tab<0>(g, a.bx, xh), hy = cell1d_tab<1>(g, a.by, halo_coord<1>(g, y, b3)), hz = cell1d_tab<2>(g, a.bz, halo_coord<2>(g, z, c3));
-			atomicAdd(&count_halo[cell_index(g, hx, hy, hz) * a.S + (uint32_t) fine_sub(xh, __ldg(a.bx + hx), a.finv, (int) a.S)], 1u);
+			atomicAdd(&count_halo[(cell_index(g, hx, hy, hz) << a.logS) + (a.S > 1 ? (uint32_t) fine_sub(xh, __ldg(a.bx + hx), a.finv, (int) a.S) : 0u)], 1u);
 		}
 	}
 }
@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict__ star
 	#pragma unroll
 	for (int k = 0; k < SCAN_V; k++) if (base + k < n) {
 		uint32_t v = start[base + k] + off; start[base + k] = v; cursor[base + k] = v + count[base + k];      // halo copies follow the ranked entries
-		if (coarse != start && (base + k) % S == 0) coarse[(base + k) / S] = v;
+		if (coarse != start && ((base + k) & (S - 1u)) == 0) coarse[(base + k) / S] = v;
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
 		const uint32_t total = *grand_total;
@@ -172,7 +172,7 @@ __global__ void __launch_bounds__(256) k_scatter(UpdArgs a, State cur, const uin
 	const Geom& g = a.g;
 	const uint32_t cell = k & ((1u << SHIFT_BITS) - 1u), mask = k >> SHIFT_BITS;
 	const uint32_t rk = rank[s];
-	const uint32_t bin = cell >= g_ncells(a) ? g_ncells(a) * a.S : cell * a.S + (rk >> RANK_BITS);      // fine bin (cell_start is the FINE array here)
+	const uint32_t bin = cell >= g_ncells(a) ? (g_ncells(a) << a.logS) : (cell << a.logS) + (rk >> RANK_BITS);      // fine bin (cell_start is the FINE array here)
 	// provisional slot: start of the bin + the rank k_key obtained from the histogram atomic (the in-bin order is made
 	// deterministic by k_gather)
 	uint32_t p = cell_start[bin] + (rk & RANK_MASK);
@@ -184,7 +184,7 @@ __global__ void __launch_bounds__(256) k_scatter(UpdArgs a, State cur, const uin
 			if ((a3 | b3 | c3) == 0 || !code_valid(mask, a3, b3, c3)) continue;
 			const double xh = halo_coord<0>(g, x, a3);
 			const int hx = cell1d_tab<0>(g, a.bx, xh), hy = cell1d_tab<1>(g, a.by, halo_coord<1>(g, y, b3)), hz = cell1d_tab<2>(g, a.bz, halo_coord<2>(g, z, c3));
-			const uint32_t hb = cell_index(g, hx, hy, hz) * a.S + (uint32_t) fine_sub(xh, __ldg(a.bx + hx), a.finv, (int) a.S);
+			const uint32_t hb = (cell_index(g, hx, hy, hz) << a.logS) + (a.S > 1 ? (uint32_t) fine_sub(xh, __ldg(a.bx + hx), a.finv, (int) a.S) : 0u);
 			p = atomicAdd(&cursor[hb], 1u);      // the periodic copies of a bin follow its ranked entries
 			if (p < a.cap) { entry[p] = (s << 5) | (uint32_t) (a3 + 3 * b3 + 9 * c3); cell_of[p] = hb; if (ekey) ekey[p] = idk | (uint64_t) (a3 + 3 * b3 + 9 * c3); }
 		}
@@ -201,7 +201,7 @@ __global__ void __launch_bounds__(256) k_gather(UpdArgs a, State cur, State nxt,
 	if (p >= n_slots) return;
 	const Geom& g = a.g;
 	const uint32_t e = entry[p], fb = cell_of[p];              // fine bin; cell_start is the FINE array
-	const uint32_t c = min(fb / a.S, g.ncells);                // reference cell (limbo: ncells)
+	const uint32_t c = min(fb >> a.logS, g.ncells);            // reference cell (limbo: ncells)
 	const uint32_t b = cell_start[fb], en = min(cell_start[fb + 1], a.cap);
 	uint32_t rank = 0;
 	if (ekey) { const uint64_t ek = ekey[p]; for (uint32_t u = b; u < en; u++) rank += (ekey[u] < ek) ? 1u : 0u; }
@@ -280,7 +280,7 @@ int do_update(ls1b200_ctx* c) {
 	if (c->n_owned == 0 && !c->dd.active) { c->sorted = true; return 0; }
 	if (c->cap == 0) return fail("ls1b200_update: call ls1b200_upload first");
 	LS1_TRY(span_begin(c, PH_UPDATE));
-	UpdArgs a; a.g = c->geom; a.cap = (uint32_t) c->cap; a.parity = c->parity; a.S = c->fine_s; a.finv = c->fine_inv;
+	UpdArgs a; a.g = c->geom; a.cap = (uint32_t) c->cap; a.parity = c->parity; a.S = c->fine_s; a.logS = c->fine_s == 8 ? 3u : c->fine_s == 4 ? 2u : c->fine_s == 2 ? 1u : 0u; a.finv = c->fine_inv;
 	a.bx = c->d_border; a.by = c->d_border + c->border_stride; a.bz = c->d_border + 2 * (size_t) c->border_stride;
 	const uint32_t nb = c->geom.ncells * c->fine_s + 1;   // fine bins + limbo bin
 	LS1_CUDA(cudaMemsetAsync(c->cell_count, 0, sizeof(uint32_t) * 2 * ((size_t) c->geom.ncells * c->fine_s + 4), c->stream));      // cell_count and cell_count_halo

@@ -87,3 +87,42 @@ def lattice_block(ens: Ensemble, n_per_dim: int, rho: float, temperature: float,
     ids = np.arange(first + 1, first + N + 1, dtype=np.uint64)
     perm = rng.permutation(N)
     return PhaseSpace(L, float(temperature), 1e10, ens, ids, cid[perm], r[perm], v[perm], q[perm], Lang[perm])
+
+
+# ---- host mirror of ls1b200_generate_cubic_grid (csrc/generate.cu), used by the parity test of the device generator ----------------
+def _splitmix64(x):
+    x = (x + np.uint64(0x9E3779B97F4A7C15)).astype(np.uint64)
+    x = ((x ^ (x >> np.uint64(30))) * np.uint64(0xBF58476D1CE4E5B9)).astype(np.uint64)
+    x = ((x ^ (x >> np.uint64(27))) * np.uint64(0x94D049BB133111EB)).astype(np.uint64)
+    return x ^ (x >> np.uint64(31))
+
+
+def cubic_grid_reference(mols_per_dim, sim_box, box_min, box_max, temperature, mass, rot_dof=0, seed=0, mixed=True):
+    """What the device generator produces for the context box [box_min, box_max): (id, r, v before momentum removal), ordered by id.
+    Same arithmetic: coordinate = origin + i * spacing rounded through the calc type, membership min <= r < max, velocity direction
+    from splitmix64(seed ^ 2 * index [+ 1]) (reference: ParticleCellBase.cpp:51-159, EqualVelocityAssigner.h:16-29)."""
+    n = np.broadcast_to(np.asarray(mols_per_dim, dtype=np.int64), (3,))
+    sim_box = np.asarray(sim_box, dtype=np.float64)
+    ids, rs = [], []
+    for s, f in enumerate((0.25, 0.25 * 3.0)):
+        axes, idxs = [], []
+        for d in range(3):
+            spacing = sim_box[d] / float(n[d])
+            i = np.arange(n[d], dtype=np.int64)
+            x = spacing * f + i.astype(np.float64) * spacing
+            if mixed:
+                x = x.astype(np.float32).astype(np.float64)
+            m = (x >= box_min[d]) & (x < box_max[d])
+            axes.append(x[m]); idxs.append(i[m])
+        X, Y, Z = np.meshgrid(*axes, indexing="ij"); I, J, K = np.meshgrid(*idxs, indexing="ij")
+        g = ((s * n[0] + I) * n[1] + J) * n[2] + K
+        ids.append(g.ravel()); rs.append(np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1))
+    gidx = np.concatenate(ids).astype(np.uint64); r = np.concatenate(rs)
+    with np.errstate(over="ignore"):
+        h1 = _splitmix64(np.uint64(seed) ^ (np.uint64(2) * gidx)); h2 = _splitmix64(np.uint64(seed) ^ (np.uint64(2) * gidx + np.uint64(1)))
+    u1 = (h1 >> np.uint64(11)).astype(np.float64) / 9007199254740992.0; u2 = (h2 >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
+    phi = 2.0 * np.pi * u1; theta = np.arccos(2.0 * u2 - 1.0)
+    vabs = np.sqrt((3.0 + rot_dof) * temperature / mass)
+    v = vabs * np.stack([np.sin(phi), np.cos(phi) * np.sin(theta), np.cos(phi) * np.cos(theta)], axis=1)
+    o = np.argsort(gidx)
+    return (gidx[o] + np.uint64(1)), r[o], v[o]

@@ -1,5 +1,9 @@
 """The named benchmark systems of BASELINE.json: component definitions and state points.
 
+  argon  configs[0]: the component and state point of the reference's examples/Argon/200K_18mol_l (config.xml, components.xml,
+         Argon_200K_18mol_l.inp: sigma = 6.4160007 a0, eps = 3.69852537e-4 Eh, m = 0.039948, T = 6.33363365e-4, rho = 1.6063e-3
+         a0^-3, dt = 0.0667516), lattice generated at N = 2 * 37^3 = 101 306 molecules with rc = 2.5 sigma = 16.04 a0 (24^3 cells;
+         the shipped example itself holds 2 048 molecules with rc = 5.15 sigma -- SURVEY.md 8d-1b)
   lj     configs[1]/[4]: reduced-unit 1CLJ liquid, sigma = eps = m = 1, rho* = 0.7, T* = 0.85, rc = 2.5 sigma, dt = 0.002
   water  configs[2]: the water-like model of the reference's test_input/VectorizationWater.inp:5-10 (1 LJ centre + 3 point
          charges, principal moments given), rho = 4.935e-3 a0^-3 (the fixture's 250 / 37^3), rc = rcLJ = 14.9 a0 (2.5 sigma),
@@ -42,7 +46,14 @@ def co2_2cljq() -> Ensemble:
         quadrupoles=[Quadrupole((0.0, 0.0, 0.0), (0.0, 0.0, 1.0), -322.873584174177)])])
 
 
+def argon() -> Ensemble:
+    return Ensemble([Component(ljcenters=[LJcenter((0.0, 0.0, 0.0), 0.039948, 0.000369852537, 6.4160007, 16.04000175, False)])])
+
+
 def get(name: str) -> Workload:
+    if name == "argon":
+        return Workload("argon", argon(), 0.00160630092, 0.000633363365, 16.04000175, 0.0667516, 37,
+                        "BASELINE.json configs[0]: examples/Argon 1CLJ (200K_18mol_l component and state point), 101 306 molecules on a lattice, rc=2.5 sigma, mixed precision, NVT")
     if name == "lj":
         return Workload("lj", lj_fluid(rc=2.5), 0.7, 0.85, 2.5, 0.002, 200,
                         "BASELINE.json configs[1]: 1CLJ LJ liquid rho*=0.7 T*=0.85 rc=2.5 sigma dt=0.002, mixed precision, NVT velocity scaling")

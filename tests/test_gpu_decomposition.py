@@ -174,6 +174,59 @@ def test_multisite_blocks(capi, n_ranks, prec):
     assert np.abs(qg - one.download("Q")[o1]).max() <= (1e-9 if prec == "double" else 1e-4)
 
 
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_balanced_blocks_on_one_device(capi, prec):
+    """Load-balanced decomposition (the tensor-product analogue of parallel/KDDecomposition.cpp): an inhomogeneous
+    film-with-vapour system cut where the molecules are, blocks of UNEQUAL width and population as contexts on one device (different
+    message capacities per block), against the decomposed CPU oracle record by record and against the single-domain CUDA path."""
+    from ls1_mardyn_b200 import generators
+    from ls1_mardyn_b200.decomposition import DomainDecomposition, balanced_cuts, exchange_local
+    rc = 2.0
+    ps = generators.lj_lattice(12, seed=8, jitter=0.1)           # 3456 molecules, L = 17.03
+    L = ps.length
+    keep = (ps.r[:, 0] < 0.4 * L[0]) | (np.arange(len(ps.id)) % 5 == 0)
+    for f in ("id", "cid", "r", "v", "q", "L"):
+        setattr(ps, f, getattr(ps, f)[keep])
+    grid = (2, 2, 1)
+    cuts = balanced_cuts(ps.r, L, grid, 2 * rc)
+    dds = [DomainDecomposition(r, 4, L, grid, cuts=cuts) for r in range(4)]
+    owner = dds[0].owner_of(ps.r)
+    counts = np.bincount(owner, minlength=4)
+    equal = np.bincount(DomainDecomposition(0, 4, L, grid).owner_of(ps.r), minlength=4)
+    assert counts.max() - counts.min() < equal.max() - equal.min(), (counts, equal)
+    ps.v *= 5.0
+    G = [Recorder(k) for k in make_gpu_ranks(capi, ps, dds, owner, prec, rc)]
+    O = [Recorder(k) for k in make_ranks(ps, dds, owner, prec, rc)]
+    one = capi.Context([0, 0, 0], list(L), rc, epsilon_rf=ps.epsilon_rf, precision=prec, geometry="xml", periodic=(1, 1, 1))
+    one.set_components(ps.ensemble); one.upload(ps.id, ps.cid, ps.r, ps.v, ps.q, ps.L)
+    one.update(); m1 = one.traverse_cells(); o1 = np.argsort(one.download("ID"))
+    dt = 0.005
+    for step in range(6):
+        tol = TOL[prec] * (1 if step == 0 else 50)
+        if step:
+            for k in G + O:
+                k.leapfrog_pre(dt)
+            one.leapfrog_pre(dt); one.update(); m1 = one.traverse_cells()
+        exchange_local(G, dds); exchange_local(O, dds)
+        for g, o in zip(G, O):
+            assert len(g.log) == len(o.log)
+            for (d, sd, a), (_, _, b) in zip(g.log, o.log):
+                assert same_records(a, b, exact=(step == 0)), (step, d, sd, len(a), len(b))
+            g.log.clear(); o.log.clear()
+        for k in G + O:
+            k.update()
+        mg = [k.traverse_cells() for k in G]
+        for k in O:
+            k.traverse_cells()
+        _, Fg = gather(G, "F"); _, Fo = gather(O, "F")
+        ok, worst = rel_close(Fg, Fo, tol); assert ok, (step, worst)
+        ok, worst = rel_close(Fg, one.download("F")[o1], 3 * tol); assert ok, (step, "vs single domain", worst)
+        up = sum(m.upot for m in mg)
+        assert abs(up - m1.upot) <= 3 * tol * abs(m1.upot)
+        kg = [k.leapfrog_post(dt) for k in G]; [k.leapfrog_post(dt) for k in O]; one.leapfrog_post(dt)
+        assert sum(k.n_molecules for k in kg) == len(ps.id)
+
+
 @pytest.mark.parametrize("transport", ["peer", "nccl"])
 def test_nccl_two_gpus(capi, tmp_path, transport):
     """The transports inside the library (ls1b200_exchange inside ls1b200_simulate), one process per GPU: records stored

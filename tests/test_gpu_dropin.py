@@ -50,3 +50,32 @@ def test_stock_simulation_loop_on_the_gpu(tmp_path, prec, tol):
     err = np.abs(a[:, 6] - b[:, 6]).max() / max(np.abs(b[:, 6]).max(), rhoT.max())
     assert err <= tol, (prec, "p", err)
     assert np.array_equal(a[:, 11], b[:, 11])
+
+
+@pytest.mark.parametrize("prec,tol", [("double", 1e-9), ("mixed", 1e-6)])
+def test_argon_config0_through_the_adapter(tmp_path, prec, tol):
+    """BASELINE.json configs[0]: the Argon example's component and state point (examples/Argon/200K_18mol_l), lattice-generated
+    at 101 306 molecules with rc = 2.5 sigma, 10 steps: MarDyn_b200 (stock Simulation loop on the GPU) against the stock binary."""
+    ref = os.path.join(ROOT, "oracle", "_ref", prec, "MarDyn")
+    b200 = os.path.join(ROOT, "adapter", "_build", prec, "MarDyn_b200")
+    if not (os.path.exists(ref) and os.path.exists(b200)):
+        pytest.skip("reference / adapter binaries not built (oracle/build_ref.sh, adapter/build_adapter.sh)")
+    from ls1_mardyn_b200 import workloads
+    from ls1_mardyn_b200.xml_config import simulation_xml
+    wl = workloads.get("argon")
+    steps = 10
+    N = 2 * wl.n_per_dim ** 3; L = (N / wl.rho) ** (1.0 / 3.0)
+    out = {}
+    for name, exe, ds, integ in (("ref", ref, "LinkedCells", "Leapfrog"), ("b200", b200, "LinkedCellsB200", "LeapfrogB200")):
+        d = tmp_path / name; d.mkdir()
+        (d / "config.xml").write_text(simulation_xml(wl.ensemble, [L, L, L], wl.temperature, wl.dt, steps, wl.rc, generator_density=N / L ** 3 * (1 + 1e-9),
+                                                     datastructure=ds, integrator=integ, longrange="homogeneous"))
+        out[name], log = run(exe, "config.xml", str(d), steps)
+    a, b = out["b200"], out["ref"]
+    assert a.shape == b.shape and a.shape[0] >= steps and int(b[0, 11]) == N
+    for name, col in (("U_pot", 2), ("U_kin", 4), ("beta_trans", 8)):
+        err = np.abs(a[:, col] - b[:, col]).max() / np.abs(b[:, col]).max()
+        assert err <= tol, (prec, name, err)
+    rhoT = (N / L ** 3) * (2.0 * b[:, 4] / (3.0 * N))
+    err = np.abs(a[:, 6] - b[:, 6]).max() / max(np.abs(b[:, 6]).max(), rhoT.max())
+    assert err <= tol, (prec, "p", err)

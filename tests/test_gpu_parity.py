@@ -329,3 +329,53 @@ def test_trace_vs_reference_binary(capi, name, prec):
     ensembles with beta_rot != 1."""
     out = check_trace_vs_reference(capi.Context, name, prec)
     print(name, prec, {k: "%.2e" % v for k, v in out.items()})
+
+
+@pytest.mark.parametrize("prec", ["mixed", "double"])
+def test_device_cubic_grid_generator(capi, prec):
+    """ls1b200_generate_cubic_grid (the reference's CubicGridGenerator on the device) against its host mirror
+    (generators.cubic_grid_reference: same lattice arithmetic as ParticleCellBase::initCubicGrid, same counter-based uniform numbers):
+    ids and positions bit-identical, velocities to rounding of sin / cos / acos, |v| = sqrt(3 T / m), total momentum removed; a
+    2 x 2 x 1 decomposition generates exactly the molecules of the single domain, block by block; the generated state then runs
+    through update / traverse_cells like an uploaded one (forces against the oracle fed with the downloaded state)."""
+    from ls1_mardyn_b200 import generators
+    from ls1_mardyn_b200.components import lj_fluid
+    from ls1_mardyn_b200.decomposition import DomainDecomposition
+    from oracle import oracle as orc
+    n, rho, T, rc = 11, 0.7, 0.85, 2.5
+    N = 2 * n ** 3; L = (N / rho) ** (1.0 / 3.0); box = [L, L, L]
+    ens = lj_fluid(rc=rc)
+    ctx = capi.Context([0, 0, 0], box, rc, precision=prec, geometry="xml", periodic=(1, 1, 1))
+    ctx.set_components(ens)
+    assert ctx.generate_cubic_grid(n, box, T, seed=7, remove_momentum=False) == N
+    ids, r, v = ctx.download("ID"), ctx.download("R"), ctx.download("V")
+    rid, rr, rv = generators.cubic_grid_reference(n, box, [0, 0, 0], box, T, 1.0, seed=7, mixed=(prec == "mixed"))
+    o = np.argsort(ids)
+    assert np.array_equal(ids[o], rid) and np.array_equal(r[o], rr)
+    assert np.abs(v[o] - rv).max() <= 1e-13 * np.abs(rv).max()
+    assert np.allclose(np.linalg.norm(v, axis=1), np.sqrt(3 * T), rtol=1e-13)
+    # momentum removal
+    ctx.generate_cubic_grid(n, box, T, seed=7, remove_momentum=True)
+    v2 = ctx.download("V")
+    assert np.abs(v2.sum(axis=0)).max() <= 1e-9 and np.abs((v2 - v) - (v2 - v)[0]).max() <= 1e-13
+    # the generated state is a normal state: forces against the oracle
+    ctx.update(); m = ctx.traverse_cells()
+    b = orc.OracleSim([0, 0, 0], box, rc, precision=prec, geometry="xml", periodic=(1, 1, 1))
+    b.set_components(ens); b.upload(ctx.download("ID"), ctx.download("CID"), ctx.download("R"), v2, None, None)
+    b.update(); mb = b.traverse_cells()
+    assert np.array_equal(ctx.download("CELL"), b.download("CELL"))
+    ok, worst = rel_close(ctx.download("F"), b.download("F"), TOL[prec]); assert ok, worst
+    assert abs(m.upot - mb.upot) <= TOL[prec] * abs(mb.upot)
+    # blocks of a decomposition: the union is the single domain, every molecule exactly once
+    seen = []
+    for rank in range(4):
+        dd = DomainDecomposition(rank, 4, np.array(box), (2, 2, 1))
+        c = capi.Context(list(dd.box_min()), list(dd.box_max()), rc, precision=prec, geometry="xml", periodic=dd.periodic())
+        c.set_components(ens); c.decomp_attach(dd)
+        nb = c.generate_cubic_grid(n, box, T, seed=7, remove_momentum=False)
+        bid, br = c.download("ID"), c.download("R")
+        assert len(bid) == nb and (br >= np.array(dd.box_min())).all() and (br < np.array(dd.box_max())).all()
+        k = np.searchsorted(rid, bid)
+        assert np.array_equal(rid[k], bid) and np.array_equal(br, rr[k]) and np.abs(c.download("V") - rv[k]).max() <= 1e-13 * np.abs(rv).max()
+        seen.append(bid)
+    assert np.array_equal(np.sort(np.concatenate(seen)), rid)
