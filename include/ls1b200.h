@@ -283,6 +283,23 @@ int ls1b200_halo_import_host(ls1b200_ctx* ctx, const ls1b200_particle* host_buf,
 int ls1b200_generate_cubic_grid(ls1b200_ctx* ctx, const uint64_t mols_per_dim[3], const double sim_box[3], double temperature,
                                 uint64_t seed, int32_t remove_momentum);
 
+/* ---- reduced-memory mode (the reference's RMM build: ENABLE_REDUCED_MEMORY_MODE, PRECISION=SINGLE) -------------------------------------
+ * The all-single-precision 1CLJ path: a molecule is 32 bytes (FP32 position, FP32 velocity, id: molecules/MoleculeRMM.h), the force
+ * goes straight into the velocities (particleContainer/adapter/VCP1CLJRMM.cpp:238-369: v += f dt / m), positions advance with
+ * r = fma(dt, v, r) (integrators/PositionCellProcessorRMM.h:43-58), sum v^2 is not mass weighted (VelocityCellProcessorRMM.h:119-127).
+ * Needs a mixed-precision, single-component 1CLJ, non-decomposed context; replaces ls1b200_upload / _simulate on it.
+ *   ls1b200_rmm_upload    FP64 host arrays are stored as FP32 (the reference's reader does the same into MoleculeRMM)
+ *   ls1b200_rmm_start     Simulation::prepare_start: binning + halo, the initial force applied with dt / 2, global values (the thermostat
+ *                         factor is reported, not applied); upot_corr / virial_corr = Domain's long-range corrections (Homogeneous.cpp)
+ *   ls1b200_rmm_simulate  n_steps of: positions, binning + halo, forces into the velocities, sum v^2, global values, velocity scaling
+ *   ls1b200_rmm_download  the owned molecules (id, r, v as FP64), order unspecified                                                   */
+int ls1b200_rmm_upload(ls1b200_ctx* ctx, uint64_t n, const uint64_t* id, const double* r /* [n][3] */, const double* v /* [n][3] */);
+int ls1b200_rmm_start(ls1b200_ctx* ctx, double dt, double target_temperature, double upot_corr, double virial_corr, ls1b200_step_record* record);
+int ls1b200_rmm_simulate(ls1b200_ctx* ctx, uint64_t n_steps, double dt, double target_temperature, double upot_corr, double virial_corr,
+                         ls1b200_step_record* records /* [n_steps] or NULL */);
+int ls1b200_rmm_download(ls1b200_ctx* ctx, uint64_t* id, double* r, double* v, uint64_t n);
+uint64_t ls1b200_rmm_state_bytes(const ls1b200_ctx* ctx);      /* 32 * number of molecules */
+
 /* Device time (ms) spent in each phase since the last reset, measured with CUDA events on the library's stream:
  * [0] update (binning+halo+SoA), [1] force kernels, [2] leapfrog pre, [3] leapfrog post + reductions. */
 int ls1b200_phase_times(ls1b200_ctx* ctx, double ms[4], uint64_t launches[4], int reset);

@@ -31,7 +31,7 @@ EXPORTS = ["ls1b200_last_error", "ls1b200_abi_version", "ls1b200_kernel_launch_c
            "ls1b200_scale_velocities", "ls1b200_simulate", "ls1b200_halo_export", "ls1b200_halo_import",
            "ls1b200_halo_import_host", "ls1b200_phase_times", "ls1b200_count_flops", "ls1b200_measure_fp32_peak", "ls1b200_measure_fp64_peak",
            "ls1b200_measure_hbm_copy", "ls1b200_stream", "ls1b200_nccl_unique_id", "ls1b200_decomp_attach", "ls1b200_download_begin", "ls1b200_download_end", "ls1b200_peer_handle", "ls1b200_peer_attach", "ls1b200_peer_detach", "ls1b200_exchange",
-           "ls1b200_allreduce_macro", "ls1b200_halo_export_host", "ls1b200_generate_cubic_grid"]
+           "ls1b200_allreduce_macro", "ls1b200_halo_export_host", "ls1b200_generate_cubic_grid", "ls1b200_rmm_upload", "ls1b200_rmm_start", "ls1b200_rmm_simulate", "ls1b200_rmm_download", "ls1b200_rmm_state_bytes"]
 
 
 class Ls1B200Error(RuntimeError):
@@ -98,6 +98,11 @@ def lib():
         L.ls1b200_destroy.argtypes = [C.c_void_p]
         L.ls1b200_set_components.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ls1b200_upload.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 6
+        L.ls1b200_rmm_upload.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
+        L.ls1b200_rmm_start.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
+        L.ls1b200_rmm_simulate.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
+        L.ls1b200_rmm_download.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_uint64]
+        L.ls1b200_rmm_state_bytes.argtypes = [C.c_void_p]; L.ls1b200_rmm_state_bytes.restype = C.c_uint64
         L.ls1b200_generate_cubic_grid.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_double, C.c_uint64, C.c_int32]
         L.ls1b200_download.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
         L.ls1b200_set_field.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_uint64]
@@ -207,6 +212,32 @@ class Context:
         L = None if L is None else np.ascontiguousarray(L, dtype=np.float64)
         _check(lib().ls1b200_upload(self.h, n, _vp(id), _vp(cid), _vp(r), _vp(v), _vp(q), _vp(L)))
         self.n = n
+
+    # ---- reduced-memory mode (rmm.cu; the reference's RMM build) ----
+    def rmm_upload(self, id, r, v):
+        n = len(id)
+        id = np.ascontiguousarray(id, dtype=np.uint64); r = np.ascontiguousarray(r, dtype=np.float64); v = np.ascontiguousarray(v, dtype=np.float64)
+        _check(lib().ls1b200_rmm_upload(self.h, n, _vp(id), _vp(r), _vp(v)))
+        self.n = n
+
+    def rmm_start(self, dt, target_temperature, upot_corr=0.0, virial_corr=0.0):
+        rec = StepRecord()
+        _check(lib().ls1b200_rmm_start(self.h, dt, target_temperature, upot_corr, virial_corr, C.byref(rec)))
+        return np.array([getattr(rec, k) for k, _ in StepRecord._fields_])
+
+    def rmm_simulate(self, nsteps, dt, target_temperature, upot_corr=0.0, virial_corr=0.0, records=True):
+        rec = (StepRecord * nsteps)() if records else None
+        _check(lib().ls1b200_rmm_simulate(self.h, nsteps, dt, target_temperature, upot_corr, virial_corr, rec))
+        if not records:
+            return None
+        return np.array([[getattr(x, k) for k, _ in StepRecord._fields_] for x in rec])
+
+    def rmm_download(self):
+        """-> (id, r, v) of the owned molecules, sorted by id."""
+        id = np.zeros(self.n, dtype=np.uint64); r = np.zeros((self.n, 3)); v = np.zeros((self.n, 3))
+        _check(lib().ls1b200_rmm_download(self.h, _vp(id), _vp(r), _vp(v), self.n))
+        o = np.argsort(id)
+        return id[o], r[o], v[o]
 
     def generate_cubic_grid(self, mols_per_dim, sim_box, temperature, seed=0, remove_momentum=True):
         """ls1b200_generate_cubic_grid: the reference's CubicGridGenerator on the device (replaces upload). Returns the number of

@@ -184,6 +184,9 @@ struct ls1b200_ctx {
 	// chunk list of the tiled 1CLJ kernel (force_1clj_tiled.cu)
 	void* chunks = nullptr; uint32_t* chunk_row_count = nullptr; uint32_t* chunk_row_start = nullptr; uint32_t* work_counter = nullptr;
 	int sm_count = 148;
+	// reduced-memory mode (rmm.cu): FP32 planes r[3][cap], v[3][cap], id[cap] (bit 63: halo copy), double buffered
+	float* rmm_r[2] = {nullptr, nullptr}; float* rmm_v[2] = {nullptr, nullptr}; uint64_t* rmm_id[2] = {nullptr, nullptr};
+	int rmm_cur = 0; bool rmm = false;
 	void* chunks2 = nullptr; size_t chunks2_bytes = 0;      // molecule-granular chunk list of force_1clj_v3.cu
 	int lj_kernel = 0;                // LS1B200_LJ_KERNEL: 0 tiled (default; shared-memory windows, TMA), 1 "global" (force_1clj.cu), 3 "mma" / 4 "tc": tensor-core prefilter experiments (force_1clj_mma.cu, force_1clj_tc.cu; measured slower, profiles/r01_tensor_prefilter.md), 5 "v3": molecule-granular chunks + x-trimmed ranges over fine bins (force_1clj_v3.cu; measured slower, profiles/r02_force_kernel_experiments.md)
 	int multi_kernel = 0;             // 0: tiled thread-per-molecule (force_multi_tiled.cu), 1: v1 thread-per-site (force_general.cu)
@@ -241,6 +244,8 @@ struct ls1b200_ctx {
 namespace ls1b200 {
 // implemented across the .cu files
 int ctx_alloc_molecules(ls1b200_ctx* c, uint64_t n_owned, uint64_t cap);
+void ctx_free_molecules(ls1b200_ctx* c);
+void rmm_release(ls1b200_ctx* c);          // rmm.cu
 void ctx_free_molecules(ls1b200_ctx* c);
 int span_begin(ls1b200_ctx* c, int phase);
 int span_end(ls1b200_ctx* c);

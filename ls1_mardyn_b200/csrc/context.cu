@@ -59,6 +59,7 @@ static int alloc_state(State& s, uint64_t cap, bool rot, bool ids) {
 static void free_state(State& s) { dev_free(s.r); dev_free(s.v); dev_free(s.q); dev_free(s.L); dev_free(s.meta); dev_free(s.id); }
 
 void ctx_free_molecules(ls1b200_ctx* c) {
+	rmm_release(c);
 	free_state(c->cur); free_state(c->nxt);
 	dev_free(c->d_id); dev_free(c->F); dev_free(c->M); dev_free(c->Vi);
 	dev_free(c->rank);

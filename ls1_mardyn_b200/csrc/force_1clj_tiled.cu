@@ -53,6 +53,8 @@ struct TArgs {
 	int nx, ny, nz;
 	C ljrc2;
 	C eps24_0, sig2_0, shift6_0;
+	// reduced-memory mode (rmm.cu; VCP1CLJRMM.cpp:238-369): the force goes straight into the FP32 velocities, v += f dt / m; F, Vi are not stored
+	float* rmm_v; float rmm_dt_m;
 };
 
 // LJ 12-6 of one pair, accumulated into FP32 partial sums (slot u). Force and virial are fused multiply-adds on the common
@@ -75,7 +77,7 @@ struct TArgs {
 		if (SINGLE) up[u] += lj12m6; else up[u] += eps24 * lj12m6 + shift6;                       \
 	}
 
-template <class C, bool SINGLE>
+template <class C, bool SINGLE, bool RMM = false>
 __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a) {
 	typedef typename Vec4<C>::type V4;
 	constexpr int TPB = TileCfg<C>::TPB, W = TileCfg<C>::W, LCAP = TileCfg<C>::LCAP, RI = TileCfg<C>::RI;
@@ -177,9 +179,13 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 				}
 				acc[0] += 0.5 * Ud; acc[1] += 0.5 * (Vd[0] + Vd[1] + Vd[2]);
 				const size_t cp = a.cap;
-				a.F[t] = Fd[0]; a.F[cp + t] = Fd[1]; a.F[2 * cp + t] = Fd[2];
-				a.Vi[t] = 0.5 * Vd[0]; a.Vi[cp + t] = 0.5 * Vd[1]; a.Vi[2 * cp + t] = 0.5 * Vd[2];
-				if (a.M) { a.M[t] = 0.; a.M[cp + t] = 0.; a.M[2 * cp + t] = 0.; }
+				if (RMM) {
+					a.rmm_v[t] += (float) Fd[0] * a.rmm_dt_m; a.rmm_v[cp + t] += (float) Fd[1] * a.rmm_dt_m; a.rmm_v[2 * cp + t] += (float) Fd[2] * a.rmm_dt_m;
+				} else {
+					a.F[t] = Fd[0]; a.F[cp + t] = Fd[1]; a.F[2 * cp + t] = Fd[2];
+					a.Vi[t] = 0.5 * Vd[0]; a.Vi[cp + t] = 0.5 * Vd[1]; a.Vi[2 * cp + t] = 0.5 * Vd[2];
+					if (a.M) { a.M[t] = 0.; a.M[cp + t] = 0.; a.M[2 * cp + t] = 0.; }
+				}
 			}
 		} else {
 		const uint32_t* csc = cs + 4 * (CH_MAXC + 3);          // centre row (relative record indices)
@@ -312,9 +318,13 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 				const uint32_t t = s_rowbase[4] + trel[l];
 				acc[0] += 0.5 * Ud[l];                          // every pair is visited from both of its ends
 				acc[1] += 0.5 * (Vd[l][0] + Vd[l][1] + Vd[l][2]);
+				if (RMM) {      // the kick in the epilogue: 12 B read + 12 B written per molecule instead of 48 B of F and Vi
+					a.rmm_v[t] += (float) Fd[l][0] * a.rmm_dt_m; a.rmm_v[cp + t] += (float) Fd[l][1] * a.rmm_dt_m; a.rmm_v[2 * cp + t] += (float) Fd[l][2] * a.rmm_dt_m;
+				} else {
 				a.F[t] = Fd[l][0]; a.F[cp + t] = Fd[l][1]; a.F[2 * cp + t] = Fd[l][2];
 				a.Vi[t] = 0.5 * Vd[l][0]; a.Vi[cp + t] = 0.5 * Vd[l][1]; a.Vi[2 * cp + t] = 0.5 * Vd[l][2];
 				if (a.M) { a.M[t] = 0.; a.M[cp + t] = 0.; a.M[2 * cp + t] = 0.; }
+				}
 			}
 		}
 		}
@@ -358,8 +368,8 @@ int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows, int per_warp) {
 	return 0;
 }
 
-template <class C>
-static int launch_tiled(ls1b200_ctx* c) {
+template <class C, bool RMM = false>
+static int launch_tiled(ls1b200_ctx* c, float* rmm_v = nullptr, float rmm_dt_m = 0.f) {
 	typedef typename Vec4<C>::type V4;
 	constexpr int TPB = TileCfg<C>::TPB, W = TileCfg<C>::W, LCAP = TileCfg<C>::LCAP, RI = TileCfg<C>::RI;
 	const Geom& g = c->geom;
@@ -376,9 +386,10 @@ static int launch_tiled(ls1b200_ctx* c) {
 	const double rclj = c->cfg.cutoff_lj;
 	a.ljrc2 = (C) (rclj * rclj);
 	a.eps24_0 = (C) c->h_eps24[0]; a.sig2_0 = (C) c->h_sig2[0]; a.shift6_0 = (C) c->h_shift6[0];
+	a.rmm_v = rmm_v; a.rmm_dt_m = rmm_dt_m;
 	// the cell_start cache is padded by three rows: the compiler hoists the (guarded) loads of the next row's entries
 	const size_t smem = (size_t) (9 * W + 1) * sizeof(V4) + (size_t) (LCAP + 1) * RI * TPB * 2 + 2 * 12 * (CH_MAXC + 3) * 4;
-	auto kern = c->comps.size() == 1 ? k_force_1clj_tiled<C, true> : k_force_1clj_tiled<C, false>;
+	auto kern = c->comps.size() == 1 ? k_force_1clj_tiled<C, true, RMM> : k_force_1clj_tiled<C, false, RMM>;
 	LS1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int per_sm = 0;
 	LS1_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, smem));
@@ -389,5 +400,7 @@ static int launch_tiled(ls1b200_ctx* c) {
 }
 
 int force_1clj_tiled(ls1b200_ctx* c) { return c->mixed ? launch_tiled<float>(c) : launch_tiled<double>(c); }
+// reduced-memory mode: FP32 only, the kick v += f dt / m in the epilogue (v: [3][cap] planes of the slots the kernel visits)
+int force_1clj_tiled_rmm(ls1b200_ctx* c, float* v, float dt_over_m) { return launch_tiled<float, true>(c, v, dt_over_m); }
 
 }  // namespace ls1b200

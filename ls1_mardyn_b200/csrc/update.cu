@@ -275,6 +275,16 @@ __global__ void __launch_bounds__(128) k_sites(State st, uint32_t cap, uint32_t 
 	}
 }
 
+// exclusive scan of cell_count + cell_count_halo over nb bins -> fstart (+ the reference cells' cell_start, the scatter cursor and
+// the slot count of the new order in DevScalars::n_slots2[parity ^ 1]); shared with the reduced-memory path (rmm.cu)
+int launch_bin_scan(ls1b200_ctx* c, uint32_t nb, uint32_t* fstart, uint32_t parity) {
+	const uint32_t sb = (nb + SCAN_B - 1) / SCAN_B;
+	LS1_LAUNCH(c, PH_UPDATE, k_scan_block, sb, SCAN_T, 0, c->cell_count, c->cell_count_halo, fstart, c->scan_tmp, nb);
+	LS1_LAUNCH(c, PH_UPDATE, k_scan_top, 1, SCAN_T, 0, c->scan_tmp, sb, c->scan_tmp + sb);
+	LS1_LAUNCH(c, PH_UPDATE, k_scan_add, sb, SCAN_T, 0, fstart, c->cursor, c->cell_count, c->scan_tmp, c->scan_tmp + sb, nb, (uint32_t) c->cap, parity, c->d_scal, c->cell_start, c->fine_s);
+	return 0;
+}
+
 int do_update(ls1b200_ctx* c) {
 	if (!c->components_set) return fail("ls1b200_update: components not set");
 	if (c->n_owned == 0 && !c->dd.active) { c->sorted = true; return 0; }
@@ -287,12 +297,9 @@ int do_update(ls1b200_ctx* c) {
 	// slot counts are only known on the device: every per-slot kernel is launched over the capacity, threads beyond exit
 	const uint32_t gs = (uint32_t) ((c->cap + 255) / 256);
 	LS1_LAUNCH(c, PH_UPDATE, k_key, gs, 256, 0, a, c->cur, c->key, c->cell_count, c->cell_count_halo, c->rank, c->d_scal);
-	const uint32_t sb = (nb + SCAN_B - 1) / SCAN_B;
 	// cell_start_fine: exclusive scan over the fine bins; cell_start (the reference cells) is every S-th entry of it
 	uint32_t* fstart = c->fine_s > 1 ? c->cell_start_fine : c->cell_start;
-	LS1_LAUNCH(c, PH_UPDATE, k_scan_block, sb, SCAN_T, 0, c->cell_count, c->cell_count_halo, fstart, c->scan_tmp, nb);
-	LS1_LAUNCH(c, PH_UPDATE, k_scan_top, 1, SCAN_T, 0, c->scan_tmp, sb, c->scan_tmp + sb);
-	LS1_LAUNCH(c, PH_UPDATE, k_scan_add, sb, SCAN_T, 0, fstart, c->cursor, c->cell_count, c->scan_tmp, c->scan_tmp + sb, nb, (uint32_t) c->cap, a.parity, c->d_scal, c->cell_start, c->fine_s);
+	LS1_TRY(launch_bin_scan(c, nb, fstart, a.parity));
 	LS1_LAUNCH(c, PH_UPDATE, k_scatter, gs, 256, 0, a, c->cur, c->key, c->rank, (const uint32_t*) fstart, c->cursor, c->entry, c->cell_of, c->d_scal, c->dd.active ? c->ekey : (uint64_t*) nullptr);
 	const uint32_t gc = gs;
 	if (c->mixed)

@@ -364,7 +364,9 @@ def test_device_cubic_grid_generator(capi, prec):
     b.set_components(ens); b.upload(ctx.download("ID"), ctx.download("CID"), ctx.download("R"), v2, None, None)
     b.update(); mb = b.traverse_cells()
     assert np.array_equal(ctx.download("CELL"), b.download("CELL"))
-    ok, worst = rel_close(ctx.download("F"), b.download("F"), TOL[prec]); assert ok, worst
+    # on the perfect lattice the forces cancel to rounding: the bound is relative to the magnitude of the pair terms (the virial)
+    ok, worst = rel_close(ctx.download("F"), b.download("F"), TOL[prec], scale=float(np.abs(b.download("VI")).mean())); assert ok, worst
+    ok, worst = rel_close(ctx.download("VI"), b.download("VI"), TOL[prec]); assert ok, worst
     assert abs(m.upot - mb.upot) <= TOL[prec] * abs(mb.upot)
     # blocks of a decomposition: the union is the single domain, every molecule exactly once
     seen = []
