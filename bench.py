@@ -182,6 +182,8 @@ def run_reference_binary(n_per_dim, steps, threads=None, prec=None, wl=None):
         else:
             from ls1_mardyn_b200.xml_config import simulation_xml
             text = simulation_xml(wl.ensemble, [L, L, L], temp, dt, steps, rc, generator_density=N / L ** 3 * (1 + 1e-9), longrange="homogeneous", result_prefix=None)
+        if prec == "rmm":
+            text = text.replace('integrator type="Leapfrog"', 'integrator type="LeapfrogRMM"')      # the reference's reduced-memory build
         open(cfg, "w").write(text)
         env = dict(os.environ, OMP_NUM_THREADS=str(threads))
         p = subprocess.run([exe, "--steps", str(steps), "--final-checkpoint=0", cfg], cwd=td, env=env, capture_output=True, text=True, timeout=3000)
@@ -311,6 +313,39 @@ def run_secondary(name, local, fp32_peak, capi, with_cpu=True, steps=10, warmup=
     ctx.close()
     if with_cpu:
         out["cpu_baseline"] = cpu_baseline(wl)
+    return out
+
+
+def run_rmm(local, fp32_peak, capi, with_cpu=True, steps=10, warmup=3, n=200):
+    """configs[1] in the reference's reduced-memory mode (all FP32, 32 B per molecule, force fused with the kick; csrc/rmm.cu),
+    device-resident loop; CPU baseline = the reference built in RMM configuration (oracle/_ref/rmm/MarDyn)."""
+    import torch
+    from ls1_mardyn_b200 import workloads
+    wl = workloads.get("lj")
+    ps = make_system(n, mixed=True, seed=0, wl=wl)
+    ctx = capi.Context([0, 0, 0], list(ps.length), wl.rc, precision="mixed", geometry="xml", periodic=(1, 1, 1), device=local)
+    ctx.set_components(ps.ensemble)
+    ctx.rmm_upload(ps.id, ps.r, ps.v)
+    N = len(ps.id)
+    ctx.rmm_start(wl.dt, wl.temperature)
+    ctx.rmm_simulate(warmup, wl.dt, wl.temperature, records=False)
+    ctx.phase_times(reset=True)
+    torch.cuda.synchronize()
+    t0 = time.perf_counter()
+    rec = ctx.rmm_simulate(steps, wl.dt, wl.temperature)
+    torch.cuda.synchronize()
+    t = time.perf_counter() - t0
+    ph_ms, _ = ctx.phase_times(reset=True)
+    out = {"workload": wl.description + " -- reduced-memory mode (FP32 state, 32 B per molecule)", "molecules": N, "steps": steps, "warmup": warmup,
+           "MMUPS": round(N * steps / t / 1e6, 2), "ms_per_step": round(1e3 * t / steps, 4), "phases_ms_per_step": {k: round(v / steps, 4) for k, v in ph_ms.items()},
+           "state_bytes_per_molecule": 32, "T_last": rec[-1, 4], "upot_last_per_molecule": rec[-1, 0] / N}
+    ctx.close()
+    if with_cpu:
+        r = run_reference_binary(CPU_SAMPLE["lj"][0], CPU_SAMPLE["lj"][1], prec="rmm")
+        if r is not None:
+            v, nn, cores, tt = r
+            out["cpu_baseline"] = {"value": round(v, 3), "unit": "MMUPS", "cores": cores, "kind": "reference",
+                                   "sample": f"oracle/_ref/rmm/MarDyn (the reference built with ENABLE_REDUCED_MEMORY_MODE, PRECISION=SINGLE, AVX2, OpenMP): lj lattice N={nn}, {CPU_SAMPLE['lj'][1]} steps, main loop {tt:.2f} s"}
     return out
 
 
@@ -508,6 +543,7 @@ def our_arm(args):
             # BASELINE.json configs[0], [2], [3] at their single-GPU sizes, measured in the same run (device-resident loop only)
             ctx.close()
             line["secondary"] = {k: run_secondary(k, local, fp32_peak, capi, with_cpu=not args.no_cpu_baseline) for k in ("argon", "water", "co2")}
+            line["secondary"]["lj_rmm"] = run_rmm(local, fp32_peak, capi, with_cpu=not args.no_cpu_baseline)
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         # orderly teardown: nobody frees receive buffers a neighbour still has mapped
