@@ -1,6 +1,7 @@
 #include "integrators/LeapfrogB200.h"
 
 #include "Domain.h"
+#include "Simulation.h"
 #include "particleContainer/LinkedCellsB200.h"
 #include "utils/Logger.h"
 #include "utils/mardyn_assert.h"
@@ -29,10 +30,23 @@ void LeapfrogB200::eventNewTimestep(ParticleContainer* moleculeContainer, Domain
 	LinkedCellsB200* c = deviceContainer(moleculeContainer);
 	if (!c->deviceMode()) return;
 	c->hostView(false);                     // from here on the device state is authoritative; host loops of the step iterate nothing
+	// What the device path does NOT implement must not be skipped silently: with component-wise thermostats the host loop that would
+	// scale the velocities is vacuous in device mode (Domain.cpp:195-215, VelocityScalingThermostat.cpp:68-89), and the
+	// TemperatureControl plugin edits host molecules the device never sees.
+	if (domain->severalThermostats()) {
+		std::ostringstream error_message;
+		error_message << "LeapfrogB200: component-wise thermostats are not supported on the device (single global velocity scaling or NVE only)" << std::endl;
+		MARDYN_EXIT(error_message.str());
+	}
+	if (global_simulation->getPlugin("TemperatureControl") != nullptr) {
+		std::ostringstream error_message;
+		error_message << "LeapfrogB200: the TemperatureControl plugin modifies host molecules every step and is not supported with LinkedCellsB200" << std::endl;
+		MARDYN_EXIT(error_message.str());
+	}
 	// VelocityScalingThermostat::apply of the previous step found an empty iterator range (device mode); its factors are
 	// Domain's global betas (Domain.cpp:248-252) and are applied here, before the kick, which is the same arithmetic
 	// (Simulation.cpp:1235-1261; single global thermostat -- the component-wise variant needs a per-component factor table).
-	if (_thermostatPending && !domain->NVE() && !domain->severalThermostats()) {
+	if (_thermostatPending && !domain->NVE()) {
 		if (ls1b200_scale_velocities(c->context(), domain->getGlobalBetaTrans(), domain->getGlobalBetaRot()) != 0) MARDYN_EXIT(ls1b200_last_error());
 	}
 	if (ls1b200_leapfrog_pre(c->context(), _timestepLength) != 0) MARDYN_EXIT(ls1b200_last_error());
@@ -47,4 +61,12 @@ void LeapfrogB200::eventForcesCalculated(ParticleContainer* moleculeContainer, D
 	domain->setLocalSumIw2(kin.sum_iw2, 0);
 	domain->setLocalNrotDOF(0, kin.n_molecules, kin.rot_dof);
 	_thermostatPending = true;
+	// Host coherence: on the steps of the container's sync schedule -- and at the last step, for the final
+	// checkpoint -- the host mirror is refreshed HERE and the host view opens for the rest of the step. What follows in the stock
+	// loop then acts on the mirror exactly as in the reference: the thermostat scales its velocities (the device applies the same
+	// factors at the next eventNewTimestep), Homogeneous adds the per-molecule virial correction, output plugins
+	// (CheckpointWriter, MmpldWriter, RDF, ...) iterate real molecules. eventNewTimestep closes the view again.
+	const unsigned long step = global_simulation->getSimulationStep();
+	const unsigned long last = global_simulation->getNumInitTimesteps() + global_simulation->getNumTimesteps();
+	if (c->wantsHostSync(step, last)) { c->syncToHost(); c->hostView(true); }
 }

@@ -12,6 +12,9 @@
 #include "particleContainer/adapter/VectorizedCellProcessor.h"
 #include "utils/Logger.h"
 #include "utils/mardyn_assert.h"
+#include "utils/xmlfileUnits.h"
+
+#include <cstdlib>
 
 #include "ls1b200.h"
 
@@ -26,6 +29,21 @@
 
 LinkedCellsB200::~LinkedCellsB200() {
 	if (_ctx) ls1b200_destroy(_ctx);
+}
+
+void LinkedCellsB200::readXML(XMLfileUnits& xmlconfig) {
+	LinkedCells::readXML(xmlconfig);
+	const int cic = xmlconfig.getNodeValue_int("cellsInCutoffRadius", 1);      // private in LinkedCells: read it again (LinkedCells.cpp:125)
+	if (cic != 1) {      // the device path is the reference's default, one cell per cutoff radius
+		std::ostringstream error_message;
+		error_message << "LinkedCellsB200: cellsInCutoffRadius = " << cic << " is not supported on the device (only 1)" << std::endl;
+		MARDYN_EXIT(error_message.str());
+	}
+	int f = 0;
+	xmlconfig.getNodeValue("hostSyncFrequency", f);
+	_hostSyncFrequency = f > 0 ? (unsigned long) f : 0ul;
+	xmlconfig.getNodeValue("device", _device);
+	Log::global_log->info() << "LinkedCellsB200: host mirror refreshed every " << _hostSyncFrequency << " steps (0: only at the last step)" << std::endl;
 }
 
 // Everything VectorizedCellProcessor's constructor derives from Domain / Ensemble (VectorizedCellProcessor.cpp:19-81) goes
@@ -47,7 +65,10 @@ void LinkedCellsB200::createContext() {
 	cfg.precision = LS1B200_MIXED;    // MARDYN_SPDP
 #endif
 	cfg.geometry = LS1B200_GEOM_XML;
-	cfg.device = 0;
+	// device ordinal: <device> of the datastructure, else LS1B200_DEVICE (one process per GPU: the launcher exports it per rank), else 0.
+	// This build of ls1 is sequential (DomainDecompBase: every dimension wraps onto itself, periodic = 1 above); under
+	// DomainDecomposition each rank would pass its block and its periodic flags and call ls1b200_decomp_attach.
+	cfg.device = _device >= 0 ? _device : (getenv("LS1B200_DEVICE") ? atoi(getenv("LS1B200_DEVICE")) : 0);
 	B200_CHECK(ls1b200_create(&cfg, &_ctx));
 
 	std::vector<Component>& components = *(global_simulation->getEnsemble()->getComponents());
@@ -173,6 +194,9 @@ void LinkedCellsB200::syncToHost() {
 		m->setF(&F[3 * i]); m->setM(&M[3 * i]); m->setVi(&Vi[3 * i]);
 	}
 	LinkedCells::update();                   // re-sort the host mirror
+	// The per-molecule part of the long-range correction (Homogeneous::calculateLongRange adds VirialCorr / 3N to every Vi,
+	// longRange/Homogeneous.cpp:143-155) is applied by the stock step right after this point: LeapfrogB200 opens the host view
+	// before Simulation calls _longRangeCorrection->calculateLongRange(), so the refreshed molecules receive it like the reference's.
 }
 
 void LinkedCellsB200::syncToDevice() {

@@ -34,10 +34,11 @@ open(sys.argv[2], "w").write(s)
 PY
   FLAGS="-std=c++17 -O3 -DNDEBUG -fopenmp -DENABLE_OPENMP -fopenmp-simd -mavx2 -mfma -DENABLE_VECTORIZED_CODE=1 $PDEF -DTIMERS -w \
 -I$OUT/inc -I$GEN -I$REF/src -I$REF/libs/rapidxml -I$REF/libs -I$ROOT/include"
-  $CXX $FLAGS -c "$OUT/Simulation_b200.cpp" -o "$OUT/Simulation_b200.o" &
-  $CXX $FLAGS -c "$HERE/LinkedCellsB200.cpp" -o "$OUT/LinkedCellsB200.o" &
-  $CXX $FLAGS -c "$HERE/LeapfrogB200.cpp" -o "$OUT/LeapfrogB200.o" &
-  wait
+  pids=()
+  $CXX $FLAGS -c "$OUT/Simulation_b200.cpp" -o "$OUT/Simulation_b200.o" & pids+=($!)
+  $CXX $FLAGS -c "$HERE/LinkedCellsB200.cpp" -o "$OUT/LinkedCellsB200.o" & pids+=($!)
+  $CXX $FLAGS -c "$HERE/LeapfrogB200.cpp" -o "$OUT/LeapfrogB200.o" & pids+=($!)
+  for p in "${pids[@]}"; do wait "$p"; done      # a failed compile must fail the build (plain `wait` returns 0)
   OBJS=$(ls "$OBJ"/*.o | grep -v '/Simulation.o$')
   $CXX -fopenmp $OBJS "$OUT/Simulation_b200.o" "$OUT/LinkedCellsB200.o" "$OUT/LeapfrogB200.o" \
       -L"$ROOT/ls1_mardyn_b200" -lls1b200 -Wl,-rpath,'$ORIGIN/../../../ls1_mardyn_b200' -Wl,-rpath,/usr/local/cuda/lib64 -o "$OUT/MarDyn_b200"

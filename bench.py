@@ -316,6 +316,36 @@ def run_secondary(name, local, fp32_peak, capi, with_cpu=True, steps=10, warmup=
     return out
 
 
+def run_adapter(n_per_dim, steps, host_sync_frequency=0, prec="mixed"):
+    """The drop-in itself: adapter/_build/<prec>/MarDyn_b200 -- the UNMODIFIED ls1 Simulation loop, XML input, CubicGridGenerator, Domain,
+    thermostat and long-range correction on the host, with <datastructure type="LinkedCellsB200"> + <integrator type="LeapfrogB200">
+    driving libls1b200.so -- on the 1CLJ workload. MMUPS from ls1's own main-loop timer. host_sync_frequency = k refreshes the host
+    Molecule objects (r, v, q, D, F, M, Vi: 7 downloads) every k steps for molecule-iterating plugins; 0 = only at the last step."""
+    exe = os.path.join(ROOT, "adapter", "_build", prec, "MarDyn_b200")
+    if not os.path.exists(exe):
+        return None
+    from ls1_mardyn_b200 import workloads
+    from ls1_mardyn_b200.xml_config import simulation_xml
+    wl = workloads.get("lj")
+    N = 2 * n_per_dim ** 3; L = (N / wl.rho) ** (1.0 / 3.0)
+    with tempfile.TemporaryDirectory() as td:
+        open(os.path.join(td, "config.xml"), "w").write(simulation_xml(
+            wl.ensemble, [L, L, L], wl.temperature, wl.dt, steps, wl.rc, generator_density=N / L ** 3 * (1 + 1e-9), datastructure="LinkedCellsB200", integrator="LeapfrogB200",
+            longrange="homogeneous", result_prefix=None, datastructure_extra="<hostSyncFrequency>%d</hostSyncFrequency>" % host_sync_frequency))
+        t0 = time.perf_counter()
+        p = subprocess.run([exe, "--steps", str(steps), "--final-checkpoint=0", "config.xml"], cwd=td, capture_output=True, text=True, timeout=3000,
+                           env=dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1)))
+        wall = time.perf_counter() - t0
+    out = p.stdout + p.stderr
+    m = re.search(r"Computation in main loop took:\s*([0-9.eE+-]+)\s*sec", out)
+    if p.returncode != 0 or not m:
+        return {"error": out[-400:]}
+    t = float(m.group(1))
+    return {"MMUPS": round(N * steps / t / 1e6, 2), "molecules": N, "steps": steps, "main_loop_s": round(t, 3), "process_wall_s": round(wall, 1),
+            "host_sync_frequency": host_sync_frequency,
+            "path": "stock ls1 Simulation loop (XML, CubicGridGenerator, Domain, thermostat, LRC on the host) -> LinkedCellsB200 / LeapfrogB200 -> libls1b200.so"}
+
+
 def run_rmm(local, fp32_peak, capi, with_cpu=True, steps=10, warmup=3, n=200):
     """configs[1] in the reference's reduced-memory mode (all FP32, 32 B per molecule, force fused with the kick; csrc/rmm.cu),
     device-resident loop; CPU baseline = the reference built in RMM configuration (oracle/_ref/rmm/MarDyn)."""
@@ -544,6 +574,9 @@ def our_arm(args):
             ctx.close()
             line["secondary"] = {k: run_secondary(k, local, fp32_peak, capi, with_cpu=not args.no_cpu_baseline) for k in ("argon", "water", "co2")}
             line["secondary"]["lj_rmm"] = run_rmm(local, fp32_peak, capi, with_cpu=not args.no_cpu_baseline)
+            # the drop-in binary on the headline workload: device-resident through the unmodified ls1 loop, and with the host Molecule
+            # objects refreshed every step (what a molecule-iterating plugin running every step would cost)
+            line["secondary"]["adapter_MarDyn_b200"] = {"device_resident": run_adapter(wl.n_per_dim, args.steps, 0), "host_mirror_every_step": run_adapter(100, 5, 1)}
         os.write(real_stdout, (json.dumps(line) + "\n").encode())
     if world > 1:
         # orderly teardown: nobody frees receive buffers a neighbour still has mapped

@@ -131,3 +131,24 @@ def write_phase_space(path: str, ps: PhaseSpace) -> None:
         for i in range(len(ps.id)):
             f.write("%d\t%d\t%.17g %.17g %.17g\t%.17g %.17g %.17g\t%.17g %.17g %.17g %.17g\t%.17g %.17g %.17g\n" % (
                 int(ps.id[i]), int(ps.cid[i]) + 1, *ps.r[i], *ps.v[i], *ps.q[i], *ps.L[i]))
+
+
+def read_molecules_only(path: str):
+    """(id, cid, r, v, q, L) of a phase-space file WITHOUT interpreting its header: what ASCIIReader::readPhaseSpace does in XML
+    mode (io/ASCIIReader.cpp:303-318 skips to NumberOfMolecules; the components come from the XML). Reads the checkpoints
+    Domain::writeCheckpoint / FullMolecule::write produce (molecules/FullMolecule.cpp:439-446: id cid r v q D, cid 1-based)."""
+    toks = open(path).read().split()
+    k = max(i for i, t in enumerate(toks) if t in ("NumberOfMolecules", "N"))
+    n = int(toks[k + 1]); k += 2
+    fmt = "ICRVQD"
+    if toks[k] in ("MoleculeFormat", "M"):
+        fmt = toks[k + 1]; k += 2
+    w = {"ICRVQD": 15, "ICRV": 8, "IRV": 7}[fmt]
+    a = np.array(toks[k:k + n * w], dtype=np.float64).reshape(n, w)
+    ids = np.array([int(t) for t in toks[k:k + n * w:w]], dtype=np.uint64)
+    if fmt == "IRV":
+        return ids, np.zeros(n, dtype=np.uint32), a[:, 1:4], a[:, 4:7], np.tile([1.0, 0, 0, 0], (n, 1)), np.zeros((n, 3))
+    cid = (a[:, 1] - 1).astype(np.uint32)
+    q = a[:, 8:12] if fmt == "ICRVQD" else np.tile([1.0, 0, 0, 0], (n, 1))
+    Lm = a[:, 12:15] if fmt == "ICRVQD" else np.zeros((n, 3))
+    return ids, cid, a[:, 2:5], a[:, 5:8], q, Lm

@@ -189,6 +189,9 @@ struct ls1b200_ctx {
 	int rmm_cur = 0; bool rmm = false;
 	void* chunks2 = nullptr; size_t chunks2_bytes = 0;      // molecule-granular chunk list of force_1clj_v3.cu
 	int lj_kernel = 0;                // LS1B200_LJ_KERNEL: 0 tiled (default; shared-memory windows, TMA), 1 "global" (force_1clj.cu), 3 "mma" / 4 "tc": tensor-core prefilter experiments (force_1clj_mma.cu, force_1clj_tc.cu; measured slower, profiles/r01_tensor_prefilter.md), 5 "v3": molecule-granular chunks + x-trimmed ranges over fine bins (force_1clj_v3.cu; measured slower, profiles/r02_force_kernel_experiments.md)
+	int multi_pd2 = 0;                // LS1B200_MULTI_PD2=1: prefetch the site records of two neighbours ahead instead of one
+	int multi_stage = 0;              // LS1B200_MULTI_STAGE=0: do not stage neighbour site records in shared memory (force_multi_tiled.cu)
+	int multi_max_ctas = 0;           // LS1B200_MULTI_MAXCTAS: resident CTAs per SM of the multi-site kernel (0: as many as fit)
 	int multi_kernel = 0;             // 0: tiled thread-per-molecule (force_multi_tiled.cu), 1: v1 thread-per-site (force_general.cu)
 
 	// reductions

@@ -264,6 +264,9 @@ int ls1b200_create(const ls1b200_config* cfg, ls1b200_ctx** out) {
 		const char* k = getenv("LS1B200_LJ_KERNEL");
 		c->lj_kernel = (k && std::string(k) == "global") ? 1 : (k && std::string(k) == "mma") ? 3 : (k && std::string(k) == "tc") ? 4 : (k && std::string(k) == "v3") ? 5 : 0;      // default: the tiled kernel (v3 measured slower, profiles/r02_force_kernel_experiments.md)
 		const char* m = getenv("LS1B200_MULTI_KERNEL");
+		if (const char* mc = getenv("LS1B200_MULTI_MAXCTAS")) c->multi_max_ctas = atoi(mc);
+		if (const char* ms = getenv("LS1B200_MULTI_STAGE")) c->multi_stage = atoi(ms);
+		if (const char* mp = getenv("LS1B200_MULTI_PD2")) c->multi_pd2 = atoi(mp);
 		c->multi_kernel = (m && std::string(m) == "general") ? 1 : (m && std::string(m) == "generic") ? 2 : 0;   // 2: tiled, but never specialised
 	}
 	if (dev_alloc(&c->d_scal, 1) || dev_alloc(&c->partials2, 1024 * 8)) return cleanup(1);

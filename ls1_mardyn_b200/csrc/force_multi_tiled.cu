@@ -182,20 +182,30 @@ template <int NLJ_, int NCH_, int NDI_, int NQU_> struct Sig {
 };
 struct SigGeneric { static constexpr int NLJ = 0, NCH = 0, NDI = 0, NQU = 0, NS = 1; static constexpr bool GENERIC = true; };
 
-template <class C, class SIG, int LOGW>
-__global__ void __launch_bounds__(MultiCfg<C>::TPB) k_force_multi_tiled(MArgs<C> a) {
+// STAGE (site signatures without oriented sites, e.g. the water-like 1 LJ + 3 charges): the site records of the 9 window rows are
+// brought to shared memory with the molecule records (9 more TMA bulk copies: spos is [slot][NS], a window row is contiguous), so
+// phase 2 reads its neighbours' sites with LDS instead of gathering them through L1 / L2 (the kernel was bound by the latency of
+// those gathers: long-scoreboard stalls 7.3 per issued instruction, profiles/r01k_multi_full_water.md).
+// MINB: resident CTAs per SM the register allocation is tuned for (__launch_bounds__): the kernel is latency bound, registers
+// decide its occupancy (5: what the compiler chose unconstrained, 128 registers; 6 -> 96 registers and 7 -> 80 registers spill
+// and were measured 25 - 150 % slower, profiles/r02_multi_site.md)
+template <class C, class SIG, int LOGW, bool STAGE = false, bool PD2 = false, int MINB = 5>
+__global__ void __launch_bounds__(MultiCfg<C>::TPB, MINB) k_force_multi_tiled(MArgs<C> a) {
 	typedef typename Vec4<C>::type V4;
 	constexpr int TPB = MultiCfg<C>::TPB, W = 1 << LOGW, LCAP = MultiCfg<C>::LCAP;
 	constexpr uint32_t VB = sizeof(V4), LSTRIDE = (uint32_t) TPB * 2u;
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	V4* win = reinterpret_cast<V4*>(smem_raw);                                         // [9][W]
-	uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw + (size_t) (9 * W) * VB);    // [LCAP+1][TPB]
+	constexpr int SNS = STAGE ? SIG::NS : 0;
+	V4* swin = win + 9 * W;                                                            // [9][W][NS] site records (STAGE)
+	uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw + (size_t) (9 * W) * (1 + SNS) * VB);    // [LCAP+1][TPB]
 	uint32_t* cs = reinterpret_cast<uint32_t*>(list + (size_t) (LCAP + 1) * TPB);      // [12][CH_MAXC+3] (3 rows of padding)
 	__shared__ uint32_t s_tb[CH_MAXC + 1];
 	__shared__ uint32_t s_rowbase[9];
 	__shared__ __align__(8) unsigned long long s_bar;
 	__shared__ uint32_t s_chunk;
 	const uint32_t win_s = smem_u32(win), list_s = smem_u32(list) + threadIdx.x * 2, bar = smem_u32(&s_bar);
+	const uint32_t swin_s = smem_u32(swin);
 	const uint32_t n_chunks = *a.n_chunks;
 	if (threadIdx.x == 0) mbar_init(bar, 1);
 	asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -251,13 +261,14 @@ __global__ void __launch_bounds__(MultiCfg<C>::TPB) k_force_multi_tiled(MArgs<C>
 		__syncthreads();
 		if (threadIdx.x == 0) {
 			uint32_t total = 0;
-			for (int r = 0; r < 9; r++) total += cs[r * (CH_MAXC + 3) + nc + 2] * VB;
+			for (int r = 0; r < 9; r++) total += cs[r * (CH_MAXC + 3) + nc + 2] * VB * (1 + SNS);
 			if (total) {
 				fence_proxy_async();      // the previous chunk's generic-proxy reads of the windows precede these async-proxy writes
 				mbar_expect_tx(bar, total);
 				for (int r = 0; r < 9; r++) {
 					const uint32_t len = cs[r * (CH_MAXC + 3) + nc + 2];
 					if (len) tma_bulk_g2s(win_s + (uint32_t) (r * W) * VB, a.mpos + s_rowbase[r], len * VB, bar);
+					if (STAGE && len) tma_bulk_g2s(swin_s + (uint32_t) (r * W * SNS) * VB, a.spos + (size_t) s_rowbase[r] * SNS, len * SNS * VB, bar);
 				}
 			}
 			uint32_t tb = 0;
@@ -350,23 +361,38 @@ __global__ void __launch_bounds__(MultiCfg<C>::TPB) k_force_multi_tiled(MArgs<C>
 					#pragma unroll
 					for (int k = 0; k < NLJ * NLJ; k++) { e24[k] = a.eps24[k]; sg2[k] = a.sig2[k]; sh6[k] = a.shift6[k]; }
 					// software pipelined: the site records of the NEXT neighbour are requested (L1 / L2) before the current one is evaluated
-					V4 mj_n = mi; SiteC<C> oj_n[NS];
-					auto fetch = [&](uint32_t e) {
+					// (PD2: TWO neighbours ahead -- the gathers go to L2 more often than not, one evaluation does not cover their latency)
+					V4 mj_n = mi, mj_n2 = mi; SiteC<C> oj_n[NS], oj_n2[NS];
+					auto fetch_into = [&](uint32_t e, V4& mj_n, SiteC<C>* oj_n) {
 						const uint32_t addr = lds16(e);
 						mj_n = lds_v4<C>(addr);
 						const uint32_t idx = (addr - win_s) / VB, rr = idx >> LOGW;
+						if (STAGE) {
+							#pragma unroll
+							for (int k = 0; k < NS; k++) {
+								const V4 p = lds_v4<C>(swin_s + (idx * (uint32_t) NS + (uint32_t) k) * VB);
+								oj_n[k].x = p.x; oj_n[k].y = p.y; oj_n[k].z = p.z; oj_n[k].p = p.w; oj_n[k].ex = oj_n[k].ey = oj_n[k].ez = C(0);
+							}
+						} else {
 						const size_t sj = ((size_t) s_rowbase[rr] + (idx & (uint32_t) (W - 1))) * a.smax;
 						#pragma unroll
 						for (int k = 0; k < NS; k++) oj_n[k] = m_load_site<C>(a, sj + k, k >= D0);
+						}
 					};
-					if (list_s < w) fetch(list_s);
+					if (list_s < w) fetch_into(list_s, mj_n, oj_n);
+					if (PD2 && list_s + LSTRIDE < w) fetch_into(list_s + LSTRIDE, mj_n2, oj_n2);
 					#pragma unroll 1
 					for (uint32_t e = list_s; e < w; e += LSTRIDE) {
 						const V4 mj = mj_n;
 						SiteC<C> oj[NS];
 						#pragma unroll
 						for (int k = 0; k < NS; k++) oj[k] = oj_n[k];
-						if (e + LSTRIDE < w) fetch(e + LSTRIDE);
+						if (PD2) {
+							mj_n = mj_n2;
+							#pragma unroll
+							for (int k = 0; k < NS; k++) oj_n[k] = oj_n2[k];
+							if (e + 2 * LSTRIDE < w) fetch_into(e + 2 * LSTRIDE, mj_n2, oj_n2);
+						} else if (e + LSTRIDE < w) fetch_into(e + LSTRIDE, mj_n, oj_n);
 						const C dmx = mi.x - mj.x, dmy = mi.y - mj.y, dmz = mi.z - mj.z;
 						bool ljin = true;
 						if (a.lj_shorter) ljin = molpair_r2<C>(mi.x, mi.y, mi.z, mj.x, mj.y, mj.z) < a.ljrc2;
@@ -466,7 +492,7 @@ __global__ void __launch_bounds__(MRED_BLOCKS) k_reduce_multi2(const double* __r
 
 int launch_calcfm(ls1b200_ctx* c);      // force_general.cu
 
-template <class C, class SIG, int LOGW>
+template <class C, class SIG, int LOGW, bool STAGE = false, bool PD2 = false, int MINB = 5>
 static int launch_multi(ls1b200_ctx* c) {
 	typedef typename Vec4<C>::type V4;
 	constexpr int TPB = MultiCfg<C>::TPB, W = 1 << LOGW, LCAP = MultiCfg<C>::LCAP;
@@ -486,12 +512,20 @@ static int launch_multi(ls1b200_ctx* c) {
 	a.lj_shorter = rclj < rc;
 	a.eps_rf_invrc3 = (C) (2. * (erf - 1.) / ((rc * rc * rc) * (2. * erf + 1.)));   // VectorizedCellProcessor.cpp:22
 	if ((uint64_t) c->geom.ncells + 64 > c->partial_blocks) return fail("force_multi_tiled: partials buffer too small");
-	const size_t smem = (size_t) (9 * W) * sizeof(V4) + (size_t) (LCAP + 1) * TPB * 2 + 12 * (CH_MAXC + 3) * 4;
-	auto kern = k_force_multi_tiled<C, SIG, LOGW>;
+	const size_t smem = (size_t) (9 * W) * (1 + (STAGE ? SIG::NS : 0)) * sizeof(V4) + (size_t) (LCAP + 1) * TPB * 2 + 12 * (CH_MAXC + 3) * 4;
+	auto kern = k_force_multi_tiled<C, SIG, LOGW, STAGE, PD2, MINB>;
 	LS1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int per_sm = 0;
 	LS1_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, smem));
 	if (per_sm < 1) return fail("force_multi_tiled: kernel does not fit on an SM");
+	// Neighbour site records are gathered through L1 (they do not fit the shared-memory tile): the kernel is latency bound on those
+	// gathers, and every CTA's tile is carved out of the same 228 KB as L1. LS1B200_MULTI_MAXCTAS caps the resident CTAs per SM and
+	// asks for a matching carve-out, leaving the rest to L1 (measured: profiles/r02_multi_site.md).
+	if (c->multi_max_ctas > 0 && c->multi_max_ctas < per_sm) {
+		per_sm = c->multi_max_ctas;
+		const int pct = (int) std::min<size_t>(100, ((size_t) per_sm * (smem + 1024) * 100 + 228 * 1024 - 1) / (228 * 1024));
+		LS1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributePreferredSharedMemoryCarveout, pct));
+	}
 	LS1_LAUNCH(c, PH_FORCE, kern, (uint32_t) (c->sm_count * per_sm), TPB, smem, a);
 	LS1_TRY(launch_calcfm(c));
 	LS1_LAUNCH(c, PH_FORCE, k_reduce_multi1, MRED_BLOCKS, 256, 0, c->partials, c->chunk_row_start + nrows, c->partials2);
@@ -504,6 +538,13 @@ template <class SIG> static int launch_sig(ls1b200_ctx* c) {
 	const double nbar = (double) c->n_slots / (double) c->geom.ncells;
 	// W = 128 suffices while a chunk of about two thirds of the CTA's threads plus its two flanking cells fits (with 15 % head room)
 	const bool narrow = 0.67 * 1.15 * (c->mixed ? 96. : 64.) + 2.3 * nbar <= 128.;
+	// site records staged in shared memory: signatures without oriented sites, narrow windows (9 x 128 x (1 + NS) x 16 B), mixed build
+	if constexpr (!SIG::GENERIC && SIG::NDI == 0 && SIG::NQU == 0 && SIG::NS <= 4) {
+		if (c->mixed && narrow && c->multi_stage && c->smax == (uint32_t) SIG::NS) return launch_multi<float, SIG, 7, true>(c);
+	}
+	if constexpr (!SIG::GENERIC) {
+		if (c->mixed && c->multi_pd2) return narrow ? launch_multi<float, SIG, 7, false, true>(c) : launch_multi<float, SIG, 8, false, true>(c);
+	}
 	if (c->mixed) return narrow ? launch_multi<float, SIG, 7>(c) : launch_multi<float, SIG, 8>(c);
 	return narrow ? launch_multi<double, SIG, 7>(c) : launch_multi<double, SIG, 8>(c);
 }

@@ -79,3 +79,52 @@ def test_argon_config0_through_the_adapter(tmp_path, prec, tol):
     rhoT = (N / L ** 3) * (2.0 * b[:, 4] / (3.0 * N))
     err = np.abs(a[:, 6] - b[:, 6]).max() / max(np.abs(b[:, 6]).max(), rhoT.max())
     assert err <= tol, (prec, "p", err)
+
+
+@pytest.mark.parametrize("prec,tol", [("double", 1e-9), ("mixed", 2e-5)])
+def test_checkpoints_written_from_the_host_mirror(tmp_path, prec, tol):
+    """Host coherence: a molecule-iterating stock plugin (CheckpointWriter, io/CheckpointWriter.cpp; record layout
+    FullMolecule::write, molecules/FullMolecule.cpp:439-470) and the final checkpoint of Simulation::finalize run on the host mirror
+    LeapfrogB200 refreshes on the container's <hostSyncFrequency> schedule and at the last step. The checkpoints of MarDyn_b200 at
+    steps 10, 20 and at the end equal the stock binary's, molecule by molecule; restarting the STOCK binary from the drop-in's
+    checkpoint continues the stock binary's own trajectory."""
+    ref = os.path.join(ROOT, "oracle", "_ref", prec, "MarDyn")
+    b200 = os.path.join(ROOT, "adapter", "_build", prec, "MarDyn_b200")
+    if not (os.path.exists(ref) and os.path.exists(b200)):
+        pytest.skip("reference / adapter binaries not built (oracle/build_ref.sh, adapter/build_adapter.sh)")
+    from ls1_mardyn_b200 import workloads
+    from ls1_mardyn_b200.ascii_reader import read_molecules_only
+    from ls1_mardyn_b200.xml_config import simulation_xml
+    wl = workloads.get("lj")
+    n, steps = 12, 20
+    N = 2 * n ** 3; L = (N / wl.rho) ** (1.0 / 3.0)
+    cpw = ('<outputplugin name="CheckpointWriter"><type>ASCII</type><writefrequency>10</writefrequency><outputprefix>cp</outputprefix>'
+           "<incremental>true</incremental></outputplugin>")
+    runs = {}
+    for name, exe, ds, integ, extra in (("ref", ref, "LinkedCells", "Leapfrog", ""), ("b200", b200, "LinkedCellsB200", "LeapfrogB200", "<hostSyncFrequency>10</hostSyncFrequency>")):
+        d = tmp_path / name; d.mkdir()
+        (d / "config.xml").write_text(simulation_xml(wl.ensemble, [L, L, L], wl.temperature, wl.dt, steps, wl.rc, generator_density=N / L ** 3 * (1 + 1e-9),
+                                                     datastructure=ds, integrator=integ, longrange="homogeneous", extra_output=cpw, datastructure_extra=extra))
+        p = subprocess.run([exe, "--steps", str(steps), "config.xml"], cwd=str(d), capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="8"))
+        assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+        runs[name] = d
+
+    def cmp(fa, fb, what):
+        (ia, _, ra, va, _, _), (ib, _, rb, vb, _, _) = read_molecules_only(str(fa)), read_molecules_only(str(fb))
+        assert len(ia) == len(ib) == N
+        oa, ob = np.argsort(ia), np.argsort(ib)
+        assert np.array_equal(ia[oa], ib[ob])
+        dr = ra[oa] - rb[ob]; dr -= L * np.round(dr / L)
+        assert np.abs(dr).max() <= tol * L, (what, np.abs(dr).max())
+        assert np.abs(va[oa] - vb[ob]).max() <= tol * np.abs(vb).max() * 10, (what, np.abs(va[oa] - vb[ob]).max())
+
+    for f in ("cp-1.restart.dat", "cp-2.restart.dat", "config.restart.dat"):      # step 10, step 20, Simulation::finalize
+        cmp(runs["b200"] / f, runs["ref"] / f, f)
+    # restart: the stock binary continues from the drop-in's step-10 checkpoint and arrives where its own run arrived
+    d = tmp_path / "restart"; d.mkdir()
+    import shutil
+    shutil.copy(runs["b200"] / "cp-1.restart.dat", d / "start.inp")
+    (d / "config.xml").write_text(simulation_xml(wl.ensemble, [L, L, L], wl.temperature, wl.dt, 10, wl.rc, phasespace_file="start.inp", longrange="homogeneous"))
+    p = subprocess.run([ref, "--steps", "10", "config.xml"], cwd=str(d), capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="8"))
+    assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
+    cmp(d / "config.restart.dat", runs["ref"] / "config.restart.dat", "restart")

@@ -305,12 +305,19 @@ def test_site_signature_kernels_vs_oracle(capi, name, prec):
     ps = generators.lattice(ens, 6, rho, T, seed=17, jitter=0.12, rc=rc)      # 432 molecules
     b = _mk(orc.OracleSim, ps, rc, prec); b.update(); mb = b.traverse_cells()
     tol = TOL[prec]
-    for kernel in ("", "generic"):
-        os.environ["LS1B200_MULTI_KERNEL"] = kernel
+    # specialised; specialised with the site records of the windows staged in shared memory (where the signature allows it); specialised
+    # with two neighbours prefetched; generic
+    for kernel in ("", "stage", "pd2", "generic"):
+        os.environ["LS1B200_MULTI_KERNEL"] = kernel if kernel == "generic" else ""
+        if kernel == "stage":
+            os.environ["LS1B200_MULTI_STAGE"] = "1"
+        if kernel == "pd2":
+            os.environ["LS1B200_MULTI_PD2"] = "1"
         try:
             a = _mk(capi.Context, ps, rc, prec)
         finally:
-            os.environ.pop("LS1B200_MULTI_KERNEL", None)
+            for k in ("LS1B200_MULTI_KERNEL", "LS1B200_MULTI_STAGE", "LS1B200_MULTI_PD2"):
+                os.environ.pop(k, None)
         a.update(); ma = a.traverse_cells()
         assert np.array_equal(a.download("CELL"), b.download("CELL"))
         for f in ("F", "M", "VI"):
@@ -381,3 +388,39 @@ def test_device_cubic_grid_generator(capi, prec):
         assert np.array_equal(rid[k], bid) and np.array_equal(br, rr[k]) and np.abs(c.download("V") - rv[k]).max() <= 1e-13 * np.abs(rv).max()
         seen.append(bid)
     assert np.array_equal(np.sort(np.concatenate(seen)), rid)
+
+
+def test_forces_one_million_molecules_vs_reference_on_the_fly(capi, tmp_path):
+    """Parity at a size where the golden fixtures cannot go (they are 250 - 1 458 molecules): a 1 024 000-molecule jittered periodic
+    1CLJ liquid (100 x 100 x... BCC lattice 2 * 80^3) is written out, the UNMODIFIED reference (oracle/_ref/mixed/refdump, the dump
+    driver linked against the reference's own objects) computes cells, forces, virials and the macroscopic sums on the GPU box's
+    host cores, and the CUDA path is held to the same bar as on the fixtures: bit-exact cells, F / Vi / Upot / virial at 1e-5 (mixed).
+    Skipped where the reference build is not in the snapshot."""
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    exe = os.path.join(root, "oracle", "_ref", "mixed", "refdump")
+    if not os.path.exists(exe):
+        pytest.skip("oracle/_ref/mixed/refdump not built (oracle/build_ref.sh)")
+    sys.path.insert(0, os.path.join(root, "tests", "golden"))
+    from make_golden import read_refdump
+    from ls1_mardyn_b200 import generators
+    from ls1_mardyn_b200.ascii_reader import write_phase_space
+    ps = generators.lj_lattice(80, seed=3, jitter=0.1)
+    ps.r = ps.r.astype(np.float32).astype(np.float64)
+    inp = str(tmp_path / "big.inp"); out = str(tmp_path / "dump.bin")
+    write_phase_space(inp, ps)
+    subprocess.check_call([exe, inp, repr(2.5), out, "vcp", "periodic", "xml"], stdout=subprocess.DEVNULL, env=dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1)), timeout=1500)
+    d = read_refdump(out)
+    sel = ~d["mol_halo"].astype(bool)
+    o = np.argsort(d["mol_id"][sel])
+    a = _mk(capi.Context, ps, 2.5, "mixed"); a.update(); m = a.traverse_cells()
+    oa = np.argsort(a.download("ID"))
+    assert np.array_equal(a.download("ID")[oa], d["mol_id"][sel][o])
+    assert np.array_equal(a.download("CELL")[oa], d["mol_cell"][sel][o]), "cell assignment differs from the reference at 1 M molecules"
+    for f, k in (("F", "mol_F"), ("VI", "mol_Vi")):
+        ok, worst = rel_close(a.download(f)[oa], d[k][sel][o], TOL["mixed"]); assert ok, (f, worst)
+    terms = float(np.abs(d["mol_Vi"][sel]).sum())
+    assert abs(m.upot - d["upot"]) <= TOL["mixed"] * max(abs(d["upot"]), terms) and abs(m.virial - d["virial"]) <= TOL["mixed"] * max(abs(d["virial"]), terms)
+    print("1 M molecules: strict relative error U_pot %.2e, virial %.2e" % (abs(m.upot - d["upot"]) / abs(d["upot"]), abs(m.virial - d["virial"]) / abs(d["virial"])))
