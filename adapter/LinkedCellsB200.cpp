@@ -1,5 +1,6 @@
 #include "particleContainer/LinkedCellsB200.h"
 
+#include <algorithm>
 #include <unordered_map>
 #include <vector>
 
@@ -43,6 +44,7 @@ void LinkedCellsB200::readXML(XMLfileUnits& xmlconfig) {
 	xmlconfig.getNodeValue("hostSyncFrequency", f);
 	_hostSyncFrequency = f > 0 ? (unsigned long) f : 0ul;
 	xmlconfig.getNodeValue("device", _device);
+	xmlconfig.getNodeValue("syncAtLastStep", _syncAtLastStep);
 	Log::global_log->info() << "LinkedCellsB200: host mirror refreshed every " << _hostSyncFrequency << " steps (0: only at the last step)" << std::endl;
 }
 
@@ -182,13 +184,33 @@ void LinkedCellsB200::syncToHost() {
 	B200_CHECK(ls1b200_download(_ctx, LS1B200_F_Q, q.data(), n)); B200_CHECK(ls1b200_download(_ctx, LS1B200_F_L, D.data(), n));
 	B200_CHECK(ls1b200_download(_ctx, LS1B200_F_F, F.data(), n)); B200_CHECK(ls1b200_download(_ctx, LS1B200_F_M, M.data(), n));
 	B200_CHECK(ls1b200_download(_ctx, LS1B200_F_VI, Vi.data(), n));
+	// id -> row of the downloaded arrays: a flat table when the ids are dense (generators, checkpoints), a hash map otherwise
+	uint64_t maxId = 0;
+	for (size_t i = 0; i < n; i++) maxId = std::max(maxId, id[i]);
+	const bool dense = maxId < 8 * n + 1024;
+	std::vector<uint32_t> flat;
 	std::unordered_map<uint64_t, size_t> at;
-	at.reserve(n);
-	for (size_t i = 0; i < n; i++) at[id[i]] = i;
+	if (dense) {
+		flat.assign(maxId + 1, 0xFFFFFFFFu);
+		for (size_t i = 0; i < n; i++) flat[id[i]] = (uint32_t) i;
+	} else {
+		at.reserve(n);
+		for (size_t i = 0; i < n; i++) at[id[i]] = i;
+	}
+	#if defined(_OPENMP)
+	#pragma omp parallel
+	#endif
 	for (auto m = LinkedCells::iterator(ParticleIterator::ALL_CELLS); m.isValid(); ++m) {
-		auto it = at.find(m->getID());
-		if (it == at.end()) continue;
-		const size_t i = it->second;
+		size_t i;
+		if (dense) {
+			const uint64_t mid = m->getID();
+			if (mid > maxId || flat[mid] == 0xFFFFFFFFu) continue;
+			i = flat[mid];
+		} else {
+			auto it = at.find(m->getID());
+			if (it == at.end()) continue;
+			i = it->second;
+		}
 		for (int d = 0; d < 3; d++) { m->setr(d, r[3 * i + d]); m->setv(d, v[3 * i + d]); m->setD(d, D[3 * i + d]); }
 		m->setq(Quaternion(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]));
 		m->setF(&F[3 * i]); m->setM(&M[3 * i]); m->setVi(&Vi[3 * i]);

@@ -23,9 +23,11 @@ public:
 	//   <hostSyncFrequency>INT</hostSyncFrequency>   every that many steps (and always at the last step, for the final checkpoint) the
 	//                                                host mirror is refreshed after the forces: output plugins, checkpoint writers,
 	//                                                RDF etc. then see the molecules of that step (0 = only at the last step)
+	//   <syncAtLastStep>BOOL</syncAtLastStep>        default true; false skips the refresh at the last step (runs with --final-checkpoint=0
+	//                                                and no molecule-reading plugin at the end: the refresh of 16 M molecules costs seconds)
 	//   <device>INT</device>                         CUDA device ordinal (default: environment LS1B200_DEVICE, else 0)
 	void readXML(XMLfileUnits& xmlconfig) override;
-	bool wantsHostSync(unsigned long step, unsigned long lastStep) const { return step >= lastStep || (_hostSyncFrequency > 0 && step % _hostSyncFrequency == 0); }
+	bool wantsHostSync(unsigned long step, unsigned long lastStep) const { return (_syncAtLastStep && step >= lastStep) || (_hostSyncFrequency > 0 && step % _hostSyncFrequency == 0); }
 	void update() override;                                  // -> ls1b200_update once the molecules live on the device
 	void traverseCells(CellProcessor& cellProcessor) override;   // -> ls1b200_traverse_cells, Domain::setLocalUpot/Virial (first call: upload)
 	void updateMoleculeCaches() override { if (!_deviceMode) LinkedCells::updateMoleculeCaches(); }
@@ -57,5 +59,6 @@ private:
 	bool _hostView = true;        // until the first time step: the init-time loops of prepare_start read the host mirror
 	unsigned long _numMolecules = 0;
 	unsigned long _hostSyncFrequency = 0;
+	bool _syncAtLastStep = true;
 	int _device = -1;
 };

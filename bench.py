@@ -46,49 +46,57 @@ def peaks():
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe). Every row carries nvidia-smi's own
+    time stamp, so rows are attributed to the timed region by the clock of the sample, not by when the pipe delivered them."""
+
+    Q = "timestamp,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         self.index = index; self.rows = []; self.proc = None
 
     def start(self):
-        q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + q, "--format=csv,noheader,nounits", "-lms", "20"],
-                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q, "--format=csv,noheader,nounits", "-lms", "20"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, bufsize=1)
             self.t = threading.Thread(target=self._read, daemon=True); self.t.start()
         except Exception:
             self.proc = None
 
     def _read(self):
+        import datetime
         for line in self.proc.stdout:
-            self.rows.append((time.perf_counter(), [x.strip() for x in line.split(",")]))
+            f = [x.strip() for x in line.split(",")]
+            try:
+                ts = datetime.datetime.strptime(f[0], "%Y/%m/%d %H:%M:%S.%f").timestamp()
+            except Exception:
+                ts = time.time()
+            self.rows.append((ts, f[1:]))
 
     def stop(self, t_begin=None, t_end=None):
-        """Summary of the rows received inside [t_begin, t_end] (the timed region). nvidia-smi needs a few hundred ms to start, so
-        the sampler is started before the warm-up steps; if the timed region is shorter than the sampling period the rows from the
-        warm-up on (the GPU is under the same load) are used and `window` says so."""
+        """Summary of the rows sampled inside [t_begin, t_end] (time.time() of the timed region's ends). If the region is shorter than
+        the sampling period, the rows of the second before it (warm-up steps: the same load) are added and `window` says so."""
         if not self.proc:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"], "samples": 0}
+        time.sleep(0.06)      # let the row of the last 20 ms arrive
         self.proc.terminate()
         try:
             self.proc.wait(timeout=5)
         except Exception:
             self.proc.kill()
-        rows = [r for (t, r) in self.rows if t_begin is None or (t_begin <= t <= t_end + 0.05)]
+        rows = [r for (t, r) in self.rows if t_begin is None or (t_begin - 0.01 <= t <= t_end + 0.03)]
         window = "timed region"
-        if not rows:
-            rows = [r for (t, r) in self.rows]; window = "warm-up + timed region (timed region shorter than the sampling period)"
-        all_rows = self.rows; self.rows = rows
-        sm = [float(r[0]) for r in self.rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
-        mx = [float(r[1]) for r in self.rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
+        if len(rows) < 2 and t_begin is not None:
+            rows = [r for (t, r) in self.rows if t_begin - 1.0 <= t <= t_end + 0.25]; window = "timed region and the second before it (warm-up steps; the region is shorter than the sampling period)"
+        sm = [float(r[0]) for r in rows if len(r) >= 7 and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in rows if len(r) >= 7 and r[1].replace(".", "").isdigit()]
         reasons = set()
-        for r in self.rows:
+        for r in rows:
             if len(r) >= 7:
                 for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
                     if v.lower().startswith("active"):
                         reasons.add(name)
-        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "window": window}
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None, "reasons": sorted(reasons), "samples": len(sm), "window": window,
+                "rows_total": len(self.rows)}
 
 
 def make_system(n_per_dim, mixed=True, seed=0, wl=None):
@@ -278,7 +286,7 @@ def reference_arm(args):
 # ----------------------------------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the force kernel, from the `ncu --set full` captures under profiles/
 # (keyed by workload, precision, molecules): reported, with its source, as roofline.traffic
-FORCE_TRAFFIC = {}
+FORCE_TRAFFIC = {("lj", "mixed", 16000000): (279817216 + 728153088, "profiles/r02m_force_full.md (ncu --set full of this kernel at this size: dram__bytes_read.sum + dram__bytes_write.sum; algorithmic: 256 MB of calc records read + 768 MB of F, Vi written)")}
 
 
 def run_secondary(name, local, fp32_peak, capi, with_cpu=True, steps=10, warmup=3):
@@ -331,7 +339,7 @@ def run_adapter(n_per_dim, steps, host_sync_frequency=0, prec="mixed"):
     with tempfile.TemporaryDirectory() as td:
         open(os.path.join(td, "config.xml"), "w").write(simulation_xml(
             wl.ensemble, [L, L, L], wl.temperature, wl.dt, steps, wl.rc, generator_density=N / L ** 3 * (1 + 1e-9), datastructure="LinkedCellsB200", integrator="LeapfrogB200",
-            longrange="homogeneous", result_prefix=None, datastructure_extra="<hostSyncFrequency>%d</hostSyncFrequency>" % host_sync_frequency))
+            longrange="homogeneous", result_prefix=None, datastructure_extra="<hostSyncFrequency>%d</hostSyncFrequency><syncAtLastStep>false</syncAtLastStep>" % host_sync_frequency))
         t0 = time.perf_counter()
         p = subprocess.run([exe, "--steps", str(steps), "--final-checkpoint=0", "config.xml"], cwd=td, capture_output=True, text=True, timeout=3000,
                            env=dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1)))
@@ -391,6 +399,7 @@ def our_arm(args):
     if world != args.gpus:
         assert world == 1 and args.gpus == 1, "for --gpus N > 1 launch with torch.distributed.run --nproc-per-node N"
     torch.cuda.set_device(local)
+    sampler = ClockSampler(local); sampler.start()      # started first: nvidia-smi takes up to a second to deliver its first row; rows are time-stamped and filtered to the timed region
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
 
@@ -465,23 +474,23 @@ def our_arm(args):
     hbm_peak, hbm_src = peaks()
 
     # ---- HBM-resident: K steps inside the library, no host round trip ----
-    sampler = ClockSampler(local); sampler.start()      # before the warm-up: nvidia-smi takes a few hundred ms to deliver its first row
     ctx.simulate(args.warmup, DT, TEMP, global_n=N_global, global_volume=V_global, records=False)
     ctx.phase_times(reset=True)
     launches0 = capi.kernel_launch_count()
     ext = torch.cuda.ExternalStream(ctx.stream(), device=local)
     e0 = torch.cuda.Event(enable_timing=True); e1 = torch.cuda.Event(enable_timing=True)
     barrier()
-    t0 = time.perf_counter()
+    t0 = time.perf_counter(); w0 = time.time()
     e0.record(ext)
     rec = ctx.simulate(args.steps, DT, TEMP, global_n=N_global, global_volume=V_global)
     e1.record(ext)
     barrier()
     t_wall = time.perf_counter() - t0
-    clocks = sampler.stop(t0, t0 + t_wall)
+    clocks = sampler.stop(w0, w0 + t_wall)
     t_dev = e0.elapsed_time(e1) * 1e-3
     launches = capi.kernel_launch_count() - launches0
     ph_ms, ph_launch = ctx.phase_times(reset=True)
+    xchg_ms = ctx.exchange_overlapped_ms(reset=True) if dd is not None else 0.0
     fc1 = ctx.count_flops()
     t = torch.tensor([t_wall, t_dev], dtype=torch.float64, device="cuda")
     if world > 1:
@@ -539,7 +548,7 @@ def our_arm(args):
         double = args.precision == "double"
         peak = fp64_peak if double else fp32_peak
         traffic, traffic_src = FORCE_TRAFFIC.get((wl.name, args.precision, N), (None, None))
-        roofline = {"kernel": ("k_force_1clj_v3<%s>" if wl.name in ("lj", "argon") else "k_force_multi_tiled<%s> (site-signature specialisation)") % ("double" if double else "float"),
+        roofline = {"kernel": ("k_force_1clj_tiled<%s, true>" if wl.name in ("lj", "argon") else "k_force_multi_tiled<%s> (site-signature specialisation)") % ("double" if double else "float"),
                     "bound": "fp64" if double else "fp32", "achieved": round(achieved, 3), "peak": round(peak, 2), "unit": "TFLOP/s", "frac": round(achieved / peak, 4),
                     # dram__bytes_read.sum + dram__bytes_write.sum of ONE launch at this size from an `ncu --set full` capture (not measured in this run)
                     "traffic": traffic, "traffic_source": traffic_src,
@@ -558,6 +567,7 @@ def our_arm(args):
                           "l2_policy": "inputs larger than L2: state %.1f GB per GPU" % (N * 150 / 1e9)},
             "ms_per_step_device_events": round(1e3 * t_dev / args.steps, 4),
             "phases_ms_per_step": {k: round(v / args.steps, 4) for k, v in ph_ms.items()},
+            "exchange_overlapped_ms_per_step": round(xchg_ms / args.steps, 4),      # multi-GPU: the exchange on its own stream beside the inner slots' integration / binning (not part of the phases)
             "gpu_launches": int(launches),
             "e2e": {"value": round(e2e_value, 2), "unit": "MMUPS", "h2d_bytes_per_step": int(h2d / e2e_steps), "d2h_bytes_per_step": int(d2h / e2e_steps), "steps": e2e_steps,
                     "path": "set_field(R,V) from pinned host -> leapfrog_pre -> update -> [ls1b200_download_begin(R): the positions travel while the forces run] traverse_cells -> leapfrog_post -> download(V), download_end + scalars"},

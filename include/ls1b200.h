@@ -303,6 +303,10 @@ uint64_t ls1b200_rmm_state_bytes(const ls1b200_ctx* ctx);      /* 32 * number of
 /* Device time (ms) spent in each phase since the last reset, measured with CUDA events on the library's stream:
  * [0] update (binning+halo+SoA), [1] force kernels, [2] leapfrog pre, [3] leapfrog post + reductions. */
 int ls1b200_phase_times(ls1b200_ctx* ctx, double ms[4], uint64_t launches[4], int reset);
+/* Decomposed contexts inside ls1b200_simulate: the exchange (export -> NVLink / NCCL -> import, three stages) runs on its own stream
+ * beside the integration and binning of the slots it cannot touch (LS1B200_OVERLAP=0 puts it back in line, inside the update
+ * phase). Device time (ms) of those overlapped exchanges since the last reset; it is NOT part of the four phases above. */
+int ls1b200_exchange_overlapped_ms(ls1b200_ctx* ctx, double* ms, int reset);
 /* Counts of the reference's FlopCounter for the current configuration (adapter/FlopCounter.cpp:20-74):
  * molecule-distance evaluations and in-range pairs per potential, Newton-3 counting (each pair once). */
 typedef struct ls1b200_flopcount {

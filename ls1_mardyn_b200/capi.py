@@ -31,7 +31,7 @@ EXPORTS = ["ls1b200_last_error", "ls1b200_abi_version", "ls1b200_kernel_launch_c
            "ls1b200_scale_velocities", "ls1b200_simulate", "ls1b200_halo_export", "ls1b200_halo_import",
            "ls1b200_halo_import_host", "ls1b200_phase_times", "ls1b200_count_flops", "ls1b200_measure_fp32_peak", "ls1b200_measure_fp64_peak",
            "ls1b200_measure_hbm_copy", "ls1b200_stream", "ls1b200_nccl_unique_id", "ls1b200_decomp_attach", "ls1b200_download_begin", "ls1b200_download_end", "ls1b200_peer_handle", "ls1b200_peer_attach", "ls1b200_peer_detach", "ls1b200_exchange",
-           "ls1b200_allreduce_macro", "ls1b200_halo_export_host", "ls1b200_generate_cubic_grid", "ls1b200_rmm_upload", "ls1b200_rmm_start", "ls1b200_rmm_simulate", "ls1b200_rmm_download", "ls1b200_rmm_state_bytes"]
+           "ls1b200_allreduce_macro", "ls1b200_halo_export_host", "ls1b200_generate_cubic_grid", "ls1b200_rmm_upload", "ls1b200_rmm_start", "ls1b200_rmm_simulate", "ls1b200_rmm_download", "ls1b200_rmm_state_bytes", "ls1b200_exchange_overlapped_ms"]
 
 
 class Ls1B200Error(RuntimeError):
@@ -98,6 +98,7 @@ def lib():
         L.ls1b200_destroy.argtypes = [C.c_void_p]
         L.ls1b200_set_components.argtypes = [C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_uint32, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ls1b200_upload.argtypes = [C.c_void_p, C.c_uint64] + [C.c_void_p] * 6
+        L.ls1b200_exchange_overlapped_ms.argtypes = [C.c_void_p, C.c_void_p, C.c_int]
         L.ls1b200_rmm_upload.argtypes = [C.c_void_p, C.c_uint64, C.c_void_p, C.c_void_p, C.c_void_p]
         L.ls1b200_rmm_start.argtypes = [C.c_void_p, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
         L.ls1b200_rmm_simulate.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_double, C.c_double, C.c_void_p]
@@ -212,6 +213,9 @@ class Context:
         L = None if L is None else np.ascontiguousarray(L, dtype=np.float64)
         _check(lib().ls1b200_upload(self.h, n, _vp(id), _vp(cid), _vp(r), _vp(v), _vp(q), _vp(L)))
         self.n = n
+
+    def exchange_overlapped_ms(self, reset=False):
+        v = C.c_double(); _check(lib().ls1b200_exchange_overlapped_ms(self.h, C.byref(v), int(reset))); return v.value
 
     # ---- reduced-memory mode (rmm.cu; the reference's RMM build) ----
     def rmm_upload(self, id, r, v):

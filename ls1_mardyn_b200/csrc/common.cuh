@@ -52,7 +52,7 @@ extern std::atomic<uint64_t> g_launches;
 		LS1_CUDA(cudaGetLastError());                                                                  \
 	} while (0)
 
-enum { PH_UPDATE = 0, PH_FORCE = 1, PH_PRE = 2, PH_POST = 3, PH_COUNT = 4 };
+enum { PH_UPDATE = 0, PH_FORCE = 1, PH_PRE = 2, PH_POST = 3, PH_COUNT = 4, PH_XCHG = 4, PH_INTERNAL = 5 };      // PH_XCHG: the exchange when it runs on its own stream beside the step (not part of ls1b200_phase_times' four)
 
 // ---------------------------------------------------------------------------------------------------------------------
 // geometry of LinkedCells, passed by value to kernels
@@ -105,6 +105,30 @@ struct State {
 	uint64_t* meta = nullptr;    // [cap] orig index | cid << 32 | fresh << 62 | halo << 63
 	uint64_t* id = nullptr;      // [cap] molecule id, travels with the molecule (decomposed mode only; otherwise ids stay in d_id)
 };
+
+// Which slots a kernel of the overlapped multi-GPU step works on. A slot is BOUNDARY if its cell at the last sort lies within four
+// layers (cells 0 .. 3, n-4 .. n-1) of a face the block shares with another rank, or in limbo, or if it was appended after the
+// sort (an import): exactly the slots k_export reads or writes and k_import appends. Everything else is INNER: nothing the exchange
+// does can touch it, so its integration and its histogram run on the main stream while the exchange runs beside them.
+struct Region {
+	const uint32_t* cell_of;      // cell of every slot at the last sort
+	uint32_t ncells;
+	int nx, ny, nz;
+	int cut[3];                   // the block has a neighbour rank in that dimension
+	int mode;                     // 0: all slots, 1: boundary slots only, 2: inner slots only
+};
+__device__ __forceinline__ bool region_selected(const Region& rg, uint32_t slot, uint32_t n_sorted) {
+	if (rg.mode == 0) return true;
+	bool boundary = true;
+	if (slot < n_sorted) {
+		const uint32_t c = rg.cell_of[slot];
+		if (c < rg.ncells) {
+			const int cx = (int) (c % (uint32_t) rg.nx), cy = (int) ((c / (uint32_t) rg.nx) % (uint32_t) rg.ny), cz = (int) (c / (uint32_t) (rg.nx * rg.ny));
+			boundary = (rg.cut[0] && (cx <= 3 || cx + 4 >= rg.nx)) || (rg.cut[1] && (cy <= 3 || cy + 4 >= rg.ny)) || (rg.cut[2] && (cz <= 3 || cz + 4 >= rg.nz));
+		}
+	}
+	return boundary == (rg.mode == 1);
+}
 
 // scalars living on the device between kernels of one step
 struct DevScalars {
@@ -187,6 +211,8 @@ struct ls1b200_ctx {
 	// reduced-memory mode (rmm.cu): FP32 planes r[3][cap], v[3][cap], id[cap] (bit 63: halo copy), double buffered
 	float* rmm_r[2] = {nullptr, nullptr}; float* rmm_v[2] = {nullptr, nullptr}; uint64_t* rmm_id[2] = {nullptr, nullptr};
 	int rmm_cur = 0; bool rmm = false;
+	// overlapped multi-GPU step (ls1b200_simulate on decomposed contexts): the exchange runs on its own stream beside the inner slots' work
+	cudaStream_t stream_x = nullptr; cudaEvent_t ev_xa = nullptr, ev_xb = nullptr; int overlap = 1; int xchg_phase = 0;
 	void* chunks2 = nullptr; size_t chunks2_bytes = 0;      // molecule-granular chunk list of force_1clj_v3.cu
 	int lj_kernel = 0;                // LS1B200_LJ_KERNEL: 0 tiled (default; shared-memory windows, TMA), 1 "global" (force_1clj.cu), 3 "mma" / 4 "tc": tensor-core prefilter experiments (force_1clj_mma.cu, force_1clj_tc.cu; measured slower, profiles/r01_tensor_prefilter.md), 5 "v3": molecule-granular chunks + x-trimmed ranges over fine bins (force_1clj_v3.cu; measured slower, profiles/r02_force_kernel_experiments.md)
 	int multi_pd2 = 0;                // LS1B200_MULTI_PD2=1: prefetch the site records of two neighbours ahead instead of one
@@ -211,8 +237,8 @@ struct ls1b200_ctx {
 	std::vector<cudaEvent_t> ev_pool; size_t ev_used = 0;
 	struct Span { int phase; cudaEvent_t a, b; };
 	std::vector<Span> spans;
-	double phase_ms[ls1b200::PH_COUNT] = {0, 0, 0, 0};
-	uint64_t phase_launches[ls1b200::PH_COUNT] = {0, 0, 0, 0};
+	double phase_ms[ls1b200::PH_INTERNAL] = {0, 0, 0, 0, 0};
+	uint64_t phase_launches[ls1b200::PH_INTERNAL] = {0, 0, 0, 0, 0};
 	bool timing = true;
 
 	// ---- 3D block decomposition (halo.cu; replaces parallel/DomainDecomposition.cpp + CommunicationPartner.cpp) ----
@@ -252,9 +278,9 @@ void rmm_release(ls1b200_ctx* c);          // rmm.cu
 void ctx_free_molecules(ls1b200_ctx* c);
 int span_begin(ls1b200_ctx* c, int phase);
 int span_end(ls1b200_ctx* c);
-int do_update(ls1b200_ctx* c);
+int do_update(ls1b200_ctx* c, int part = 0);      // part 0: everything; 1: histogram of the INNER slots only (overlapped step); 2: the remaining slots + scan, scatter, gather
 int do_forces(ls1b200_ctx* c);
-int do_leapfrog_pre(ls1b200_ctx* c, double dt, bool use_beta);
+int do_leapfrog_pre(ls1b200_ctx* c, double dt, bool use_beta, int region = 0);      // region: see Region::mode
 int do_leapfrog_post(ls1b200_ctx* c, double dt);
 int do_globals(ls1b200_ctx* c, double target_T, uint64_t global_n, double global_volume, ls1b200_step_record* d_rec);
 int force_general(ls1b200_ctx* c);

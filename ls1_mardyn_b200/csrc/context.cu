@@ -267,6 +267,7 @@ int ls1b200_create(const ls1b200_config* cfg, ls1b200_ctx** out) {
 		if (const char* mc = getenv("LS1B200_MULTI_MAXCTAS")) c->multi_max_ctas = atoi(mc);
 		if (const char* ms = getenv("LS1B200_MULTI_STAGE")) c->multi_stage = atoi(ms);
 		if (const char* mp = getenv("LS1B200_MULTI_PD2")) c->multi_pd2 = atoi(mp);
+		if (const char* ov = getenv("LS1B200_OVERLAP")) c->overlap = atoi(ov);
 		c->multi_kernel = (m && std::string(m) == "general") ? 1 : (m && std::string(m) == "generic") ? 2 : 0;   // 2: tiled, but never specialised
 	}
 	if (dev_alloc(&c->d_scal, 1) || dev_alloc(&c->partials2, 1024 * 8)) return cleanup(1);
@@ -295,6 +296,7 @@ int ls1b200_destroy(ls1b200_ctx* c) {
 	for (auto e : c->xprof_ev) if (e) cudaEventDestroy(e);
 	decomp_free(c);
 	if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+	if (c->stream_x) { cudaStreamSynchronize(c->stream_x); cudaStreamDestroy(c->stream_x); if (c->ev_xa) cudaEventDestroy(c->ev_xa); if (c->ev_xb) cudaEventDestroy(c->ev_xb); }
 	if (c->ev_dl) cudaEventDestroy(c->ev_dl);
 	if (c->stage2) cudaFree(c->stage2);
 	if (c->stage) cudaFree(c->stage);
@@ -620,6 +622,15 @@ int ls1b200_phase_times(ls1b200_ctx* c, double ms[4], uint64_t launches[4], int 
 	LS1_TRY(spans_collect(c));
 	for (int i = 0; i < PH_COUNT; i++) { if (ms) ms[i] = c->phase_ms[i]; if (launches) launches[i] = c->phase_launches[i]; }
 	if (reset) for (int i = 0; i < PH_COUNT; i++) { c->phase_ms[i] = 0.; c->phase_launches[i] = 0; }
+	return 0;
+}
+
+int ls1b200_exchange_overlapped_ms(ls1b200_ctx* c, double* ms, int reset) {
+	if (!c || !ms) return fail("ls1b200_exchange_overlapped_ms: null argument");
+	LS1_CUDA(cudaSetDevice(c->device));
+	LS1_TRY(spans_collect(c));
+	*ms = c->phase_ms[PH_XCHG];
+	if (reset) { c->phase_ms[PH_XCHG] = 0.; c->phase_launches[PH_XCHG] = 0; }
 	return 0;
 }
 

@@ -448,7 +448,7 @@ int do_exchange(ls1b200_ctx* c) {
 	if (!c->dd.active) return 0;
 	if (!c->dd.comm && !c->peer_ok) return fail("ls1b200_exchange: this context has no transport (use_nccl = 0 and no ls1b200_peer_attach): move the messages with ls1b200_halo_export / import");
 	if (!c->msg_out[0]) return fail("ls1b200_exchange: call ls1b200_upload first");
-	LS1_TRY(span_begin(c, PH_UPDATE));
+	LS1_TRY(span_begin(c, c->xchg_phase));
 	const bool full = c->rotates;
 	const size_t rec = full ? sizeof(ls1b200_particle) : sizeof(RecCompact);
 	const size_t bytes = MSG_HEADER + c->msg_cap * rec;
@@ -485,8 +485,8 @@ int do_exchange(ls1b200_ctx* c) {
 			LS1_CUDA(cudaMemsetAsync(c->msg_out[0], 0, MSG_HEADER, c->stream));
 			LS1_CUDA(cudaMemsetAsync(c->msg_out[1], 0, MSG_HEADER, c->stream));
 		}
-		if (full) LS1_LAUNCH(c, PH_UPDATE, k_export<true>, g, 256, 0, a, c->cur, o, c->d_scal, 3);
-		else LS1_LAUNCH(c, PH_UPDATE, k_export<false>, g, 256, 0, a, c->cur, o, c->d_scal, 3);
+		if (full) LS1_LAUNCH(c, c->xchg_phase, k_export<true>, g, 256, 0, a, c->cur, o, c->d_scal, 3);
+		else LS1_LAUNCH(c, c->xchg_phase, k_export<false>, g, 256, 0, a, c->cur, o, c->d_scal, 3);
 		if (peer) LS1_LAUNCH(c, PH_UPDATE, k_publish, 1, 32, 0, o);
 		if (prof) cudaEventRecord(pe[1], c->stream);
 		if (!peer) {
@@ -695,7 +695,7 @@ int ls1b200_halo_export(ls1b200_ctx* c, int32_t dim, int32_t side, void** device
 	LS1_CUDA(cudaSetDevice(c->device));
 	const XArgs a = stage_args(c, dim);
 	LS1_CUDA(cudaMemsetAsync(c->msg_out[side], 0, MSG_HEADER, c->stream));
-	LS1_LAUNCH(c, PH_UPDATE, k_export<true>, std::min<uint32_t>((uint32_t) ((c->cap + 255) / 256), (uint32_t) c->sm_count * 8u), 256, 0, a, c->cur, local_out(c), c->d_scal, side ? 2 : 1);
+	LS1_LAUNCH(c, c->xchg_phase, k_export<true>, std::min<uint32_t>((uint32_t) ((c->cap + 255) / 256), (uint32_t) c->sm_count * 8u), 256, 0, a, c->cur, local_out(c), c->d_scal, side ? 2 : 1);
 	uint32_t n = 0;
 	LS1_CUDA(cudaMemcpyAsync(&n, c->msg_out[side], 4, cudaMemcpyDeviceToHost, c->stream));
 	LS1_CUDA(cudaStreamSynchronize(c->stream));

@@ -31,10 +31,11 @@ __device__ __forceinline__ void q_differentiate(const double* q, const double* w
 // VelocityScalingThermostat::apply does between two steps; nothing reads v or L in between).
 __global__ void __launch_bounds__(256) k_leapfrog_pre(State st, const double* __restrict__ F, const double* __restrict__ M, uint32_t cap,
                                                        const CompDev* __restrict__ comps, double dt, const DevScalars* __restrict__ scal,
-                                                       uint32_t parity, int use_beta, int rotates) {
+                                                       uint32_t parity, int use_beta, int rotates, Region rg) {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (scal->overflow) return;      // a failed step (lost message, peer time-out, another rank's fault): the state stays as it is
 	if (t >= min(scal->n_slots2[parity], cap)) return;
+	if (!region_selected(rg, t, scal->n_sorted)) return;
 	const uint64_t meta = st.meta[t];
 	if (meta_halo(meta)) return;
 	const CompDev& cp = comps[meta_cid(meta)];
@@ -73,12 +74,13 @@ __global__ void __launch_bounds__(256) k_leapfrog_pre(State st, const double* __
 // The same two kernels for ensembles without rotation, two slots per thread with 16-byte loads / stores (the slot planes are
 // 16-byte aligned and the capacity is even): more bytes in flight per thread, the streaming kernels get closer to the HBM roofline.
 __global__ void __launch_bounds__(256) k_leapfrog_pre_v2(State st, const double* __restrict__ F, uint32_t cap, const CompDev* __restrict__ comps, double dt,
-                                                          const DevScalars* __restrict__ scal, uint32_t parity, int use_beta) {
+                                                          const DevScalars* __restrict__ scal, uint32_t parity, int use_beta, Region rg) {
 	const uint32_t t = 2u * (blockIdx.x * blockDim.x + threadIdx.x);
 	const uint32_t n = min(scal->n_slots2[parity], cap);
 	if (t >= n || scal->overflow) return;      // overflow: see k_leapfrog_pre
 	const ulonglong2 m2 = *reinterpret_cast<const ulonglong2*>(st.meta + t);
-	const bool on0 = !meta_halo(m2.x), on1 = (t + 1 < n) && !meta_halo(m2.y);
+	const uint32_t ns = scal->n_sorted;
+	const bool on0 = !meta_halo(m2.x) && region_selected(rg, t, ns), on1 = (t + 1 < n) && !meta_halo(m2.y) && region_selected(rg, t + 1, ns);
 	if (!on0 && !on1) return;
 	const double bt = use_beta ? scal->beta_trans : 1.;
 	const double dth = .5 * dt;
@@ -208,14 +210,23 @@ int do_forces(ls1b200_ctx* c) {
 	return 0;
 }
 
-int do_leapfrog_pre(ls1b200_ctx* c, double dt, bool use_beta) {
+Region make_region(const ls1b200_ctx* c, int mode) {
+	Region rg;
+	rg.cell_of = c->cell_of2; rg.ncells = c->geom.ncells; rg.nx = c->geom.cells[0]; rg.ny = c->geom.cells[1]; rg.nz = c->geom.cells[2];
+	for (int d = 0; d < 3; d++) rg.cut[d] = c->dd.active && c->dd.grid[d] > 1;
+	rg.mode = mode;
+	return rg;
+}
+
+int do_leapfrog_pre(ls1b200_ctx* c, double dt, bool use_beta, int region) {
 	if (c->n_owned == 0 && !c->dd.active) return 0;
 	LS1_TRY(span_begin(c, PH_PRE));
 	const uint32_t g = (uint32_t) ((c->cap + 255) / 256);
+	const Region rg = make_region(c, region);
 	if (!c->rotates && c->cap % 2 == 0)
-		LS1_LAUNCH(c, PH_PRE, k_leapfrog_pre_v2, (g + 1) / 2, 256, 0, c->cur, c->F, (uint32_t) c->cap, c->d_comps, dt, c->d_scal, c->parity, (int) use_beta);
+		LS1_LAUNCH(c, PH_PRE, k_leapfrog_pre_v2, (g + 1) / 2, 256, 0, c->cur, c->F, (uint32_t) c->cap, c->d_comps, dt, c->d_scal, c->parity, (int) use_beta, rg);
 	else
-	LS1_LAUNCH(c, PH_PRE, k_leapfrog_pre, g, 256, 0, c->cur, c->F, c->M, (uint32_t) c->cap, c->d_comps, dt, c->d_scal, c->parity, (int) use_beta, (int) c->rotates);
+	LS1_LAUNCH(c, PH_PRE, k_leapfrog_pre, g, 256, 0, c->cur, c->F, c->M, (uint32_t) c->cap, c->d_comps, dt, c->d_scal, c->parity, (int) use_beta, (int) c->rotates, rg);
 	LS1_TRY(span_end(c));
 	c->forces_valid = false;
 	return 0;
@@ -311,10 +322,36 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 	// thermostat factors of the previous call have already been applied: start from 1
 	c->h_scal->beta_trans = 1.; c->h_scal->beta_rot = 1.;
 	LS1_CUDA(cudaMemcpyAsync(&c->d_scal->beta_trans, &c->h_scal->beta_trans, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	// Multi-GPU: the exchange is overlapped with the work on the INNER slots (Region, common.cuh) -- the analogue of the reference's
+	// overlapping scheme (parallel/NonBlockingMPIMultiStepHandler.cpp:28-93: inner cells are processed while the messages travel), at
+	// the stages that do not need the imports: boundary slots are integrated first, then the three export / transport / import
+	// stages run on their own stream while the main stream integrates the inner slots and builds their part of the cell
+	// histogram; the sort proper waits for the imports. (The force traversal cannot start earlier: one cell-sorted slot array.)
+	const bool overlap = c->dd.active && c->overlap && c->ever_sorted && (c->dd.comm || c->peer_ok);
+	if (overlap && !c->stream_x) {
+		LS1_CUDA(cudaStreamCreateWithFlags(&c->stream_x, cudaStreamNonBlocking));
+		LS1_CUDA(cudaEventCreateWithFlags(&c->ev_xa, cudaEventDisableTiming)); LS1_CUDA(cudaEventCreateWithFlags(&c->ev_xb, cudaEventDisableTiming));
+	}
 	for (uint64_t s = 0; s < n_steps; s++) {
+		if (overlap) {
+			LS1_TRY(do_leapfrog_pre(c, dt, target_temperature > 0., 1));      // boundary slots: what the exchange reads
+			LS1_CUDA(cudaEventRecord(c->ev_xa, c->stream));
+			LS1_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_xa, 0));
+			cudaStream_t main_stream = c->stream;
+			c->stream = c->stream_x; c->xchg_phase = PH_XCHG;
+			const int rc = do_exchange(c);                                      // export -> NVLink / NCCL -> import, three stages, on stream_x
+			c->stream = main_stream; c->xchg_phase = PH_UPDATE;
+			if (rc) return rc;
+			LS1_CUDA(cudaEventRecord(c->ev_xb, c->stream_x));
+			LS1_TRY(do_leapfrog_pre(c, dt, target_temperature > 0., 2));      // inner slots, beside the exchange
+			LS1_TRY(do_update(c, 1));                                           // ... and their keys / histogram
+			LS1_CUDA(cudaStreamWaitEvent(c->stream, c->ev_xb, 0));
+			LS1_TRY(do_update(c, 2));                                           // boundary slots + imports, scan, scatter, gather
+		} else {
 		LS1_TRY(do_leapfrog_pre(c, dt, target_temperature > 0.));
 		LS1_TRY(do_exchange(c));                 // multi-GPU: leaving molecules + halo copies over NCCL (no-op on one GPU)
 		LS1_TRY(do_update(c));
+		}
 		LS1_TRY(do_forces(c));
 		LS1_TRY(do_leapfrog_post(c, dt));
 		LS1_TRY(do_allreduce_scalars(c));        // multi-GPU: Upot, virial, sum m v^2, sum I w^2 over the ranks

@@ -39,9 +39,10 @@ __device__ __forceinline__ bool code_valid(uint32_t mask, int a, int b, int c) {
 }
 
 __global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __restrict__ key, uint32_t* __restrict__ count, uint32_t* __restrict__ count_halo,
-                                              uint32_t* __restrict__ rank, const DevScalars* __restrict__ scal) {
+                                              uint32_t* __restrict__ rank, const DevScalars* __restrict__ scal, Region rg) {
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	const bool in_range = s < min(scal->n_slots2[a.parity], a.cap);
+	// (overlapped multi-GPU step: two launches, inner slots before the imports have arrived, the rest after -- every slot in exactly one)
+	const bool in_range = s < min(scal->n_slots2[a.parity], a.cap) && region_selected(rg, s, scal->n_sorted);
 	const Geom& g = a.g;
 	uint32_t bin = KEY_NONE, mask = 0, sub = 0;      // bin: FINE bin (reference cell * S + x sub-bin)
 	double x = 0., y = 0., z = 0.;
@@ -285,7 +286,9 @@ int launch_bin_scan(ls1b200_ctx* c, uint32_t nb, uint32_t* fstart, uint32_t pari
 	return 0;
 }
 
-int do_update(ls1b200_ctx* c) {
+Region make_region(const ls1b200_ctx* c, int mode);      // integrate.cu
+
+int do_update(ls1b200_ctx* c, int part) {
 	if (!c->components_set) return fail("ls1b200_update: components not set");
 	if (c->n_owned == 0 && !c->dd.active) { c->sorted = true; return 0; }
 	if (c->cap == 0) return fail("ls1b200_update: call ls1b200_upload first");
@@ -293,10 +296,11 @@ int do_update(ls1b200_ctx* c) {
 	UpdArgs a; a.g = c->geom; a.cap = (uint32_t) c->cap; a.parity = c->parity; a.S = c->fine_s; a.logS = c->fine_s == 8 ? 3u : c->fine_s == 4 ? 2u : c->fine_s == 2 ? 1u : 0u; a.finv = c->fine_inv;
 	a.bx = c->d_border; a.by = c->d_border + c->border_stride; a.bz = c->d_border + 2 * (size_t) c->border_stride;
 	const uint32_t nb = c->geom.ncells * c->fine_s + 1;   // fine bins + limbo bin
-	LS1_CUDA(cudaMemsetAsync(c->cell_count, 0, sizeof(uint32_t) * 2 * ((size_t) c->geom.ncells * c->fine_s + 4), c->stream));      // cell_count and cell_count_halo
 	// slot counts are only known on the device: every per-slot kernel is launched over the capacity, threads beyond exit
 	const uint32_t gs = (uint32_t) ((c->cap + 255) / 256);
-	LS1_LAUNCH(c, PH_UPDATE, k_key, gs, 256, 0, a, c->cur, c->key, c->cell_count, c->cell_count_halo, c->rank, c->d_scal);
+	if (part != 2) LS1_CUDA(cudaMemsetAsync(c->cell_count, 0, sizeof(uint32_t) * 2 * ((size_t) c->geom.ncells * c->fine_s + 4), c->stream));      // cell_count and cell_count_halo
+	LS1_LAUNCH(c, PH_UPDATE, k_key, gs, 256, 0, a, c->cur, c->key, c->cell_count, c->cell_count_halo, c->rank, c->d_scal, make_region(c, part == 0 ? 0 : part == 1 ? 2 : 1));
+	if (part == 1) { LS1_TRY(span_end(c)); return 0; }
 	// cell_start_fine: exclusive scan over the fine bins; cell_start (the reference cells) is every S-th entry of it
 	uint32_t* fstart = c->fine_s > 1 ? c->cell_start_fine : c->cell_start;
 	LS1_TRY(launch_bin_scan(c, nb, fstart, a.parity));
