@@ -111,23 +111,19 @@ struct State {
 // sort (an import): exactly the slots k_export reads or writes and k_import appends. Everything else is INNER: nothing the exchange
 // does can touch it, so its integration and its histogram run on the main stream while the exchange runs beside them.
 struct Region {
-	const uint32_t* cell_of;      // cell of every slot at the last sort
-	uint32_t ncells;
-	int nx, ny, nz;
-	int cut[3];                   // the block has a neighbour rank in that dimension
+	const uint8_t* flag;          // per slot, written by the sort (k_gather): 1 = boundary cell (see above), 0 = inner
 	int mode;                     // 0: all slots, 1: boundary slots only, 2: inner slots only
 };
 __device__ __forceinline__ bool region_selected(const Region& rg, uint32_t slot, uint32_t n_sorted) {
 	if (rg.mode == 0) return true;
-	bool boundary = true;
-	if (slot < n_sorted) {
-		const uint32_t c = rg.cell_of[slot];
-		if (c < rg.ncells) {
-			const int cx = (int) (c % (uint32_t) rg.nx), cy = (int) ((c / (uint32_t) rg.nx) % (uint32_t) rg.ny), cz = (int) (c / (uint32_t) (rg.nx * rg.ny));
-			boundary = (rg.cut[0] && (cx <= 3 || cx + 4 >= rg.nx)) || (rg.cut[1] && (cy <= 3 || cy + 4 >= rg.ny)) || (rg.cut[2] && (cz <= 3 || cz + 4 >= rg.nz));
-		}
-	}
+	const bool boundary = slot >= n_sorted || rg.flag[slot] != 0;      // one byte per slot: the kernels the step is split into stay bandwidth bound
 	return boundary == (rg.mode == 1);
+}
+// the definition of a boundary cell (evaluated once per slot and sort)
+__device__ __forceinline__ bool cell_is_boundary(uint32_t c, uint32_t ncells, int nx, int ny, int nz, const int* cut) {
+	if (c >= ncells) return true;
+	const int cx = (int) (c % (uint32_t) nx), cy = (int) ((c / (uint32_t) nx) % (uint32_t) ny), cz = (int) (c / (uint32_t) (nx * ny));
+	return (cut[0] && (cx <= 3 || cx + 4 >= nx)) || (cut[1] && (cy <= 3 || cy + 4 >= ny)) || (cut[2] && (cz <= 3 || cz + 4 >= nz));
 }
 
 // scalars living on the device between kernels of one step
@@ -198,6 +194,7 @@ struct ls1b200_ctx {
 	uint32_t* entry = nullptr;        // [cap] src << 5 | shift code, per provisional slot
 	uint32_t* cell_of = nullptr;      // [cap] cell of provisional / final slot
 	uint32_t* cell_of2 = nullptr;     // [cap]
+	uint8_t* region_flag = nullptr;   // [cap] decomposed contexts: 1 = slot in a boundary cell of a cut dimension (Region)
 
 	// calc-precision copies
 	void* mpos = nullptr;             // float4 / double4 [cap]
@@ -212,7 +209,7 @@ struct ls1b200_ctx {
 	float* rmm_r[2] = {nullptr, nullptr}; float* rmm_v[2] = {nullptr, nullptr}; uint64_t* rmm_id[2] = {nullptr, nullptr};
 	int rmm_cur = 0; bool rmm = false;
 	// overlapped multi-GPU step (ls1b200_simulate on decomposed contexts): the exchange runs on its own stream beside the inner slots' work
-	cudaStream_t stream_x = nullptr; cudaEvent_t ev_xa = nullptr, ev_xb = nullptr; int overlap = 1; int xchg_phase = 0;
+	cudaStream_t stream_x = nullptr; cudaEvent_t ev_xa = nullptr, ev_xb = nullptr; int overlap = 0; int xchg_phase = 0; int split_test = 0;      // overlap: LS1B200_OVERLAP=1 (measured neutral to slower, profiles/r02_multi_gpu.md: off by default)
 	void* chunks2 = nullptr; size_t chunks2_bytes = 0;      // molecule-granular chunk list of force_1clj_v3.cu
 	int lj_kernel = 0;                // LS1B200_LJ_KERNEL: 0 tiled (default; shared-memory windows, TMA), 1 "global" (force_1clj.cu), 3 "mma" / 4 "tc": tensor-core prefilter experiments (force_1clj_mma.cu, force_1clj_tc.cu; measured slower, profiles/r01_tensor_prefilter.md), 5 "v3": molecule-granular chunks + x-trimmed ranges over fine bins (force_1clj_v3.cu; measured slower, profiles/r02_force_kernel_experiments.md)
 	int multi_pd2 = 0;                // LS1B200_MULTI_PD2=1: prefetch the site records of two neighbours ahead instead of one

@@ -268,6 +268,7 @@ int ls1b200_create(const ls1b200_config* cfg, ls1b200_ctx** out) {
 		if (const char* ms = getenv("LS1B200_MULTI_STAGE")) c->multi_stage = atoi(ms);
 		if (const char* mp = getenv("LS1B200_MULTI_PD2")) c->multi_pd2 = atoi(mp);
 		if (const char* ov = getenv("LS1B200_OVERLAP")) c->overlap = atoi(ov);
+		if (const char* st = getenv("LS1B200_SPLIT_TEST")) c->split_test = atoi(st);
 		c->multi_kernel = (m && std::string(m) == "general") ? 1 : (m && std::string(m) == "generic") ? 2 : 0;   // 2: tiled, but never specialised
 	}
 	if (dev_alloc(&c->d_scal, 1) || dev_alloc(&c->partials2, 1024 * 8)) return cleanup(1);
@@ -458,6 +459,10 @@ static int sync_scalars(ls1b200_ctx* c, bool owned_index = false) {
 int ls1b200_update(ls1b200_ctx* c) {
 	if (!c) return fail("ls1b200_update: null context");
 	LS1_CUDA(cudaSetDevice(c->device));
+	if (c->split_test && c->dd.active && c->region_flag && c->ever_sorted) {      // LS1B200_SPLIT_TEST: inner slots' histogram first, then the rest + the sort
+		LS1_TRY(do_update(c, 1));
+		LS1_TRY(do_update(c, 2));
+	} else
 	LS1_TRY(do_update(c));
 	return sync_scalars(c);
 }

@@ -88,6 +88,10 @@ struct XArgs {
 	// a molecule that leaves or needs a halo copy (a molecule moves less than a cell per step); cell_of == nullptr: scan everything
 	const uint32_t* cell_of;
 	uint32_t cstride, ncd, ncells;         // cell coordinate in dim = (cell / cstride) % ncd
+	// the same filter as slot RANGES (slots are cell sorted): k_export walks only the rows / row ends within four cell layers of the
+	// two faces of dimension dim, the limbo bin and the slots appended after the sort -- work proportional to the boundary, not to N
+	const uint32_t* cell_start;
+	int nx, ny, nz;
 };
 
 // writes one record (local message buffer or, peer transport, the neighbour's receive buffer over NVLink)
@@ -134,15 +138,41 @@ __global__ void __launch_bounds__(256) k_export(XArgs a, State st, XOut o, DevSc
 	constexpr int REC = FULL ? (int) sizeof(ls1b200_particle) : (int) sizeof(RecCompact);
 	__shared__ __align__(16) unsigned char stage[8][32 * REC];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
-	for (uint32_t s0 = blockIdx.x * blockDim.x; s0 < n_slots; s0 += gridDim.x * blockDim.x) {
-	const uint32_t s = s0 + threadIdx.x;
+	// Work units of one warp: a cell range of one x-row (d = 0: the four cells at either end of every row; d = 1, 2: the whole rows of
+	// the four layers at either face), or 32 slots of the tail (limbo bin + slots appended after the sort). Without a valid sort
+	// (first exchange after an upload) the tail is everything.
+	const bool ranged = a.cell_of != nullptr;
+	const int lay = 4;
+	const int nb0 = min(2 * lay, a.nx), nb1 = min(2 * lay, a.ny), nb2 = min(2 * lay, a.nz);
+	const uint32_t ntask = !ranged ? 0u : a.dim == 0 ? (uint32_t) (a.ny * a.nz) * (a.nx > 2 * lay ? 2u : 1u) : a.dim == 1 ? (uint32_t) (a.nz * nb1) : (uint32_t) (nb2 * a.ny);
+	const uint32_t tail0 = ranged ? min(a.cell_start[a.ncells], n_sorted) : 0u;
+	const uint32_t ntail = n_slots > tail0 ? (n_slots - tail0 + 31u) / 32u : 0u;
+	(void) nb0;
+	for (uint32_t task = blockIdx.x * 8u + (uint32_t) wid; task < ntask + ntail; task += gridDim.x * 8u) {
+	uint32_t rb, re;
+	if (task >= ntask) { rb = tail0 + (task - ntask) * 32u; re = min(rb + 32u, n_slots); }
+	else if (a.dim == 0) {
+		const bool two = a.nx > 2 * lay;
+		const uint32_t row = two ? task >> 1 : task;
+		const int c0 = !two ? 0 : (task & 1u) ? a.nx - lay : 0, c1 = !two ? a.nx : (task & 1u) ? a.nx : lay;
+		rb = a.cell_start[row * (uint32_t) a.nx + c0]; re = a.cell_start[row * (uint32_t) a.nx + c1];
+	} else if (a.dim == 1) {
+		const int cz = (int) (task / (uint32_t) nb1), k = (int) (task % (uint32_t) nb1);
+		const int cy = a.ny <= 2 * lay ? k : (k < lay ? k : a.ny - 2 * lay + k);
+		const uint32_t row = (uint32_t) (cz * a.ny + cy);
+		rb = a.cell_start[row * (uint32_t) a.nx]; re = a.cell_start[(row + 1u) * (uint32_t) a.nx];
+	} else {
+		const int k = (int) (task / (uint32_t) a.ny), cy = (int) (task % (uint32_t) a.ny);
+		const int cz = a.nz <= 2 * lay ? k : (k < lay ? k : a.nz - 2 * lay + k);
+		const uint32_t row = (uint32_t) (cz * a.ny + cy);
+		rb = a.cell_start[row * (uint32_t) a.nx]; re = a.cell_start[(row + 1u) * (uint32_t) a.nx];
+	}
+	re = min(re, n_slots);
+	for (uint32_t s0 = rb; s0 < re; s0 += 32u) {
+	const uint32_t s = s0 + (uint32_t) lane;
 	bool want[2] = {false, false}; double xn[2] = {0., 0.}; uint32_t fl[2] = {0u, 0u};
 	uint64_t meta = 0;
-	bool candidate = s < n_slots;
-	if (candidate && a.cell_of && s < n_sorted) {
-		const uint32_t cell = a.cell_of[s];
-		if (cell < a.ncells) { const uint32_t k = (cell / a.cstride) % a.ncd; candidate = k <= 3u || k + 4u >= a.ncd; }
-	}
+	const bool candidate = s < re;
 	if (candidate) {
 		meta = st.meta[s];
 		const bool halo = meta_halo(meta);
@@ -212,6 +242,7 @@ __global__ void __launch_bounds__(256) k_export(XArgs a, State st, XOut o, DevSc
 			for (uint32_t i = lane; i < n_copy * (REC / 16); i += 32) dst[i] = src[i];
 		}
 		__syncwarp();
+	}
 	}
 	}
 }
@@ -381,6 +412,7 @@ static XArgs stage_args(const ls1b200_ctx* c, int d) {
 	a.cell_of = c->ever_sorted ? c->cell_of2 : nullptr;
 	a.cstride = d == 0 ? 1u : d == 1 ? (uint32_t) c->geom.cells[0] : (uint32_t) (c->geom.cells[0] * c->geom.cells[1]);
 	a.ncd = (uint32_t) c->geom.cells[d]; a.ncells = c->geom.ncells;
+	a.cell_start = c->cell_start; a.nx = c->geom.cells[0]; a.ny = c->geom.cells[1]; a.nz = c->geom.cells[2];
 	return a;
 }
 
@@ -412,6 +444,10 @@ int decomp_alloc(ls1b200_ctx* c) {
 		LS1_CUDA(cudaMemsetAsync(c->msg_in[k], 0, MSG_HEADER, c->stream));
 	}
 	LS1_CUDA(cudaMalloc((void**) &c->ekey, sizeof(uint64_t) * c->cap));
+	if (c->overlap || c->split_test) {      // the split step's per-slot region flag (k_gather writes it)
+		LS1_CUDA(cudaMalloc((void**) &c->region_flag, c->cap));
+		LS1_CUDA(cudaMemsetAsync(c->region_flag, 1, c->cap, c->stream));
+	}
 	// receive buffers of the peer-memory transport: [step parity][stage][side], one allocation (one IPC handle)
 	c->pin_stride = (bytes + 255) & ~(size_t) 255;
 	LS1_CUDA(cudaMalloc((void**) &c->pin_base, 12 * c->pin_stride));
@@ -427,6 +463,7 @@ void decomp_free(ls1b200_ctx* c) {
 		if (c->msg_in[k]) cudaFree(c->msg_in[k]); c->msg_in[k] = nullptr;
 	}
 	if (c->ekey) cudaFree(c->ekey); c->ekey = nullptr;
+	if (c->region_flag) cudaFree(c->region_flag); c->region_flag = nullptr;
 	for (int k = 0; k < 6; k++) { if (c->peer_opened[k]) cudaIpcCloseMemHandle(c->peer_opened[k]); c->peer_opened[k] = nullptr; c->peer_opened_rank[k] = -1; }
 	for (int d = 0; d < 3; d++) c->peer_base[d][0] = c->peer_base[d][1] = nullptr;
 	c->peer_ok = false;

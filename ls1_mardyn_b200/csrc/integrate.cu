@@ -78,9 +78,11 @@ __global__ void __launch_bounds__(256) k_leapfrog_pre_v2(State st, const double*
 	const uint32_t t = 2u * (blockIdx.x * blockDim.x + threadIdx.x);
 	const uint32_t n = min(scal->n_slots2[parity], cap);
 	if (t >= n || scal->overflow) return;      // overflow: see k_leapfrog_pre
-	const ulonglong2 m2 = *reinterpret_cast<const ulonglong2*>(st.meta + t);
 	const uint32_t ns = scal->n_sorted;
-	const bool on0 = !meta_halo(m2.x) && region_selected(rg, t, ns), on1 = (t + 1 < n) && !meta_halo(m2.y) && region_selected(rg, t + 1, ns);
+	const bool sel0 = region_selected(rg, t, ns), sel1 = (t + 1 < n) && region_selected(rg, t + 1, ns);      // 4 bytes per slot: the other region's slots cost nothing more
+	if (!sel0 && !sel1) return;
+	const ulonglong2 m2 = *reinterpret_cast<const ulonglong2*>(st.meta + t);
+	const bool on0 = sel0 && !meta_halo(m2.x), on1 = sel1 && !meta_halo(m2.y);
 	if (!on0 && !on1) return;
 	const double bt = use_beta ? scal->beta_trans : 1.;
 	const double dth = .5 * dt;
@@ -212,9 +214,7 @@ int do_forces(ls1b200_ctx* c) {
 
 Region make_region(const ls1b200_ctx* c, int mode) {
 	Region rg;
-	rg.cell_of = c->cell_of2; rg.ncells = c->geom.ncells; rg.nx = c->geom.cells[0]; rg.ny = c->geom.cells[1]; rg.nz = c->geom.cells[2];
-	for (int d = 0; d < 3; d++) rg.cut[d] = c->dd.active && c->dd.grid[d] > 1;
-	rg.mode = mode;
+	rg.flag = c->region_flag; rg.mode = c->region_flag ? mode : 0;
 	return rg;
 }
 
@@ -266,6 +266,10 @@ extern "C" {
 int ls1b200_leapfrog_pre(ls1b200_ctx* c, double dt) {
 	if (!c) return fail("ls1b200_leapfrog_pre: null context");
 	LS1_CUDA(cudaSetDevice(c->device));
+	if (c->split_test && c->dd.active && c->region_flag && c->ever_sorted) {      // LS1B200_SPLIT_TEST: the two launches of the overlapped step, back to back
+		LS1_TRY(do_leapfrog_pre(c, dt, false, 1));
+		return do_leapfrog_pre(c, dt, false, 2);
+	}
 	return do_leapfrog_pre(c, dt, false);
 }
 
@@ -327,9 +331,13 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 	// the stages that do not need the imports: boundary slots are integrated first, then the three export / transport / import
 	// stages run on their own stream while the main stream integrates the inner slots and builds their part of the cell
 	// histogram; the sort proper waits for the imports. (The force traversal cannot start earlier: one cell-sorted slot array.)
-	const bool overlap = c->dd.active && c->overlap && c->ever_sorted && (c->dd.comm || c->peer_ok);
+	const bool overlap = c->dd.active && c->overlap && c->region_flag && c->ever_sorted && (c->dd.comm || c->peer_ok);
 	if (overlap && !c->stream_x) {
-		LS1_CUDA(cudaStreamCreateWithFlags(&c->stream_x, cudaStreamNonBlocking));
+		// highest priority: the exchange is a chain of small kernels (scan, publish, wait, append) whose blocks must not queue behind
+		// the thousands of blocks of the streaming kernels it runs beside
+		int prio_lo = 0, prio_hi = 0;
+		LS1_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+		LS1_CUDA(cudaStreamCreateWithPriority(&c->stream_x, cudaStreamNonBlocking, prio_hi));
 		LS1_CUDA(cudaEventCreateWithFlags(&c->ev_xa, cudaEventDisableTiming)); LS1_CUDA(cudaEventCreateWithFlags(&c->ev_xb, cudaEventDisableTiming));
 	}
 	for (uint64_t s = 0; s < n_steps; s++) {

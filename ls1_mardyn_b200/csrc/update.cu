@@ -27,6 +27,7 @@ constexpr uint32_t RANK_BITS = 28, RANK_MASK = (1u << RANK_BITS) - 1u;      // r
 struct UpdArgs {
 	Geom g;
 	uint32_t cap;
+	int cut[3];          // decomposed contexts: the block has a neighbour rank in that dimension (k_gather flags the boundary slots)
 	uint32_t S, logS;    // fine x-bins per reference cell (1, 2, 4 or 8 = 1 << logS); histogram bin = cell * S + fine_sub (limbo: ncells * S)
 	double finv;         // S / cell length in x
 	uint32_t parity;     // DevScalars::n_slots2[parity] = source slots of this update, [parity^1] receives the new count
@@ -42,7 +43,7 @@ __global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __r
                                               uint32_t* __restrict__ rank, const DevScalars* __restrict__ scal, Region rg) {
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	// (overlapped multi-GPU step: two launches, inner slots before the imports have arrived, the rest after -- every slot in exactly one)
-	const bool in_range = s < min(scal->n_slots2[a.parity], a.cap) && region_selected(rg, s, scal->n_sorted);
+	const bool in_range = s < min(scal->n_slots2[a.parity], a.cap) && region_selected(rg, s, scal->n_sorted);      // the region test reads 4 bytes per slot, before anything else
 	const Geom& g = a.g;
 	uint32_t bin = KEY_NONE, mask = 0, sub = 0;      // bin: FINE bin (reference cell * S + x sub-bin)
 	double x = 0., y = 0., z = 0.;
@@ -196,7 +197,8 @@ template <class C>
 __global__ void __launch_bounds__(256) k_gather(UpdArgs a, State cur, State nxt, const uint32_t* __restrict__ entry, const uint32_t* __restrict__ cell_of,
                                                  const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_of2,
                                                  typename Vec4<C>::type* __restrict__ mpos, const DevScalars* __restrict__ scal, int rotates,
-                                                 double* __restrict__ F, double* __restrict__ Vi, double* __restrict__ M, const uint64_t* __restrict__ ekey) {
+                                                 double* __restrict__ F, double* __restrict__ Vi, double* __restrict__ M, const uint64_t* __restrict__ ekey,
+                                                 uint8_t* __restrict__ region_flag) {
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	const uint32_t n_slots = min(scal->n_slots2[a.parity ^ 1u], a.cap);
 	if (p >= n_slots) return;
@@ -229,6 +231,7 @@ __global__ void __launch_bounds__(256) k_gather(UpdArgs a, State cur, State nxt,
 		for (int d = 0; d < 3; d++) nxt.L[d * cap + t] = cur.L[d * cap + s];
 	}
 	cell_of2[t] = c;
+	if (region_flag) region_flag[t] = cell_is_boundary(c, g.ncells, g.cells[0], g.cells[1], g.cells[2], a.cut) ? 1 : 0;
 	// the limbo bin and halo cells never hold "i" molecules: flag them like halo copies in the calc record
 	const bool inert = meta_halo(meta) || c >= g.ncells || is_halo_cell(g, c);
 	mpos[t] = make_mrec<C>(x, y, z, meta_cid(meta) | (inert ? 0x80000000u : 0u));
@@ -293,7 +296,8 @@ int do_update(ls1b200_ctx* c, int part) {
 	if (c->n_owned == 0 && !c->dd.active) { c->sorted = true; return 0; }
 	if (c->cap == 0) return fail("ls1b200_update: call ls1b200_upload first");
 	LS1_TRY(span_begin(c, PH_UPDATE));
-	UpdArgs a; a.g = c->geom; a.cap = (uint32_t) c->cap; a.parity = c->parity; a.S = c->fine_s; a.logS = c->fine_s == 8 ? 3u : c->fine_s == 4 ? 2u : c->fine_s == 2 ? 1u : 0u; a.finv = c->fine_inv;
+	UpdArgs a; a.g = c->geom; a.cap = (uint32_t) c->cap; a.parity = c->parity; for (int d = 0; d < 3; d++) a.cut[d] = c->dd.active && c->dd.grid[d] > 1;
+	a.S = c->fine_s; a.logS = c->fine_s == 8 ? 3u : c->fine_s == 4 ? 2u : c->fine_s == 2 ? 1u : 0u; a.finv = c->fine_inv;
 	a.bx = c->d_border; a.by = c->d_border + c->border_stride; a.bz = c->d_border + 2 * (size_t) c->border_stride;
 	const uint32_t nb = c->geom.ncells * c->fine_s + 1;   // fine bins + limbo bin
 	// slot counts are only known on the device: every per-slot kernel is launched over the capacity, threads beyond exit
@@ -307,9 +311,9 @@ int do_update(ls1b200_ctx* c, int part) {
 	LS1_LAUNCH(c, PH_UPDATE, k_scatter, gs, 256, 0, a, c->cur, c->key, c->rank, (const uint32_t*) fstart, c->cursor, c->entry, c->cell_of, c->d_scal, c->dd.active ? c->ekey : (uint64_t*) nullptr);
 	const uint32_t gc = gs;
 	if (c->mixed)
-		LS1_LAUNCH(c, PH_UPDATE, k_gather<float>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, (const uint32_t*) fstart, c->cell_of2, (float4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr);
+		LS1_LAUNCH(c, PH_UPDATE, k_gather<float>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, (const uint32_t*) fstart, c->cell_of2, (float4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr, c->region_flag);
 	else
-		LS1_LAUNCH(c, PH_UPDATE, k_gather<double>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, (const uint32_t*) fstart, c->cell_of2, (double4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr);
+		LS1_LAUNCH(c, PH_UPDATE, k_gather<double>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, (const uint32_t*) fstart, c->cell_of2, (double4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr, c->region_flag);
 	std::swap(c->cur, c->nxt);
 	c->parity ^= 1u;
 	if (!c->all_1clj) {

@@ -174,6 +174,17 @@ def test_multisite_blocks(capi, n_ranks, prec):
     assert np.abs(qg - one.download("Q")[o1]).max() <= (1e-9 if prec == "double" else 1e-4)
 
 
+@pytest.mark.parametrize("n_ranks", [2, 8])
+def test_split_step_kernels_on_one_device(capi, n_ranks, monkeypatch):
+    """The overlapped multi-GPU step integrates and bins BOUNDARY and INNER slots in separate launches (Region, csrc/common.cuh:
+    the exchange runs between them on its own stream inside ls1b200_simulate). With LS1B200_SPLIT_TEST=1 the phase calls of a
+    decomposed context run exactly those two launches back to back, so the partition of the slots -- every slot in exactly one
+    launch, imports with the boundary -- is checked on ONE device against the decomposed oracle, like the unsplit path."""
+    monkeypatch.setenv("LS1B200_SPLIT_TEST", "1")
+    test_blocks_on_one_device_vs_oracle(capi, n_ranks, None, "double")
+    test_multisite_blocks(capi, n_ranks, "double")
+
+
 @pytest.mark.parametrize("prec", ["double", "mixed"])
 def test_balanced_blocks_on_one_device(capi, prec):
     """Load-balanced decomposition (the tensor-product analogue of parallel/KDDecomposition.cpp): an inhomogeneous
@@ -227,14 +238,15 @@ def test_balanced_blocks_on_one_device(capi, prec):
         assert sum(k.n_molecules for k in kg) == len(ps.id)
 
 
-@pytest.mark.parametrize("transport", ["peer", "nccl"])
+@pytest.mark.parametrize("transport", ["peer", "nccl", "peer-overlap", "nccl-overlap"])
 def test_nccl_two_gpus(capi, tmp_path, transport):
     """The transports inside the library (ls1b200_exchange inside ls1b200_simulate), one process per GPU: records stored
-    straight into the neighbour's memory over NVLink (CUDA IPC, ls1b200_peer_attach), and NCCL send / recv."""
+    straight into the neighbour's memory over NVLink (CUDA IPC, ls1b200_peer_attach), and NCCL send / recv; "-overlap": the
+    exchange on its own stream beside the integration / binning of the inner slots (LS1B200_OVERLAP=1)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29641",
            os.path.join(ROOT, "tests", "nccl_decomposition_worker.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PYTHONPATH=ROOT, LS1B200_TRANSPORT=transport))
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PYTHONPATH=ROOT, LS1B200_TRANSPORT=transport.split("-")[0], LS1B200_OVERLAP="1" if transport.endswith("overlap") else "0"))
     assert p.returncode == 0 and "NCCL-DECOMP-OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]
