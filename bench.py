@@ -545,6 +545,18 @@ def our_arm(args):
             ms = ph_ms[name] / max(args.steps, 1)
             hbm[name] = {"ms": round(ms, 4), "algorithmic_bytes_per_molecule": bpm, "achieved_gbs": round(bpm * N / (ms * 1e-3) / 1e9, 1) if ms > 0 else None,
                          "frac": round(bpm * N / (ms * 1e-3) / 1e9 / hbm_peak, 4) if ms > 0 else None}
+        # Fused step of ls1b200_simulate (ensembles without rotation, tiled 1CLJ kernel; LS1B200_FUSED=0 turns it off): the second half
+        # kick and the binning run inside the first kernel of the next step, the kinetic sum inside the force kernel -- the three
+        # phases no longer map onto SURVEY 8(d)'s three byte counts one by one, so the roofline is taken over their SUM:
+        # 356 B of algorithmic traffic per molecule (164 + 120 + 72) over the time of everything in the step that is not the force kernel.
+        fused = os.environ.get("LS1B200_FUSED", "1") != "0" and wl.name in ("lj", "argon") and not os.environ.get("LS1B200_LJ_KERNEL") and args.steps >= 2
+        if fused:
+            ms = sum(ph_ms[k] for k in ("update", "leapfrog_pre", "leapfrog_post")) / max(args.steps, 1)
+            hbm = {"fused_step": True,
+                   "integrate_bin_sort": {"ms": round(ms, 4), "algorithmic_bytes_per_molecule": 356.0, "achieved_gbs": round(356.0 * N / (ms * 1e-3) / 1e9, 1),
+                                          "frac": round(356.0 * N / (ms * 1e-3) / 1e9 / hbm_peak, 4),
+                                          "note": "update + leapfrog_pre + leapfrog_post of SURVEY 8(d) = 164 + 120 + 72 B; the fused kernels move less than that (the state is read and written once)"},
+                   "phase_ms": {k: round(ph_ms[k] / max(args.steps, 1), 4) for k in ("update", "leapfrog_pre", "leapfrog_post")}}
         double = args.precision == "double"
         peak = fp64_peak if double else fp32_peak
         traffic, traffic_src = FORCE_TRAFFIC.get((wl.name, args.precision, N), (None, None))

@@ -14,7 +14,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 OBJ = os.path.join(HERE, "csrc", "build")
 LIB = os.path.join(HERE, "libls1b200.so")
-SOURCES = ["context.cu", "update.cu", "force_general.cu", "force_1clj.cu", "force_1clj_tiled.cu", "force_1clj_v3.cu", "force_1clj_mma.cu", "force_1clj_tc.cu", "force_multi_tiled.cu", "integrate.cu", "measure.cu", "halo.cu", "generate.cu", "rmm.cu"]
+SOURCES = ["context.cu", "update.cu", "force_general.cu", "force_1clj.cu", "force_1clj_tiled.cu", "force_1clj_v3.cu", "force_1clj_pf.cu", "force_1clj_mma.cu", "force_1clj_tc.cu", "force_multi_tiled.cu", "integrate.cu", "measure.cu", "halo.cu", "generate.cu", "rmm.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17", "-Xcompiler", "-fPIC,-O2",
          "--expt-relaxed-constexpr", "-Xptxas", "-v"]

@@ -18,7 +18,7 @@ import numpy as np
 from .components import CComponent, CSite, Ensemble
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libls1b200.so")
+LIB_PATH = os.environ.get("LS1B200_LIB") or os.path.join(_HERE, "libls1b200.so")      # LS1B200_LIB: another build of the same library (kernel sweeps)
 _LIB = None
 
 FIELDS = dict(ID=0, CID=1, R=2, V=3, Q=4, L=5, F=6, M=7, VI=8, CELL=9)

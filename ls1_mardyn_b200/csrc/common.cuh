@@ -112,10 +112,11 @@ struct State {
 // does can touch it, so its integration and its histogram run on the main stream while the exchange runs beside them.
 struct Region {
 	const uint8_t* flag;          // per slot, written by the sort (k_gather): 1 = boundary cell (see above), 0 = inner
-	int mode;                     // 0: all slots, 1: boundary slots only, 2: inner slots only
+	int mode;                     // 0: all slots, 1: boundary slots only, 2: inner slots only, 3: only the slots appended behind the sorted ones (needs no flag)
 };
 __device__ __forceinline__ bool region_selected(const Region& rg, uint32_t slot, uint32_t n_sorted) {
 	if (rg.mode == 0) return true;
+	if (rg.mode == 3) return slot >= n_sorted;
 	const bool boundary = slot >= n_sorted || rg.flag[slot] != 0;      // one byte per slot: the kernels the step is split into stay bandwidth bound
 	return boundary == (rg.mode == 1);
 }
@@ -211,6 +212,7 @@ struct ls1b200_ctx {
 	// overlapped multi-GPU step (ls1b200_simulate on decomposed contexts): the exchange runs on its own stream beside the inner slots' work
 	cudaStream_t stream_x = nullptr; cudaEvent_t ev_xa = nullptr, ev_xb = nullptr; int overlap = 0; int xchg_phase = 0; int split_test = 0;      // overlap: LS1B200_OVERLAP=1 (measured neutral to slower, profiles/r02_multi_gpu.md: off by default)
 	void* chunks2 = nullptr; size_t chunks2_bytes = 0;      // molecule-granular chunk list of force_1clj_v3.cu
+	int pf_check = 0;                 // LS1B200_PF_CHECK=1: force_1clj_pf verifies that every window translation is exact (overflow code 6)
 	int lj_kernel = 0;                // LS1B200_LJ_KERNEL: 0 tiled (default; shared-memory windows, TMA), 1 "global" (force_1clj.cu), 3 "mma" / 4 "tc": tensor-core prefilter experiments (force_1clj_mma.cu, force_1clj_tc.cu; measured slower, profiles/r01_tensor_prefilter.md), 5 "v3": molecule-granular chunks + x-trimmed ranges over fine bins (force_1clj_v3.cu; measured slower, profiles/r02_force_kernel_experiments.md)
 	int multi_pd2 = 0;                // LS1B200_MULTI_PD2=1: prefetch the site records of two neighbours ahead instead of one
 	int multi_stage = 0;              // LS1B200_MULTI_STAGE=0: do not stage neighbour site records in shared memory (force_multi_tiled.cu)
@@ -220,6 +222,11 @@ struct ls1b200_ctx {
 	// reductions
 	double* partials = nullptr;       // [n_partial_blocks][8]
 	double* partials2 = nullptr;      // [1024][8] second reduction level
+	// chunk list of the tiled 1CLJ kernel built beside the sort's scatter / gather (it needs cell_start only): update.cu forks, force_1clj_tiled.cu joins
+	cudaStream_t stream_c = nullptr; cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr; bool chunks_ready = false; uint32_t chunks_nrows = 0; int chunks_early = 1;      // LS1B200_CHUNKS_EARLY=0: inside the force phase
+	double* partials_kin = nullptr;   // [n_partial_blocks][4] kinetic partial sums of the fused step (force_1clj_tiled.cu)
+	double kin_dth = 0.;              // != 0: the next force traversal also delivers sum m (v + kin_dth / m F)^2 (fused step of ls1b200_simulate)
+	int fused = 1;                    // LS1B200_FUSED=0: ls1b200_simulate runs the phases as separate kernels
 	uint32_t partial_blocks = 0;
 	ls1b200::DevScalars* d_scal = nullptr;
 	ls1b200::DevScalars* h_scal = nullptr;   // pinned
@@ -275,7 +282,9 @@ void rmm_release(ls1b200_ctx* c);          // rmm.cu
 void ctx_free_molecules(ls1b200_ctx* c);
 int span_begin(ls1b200_ctx* c, int phase);
 int span_end(ls1b200_ctx* c);
-int do_update(ls1b200_ctx* c, int part = 0);      // part 0: everything; 1: histogram of the INNER slots only (overlapped step); 2: the remaining slots + scan, scatter, gather
+int do_update(ls1b200_ctx* c, int part = 0);      // part 0: everything; 1: histogram of the INNER slots only (overlapped step); 2: the remaining slots + scan, scatter, gather; 3: after do_pre_key (imports + scan, scatter, gather)
+int build_chunks_tiled_1clj(ls1b200_ctx* c, uint32_t* nrows);      // force_1clj_tiled.cu: the chunk list of the production 1CLJ kernel (launches on c->stream)
+int do_pre_key(ls1b200_ctx* c, double dt, bool use_beta, bool post_kick);      // fused step: [post kick +] thermostat + pre kick + drift + binning (update.cu)
 int do_forces(ls1b200_ctx* c);
 int do_leapfrog_pre(ls1b200_ctx* c, double dt, bool use_beta, int region = 0);      // region: see Region::mode
 int do_leapfrog_post(ls1b200_ctx* c, double dt);
@@ -283,7 +292,9 @@ int do_globals(ls1b200_ctx* c, double target_T, uint64_t global_n, double global
 int force_general(ls1b200_ctx* c);
 int force_1clj(ls1b200_ctx* c);
 int force_1clj_tiled(ls1b200_ctx* c);
-int force_1clj_v3(ls1b200_ctx* c);          // round-2 production kernel (force_1clj_v3.cu)
+int force_1clj_v3(ls1b200_ctx* c);          // round-2 experiment (force_1clj_v3.cu)
+int force_1clj_pf(ls1b200_ctx* c);          // prefilter kernel, single-component FP32 (force_1clj_pf.cu)
+int force_1clj_pf_rmm(ls1b200_ctx* c, float* v, float dt_over_m);
 int force_1clj_mma(ls1b200_ctx* c);
 int force_1clj_tc(ls1b200_ctx* c);
 int force_multi_tiled(ls1b200_ctx* c);

@@ -67,7 +67,7 @@ void ctx_free_molecules(ls1b200_ctx* c) {
 	if (c->mpos) cudaFree(c->mpos); c->mpos = nullptr;
 	if (c->spos) cudaFree(c->spos); c->spos = nullptr;
 	if (c->sori) cudaFree(c->sori); c->sori = nullptr;
-	dev_free(c->sf); dev_free(c->partials);
+	dev_free(c->sf); dev_free(c->partials); dev_free(c->partials_kin);
 	decomp_free(c);
 	c->cap = 0; c->n_owned = 0; c->n_slots = 0;
 }
@@ -104,6 +104,7 @@ int ctx_alloc_molecules(ls1b200_ctx* c, uint64_t n_owned, uint64_t cap) {
 		c->partial_blocks = (uint32_t) std::max<uint64_t>(c->partial_blocks, (uint64_t) c->geom.ncells + cap / 32 + nrows + 64);
 	}
 	LS1_TRY(dev_alloc(&c->partials, (size_t) c->partial_blocks * 8));
+	LS1_TRY(dev_alloc(&c->partials_kin, (size_t) c->partial_blocks * 4));
 	if (c->dd.active) LS1_TRY(decomp_alloc(c));
 	LS1_CUDA(cudaMemsetAsync(c->F, 0, sizeof(double) * 3 * cap, c->stream));
 	LS1_CUDA(cudaMemsetAsync(c->Vi, 0, sizeof(double) * 3 * cap, c->stream));
@@ -262,7 +263,10 @@ int ls1b200_create(const ls1b200_config* cfg, ls1b200_ctx** out) {
 		if (dev_alloc(&c->chunk_row_count, nrows) || dev_alloc(&c->chunk_row_start, nrows) || dev_alloc(&c->work_counter, 4)) return cleanup(1);
 		cudaDeviceGetAttribute(&c->sm_count, cudaDevAttrMultiProcessorCount, c->device);
 		const char* k = getenv("LS1B200_LJ_KERNEL");
-		c->lj_kernel = (k && std::string(k) == "global") ? 1 : (k && std::string(k) == "mma") ? 3 : (k && std::string(k) == "tc") ? 4 : (k && std::string(k) == "v3") ? 5 : 0;      // default: the tiled kernel (v3 measured slower, profiles/r02_force_kernel_experiments.md)
+		c->lj_kernel = (k && std::string(k) == "global") ? 1 : (k && std::string(k) == "mma") ? 3 : (k && std::string(k) == "tc") ? 4 : (k && std::string(k) == "v3") ? 5 : (k && std::string(k) == "pf") ? 6 : 0;      // default: the tiled kernel (v3 measured slower, profiles/r02_force_kernel_experiments.md)
+		if (const char* pc = getenv("LS1B200_PF_CHECK")) c->pf_check = atoi(pc);
+		if (const char* fu = getenv("LS1B200_FUSED")) c->fused = atoi(fu);
+		if (const char* ce = getenv("LS1B200_CHUNKS_EARLY")) c->chunks_early = atoi(ce);
 		const char* m = getenv("LS1B200_MULTI_KERNEL");
 		if (const char* mc = getenv("LS1B200_MULTI_MAXCTAS")) c->multi_max_ctas = atoi(mc);
 		if (const char* ms = getenv("LS1B200_MULTI_STAGE")) c->multi_stage = atoi(ms);
@@ -297,6 +301,7 @@ int ls1b200_destroy(ls1b200_ctx* c) {
 	for (auto e : c->xprof_ev) if (e) cudaEventDestroy(e);
 	decomp_free(c);
 	if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+	if (c->stream_c) { cudaStreamSynchronize(c->stream_c); cudaStreamDestroy(c->stream_c); if (c->ev_c0) cudaEventDestroy(c->ev_c0); if (c->ev_c1) cudaEventDestroy(c->ev_c1); }
 	if (c->stream_x) { cudaStreamSynchronize(c->stream_x); cudaStreamDestroy(c->stream_x); if (c->ev_xa) cudaEventDestroy(c->ev_xa); if (c->ev_xb) cudaEventDestroy(c->ev_xb); }
 	if (c->ev_dl) cudaEventDestroy(c->ev_dl);
 	if (c->stage2) cudaFree(c->stage2);
@@ -440,6 +445,7 @@ const char* overflow_message(uint32_t code) {
 		case 2: return "a halo message buffer was too small (more boundary molecules than the message capacity)";
 		case 4: return "a neighbour's message did not arrive within the time limit (peer-memory transport, LS1B200_PEER_TIMEOUT_S: did a rank fail or skip ls1b200_exchange?); the state was frozen at the failed step";
 		case 5: return "another rank of the decomposition reported a failed step (overflow or time-out); the state was frozen at that step";
+		case 6: return "force_1clj_pf (LS1B200_PF_CHECK): a window translation was not exact";
 		default: return "slot capacity exceeded (more halo copies than reserved)";
 	}
 }

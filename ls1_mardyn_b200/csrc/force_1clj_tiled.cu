@@ -55,6 +55,9 @@ struct TArgs {
 	C eps24_0, sig2_0, shift6_0;
 	// reduced-memory mode (rmm.cu; VCP1CLJRMM.cpp:238-369): the force goes straight into the FP32 velocities, v += f dt / m; F, Vi are not stored
 	float* rmm_v; float rmm_dt_m;
+	// fused step (ls1b200_simulate): the kinetic sum of Leapfrog::transition2to3 (Leapfrog.cpp:113-143), sum of m (v + dt/2m F)^2 over the
+	// molecules this kernel visits, from the force still in registers; the kick itself is applied by the next step's first kernel
+	const double* kin_v; double kin_dth; const CompDev* comps; double* partials_kin;      // partials_kin: [chunk][4 warps]
 };
 
 // LJ 12-6 of one pair, accumulated into FP32 partial sums (slot u). Force and virial are fused multiply-adds on the common
@@ -78,7 +81,14 @@ struct TArgs {
 	}
 
 template <class C, bool SINGLE, bool RMM = false>
+#ifndef LS1_TILE_MINB
+#define LS1_TILE_MINB 6      // measured (gpurun_out/minb, minb2): 1 / 5 / 6 / 7 / 8 resident CTAs asked for -> 89 / 85 / 78 / 71 / 64 registers -> 6.082 / 6.075 / 6.000 / 6.105 / 6.289 ms per step; without the second argument ptxas stops at 64 registers and spills
+#endif
+#ifdef LS1_TILE_NOMINB
 __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a) {
+#else
+__global__ void __launch_bounds__(TileCfg<C>::TPB, LS1_TILE_MINB) k_force_1clj_tiled(TArgs<C> a) {
+#endif
 	typedef typename Vec4<C>::type V4;
 	constexpr int TPB = TileCfg<C>::TPB, W = TileCfg<C>::W, LCAP = TileCfg<C>::LCAP, RI = TileCfg<C>::RI;
 	constexpr uint32_t VB = sizeof(V4), LSTRIDE = (uint32_t) TPB * 2u * RI;      // bytes between consecutive entries of one list
@@ -150,7 +160,7 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 		const uint32_t nch = s_next;
 		Chunk ncd; ncd.cell0 = 0; ncd.ncells = 0; ncd.flags = 0;
 		if (nch < n_chunks) { ncd = a.chunks[nch]; if (!(ncd.flags & CHUNK_BIG)) fill_cs(ncd, cs_all + (cur ^ 1) * CSB, s_rowbase_all[cur ^ 1]); }
-		double acc[2] = {0., 0.};
+		double acc[3] = {0., 0., 0.};
 		if (big) {
 			// ---- slow generic path: a cell denser than the tile. Global loads, pair evaluated as soon as it is found. ----
 			const uint32_t ib = a.cell_start[cd.cell0], ie = a.cell_start[cd.cell0 + nc];
@@ -179,6 +189,11 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 				}
 				acc[0] += 0.5 * Ud; acc[1] += 0.5 * (Vd[0] + Vd[1] + Vd[2]);
 				const size_t cp = a.cap;
+				if (!RMM && a.kin_v) {
+					const double mass = a.comps[cid_i].mass, am = a.kin_dth / mass;
+					const double v0 = a.kin_v[t] + am * Fd[0], v1 = a.kin_v[cp + t] + am * Fd[1], v2 = a.kin_v[2 * cp + t] + am * Fd[2];
+					acc[2] += mass * (v0 * v0 + v1 * v1 + v2 * v2);
+				}
 				if (RMM) {
 					a.rmm_v[t] += (float) Fd[0] * a.rmm_dt_m; a.rmm_v[cp + t] += (float) Fd[1] * a.rmm_dt_m; a.rmm_v[2 * cp + t] += (float) Fd[2] * a.rmm_dt_m;
 				} else {
@@ -318,6 +333,11 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 				const uint32_t t = s_rowbase[4] + trel[l];
 				acc[0] += 0.5 * Ud[l];                          // every pair is visited from both of its ends
 				acc[1] += 0.5 * (Vd[l][0] + Vd[l][1] + Vd[l][2]);
+				if (!RMM && a.kin_v) {
+					const double mass = a.comps[cid_i[l]].mass, am = a.kin_dth / mass;
+					const double v0 = a.kin_v[t] + am * Fd[l][0], v1 = a.kin_v[cp + t] + am * Fd[l][1], v2 = a.kin_v[2 * cp + t] + am * Fd[l][2];
+					acc[2] += mass * (v0 * v0 + v1 * v1 + v2 * v2);
+				}
 				if (RMM) {      // the kick in the epilogue: 12 B read + 12 B written per molecule instead of 48 B of F and Vi
 					a.rmm_v[t] += (float) Fd[l][0] * a.rmm_dt_m; a.rmm_v[cp + t] += (float) Fd[l][1] * a.rmm_dt_m; a.rmm_v[2 * cp + t] += (float) Fd[l][2] * a.rmm_dt_m;
 				} else {
@@ -334,6 +354,12 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 			#pragma unroll
 			for (int o = 16; o > 0; o >>= 1) acc[k] += __shfl_xor_sync(0xffffffffu, acc[k], o);
 		}
+		if (!RMM && a.kin_v) {
+			#pragma unroll
+			for (int o = 16; o > 0; o >>= 1) acc[2] += __shfl_xor_sync(0xffffffffu, acc[2], o);
+			if ((threadIdx.x & 31) == 0) a.partials_kin[(size_t) ch * 4 + (threadIdx.x >> 5)] = acc[2];
+			if (TPB < 128 && threadIdx.x >= TPB / 32 && threadIdx.x < 4) a.partials_kin[(size_t) ch * 4 + threadIdx.x] = 0.;
+		}
 		if ((threadIdx.x & 31) == 0) *reinterpret_cast<double2*>(a.partials + (size_t) ch * 8 + 2 * (threadIdx.x >> 5)) = make_double2(acc[0], acc[1]);
 		if (TPB < 128 && threadIdx.x >= TPB / 32 && threadIdx.x < 4) *reinterpret_cast<double2*>(a.partials + (size_t) ch * 8 + 2 * threadIdx.x) = make_double2(0., 0.);
 		__syncthreads();      // windows and lists are reused by the next chunk; its cell_start cache is complete
@@ -343,28 +369,33 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB) k_force_1clj_tiled(TArgs<C> a
 
 // deterministic two-level reduction of the per-chunk partial sums (fixed assignment chunk -> block -> thread, fixed order)
 constexpr int RED_BLOCKS = 128;
-__global__ void __launch_bounds__(256) k_reduce_force_chunks1(const double* __restrict__ partials, const uint32_t* __restrict__ n_chunks, double* __restrict__ partials2, int per_warp) {
-	double v[2] = {0., 0.};
+__global__ void __launch_bounds__(256) k_reduce_force_chunks1(const double* __restrict__ partials, const uint32_t* __restrict__ n_chunks, double* __restrict__ partials2, int per_warp,
+                                                               const double* __restrict__ partials_kin) {
+	double v[3] = {0., 0., 0.};
 	const uint32_t n = *n_chunks;
 	for (uint32_t b = blockIdx.x * blockDim.x + threadIdx.x; b < n; b += gridDim.x * blockDim.x) {
 		const double2* q = reinterpret_cast<const double2*>(partials + (size_t) b * 8);
 		if (per_warp) { const double2 p0 = q[0], p1 = q[1], p2 = q[2], p3 = q[3]; v[0] += (p0.x + p1.x) + (p2.x + p3.x); v[1] += (p0.y + p1.y) + (p2.y + p3.y); }
 		else { const double2 p = q[0]; v[0] += p.x; v[1] += p.y; }
+		if (partials_kin) { const double2* k = reinterpret_cast<const double2*>(partials_kin + (size_t) b * 4); const double2 k0 = k[0], k1 = k[1]; v[2] += (k0.x + k0.y) + (k1.x + k1.y); }
 	}
-	block_reduce_store<2>(v, partials2, blockIdx.x);
+	block_reduce_store<3>(v, partials2, blockIdx.x);
 }
-__global__ void __launch_bounds__(RED_BLOCKS) k_reduce_force_chunks2(const double* __restrict__ partials2, DevScalars* scal) {
-	double v[2] = {partials2[(size_t) threadIdx.x * 8], partials2[(size_t) threadIdx.x * 8 + 1]};
+__global__ void __launch_bounds__(RED_BLOCKS) k_reduce_force_chunks2(const double* __restrict__ partials2, DevScalars* scal, int kin) {
+	double v[3] = {partials2[(size_t) threadIdx.x * 8], partials2[(size_t) threadIdx.x * 8 + 1], partials2[(size_t) threadIdx.x * 8 + 2]};
 	__shared__ double out[8];
-	block_reduce_store<2>(v, out, 0);
+	block_reduce_store<3>(v, out, 0);
 	__syncthreads();
-	if (threadIdx.x == 0) { scal->upot6lj = out[0]; scal->upot_xpoles = 0.; scal->virial = out[1]; scal->my_rf = 0.; }
+	if (threadIdx.x == 0) {
+		scal->upot6lj = out[0]; scal->upot_xpoles = 0.; scal->virial = out[1]; scal->my_rf = 0.;
+		if (kin) { scal->summv2 = out[2]; scal->sum_iw2 = 0.; scal->fault = scal->overflow ? 1. : 0.; }      // what k_reduce_kinetic delivers after leapfrog_post
+	}
 }
 
 // sums the per-chunk partials of a chunked force kernel into DevScalars (also used by force_1clj_mma.cu)
-int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows, int per_warp) {
-	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks1, RED_BLOCKS, 256, 0, c->partials, c->chunk_row_start + nrows, c->partials2, per_warp);
-	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks2, 1, RED_BLOCKS, 0, c->partials2, c->d_scal);
+int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows, int per_warp, bool kin) {
+	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks1, RED_BLOCKS, 256, 0, c->partials, c->chunk_row_start + nrows, c->partials2, per_warp, kin ? (const double*) c->partials_kin : (const double*) nullptr);
+	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks2, 1, RED_BLOCKS, 0, c->partials2, c->d_scal, (int) kin);
 	return 0;
 }
 
@@ -374,6 +405,10 @@ static int launch_tiled(ls1b200_ctx* c, float* rmm_v = nullptr, float rmm_dt_m =
 	constexpr int TPB = TileCfg<C>::TPB, W = TileCfg<C>::W, LCAP = TileCfg<C>::LCAP, RI = TileCfg<C>::RI;
 	const Geom& g = c->geom;
 	uint32_t nrows = 0;
+	if (c->chunks_ready) {      // built on the side stream while the sort permuted the state (update.cu)
+		LS1_CUDA(cudaStreamWaitEvent(c->stream, c->ev_c1, 0));
+		nrows = c->chunks_nrows; c->chunks_ready = false;
+	} else
 	LS1_TRY(build_chunks(c, TPB * RI, W, 1, &nrows));      // a chunk holds at most TPB * RI molecules
 	Chunk* chunks = (Chunk*) c->chunks;
 	TArgs<C> a;
@@ -387,6 +422,9 @@ static int launch_tiled(ls1b200_ctx* c, float* rmm_v = nullptr, float rmm_dt_m =
 	a.ljrc2 = (C) (rclj * rclj);
 	a.eps24_0 = (C) c->h_eps24[0]; a.sig2_0 = (C) c->h_sig2[0]; a.shift6_0 = (C) c->h_shift6[0];
 	a.rmm_v = rmm_v; a.rmm_dt_m = rmm_dt_m;
+	const bool kin = !RMM && c->kin_dth != 0.;
+	a.kin_v = kin ? c->cur.v : nullptr; a.kin_dth = c->kin_dth; a.comps = c->d_comps; a.partials_kin = c->partials_kin;
+	if (kin && !c->partials_kin) return fail("force_1clj_tiled: no buffer for the kinetic partial sums");
 	// the cell_start cache is padded by three rows: the compiler hoists the (guarded) loads of the next row's entries
 	const size_t smem = (size_t) (9 * W + 1) * sizeof(V4) + (size_t) (LCAP + 1) * RI * TPB * 2 + 2 * 12 * (CH_MAXC + 3) * 4;
 	auto kern = c->comps.size() == 1 ? k_force_1clj_tiled<C, true, RMM> : k_force_1clj_tiled<C, false, RMM>;
@@ -396,7 +434,12 @@ static int launch_tiled(ls1b200_ctx* c, float* rmm_v = nullptr, float rmm_dt_m =
 	if (per_sm < 1) return fail("force_1clj_tiled: kernel does not fit on an SM");
 	const uint32_t grid = (uint32_t) (c->sm_count * per_sm);
 	LS1_LAUNCH(c, PH_FORCE, kern, grid, TPB, smem, a);
-	return reduce_force_chunks(c, nrows, 1);
+	return reduce_force_chunks(c, nrows, 1, kin);
+}
+
+int build_chunks_tiled_1clj(ls1b200_ctx* c, uint32_t* nrows) {
+	return c->mixed ? build_chunks(c, TileCfg<float>::TPB * TileCfg<float>::RI, TileCfg<float>::W, 1, nrows)
+	                : build_chunks(c, TileCfg<double>::TPB * TileCfg<double>::RI, TileCfg<double>::W, 1, nrows);
 }
 
 int force_1clj_tiled(ls1b200_ctx* c) { return c->mixed ? launch_tiled<float>(c) : launch_tiled<double>(c); }

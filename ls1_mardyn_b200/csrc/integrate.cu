@@ -206,7 +206,7 @@ __global__ void k_globals(DevScalars* scal, double target_T, unsigned long long 
 int do_forces(ls1b200_ctx* c) {
 	if (c->n_owned == 0 && !c->dd.active) { c->forces_valid = true; return 0; }
 	LS1_TRY(span_begin(c, PH_FORCE));
-	LS1_TRY(c->all_1clj ? (c->lj_kernel == 5 ? force_1clj_v3(c) : c->lj_kernel == 0 ? force_1clj_tiled(c) : c->lj_kernel == 1 ? force_1clj(c) : c->lj_kernel == 3 ? force_1clj_mma(c) : force_1clj_tc(c)) : (c->multi_kernel != 1 ? force_multi_tiled(c) : force_general(c)));
+	LS1_TRY(c->all_1clj ? (c->lj_kernel == 6 && c->mixed && c->comps.size() == 1 ? force_1clj_pf(c) : c->lj_kernel == 5 ? force_1clj_v3(c) : (c->lj_kernel == 0 || c->lj_kernel == 6) ? force_1clj_tiled(c) : c->lj_kernel == 1 ? force_1clj(c) : c->lj_kernel == 3 ? force_1clj_mma(c) : force_1clj_tc(c)) : (c->multi_kernel != 1 ? force_multi_tiled(c) : force_general(c)));
 	LS1_TRY(span_end(c));
 	c->forces_valid = true;
 	return 0;
@@ -214,7 +214,7 @@ int do_forces(ls1b200_ctx* c) {
 
 Region make_region(const ls1b200_ctx* c, int mode) {
 	Region rg;
-	rg.flag = c->region_flag; rg.mode = c->region_flag ? mode : 0;
+	rg.flag = c->region_flag; rg.mode = (c->region_flag || mode == 3) ? mode : 0;
 	return rg;
 }
 
@@ -340,7 +340,14 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 		LS1_CUDA(cudaStreamCreateWithPriority(&c->stream_x, cudaStreamNonBlocking, prio_hi));
 		LS1_CUDA(cudaEventCreateWithFlags(&c->ev_xa, cudaEventDisableTiming)); LS1_CUDA(cudaEventCreateWithFlags(&c->ev_xb, cudaEventDisableTiming));
 	}
+	// Fused step (ensembles without rotation, the tiled 1CLJ kernel): the second half kick of a step moves into the first kernel of
+	// the NEXT step, which also bins the molecules (k_pre_key), and the kinetic sum the thermostat needs comes out of the force
+	// kernel's epilogue -- per step the slot state is read and written once instead of three times, and three launches go away.
+	// Same floating-point sequence per molecule; the last step of the call runs the ordinary leapfrog_post.
+	bool fused = c->fused && !overlap && !c->rotates && c->all_1clj && c->lj_kernel == 0 && c->fine_s == 1;
+	for (int d = 0; d < 3; d++) if (!c->geom.periodic[d] && !(c->dd.active && c->dd.grid[d] > 1)) fused = false;      // open faces: owned molecules may sit in halo cells, where no force kernel visits them
 	for (uint64_t s = 0; s < n_steps; s++) {
+		const bool kin_here = fused && s + 1 < n_steps;      // this step's kinetic sum comes from the force kernel, its kick from the next step
 		if (overlap) {
 			LS1_TRY(do_leapfrog_pre(c, dt, target_temperature > 0., 1));      // boundary slots: what the exchange reads
 			LS1_CUDA(cudaEventRecord(c->ev_xa, c->stream));
@@ -355,13 +362,20 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 			LS1_TRY(do_update(c, 1));                                           // ... and their keys / histogram
 			LS1_CUDA(cudaStreamWaitEvent(c->stream, c->ev_xb, 0));
 			LS1_TRY(do_update(c, 2));                                           // boundary slots + imports, scan, scatter, gather
+		} else if (fused) {
+			LS1_TRY(do_pre_key(c, dt, target_temperature > 0., s > 0));
+			LS1_TRY(do_exchange(c));
+			LS1_TRY(do_update(c, 3));
 		} else {
 		LS1_TRY(do_leapfrog_pre(c, dt, target_temperature > 0.));
 		LS1_TRY(do_exchange(c));                 // multi-GPU: leaving molecules + halo copies over NCCL (no-op on one GPU)
 		LS1_TRY(do_update(c));
 		}
-		LS1_TRY(do_forces(c));
-		LS1_TRY(do_leapfrog_post(c, dt));
+		c->kin_dth = kin_here ? .5 * dt : 0.;
+		const int frc = do_forces(c);
+		c->kin_dth = 0.;
+		if (frc) return frc;
+		if (!kin_here) LS1_TRY(do_leapfrog_post(c, dt));
 		LS1_TRY(do_allreduce_scalars(c));        // multi-GPU: Upot, virial, sum m v^2, sum I w^2 over the ranks
 		LS1_TRY(do_globals(c, target_temperature, global_n, global_volume, c->d_records + s));
 	}

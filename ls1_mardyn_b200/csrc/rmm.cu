@@ -242,6 +242,7 @@ static int rmm_update(ls1b200_ctx* c, float dt, int advance, int use_beta) {
 	const uint32_t gs = (uint32_t) ((c->cap + 255) / 256);
 	LS1_LAUNCH(c, PH_UPDATE, k_rmm_move_key, gs, 256, 0, a, c->rmm_r[cur], c->rmm_v[cur], (const uint64_t*) c->rmm_id[cur], dt, advance, use_beta, c->key, c->cell_count, c->cell_count_halo, c->rank, c->d_scal);
 	LS1_TRY(launch_bin_scan(c, nb, c->cell_start, a.parity));
+	c->chunks_ready = false;      // the chunk list of an earlier ls1b200_update does not describe this order
 	LS1_LAUNCH(c, PH_UPDATE, k_rmm_scatter, gs, 256, 0, a, (const float*) c->rmm_r[cur], (const uint32_t*) c->key, (const uint32_t*) c->rank, (const uint32_t*) c->cell_start, c->cursor, c->entry, c->cell_of, c->d_scal);
 	LS1_LAUNCH(c, PH_UPDATE, k_rmm_gather, gs, 256, 0, a, (const float*) c->rmm_r[cur], (const float*) c->rmm_v[cur], (const uint64_t*) c->rmm_id[cur], c->rmm_r[nxt], c->rmm_v[nxt], c->rmm_id[nxt],
 	           (const uint32_t*) c->entry, (const uint32_t*) c->cell_of, (const uint32_t*) c->cell_start, c->cell_of2, (float4*) c->mpos, c->d_scal);

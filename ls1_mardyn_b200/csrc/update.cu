@@ -39,32 +39,27 @@ __device__ __forceinline__ bool code_valid(uint32_t mask, int a, int b, int c) {
 	return (a == 0 || ((mask >> (a - 1)) & 1u)) && (b == 0 || ((mask >> (2 + b - 1)) & 1u)) && (c == 0 || ((mask >> (4 + c - 1)) & 1u));
 }
 
-__global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __restrict__ key, uint32_t* __restrict__ count, uint32_t* __restrict__ count_halo,
-                                              uint32_t* __restrict__ rank, const DevScalars* __restrict__ scal, Region rg) {
-	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	// (overlapped multi-GPU step: two launches, inner slots before the imports have arrived, the rest after -- every slot in exactly one)
-	const bool in_range = s < min(scal->n_slots2[a.parity], a.cap) && region_selected(rg, s, scal->n_sorted);      // the region test reads 4 bytes per slot, before anything else
+// Binning of one slot (shared by k_key and by the fused integrate + key kernel k_pre_key): wrap, cell index (bit exact), key,
+// histogram of owned molecules + periodic copies. `live`: the slot takes part in the binning (x, y, z hold its position);
+// every thread of the warp must call this (shuffles).
+__device__ __forceinline__ void key_slot(const UpdArgs& a, State& cur, uint32_t s, bool in_range, bool live, double x, double y, double z,
+                                         uint32_t* __restrict__ key, uint32_t* __restrict__ count, uint32_t* __restrict__ count_halo, uint32_t* __restrict__ rank) {
 	const Geom& g = a.g;
 	uint32_t bin = KEY_NONE, mask = 0, sub = 0;      // bin: FINE bin (reference cell * S + x sub-bin)
-	double x = 0., y = 0., z = 0.;
-	if (in_range) {
-		const uint64_t meta = cur.meta[s];
-		if (meta_halo(meta) && !meta_fresh(meta)) key[s] = KEY_NONE;      // stale halo slot; fresh halo copies (halo.cu) are binned
+	if (in_range && !live) key[s] = KEY_NONE;         // stale halo slot; fresh halo copies (halo.cu) are binned
+	if (live) {
+		if (g.periodic[0]) { double w = wrap_coord<0>(g, x); if (w != x) { x = w; cur.r[s] = w; } }
+		if (g.periodic[1]) { double w = wrap_coord<1>(g, y); if (w != y) { y = w; cur.r[(size_t) a.cap + s] = w; } }
+		if (g.periodic[2]) { double w = wrap_coord<2>(g, z); if (w != z) { z = w; cur.r[2 * (size_t) a.cap + s] = w; } }
+		const int cx = cell1d_tab<0>(g, a.bx, x), cy = cell1d_tab<1>(g, a.by, y), cz = cell1d_tab<2>(g, a.bz, z);
+		const bool out = cx < 0 || cy < 0 || cz < 0 || cx >= g.cells[0] || cy >= g.cells[1] || cz >= g.cells[2];
+		if (out) { key[s] = g.ncells; bin = g.ncells * a.S; }
 		else {
-			x = cur.r[s]; y = cur.r[(size_t) a.cap + s]; z = cur.r[2 * (size_t) a.cap + s];
-			if (g.periodic[0]) { double w = wrap_coord<0>(g, x); if (w != x) { x = w; cur.r[s] = w; } }
-			if (g.periodic[1]) { double w = wrap_coord<1>(g, y); if (w != y) { y = w; cur.r[(size_t) a.cap + s] = w; } }
-			if (g.periodic[2]) { double w = wrap_coord<2>(g, z); if (w != z) { z = w; cur.r[2 * (size_t) a.cap + s] = w; } }
-			const int cx = cell1d_tab<0>(g, a.bx, x), cy = cell1d_tab<1>(g, a.by, y), cz = cell1d_tab<2>(g, a.bz, z);
-			const bool out = cx < 0 || cy < 0 || cz < 0 || cx >= g.cells[0] || cy >= g.cells[1] || cz >= g.cells[2];
-			if (out) { key[s] = g.ncells; bin = g.ncells * a.S; }
-			else {
-				const uint32_t cell = cell_index(g, cx, cy, cz);
-				mask = shift_mask<0>(g, x) | (shift_mask<1>(g, y) << 2) | (shift_mask<2>(g, z) << 4);
-				key[s] = cell | (mask << SHIFT_BITS);
-				if (a.S > 1) sub = (uint32_t) fine_sub(x, __ldg(a.bx + cx), a.finv, (int) a.S);      // S == 1: the reference cell is the bin
-				bin = (cell << a.logS) + sub;
-			}
+			const uint32_t cell = cell_index(g, cx, cy, cz);
+			mask = shift_mask<0>(g, x) | (shift_mask<1>(g, y) << 2) | (shift_mask<2>(g, z) << 4);
+			key[s] = cell | (mask << SHIFT_BITS);
+			if (a.S > 1) sub = (uint32_t) fine_sub(x, __ldg(a.bx + cx), a.finv, (int) a.S);      // S == 1: the reference cell is the bin
+			bin = (cell << a.logS) + sub;
 		}
 	}
 	// Histogram: slots are in the cell order of the previous step, so the lanes of a warp fall into a handful of bins -- one
@@ -93,6 +88,84 @@ __global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __r
 			atomicAdd(&count_halo[(cell_index(g, hx, hy, hz) << a.logS) + (a.S > 1 ? (uint32_t) fine_sub(xh, __ldg(a.bx + hx), a.finv, (int) a.S) : 0u)], 1u);
 		}
 	}
+}
+
+__global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __restrict__ key, uint32_t* __restrict__ count, uint32_t* __restrict__ count_halo,
+                                              uint32_t* __restrict__ rank, const DevScalars* __restrict__ scal, Region rg) {
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	// (overlapped multi-GPU step: two launches, inner slots before the imports have arrived, the rest after -- every slot in exactly one;
+	//  fused step: mode 3, only the imports appended behind the sorted slots -- the others were binned by k_pre_key)
+	const bool in_range = s < min(scal->n_slots2[a.parity], a.cap) && region_selected(rg, s, scal->n_sorted);      // the region test reads 4 bytes per slot, before anything else
+	bool live = false;
+	double x = 0., y = 0., z = 0.;
+	if (in_range) {
+		const uint64_t meta = cur.meta[s];
+		live = !(meta_halo(meta) && !meta_fresh(meta));
+		if (live) { x = cur.r[s]; y = cur.r[(size_t) a.cap + s]; z = cur.r[2 * (size_t) a.cap + s]; }
+	}
+	key_slot(a, cur, s, in_range, live, x, y, z, key, count, count_halo, rank);
+}
+
+// fused step, decomposed contexts: the imports the exchange appended behind the sorted slots (a few per cent of the slots) -- a small
+// grid that starts at n_sorted instead of a launch over the whole capacity
+__global__ void __launch_bounds__(256) k_key_tail(UpdArgs a, State cur, uint32_t* __restrict__ key, uint32_t* __restrict__ count, uint32_t* __restrict__ count_halo,
+                                                   uint32_t* __restrict__ rank, const DevScalars* __restrict__ scal) {
+	const uint32_t n = min(scal->n_slots2[a.parity], a.cap), first = min(scal->n_sorted, n);
+	for (uint32_t base = first + blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {      // uniform per block: every warp calls key_slot together
+		const uint32_t s = base + threadIdx.x;
+		const bool in_range = s < n;
+		bool live = false;
+		double x = 0., y = 0., z = 0.;
+		if (in_range) {
+			const uint64_t meta = cur.meta[s];
+			live = !(meta_halo(meta) && !meta_fresh(meta));
+			if (live) { x = cur.r[s]; y = cur.r[(size_t) a.cap + s]; z = cur.r[2 * (size_t) a.cap + s]; }
+		}
+		key_slot(a, cur, s, in_range, live, x, y, z, key, count, count_halo, rank);
+	}
+}
+
+// The fused first kernel of a time step of ls1b200_simulate (ensembles without rotation): [the second half kick of the PREVIOUS
+// step (Leapfrog::transition2to3 -> upd_postF, whose sum of m v^2 the force kernel already delivered) +] thermostat factor on
+// load + upd_preF (half kick, drift) + the binning of k_key on the new position, which is still in registers: the slot state
+// is read and written once, the FP64 compares of the binning hide behind the memory traffic of the integration.
+// Same floating-point sequence per molecule as k_leapfrog_post -> k_scale -> k_leapfrog_pre -> k_key.
+__global__ void __launch_bounds__(256) k_pre_key(UpdArgs a, State cur, const double* __restrict__ F, const CompDev* __restrict__ comps, double dt, int use_beta, int post_kick,
+                                                  uint32_t* __restrict__ key, uint32_t* __restrict__ count, uint32_t* __restrict__ count_halo, uint32_t* __restrict__ rank,
+                                                  const DevScalars* __restrict__ scal) {
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	const bool in_range = s < min(scal->n_slots2[a.parity], a.cap);
+	bool live = false;
+	double r[3] = {0., 0., 0.};
+	if (in_range) {
+		const uint64_t meta = cur.meta[s];
+		const size_t c = a.cap;
+		if (!meta_halo(meta)) {
+			live = true;
+			#pragma unroll
+			for (int d = 0; d < 3; d++) r[d] = cur.r[d * c + s];
+			if (!scal->overflow) {      // a failed step: the state stays as it is (k_leapfrog_pre)
+				const double bt = use_beta ? scal->beta_trans : 1.;
+				const double a0 = (.5 * dt) / comps[meta_cid(meta)].mass;
+				#pragma unroll
+				for (int d = 0; d < 3; d++) {
+					double v = cur.v[d * c + s];
+					const double f = F[d * c + s];
+					if (post_kick) v += a0 * f;
+					if (use_beta) v *= bt;
+					v += a0 * f;
+					cur.v[d * c + s] = v;
+					r[d] += dt * v;
+					cur.r[d * c + s] = r[d];
+				}
+			}
+		} else if (meta_fresh(meta)) {
+			live = true;
+			#pragma unroll
+			for (int d = 0; d < 3; d++) r[d] = cur.r[d * c + s];
+		}
+	}
+	key_slot(a, cur, s, in_range, live, r[0], r[1], r[2], key, count, count_halo, rank);
 }
 
 // ---- exclusive scan (three small kernels; n = ncells + 1 bins) ----------------------------------------------------
@@ -291,23 +364,66 @@ int launch_bin_scan(ls1b200_ctx* c, uint32_t nb, uint32_t* fstart, uint32_t pari
 
 Region make_region(const ls1b200_ctx* c, int mode);      // integrate.cu
 
+static UpdArgs make_upd_args(const ls1b200_ctx* c) {
+	UpdArgs a; a.g = c->geom; a.cap = (uint32_t) c->cap; a.parity = c->parity; for (int d = 0; d < 3; d++) a.cut[d] = c->dd.active && c->dd.grid[d] > 1;
+	a.S = c->fine_s; a.logS = c->fine_s == 8 ? 3u : c->fine_s == 4 ? 2u : c->fine_s == 2 ? 1u : 0u; a.finv = c->fine_inv;
+	a.bx = c->d_border; a.by = c->d_border + c->border_stride; a.bz = c->d_border + 2 * (size_t) c->border_stride;
+	return a;
+}
+
+// fused step (ls1b200_simulate, ensembles without rotation): integration + binning of every slot in one kernel; do_update(c, 3) continues
+int do_pre_key(ls1b200_ctx* c, double dt, bool use_beta, bool post_kick) {
+	if (c->n_owned == 0 && !c->dd.active) return 0;
+	if (c->rotates || c->fine_s != 1) return fail("do_pre_key: ensembles without rotation, one bin per cell");
+	LS1_TRY(span_begin(c, PH_PRE));
+	const UpdArgs a = make_upd_args(c);
+	const uint32_t gs = (uint32_t) ((c->cap + 255) / 256);
+	LS1_CUDA(cudaMemsetAsync(c->cell_count, 0, sizeof(uint32_t) * 2 * ((size_t) c->geom.ncells * c->fine_s + 4), c->stream));      // cell_count and cell_count_halo
+	LS1_LAUNCH(c, PH_PRE, k_pre_key, gs, 256, 0, a, c->cur, c->F, c->d_comps, dt, (int) use_beta, (int) post_kick, c->key, c->cell_count, c->cell_count_halo, c->rank, c->d_scal);
+	LS1_TRY(span_end(c));
+	c->forces_valid = false;
+	return 0;
+}
+
 int do_update(ls1b200_ctx* c, int part) {
 	if (!c->components_set) return fail("ls1b200_update: components not set");
 	if (c->n_owned == 0 && !c->dd.active) { c->sorted = true; return 0; }
 	if (c->cap == 0) return fail("ls1b200_update: call ls1b200_upload first");
 	LS1_TRY(span_begin(c, PH_UPDATE));
-	UpdArgs a; a.g = c->geom; a.cap = (uint32_t) c->cap; a.parity = c->parity; for (int d = 0; d < 3; d++) a.cut[d] = c->dd.active && c->dd.grid[d] > 1;
-	a.S = c->fine_s; a.logS = c->fine_s == 8 ? 3u : c->fine_s == 4 ? 2u : c->fine_s == 2 ? 1u : 0u; a.finv = c->fine_inv;
-	a.bx = c->d_border; a.by = c->d_border + c->border_stride; a.bz = c->d_border + 2 * (size_t) c->border_stride;
+	const UpdArgs a = make_upd_args(c);
 	const uint32_t nb = c->geom.ncells * c->fine_s + 1;   // fine bins + limbo bin
 	// slot counts are only known on the device: every per-slot kernel is launched over the capacity, threads beyond exit
 	const uint32_t gs = (uint32_t) ((c->cap + 255) / 256);
-	if (part != 2) LS1_CUDA(cudaMemsetAsync(c->cell_count, 0, sizeof(uint32_t) * 2 * ((size_t) c->geom.ncells * c->fine_s + 4), c->stream));      // cell_count and cell_count_halo
-	LS1_LAUNCH(c, PH_UPDATE, k_key, gs, 256, 0, a, c->cur, c->key, c->cell_count, c->cell_count_halo, c->rank, c->d_scal, make_region(c, part == 0 ? 0 : part == 1 ? 2 : 1));
+	if (part == 0 || part == 1) LS1_CUDA(cudaMemsetAsync(c->cell_count, 0, sizeof(uint32_t) * 2 * ((size_t) c->geom.ncells * c->fine_s + 4), c->stream));      // cell_count and cell_count_halo
+	// part 3: the sorted slots were binned by k_pre_key; only the imports the exchange appended behind them are left (decomposed contexts)
+	if (part == 3) {
+		if (c->dd.active) LS1_LAUNCH(c, PH_UPDATE, k_key_tail, 592, 256, 0, a, c->cur, c->key, c->cell_count, c->cell_count_halo, c->rank, c->d_scal);
+	} else
+		LS1_LAUNCH(c, PH_UPDATE, k_key, gs, 256, 0, a, c->cur, c->key, c->cell_count, c->cell_count_halo, c->rank, c->d_scal, make_region(c, part == 0 ? 0 : part == 1 ? 2 : part == 2 ? 1 : 3));
 	if (part == 1) { LS1_TRY(span_end(c)); return 0; }
 	// cell_start_fine: exclusive scan over the fine bins; cell_start (the reference cells) is every S-th entry of it
 	uint32_t* fstart = c->fine_s > 1 ? c->cell_start_fine : c->cell_start;
 	LS1_TRY(launch_bin_scan(c, nb, fstart, a.parity));
+	// The chunk list of the production 1CLJ kernel needs cell_start only: it is built on a side stream while scatter and gather
+	// (HBM bound) permute the state; the force kernel waits for it (force_1clj_tiled.cu). The reduced-memory path has its own sort.
+	c->chunks_ready = false;
+	if (c->all_1clj && c->lj_kernel == 0 && c->fine_s == 1 && c->chunks_early) {
+		if (!c->stream_c) {
+			int prio_lo = 0, prio_hi = 0;      // high priority: a few small latency-bound kernels beside the 67 k blocks of the gather
+			LS1_CUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
+			LS1_CUDA(cudaStreamCreateWithPriority(&c->stream_c, cudaStreamNonBlocking, prio_hi));
+			LS1_CUDA(cudaEventCreateWithFlags(&c->ev_c0, cudaEventDisableTiming)); LS1_CUDA(cudaEventCreateWithFlags(&c->ev_c1, cudaEventDisableTiming));
+		}
+		LS1_CUDA(cudaEventRecord(c->ev_c0, c->stream));
+		LS1_CUDA(cudaStreamWaitEvent(c->stream_c, c->ev_c0, 0));
+		cudaStream_t main_stream = c->stream;
+		c->stream = c->stream_c;
+		const int rc = build_chunks_tiled_1clj(c, &c->chunks_nrows);
+		c->stream = main_stream;
+		if (rc) return rc;
+		LS1_CUDA(cudaEventRecord(c->ev_c1, c->stream_c));
+		c->chunks_ready = true;
+	}
 	LS1_LAUNCH(c, PH_UPDATE, k_scatter, gs, 256, 0, a, c->cur, c->key, c->rank, (const uint32_t*) fstart, c->cursor, c->entry, c->cell_of, c->d_scal, c->dd.active ? c->ekey : (uint64_t*) nullptr);
 	const uint32_t gc = gs;
 	if (c->mixed)
