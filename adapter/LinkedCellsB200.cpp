@@ -35,11 +35,15 @@ LinkedCellsB200::~LinkedCellsB200() {
 void LinkedCellsB200::readXML(XMLfileUnits& xmlconfig) {
 	LinkedCells::readXML(xmlconfig);
 	const int cic = xmlconfig.getNodeValue_int("cellsInCutoffRadius", 1);      // private in LinkedCells: read it again (LinkedCells.cpp:125)
-	if (cic != 1) {      // the device path is the reference's default, one cell per cutoff radius
+	if (cic < 1) {
 		std::ostringstream error_message;
-		error_message << "LinkedCellsB200: cellsInCutoffRadius = " << cic << " is not supported on the device (only 1)" << std::endl;
+		error_message << "LinkedCellsB200: cellsInCutoffRadius = " << cic << " is not valid" << std::endl;
 		MARDYN_EXIT(error_message.str());
 	}
+	// cellsInCutoffRadius > 1 refines the HOST cell grid (the inherited mirror, its iterators and plugins see the cells the input asked for).
+	// The device keeps one cell per cutoff radius: which pairs interact is decided by the cutoff test alone, so forces, energies and the
+	// virial are those of the reference with any cell size (tests/test_gpu_dropin.py::test_cells_in_cutoff_radius_2, against the stock binary).
+	if (cic != 1) Log::global_log->info() << "LinkedCellsB200: cellsInCutoffRadius = " << cic << " applies to the host mirror; the device traversal uses cells of one cutoff radius" << std::endl;
 	int f = 0;
 	xmlconfig.getNodeValue("hostSyncFrequency", f);
 	_hostSyncFrequency = f > 0 ? (unsigned long) f : 0ul;

@@ -139,7 +139,7 @@ struct DevScalars {
 	                                              // Once set, the integration kernels leave the state untouched (the step loop is frozen) until the host reports it
 	uint32_t n_owned_dev;                         // owned molecules counted by the last count_owned() (decomposed mode)
 	uint32_t n_sorted;                            // slots in cell order (count of the last update); imports of the exchange follow behind
-	uint32_t pad0;
+	uint32_t n_pre;                               // fused step: slots binned by k_pre_key (the imports of this step's exchange are appended behind them)
 };
 
 }  // namespace ls1b200
@@ -191,6 +191,8 @@ struct ls1b200_ctx {
 	double* d_border = nullptr;       // [3][border_stride] cell borders (bit-identical to CellBorderAndFlagManager::getBorder)
 	uint32_t border_stride = 0;
 	uint32_t* scan_tmp = nullptr;
+	uint32_t* cell_start_alt = nullptr;      // overlapped multi-GPU step: cell_start is double buffered (the exchange reads the previous order's while the sort writes the next)
+	uint32_t* cell_count_b = nullptr; uint32_t* cell_start_b = nullptr; uint32_t* cursor_b = nullptr; uint32_t* scan_tmp_b = nullptr;      // bins of the imports (overlapped multi-GPU step; one allocation, update.cu)
 	uint32_t* key = nullptr;          // [cap] cell | shiftmask << 26 per source slot
 	uint32_t* entry = nullptr;        // [cap] src << 5 | shift code, per provisional slot
 	uint32_t* cell_of = nullptr;      // [cap] cell of provisional / final slot
@@ -205,6 +207,8 @@ struct ls1b200_ctx {
 
 	// chunk list of the tiled 1CLJ kernel (force_1clj_tiled.cu)
 	void* chunks = nullptr; uint32_t* chunk_row_count = nullptr; uint32_t* chunk_row_start = nullptr; uint32_t* work_counter = nullptr;
+	void* chunks_b = nullptr; uint32_t* chunk_row_count_b = nullptr; uint32_t* chunk_row_start_b = nullptr; uint32_t* work_counter_b = nullptr;      // boundary chunks of the overlapped multi-GPU step (tile.cuh); chunks_b_nrows: rows of that list
+	uint32_t chunks_b_nrows = 0; bool chunks_b_ready = false;
 	int sm_count = 148;
 	// reduced-memory mode (rmm.cu): FP32 planes r[3][cap], v[3][cap], id[cap] (bit 63: halo copy), double buffered
 	float* rmm_r[2] = {nullptr, nullptr}; float* rmm_v[2] = {nullptr, nullptr}; uint64_t* rmm_id[2] = {nullptr, nullptr};
@@ -226,6 +230,10 @@ struct ls1b200_ctx {
 	cudaStream_t stream_c = nullptr; cudaEvent_t ev_c0 = nullptr, ev_c1 = nullptr; bool chunks_ready = false; uint32_t chunks_nrows = 0; int chunks_early = 1;      // LS1B200_CHUNKS_EARLY=0: inside the force phase
 	double* partials_kin = nullptr;   // [n_partial_blocks][4] kinetic partial sums of the fused step (force_1clj_tiled.cu)
 	double kin_dth = 0.;              // != 0: the next force traversal also delivers sum m (v + kin_dth / m F)^2 (fused step of ls1b200_simulate)
+	int tile_max_ctas = 0, tile_pass1_ctas = 0;      // LS1B200_TILE_MAXCTAS / LS1B200_TILE_PASS1_CTAS: resident CTAs per SM of the tiled 1CLJ kernel (0: what fits)
+	int force_pass = 0;               // overlapped multi-GPU step: which chunks the next force traversal visits (force_1clj_tiled.cu)
+	int overlap2 = 0;                 // LS1B200_OVERLAP2=1: the exchange on its own stream beside the sort and the inner chunks (measured slower, profiles/r02_multi_gpu.md: off by default)
+	cudaEvent_t ev_m = nullptr;       // overlapped step: the main sort has finished (the imports' sort may start)
 	int fused = 1;                    // LS1B200_FUSED=0: ls1b200_simulate runs the phases as separate kernels
 	uint32_t partial_blocks = 0;
 	ls1b200::DevScalars* d_scal = nullptr;
@@ -283,7 +291,8 @@ void ctx_free_molecules(ls1b200_ctx* c);
 int span_begin(ls1b200_ctx* c, int phase);
 int span_end(ls1b200_ctx* c);
 int do_update(ls1b200_ctx* c, int part = 0);      // part 0: everything; 1: histogram of the INNER slots only (overlapped step); 2: the remaining slots + scan, scatter, gather; 3: after do_pre_key (imports + scan, scatter, gather)
-int build_chunks_tiled_1clj(ls1b200_ctx* c, uint32_t* nrows);      // force_1clj_tiled.cu: the chunk list of the production 1CLJ kernel (launches on c->stream)
+int build_chunks_tiled_1clj(ls1b200_ctx* c, uint32_t* nrows, int mode = 0, int set = 0);      // force_1clj_tiled.cu: the chunk list of the production 1CLJ kernel (launches on c->stream)
+int do_update_imports(ls1b200_ctx* c);      // overlapped multi-GPU step: sorts the imports behind the slots of do_update(c, 4) (update.cu)
 int do_pre_key(ls1b200_ctx* c, double dt, bool use_beta, bool post_kick);      // fused step: [post kick +] thermostat + pre kick + drift + binning (update.cu)
 int do_forces(ls1b200_ctx* c);
 int do_leapfrog_pre(ls1b200_ctx* c, double dt, bool use_beta, int region = 0);      // region: see Region::mode

@@ -267,6 +267,9 @@ int ls1b200_create(const ls1b200_config* cfg, ls1b200_ctx** out) {
 		if (const char* pc = getenv("LS1B200_PF_CHECK")) c->pf_check = atoi(pc);
 		if (const char* fu = getenv("LS1B200_FUSED")) c->fused = atoi(fu);
 		if (const char* ce = getenv("LS1B200_CHUNKS_EARLY")) c->chunks_early = atoi(ce);
+		if (const char* o2 = getenv("LS1B200_OVERLAP2")) c->overlap2 = atoi(o2);
+		if (const char* tm = getenv("LS1B200_TILE_MAXCTAS")) c->tile_max_ctas = atoi(tm);
+		if (const char* tp = getenv("LS1B200_TILE_PASS1_CTAS")) c->tile_pass1_ctas = atoi(tp);
 		const char* m = getenv("LS1B200_MULTI_KERNEL");
 		if (const char* mc = getenv("LS1B200_MULTI_MAXCTAS")) c->multi_max_ctas = atoi(mc);
 		if (const char* ms = getenv("LS1B200_MULTI_STAGE")) c->multi_stage = atoi(ms);
@@ -291,9 +294,13 @@ int ls1b200_destroy(ls1b200_ctx* c) {
 	ctx_free_molecules(c);
 	dev_free(c->d_comps); dev_free(c->d_sites);
 	dev_free(c->d_eps24); dev_free(c->d_sig2); dev_free(c->d_shift6); dev_free(c->d_eps24f); dev_free(c->d_sig2f); dev_free(c->d_shift6f);
+	dev_free(c->cell_start_alt);
+	dev_free(c->cell_count_b); c->cell_start_b = c->cursor_b = c->scan_tmp_b = nullptr;
 	dev_free(c->cell_count); dev_free(c->cell_start); dev_free(c->cell_start_fine); dev_free(c->cursor); dev_free(c->scan_tmp); dev_free(c->d_border);
 	dev_free(c->d_scal); dev_free(c->d_records); dev_free(c->partials2);
 	if (c->chunks) cudaFree(c->chunks);
+	if (c->chunks_b) cudaFree(c->chunks_b);
+	dev_free(c->chunk_row_count_b);
 	if (c->chunks2) cudaFree(c->chunks2);
 	dev_free(c->chunk_row_count); dev_free(c->chunk_row_start); dev_free(c->work_counter);
 	if (c->h_scal) cudaFreeHost(c->h_scal);
@@ -301,6 +308,7 @@ int ls1b200_destroy(ls1b200_ctx* c) {
 	for (auto e : c->xprof_ev) if (e) cudaEventDestroy(e);
 	decomp_free(c);
 	if (c->stream2) { cudaStreamSynchronize(c->stream2); cudaStreamDestroy(c->stream2); }
+	if (c->ev_m) cudaEventDestroy(c->ev_m);
 	if (c->stream_c) { cudaStreamSynchronize(c->stream_c); cudaStreamDestroy(c->stream_c); if (c->ev_c0) cudaEventDestroy(c->ev_c0); if (c->ev_c1) cudaEventDestroy(c->ev_c1); }
 	if (c->stream_x) { cudaStreamSynchronize(c->stream_x); cudaStreamDestroy(c->stream_x); if (c->ev_xa) cudaEventDestroy(c->ev_xa); if (c->ev_xb) cudaEventDestroy(c->ev_xb); }
 	if (c->ev_dl) cudaEventDestroy(c->ev_dl);

@@ -333,7 +333,7 @@ __global__ void __launch_bounds__(M_TPB, 3) k_force_1clj_mma(MArgs a) {
 
 }  // namespace
 
-int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows, int per_warp, bool kin = false);      // force_1clj_tiled.cu
+int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows, int per_warp, bool kin = false, bool accumulate = false);      // force_1clj_tiled.cu
 
 // mixed-precision ensembles of 1CLJ components whose cells are wider than the cutoff by more than FP32 rounding (otherwise a
 // molecule two cells away could pass the FP32 test although the reference never pairs those cells): everything else takes

@@ -323,7 +323,7 @@ __global__ void __launch_bounds__(PF_TPB, 4) k_force_1clj_pf(PFArgs a) {
 	}
 }
 
-int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows, int per_warp, bool kin = false);      // force_1clj_tiled.cu
+int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows, int per_warp, bool kin = false, bool accumulate = false);      // force_1clj_tiled.cu
 
 template <bool RMM>
 static int launch_pf(ls1b200_ctx* c, float* rmm_v, float rmm_dt_m) {

@@ -58,6 +58,9 @@ struct TArgs {
 	// fused step (ls1b200_simulate): the kinetic sum of Leapfrog::transition2to3 (Leapfrog.cpp:113-143), sum of m (v + dt/2m F)^2 over the
 	// molecules this kernel visits, from the force still in registers; the kick itself is applied by the next step's first kernel
 	const double* kin_v; double kin_dth; const CompDev* comps; double* partials_kin;      // partials_kin: [chunk][4 warps]
+	// overlapped multi-GPU step, boundary chunks (BND): the imports of this step's exchange are a second slot range per cell, sorted on
+	// their own behind the slots of the main sort (update.cu: do_update_imports); cell_start_b is absolute
+	const uint32_t* cell_start_b;
 };
 
 // LJ 12-6 of one pair, accumulated into FP32 partial sums (slot u). Force and virial are fused multiply-adds on the common
@@ -80,7 +83,7 @@ struct TArgs {
 		if (SINGLE) up[u] += lj12m6; else up[u] += eps24 * lj12m6 + shift6;                       \
 	}
 
-template <class C, bool SINGLE, bool RMM = false>
+template <class C, bool SINGLE, bool RMM = false, bool BND = false>
 #ifndef LS1_TILE_MINB
 #define LS1_TILE_MINB 6      // measured (gpurun_out/minb, minb2): 1 / 5 / 6 / 7 / 8 resident CTAs asked for -> 89 / 85 / 78 / 71 / 64 registers -> 6.082 / 6.075 / 6.000 / 6.105 / 6.289 ms per step; without the second argument ptxas stops at 64 registers and spills
 #endif
@@ -95,9 +98,17 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB, LS1_TILE_MINB) k_force_1clj_t
 	extern __shared__ __align__(128) unsigned char smem_raw[];
 	V4* win = reinterpret_cast<V4*>(smem_raw);                                         // [9][W] (+1 sentinel record at [9*W])
 	uint16_t* list = reinterpret_cast<uint16_t*>(smem_raw + (size_t) (9 * W + 1) * VB);   // [LCAP+1][RI][TPB]
-	uint32_t* cs_all = reinterpret_cast<uint32_t*>(list + (size_t) (LCAP + 1) * RI * TPB);   // [2][12][CH_MAXC+3]: this chunk's and the next one's
+	// cell_start caches (entries are record indices relative to the window row, <= W): 16-bit in the boundary kernel, whose two tables
+	// then take the room of the inner kernel's one -- the same number of CTAs per SM (one less costs 12 %, gpurun_out/ctas)
+	typedef typename std::conditional<BND, uint16_t, uint32_t>::type cs_t;
+	cs_t* cs_all = reinterpret_cast<cs_t*>(list + (size_t) (LCAP + 1) * RI * TPB);           // [2][12][CH_MAXC+3]: this chunk's and the next one's
 	constexpr int CSB = 12 * (CH_MAXC + 3);
+	static_assert(!BND || RI == 1, "boundary chunks: one molecule per thread");
+	cs_t* csb_all = cs_all + 2 * CSB;                                                        // BND: the same for the imports' ranges
 	__shared__ uint32_t s_rowbase_all[2][9];
+	// BND: the absolute starts of the imports' 9 rows live in the two spare rows (10, 11) of the imports' table: the footprint is the inner kernel's
+	auto rowbaseB_of = [&](int buf) -> uint32_t* { return reinterpret_cast<uint32_t*>(csb_all + buf * CSB + 10 * (CH_MAXC + 3)); };
+	constexpr int NR = BND ? 18 : 9;                                                         // candidate ranges per molecule: 9 rows (x 2 with imports)
 	__shared__ __align__(8) unsigned long long s_bar;
 	__shared__ uint32_t s_next;
 	const uint32_t win_s = smem_u32(win), list_s = smem_u32(list) + threadIdx.x * 2, bar = smem_u32(&s_bar);
@@ -113,7 +124,7 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB, LS1_TILE_MINB) k_force_1clj_t
 	__syncthreads();
 	// cell_start cache of the 9 rows of a chunk (cells xa-1 .. xb+2 -> nc+3 entries each), stored RELATIVE to the first record of
 	// the window (the absolute start goes to rowbase): the per-thread row set-up then needs two loads per row and no subtraction
-	auto fill_cs = [&](const Chunk& q, uint32_t* csq, uint32_t* rbq) {
+	auto fill_cs = [&](const Chunk& q, cs_t* csq, uint32_t* rbq, cs_t* csbq, uint32_t* rbbq) {
 		const int qn = q.ncells;
 		const uint32_t qR = q.cell0 / (uint32_t) a.nx;
 		const int qxa = (int) (q.cell0 % (uint32_t) a.nx);
@@ -121,8 +132,13 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB, LS1_TILE_MINB) k_force_1clj_t
 			const int r = k / (qn + 3), c = k % (qn + 3);
 			const uint32_t row = (uint32_t) ((int) qR + (r / 3 - 1) * a.ny + (r % 3 - 1)) * a.nx;
 			const uint32_t b0 = a.cell_start[row + qxa - 1];
-			csq[r * (CH_MAXC + 3) + c] = a.cell_start[row + qxa - 1 + c] - b0;
+			csq[r * (CH_MAXC + 3) + c] = (cs_t) (a.cell_start[row + qxa - 1 + c] - b0);
 			if (c == 0) rbq[r] = b0;
+			if (BND) {
+				const uint32_t bb = a.cell_start_b[row + qxa - 1];
+				csbq[r * (CH_MAXC + 3) + c] = (cs_t) (a.cell_start_b[row + qxa - 1 + c] - bb);
+				if (c == 0) rbbq[r] = bb;
+			}
 		}
 	};
 	// The chunk loop is software pipelined: while chunk n is computed, the id of chunk n + 1 is claimed from the work counter,
@@ -131,12 +147,14 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB, LS1_TILE_MINB) k_force_1clj_t
 	uint32_t ch = s_next;
 	Chunk cd; cd.cell0 = 0; cd.ncells = 0; cd.flags = 0;
 	int cur = 0;
-	if (ch < n_chunks) { cd = a.chunks[ch]; if (!(cd.flags & CHUNK_BIG)) fill_cs(cd, cs_all, s_rowbase_all[0]); }
+	if (ch < n_chunks) { cd = a.chunks[ch]; if (!(cd.flags & CHUNK_BIG)) fill_cs(cd, cs_all, s_rowbase_all[0], csb_all, rowbaseB_of(0)); }
 	__syncthreads();
 	uint32_t parity = 0;
 	while (ch < n_chunks) {
-		uint32_t* cs = cs_all + cur * CSB;
+		cs_t* cs = cs_all + cur * CSB;
 		uint32_t* s_rowbase = s_rowbase_all[cur];
+		cs_t* csb = csb_all + cur * CSB;
+		uint32_t* s_rowbaseB = rowbaseB_of(cur);
 		const bool big = (cd.flags & CHUNK_BIG) != 0;
 		const int nc = cd.ncells;
 		const uint32_t R = cd.cell0 / (uint32_t) a.nx;                 // row index cz*ny + cy
@@ -144,13 +162,17 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB, LS1_TILE_MINB) k_force_1clj_t
 		if (threadIdx.x == 0) {
 			if (!big) {
 				uint32_t total = 0;
-				for (int r = 0; r < 9; r++) total += cs[r * (CH_MAXC + 3) + nc + 2] * VB;
+				for (int r = 0; r < 9; r++) total += ((uint32_t) cs[r * (CH_MAXC + 3) + nc + 2] + (BND ? (uint32_t) csb[r * (CH_MAXC + 3) + nc + 2] : 0u)) * VB;
 				if (total) {
 					fence_proxy_async();      // the previous chunk's generic-proxy reads of the windows precede these async-proxy writes
 					mbar_expect_tx(bar, total);
 					for (int r = 0; r < 9; r++) {
 						const uint32_t b = s_rowbase[r], len = cs[r * (CH_MAXC + 3) + nc + 2];
 						if (len) tma_bulk_g2s(win_s + (uint32_t) (r * W) * VB, a.mpos + b, len * VB, bar);
+						if (BND) {      // the imports of the row follow its sorted records in the window
+							const uint32_t bb = s_rowbaseB[r], lenb = csb[r * (CH_MAXC + 3) + nc + 2];
+							if (lenb) tma_bulk_g2s(win_s + (uint32_t) (r * W + (int) len) * VB, a.mpos + bb, lenb * VB, bar);
+						}
 					}
 				}
 			}
@@ -159,20 +181,21 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB, LS1_TILE_MINB) k_force_1clj_t
 		__syncthreads();
 		const uint32_t nch = s_next;
 		Chunk ncd; ncd.cell0 = 0; ncd.ncells = 0; ncd.flags = 0;
-		if (nch < n_chunks) { ncd = a.chunks[nch]; if (!(ncd.flags & CHUNK_BIG)) fill_cs(ncd, cs_all + (cur ^ 1) * CSB, s_rowbase_all[cur ^ 1]); }
+		if (nch < n_chunks) { ncd = a.chunks[nch]; if (!(ncd.flags & CHUNK_BIG)) fill_cs(ncd, cs_all + (cur ^ 1) * CSB, s_rowbase_all[cur ^ 1], csb_all + (cur ^ 1) * CSB, rowbaseB_of(cur ^ 1)); }
 		double acc[3] = {0., 0., 0.};
 		if (big) {
 			// ---- slow generic path: a cell denser than the tile. Global loads, pair evaluated as soon as it is found. ----
-			const uint32_t ib = a.cell_start[cd.cell0], ie = a.cell_start[cd.cell0 + nc];
-			for (uint32_t t = ib + threadIdx.x; t < ie; t += TPB) {
+			auto big_i = [&](uint32_t t) {
 				const V4 mi = a.mpos[t];
 				const uint32_t cid_i = wbits<C>(mi.w) & 0xFFFFu;
 				const int cx = (int) (a.cell_of[t] % (uint32_t) a.nx);
 				C eps24 = a.eps24_0, sig2 = a.sig2_0, shift6 = a.shift6_0;
 				double Fd[3] = {0., 0., 0.}, Vd[3] = {0., 0., 0.}, Ud = 0.;
-				for (int r = 0; r < 9; r++) {
+				for (int rr = 0; rr < NR; rr++) {
+					const int r = rr >= 9 ? rr - 9 : rr;
+					const uint32_t* cst = rr >= 9 ? a.cell_start_b : a.cell_start;
 					const uint32_t row = (uint32_t) ((int) R + (r / 3 - 1) * a.ny + (r % 3 - 1)) * a.nx + cx - 1;
-					const uint32_t jb = a.cell_start[row], je = a.cell_start[row + 3];
+					const uint32_t jb = cst[row], je = cst[row + 3];
 					for (uint32_t j0 = jb; j0 < je; j0 += 32) {
 						C fx[1] = {C(0)}, fy[1] = {C(0)}, fz[1] = {C(0)}, vx[1] = {C(0)}, vy[1] = {C(0)}, vz[1] = {C(0)}, up[1] = {C(0)};
 						int nh = 0;
@@ -201,16 +224,24 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB, LS1_TILE_MINB) k_force_1clj_t
 					a.Vi[t] = 0.5 * Vd[0]; a.Vi[cp + t] = 0.5 * Vd[1]; a.Vi[2 * cp + t] = 0.5 * Vd[2];
 					if (a.M) { a.M[t] = 0.; a.M[cp + t] = 0.; a.M[2 * cp + t] = 0.; }
 				}
-			}
+			};
+			for (uint32_t t = a.cell_start[cd.cell0] + threadIdx.x; t < a.cell_start[cd.cell0 + nc]; t += TPB) big_i(t);
+			if (BND) for (uint32_t t = a.cell_start_b[cd.cell0] + threadIdx.x; t < a.cell_start_b[cd.cell0 + nc]; t += TPB) big_i(t);
 		} else {
-		const uint32_t* csc = cs + 4 * (CH_MAXC + 3);          // centre row (relative record indices)
+		const cs_t* csc = cs + 4 * (CH_MAXC + 3);          // centre row (relative record indices)
 		// thread -> RI consecutive molecules of the chunk (slot order); they may lie in two neighbouring cells
-		const uint32_t n_mol = csc[nc + 1] - csc[1];
+		const cs_t* csbc = csb + 4 * (CH_MAXC + 3);
+		const uint32_t n_molA = (uint32_t) csc[nc + 1] - (uint32_t) csc[1];
+		const uint32_t n_mol = n_molA + (BND ? (uint32_t) csbc[nc + 1] - (uint32_t) csbc[1] : 0u);      // BND: the imports of the chunk's cells are molecules of the chunk too (arrivals)
+		const bool isB = BND && threadIdx.x >= n_molA;                             // my molecule is one of them
 		uint32_t trel[RI]; bool have[RI];
 		#pragma unroll
 		for (int l = 0; l < RI; l++) { have[l] = (uint32_t) RI * threadIdx.x + l < n_mol; trel[l] = csc[1] + (uint32_t) RI * threadIdx.x + l; }
+		const cs_t* cst = isB ? csbc : csc;                                    // the table my molecule is listed in, and its index there
+		const uint32_t tkey = isB ? (uint32_t) csbc[1] + (threadIdx.x - n_molA) : trel[0];
+		if (isB) trel[0] = (uint32_t) csc[nc + 2] + tkey;                                     // its record in the centre row of the window (imports follow the sorted records)
 		int kxa = 0;                                            // cell (inside the chunk) of my first molecule ...
-		while (kxa + 1 < nc && csc[kxa + 2] <= trel[0]) kxa++;
+		while (kxa + 1 < nc && cst[kxa + 2] <= tkey) kxa++;
 		int kxb = kxa;                                          // ... and of my last one
 		if (RI > 1 && have[RI - 1]) { while (kxb + 1 < nc && csc[kxb + 2] <= trel[RI - 1]) kxb++; }
 		mbar_wait(bar, parity); parity ^= 1u;
@@ -241,8 +272,8 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB, LS1_TILE_MINB) k_force_1clj_t
 		auto room = [&]() -> bool { bool ok = true; _Pragma("unroll") for (int l = 0; l < RI; l++) ok = ok && (w[l] <= wlimit[l]); return ok; };
 		for (;;) {
 			bool flush = true;
-			if (r < 9) {
-				if (r == 4) {
+			if (r < NR) {
+				if (r == 4 || (BND && r == 13)) {
 					while (src + 4 * VB <= end && room()) {
 						const V4 m0 = lds_v4<C>(src), m1 = lds_v4<C>(src + VB), m2 = lds_v4<C>(src + 2 * VB), m3 = lds_v4<C>(src + 3 * VB);
 						#pragma unroll
@@ -277,14 +308,19 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB, LS1_TILE_MINB) k_force_1clj_t
 						#pragma unroll
 						for (int l = 0; l < RI; l++) {
 							const C rr = molpair_r2<C>(mi[l].x, mi[l].y, mi[l].z, mj.x, mj.y, mj.z);
-							if (rr < a.ljrc2 && (r != 4 || rr != C(0))) { sts16(w[l], src); w[l] += LSTRIDE; }
+							if (rr < a.ljrc2 && ((r != 4 && !(BND && r == 13)) || rr != C(0))) { sts16(w[l], src); w[l] += LSTRIDE; }
 						}
 					}
 					r++;
-					if (r < 9) {
+					if (r < NR) {
 						uint32_t kb = 0, ke = 0;
+						const int row = (BND && r >= 9) ? r - 9 : r;
+						if (BND && r >= 9) {      // the imports of the row: behind its sorted records
+							const uint32_t off = cs[row * (CH_MAXC + 3) + nc + 2];
+							if (have[0]) { kb = off + csb[row * (CH_MAXC + 3) + kxa]; ke = off + csb[row * (CH_MAXC + 3) + kxb + 3]; }
+						} else
 						if (have[0]) { kb = cs[r * (CH_MAXC + 3) + kxa]; ke = cs[r * (CH_MAXC + 3) + kxb + 3]; }      // cells cxa-1 .. cxb+1 of this row
-						src = win_s + (uint32_t) (r * W + (int) kb) * VB; end = win_s + (uint32_t) (r * W + (int) ke) * VB;
+						src = win_s + (uint32_t) (row * W + (int) kb) * VB; end = win_s + (uint32_t) (row * W + (int) ke) * VB;
 						flush = false;
 					}
 				}
@@ -322,7 +358,7 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB, LS1_TILE_MINB) k_force_1clj_t
 					Ud[l] += (double) up[0] + (double) up[1];
 					w[l] = lbase[l];
 				}
-				if (r >= 9) break;
+				if (r >= NR) break;
 			}
 		}
 		// ---- 4. results ----
@@ -330,7 +366,7 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB, LS1_TILE_MINB) k_force_1clj_t
 		for (int l = 0; l < RI; l++) {
 			if (have[l]) {
 				const size_t cp = a.cap;
-				const uint32_t t = s_rowbase[4] + trel[l];
+				const uint32_t t = isB ? s_rowbaseB[4] + tkey : s_rowbase[4] + trel[l];
 				acc[0] += 0.5 * Ud[l];                          // every pair is visited from both of its ends
 				acc[1] += 0.5 * (Vd[l][0] + Vd[l][1] + Vd[l][2]);
 				if (!RMM && a.kin_v) {
@@ -381,21 +417,26 @@ __global__ void __launch_bounds__(256) k_reduce_force_chunks1(const double* __re
 	}
 	block_reduce_store<3>(v, partials2, blockIdx.x);
 }
-__global__ void __launch_bounds__(RED_BLOCKS) k_reduce_force_chunks2(const double* __restrict__ partials2, DevScalars* scal, int kin) {
+__global__ void __launch_bounds__(RED_BLOCKS) k_reduce_force_chunks2(const double* __restrict__ partials2, DevScalars* scal, int kin, int accumulate) {
 	double v[3] = {partials2[(size_t) threadIdx.x * 8], partials2[(size_t) threadIdx.x * 8 + 1], partials2[(size_t) threadIdx.x * 8 + 2]};
 	__shared__ double out[8];
 	block_reduce_store<3>(v, out, 0);
 	__syncthreads();
 	if (threadIdx.x == 0) {
+		if (accumulate) {      // second pass of the overlapped multi-GPU step (boundary chunks): adds to the sums of the inner chunks
+			scal->upot6lj += out[0]; scal->virial += out[1];
+			if (kin) { scal->summv2 += out[2]; scal->fault = scal->overflow ? 1. : 0.; }
+		} else {
 		scal->upot6lj = out[0]; scal->upot_xpoles = 0.; scal->virial = out[1]; scal->my_rf = 0.;
 		if (kin) { scal->summv2 = out[2]; scal->sum_iw2 = 0.; scal->fault = scal->overflow ? 1. : 0.; }      // what k_reduce_kinetic delivers after leapfrog_post
+		}
 	}
 }
 
 // sums the per-chunk partials of a chunked force kernel into DevScalars (also used by force_1clj_mma.cu)
-int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows, int per_warp, bool kin) {
-	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks1, RED_BLOCKS, 256, 0, c->partials, c->chunk_row_start + nrows, c->partials2, per_warp, kin ? (const double*) c->partials_kin : (const double*) nullptr);
-	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks2, 1, RED_BLOCKS, 0, c->partials2, c->d_scal, (int) kin);
+int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows, int per_warp, bool kin, bool accumulate) {
+	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks1, RED_BLOCKS, 256, 0, c->partials, (accumulate ? c->chunk_row_start_b : c->chunk_row_start) + nrows, c->partials2, per_warp, kin ? (const double*) c->partials_kin : (const double*) nullptr);
+	LS1_LAUNCH(c, PH_FORCE, k_reduce_force_chunks2, 1, RED_BLOCKS, 0, c->partials2, c->d_scal, (int) kin, (int) accumulate);
 	return 0;
 }
 
@@ -405,18 +446,24 @@ static int launch_tiled(ls1b200_ctx* c, float* rmm_v = nullptr, float rmm_dt_m =
 	constexpr int TPB = TileCfg<C>::TPB, W = TileCfg<C>::W, LCAP = TileCfg<C>::LCAP, RI = TileCfg<C>::RI;
 	const Geom& g = c->geom;
 	uint32_t nrows = 0;
-	if (c->chunks_ready) {      // built on the side stream while the sort permuted the state (update.cu)
+	// overlapped multi-GPU step (c->force_pass): 1 = the chunks no import can touch (while the exchange runs), 2 = the others, with the
+	// imports as a second slot range per cell (BND kernel), added to the sums of pass 1; 0 = everything in one pass
+	const int pass = RMM ? 0 : c->force_pass;
+	if (c->chunks_ready && pass != 2) {      // built on the side stream while the sort permuted the state (update.cu)
 		LS1_CUDA(cudaStreamWaitEvent(c->stream, c->ev_c1, 0));
 		nrows = c->chunks_nrows; c->chunks_ready = false;
+	} else if (pass == 2 && c->chunks_b_ready) {      // built on the exchange stream behind the imports' sort (update.cu); the caller has waited for that stream
+		nrows = c->chunks_b_nrows; c->chunks_b_ready = false;
 	} else
-	LS1_TRY(build_chunks(c, TPB * RI, W, 1, &nrows));      // a chunk holds at most TPB * RI molecules
-	Chunk* chunks = (Chunk*) c->chunks;
+	LS1_TRY(build_chunks(c, TPB * RI, W, 1, &nrows, pass, pass == 2 ? (const uint32_t*) c->cell_start_b : (const uint32_t*) nullptr, pass == 2 ? 1 : 0));      // a chunk holds at most TPB * RI molecules
+	Chunk* chunks = (Chunk*) (pass == 2 ? c->chunks_b : c->chunks);
+	uint32_t* row_start = pass == 2 ? c->chunk_row_start_b : c->chunk_row_start;
 	TArgs<C> a;
 	a.mpos = (const V4*) c->mpos; a.cell_start = c->cell_start; a.cell_of = c->cell_of2;
 	if (sizeof(C) == 4) { a.eps24 = (const C*) c->d_eps24f; a.sig2 = (const C*) c->d_sig2f; a.shift6 = (const C*) c->d_shift6f; }
 	else { a.eps24 = (const C*) c->d_eps24; a.sig2 = (const C*) c->d_sig2; a.shift6 = (const C*) c->d_shift6; }
 	a.F = c->F; a.M = c->rotates ? c->M : nullptr; a.Vi = c->Vi; a.partials = c->partials;
-	a.chunks = chunks; a.n_chunks = c->chunk_row_start + nrows; a.work_counter = c->work_counter;
+	a.chunks = chunks; a.n_chunks = row_start + nrows; a.work_counter = pass == 2 ? c->work_counter_b : c->work_counter;
 	a.cap = (uint32_t) c->cap; a.n_lj = c->n_lj; a.nx = g.cells[0]; a.ny = g.cells[1]; a.nz = g.cells[2];
 	const double rclj = c->cfg.cutoff_lj;
 	a.ljrc2 = (C) (rclj * rclj);
@@ -426,20 +473,29 @@ static int launch_tiled(ls1b200_ctx* c, float* rmm_v = nullptr, float rmm_dt_m =
 	a.kin_v = kin ? c->cur.v : nullptr; a.kin_dth = c->kin_dth; a.comps = c->d_comps; a.partials_kin = c->partials_kin;
 	if (kin && !c->partials_kin) return fail("force_1clj_tiled: no buffer for the kinetic partial sums");
 	// the cell_start cache is padded by three rows: the compiler hoists the (guarded) loads of the next row's entries
-	const size_t smem = (size_t) (9 * W + 1) * sizeof(V4) + (size_t) (LCAP + 1) * RI * TPB * 2 + 2 * 12 * (CH_MAXC + 3) * 4;
-	auto kern = c->comps.size() == 1 ? k_force_1clj_tiled<C, true, RMM> : k_force_1clj_tiled<C, false, RMM>;
+	a.cell_start_b = c->cell_start_b;
+	const size_t smem = (size_t) (9 * W + 1) * sizeof(V4) + (size_t) (LCAP + 1) * RI * TPB * 2 + 2 * 12 * (CH_MAXC + 3) * 4;      // (boundary kernel: two 16-bit tables in the room of the one 32-bit table)
+	if (pass == 2 && (!c->cell_start_b || RI != 1)) return fail("force_1clj_tiled: boundary pass without the imports' cell table");
+	auto kern = pass == 2 ? (c->comps.size() == 1 ? k_force_1clj_tiled<C, true, false, true> : k_force_1clj_tiled<C, false, false, true>)
+	                      : (c->comps.size() == 1 ? k_force_1clj_tiled<C, true, RMM> : k_force_1clj_tiled<C, false, RMM>);
 	LS1_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int) smem));
 	int per_sm = 0;
 	LS1_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kern, TPB, smem));
 	if (per_sm < 1) return fail("force_1clj_tiled: kernel does not fit on an SM");
+	// overlapped multi-GPU step, inner pass: the persistent CTAs of this kernel would hold every byte of shared memory until they finish, and
+	// the kernels of the exchange stream (record staging, scans, chunk lists: all need some) could not start beside them -- one CTA less per SM
+	// leaves them room (LS1B200_TILE_MAXCTAS overrides, for measurements)
+	if (pass == 1 && c->tile_pass1_ctas > 0) per_sm = std::min(per_sm, c->tile_pass1_ctas);
+	if (c->tile_max_ctas > 0) per_sm = std::min(per_sm, c->tile_max_ctas);
 	const uint32_t grid = (uint32_t) (c->sm_count * per_sm);
 	LS1_LAUNCH(c, PH_FORCE, kern, grid, TPB, smem, a);
-	return reduce_force_chunks(c, nrows, 1, kin);
+	return reduce_force_chunks(c, nrows, 1, kin, pass == 2);
 }
 
-int build_chunks_tiled_1clj(ls1b200_ctx* c, uint32_t* nrows) {
-	return c->mixed ? build_chunks(c, TileCfg<float>::TPB * TileCfg<float>::RI, TileCfg<float>::W, 1, nrows)
-	                : build_chunks(c, TileCfg<double>::TPB * TileCfg<double>::RI, TileCfg<double>::W, 1, nrows);
+int build_chunks_tiled_1clj(ls1b200_ctx* c, uint32_t* nrows, int mode, int set) {
+	const uint32_t* csb = mode == 2 ? (const uint32_t*) c->cell_start_b : (const uint32_t*) nullptr;
+	return c->mixed ? build_chunks(c, TileCfg<float>::TPB * TileCfg<float>::RI, TileCfg<float>::W, 1, nrows, mode, csb, set)
+	                : build_chunks(c, TileCfg<double>::TPB * TileCfg<double>::RI, TileCfg<double>::W, 1, nrows, mode, csb, set);
 }
 
 int force_1clj_tiled(ls1b200_ctx* c) { return c->mixed ? launch_tiled<float>(c) : launch_tiled<double>(c); }

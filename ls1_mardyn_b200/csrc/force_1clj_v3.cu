@@ -409,7 +409,7 @@ __global__ void __launch_bounds__(V3Cfg<C>::TPB) k_force_1clj_v3(V3Args<C> a) {
 	}
 }
 
-int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows, int per_warp, bool kin = false);      // force_1clj_tiled.cu
+int reduce_force_chunks(ls1b200_ctx* c, uint32_t nrows, int per_warp, bool kin = false, bool accumulate = false);      // force_1clj_tiled.cu
 
 template <class C, int S, int ALIGN>
 static int launch_v3(ls1b200_ctx* c) {

@@ -134,7 +134,7 @@ template <bool FULL>
 __global__ void __launch_bounds__(256) k_export(XArgs a, State st, XOut o, DevScalars* scal, int which) {
 	// persistent blocks striding over the slots: 68 000 blocks of a few hundred nanoseconds each cost more than the scan itself
 	const size_t cap = a.cap;
-	const uint32_t n_slots = scal->overflow ? 0u : min(scal->n_slots2[a.parity], a.cap), n_sorted = scal->n_sorted;      // a failed step exports nothing (the step loop is frozen)
+	const uint32_t n_slots = scal->overflow ? 0u : min(scal->n_slots2[a.parity], a.cap);      // a failed step exports nothing (the step loop is frozen)
 	constexpr int REC = FULL ? (int) sizeof(ls1b200_particle) : (int) sizeof(RecCompact);
 	__shared__ __align__(16) unsigned char stage[8][32 * REC];
 	const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
@@ -145,7 +145,9 @@ __global__ void __launch_bounds__(256) k_export(XArgs a, State st, XOut o, DevSc
 	const int lay = 4;
 	const int nb0 = min(2 * lay, a.nx), nb1 = min(2 * lay, a.ny), nb2 = min(2 * lay, a.nz);
 	const uint32_t ntask = !ranged ? 0u : a.dim == 0 ? (uint32_t) (a.ny * a.nz) * (a.nx > 2 * lay ? 2u : 1u) : a.dim == 1 ? (uint32_t) (a.nz * nb1) : (uint32_t) (nb2 * a.ny);
-	const uint32_t tail0 = ranged ? min(a.cell_start[a.ncells], n_sorted) : 0u;
+	// (cell_start[ncells], the start of the limbo bin, never exceeds the number of sorted slots; DevScalars::n_sorted is not read here: in the
+	//  overlapped step the main stream's sort rewrites it while this kernel still walks the previous order, whose cell_start it was given)
+	const uint32_t tail0 = ranged ? a.cell_start[a.ncells] : 0u;
 	const uint32_t ntail = n_slots > tail0 ? (n_slots - tail0 + 31u) / 32u : 0u;
 	(void) nb0;
 	for (uint32_t task = blockIdx.x * 8u + (uint32_t) wid; task < ntask + ntail; task += gridDim.x * 8u) {

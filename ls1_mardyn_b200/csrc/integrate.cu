@@ -332,7 +332,7 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 	// stages run on their own stream while the main stream integrates the inner slots and builds their part of the cell
 	// histogram; the sort proper waits for the imports. (The force traversal cannot start earlier: one cell-sorted slot array.)
 	const bool overlap = c->dd.active && c->overlap && c->region_flag && c->ever_sorted && (c->dd.comm || c->peer_ok);
-	if (overlap && !c->stream_x) {
+	if ((overlap || (c->dd.active && c->overlap2 && c->fused)) && !c->stream_x) {
 		// highest priority: the exchange is a chain of small kernels (scan, publish, wait, append) whose blocks must not queue behind
 		// the thousands of blocks of the streaming kernels it runs beside
 		int prio_lo = 0, prio_hi = 0;
@@ -346,6 +346,8 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 	// Same floating-point sequence per molecule; the last step of the call runs the ordinary leapfrog_post.
 	bool fused = c->fused && !overlap && !c->rotates && c->all_1clj && c->lj_kernel == 0 && c->fine_s == 1;
 	for (int d = 0; d < 3; d++) if (!c->geom.periodic[d] && !(c->dd.active && c->dd.grid[d] > 1)) fused = false;      // open faces: owned molecules may sit in halo cells, where no force kernel visits them
+	const bool overlap2 = fused && c->dd.active && c->overlap2 && c->ever_sorted && (c->dd.comm || c->peer_ok);
+	if (overlap2 && !c->ev_m) LS1_CUDA(cudaEventCreateWithFlags(&c->ev_m, cudaEventDisableTiming));
 	for (uint64_t s = 0; s < n_steps; s++) {
 		const bool kin_here = fused && s + 1 < n_steps;      // this step's kinetic sum comes from the force kernel, its kick from the next step
 		if (overlap) {
@@ -362,6 +364,27 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 			LS1_TRY(do_update(c, 1));                                           // ... and their keys / histogram
 			LS1_CUDA(cudaStreamWaitEvent(c->stream, c->ev_xb, 0));
 			LS1_TRY(do_update(c, 2));                                           // boundary slots + imports, scan, scatter, gather
+		} else if (overlap2) {
+			// Exchange overlapped with the inner-cell force computation (NonBlockingMPIMultiStepHandler.cpp:28-93). The first kernel has
+			// integrated every slot; from here the three export -> NVLink / NCCL -> import stages run on their own stream and append the
+			// imports behind the previous order, while the main stream sorts the slots it already has and traverses the chunks no
+			// import can touch. The imports get a sort of their own behind the sorted slots; the boundary chunks, which read every cell
+			// as two slot ranges, follow.
+			LS1_TRY(do_pre_key(c, dt, target_temperature > 0., s > 0));
+			LS1_CUDA(cudaEventRecord(c->ev_xa, c->stream));
+			LS1_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_xa, 0));
+			cudaStream_t main_stream = c->stream;
+			c->stream = c->stream_x; c->xchg_phase = PH_XCHG;
+			int rc = do_exchange(c);
+			c->stream = main_stream; c->xchg_phase = PH_UPDATE;
+			if (rc) return rc;
+			LS1_TRY(do_update(c, 4));                                   // records ev_m behind its scan
+			LS1_CUDA(cudaStreamWaitEvent(c->stream_x, c->ev_m, 0));
+			c->stream = c->stream_x;
+			rc = do_update_imports(c);
+			c->stream = main_stream;
+			if (rc) return rc;
+			LS1_CUDA(cudaEventRecord(c->ev_xb, c->stream_x));
 		} else if (fused) {
 			LS1_TRY(do_pre_key(c, dt, target_temperature > 0., s > 0));
 			LS1_TRY(do_exchange(c));
@@ -372,7 +395,30 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 		LS1_TRY(do_update(c));
 		}
 		c->kin_dth = kin_here ? .5 * dt : 0.;
-		const int frc = do_forces(c);
+		int frc;
+		if (overlap2) {
+			// LS1B200_OV2_PROFILE=1: CUDA-event breakdown of the two passes and of the wait between them (synchronises every step)
+			static const bool prof2 = getenv("LS1B200_OV2_PROFILE") != nullptr;
+			static cudaEvent_t pe[4]; static double pacc[3] = {0., 0., 0.}; static int pcalls = 0;
+			if (prof2 && pcalls == 0) for (int k = 0; k < 4; k++) cudaEventCreate(&pe[k]);
+			if (prof2) cudaEventRecord(pe[0], c->stream);
+			c->force_pass = 1;
+			frc = do_forces(c);                                        // the chunks no import can touch, beside the exchange
+			if (prof2) cudaEventRecord(pe[1], c->stream);
+			if (!frc) frc = cudaStreamWaitEvent(c->stream, c->ev_xb, 0) == cudaSuccess ? 0 : fail("ls1b200_simulate: cudaStreamWaitEvent failed");
+			if (prof2) cudaEventRecord(pe[2], c->stream);
+			c->force_pass = 2;
+			if (!frc) frc = do_forces(c);                              // the boundary chunks, imports included
+			c->force_pass = 0;
+			if (prof2) {
+				cudaEventRecord(pe[3], c->stream); cudaEventSynchronize(pe[3]);
+				++pcalls;
+				for (int k = 0; k < 3; k++) { float ms = 0.f; cudaEventElapsedTime(&ms, pe[k], pe[k + 1]); if (pcalls > 5) pacc[k] += ms; }
+				if (pcalls > 5 && pcalls % 10 == 0 && c->dd.rank == 0)
+					fprintf(stderr, "[ls1b200 overlap] inner pass %.3f ms, wait for the imports %.3f ms, boundary pass %.3f ms\n", pacc[0] / (pcalls - 5), pacc[1] / (pcalls - 5), pacc[2] / (pcalls - 5));
+			}
+		} else
+		frc = do_forces(c);
 		c->kin_dth = 0.;
 		if (frc) return frc;
 		if (!kin_here) LS1_TRY(do_leapfrog_post(c, dt));

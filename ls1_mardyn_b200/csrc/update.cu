@@ -32,9 +32,35 @@ struct UpdArgs {
 	double finv;         // S / cell length in x
 	uint32_t parity;     // DevScalars::n_slots2[parity] = source slots of this update, [parity^1] receives the new count
 	const double* bx; const double* by; const double* bz;      // cell border tables (context.cu)
+	// Overlapped multi-GPU step (the exchange runs beside this sort and converts leaving molecules in place): the gather
+	// re-applies the conversion, which is idempotent, to the slots it finds in a halo cell of a cut dimension -- the result does not
+	// depend on whether it read the slot before or after k_export touched it (halo.cu: k_export, LEAVING / HALO shift + clamp)
+	int fix_leavers;
+	int lo_wrap[3], hi_wrap[3];
+	double glen[3], gmin[3], gmax[3], wrap_hi[3], halo_hi[3], halo_lo[3];
 };
 
 __device__ __forceinline__ uint32_t g_ncells(const UpdArgs& a) { return a.g.ncells; }
+
+// Cells (and fine x-bins) of the periodic copies of one molecule: per dimension the cell coordinate of the +L copy (index 1) and of the
+// -L copy (index 2) is evaluated ONCE (bit-exact binning of the shifted coordinate, three FP64 compares each) -- a copy with shift
+// code (a3, b3, c3) lies in cell (hx[a3], hy[b3], hz[c3]); index 0 is the molecule's own cell coordinate.
+struct CopyCells { int hx[3], hy[3], hz[3]; uint32_t fsub[3]; };
+__device__ __forceinline__ void copy_cells(const UpdArgs& a, uint32_t mask, int cx, int cy, int cz, uint32_t sub, double x, double y, double z, CopyCells& h) {
+	const Geom& g = a.g;
+	h.hx[0] = cx; h.hy[0] = cy; h.hz[0] = cz; h.fsub[0] = sub;
+	#pragma unroll
+	for (int k = 1; k < 3; k++) {
+		h.hx[k] = h.hy[k] = h.hz[k] = 0; h.fsub[k] = 0;
+		if ((mask >> (k - 1)) & 1u) {
+			const double xh = halo_coord<0>(g, x, k);
+			h.hx[k] = cell1d_tab<0>(g, a.bx, xh);
+			if (a.S > 1) h.fsub[k] = (uint32_t) fine_sub(xh, __ldg(a.bx + h.hx[k]), a.finv, (int) a.S);
+		}
+		if ((mask >> (2 + k - 1)) & 1u) h.hy[k] = cell1d_tab<1>(g, a.by, halo_coord<1>(g, y, k));
+		if ((mask >> (4 + k - 1)) & 1u) h.hz[k] = cell1d_tab<2>(g, a.bz, halo_coord<2>(g, z, k));
+	}
+}
 __device__ __forceinline__ bool code_valid(uint32_t mask, int a, int b, int c) {
 	return (a == 0 || ((mask >> (a - 1)) & 1u)) && (b == 0 || ((mask >> (2 + b - 1)) & 1u)) && (c == 0 || ((mask >> (4 + c - 1)) & 1u));
 }
@@ -46,6 +72,7 @@ __device__ __forceinline__ void key_slot(const UpdArgs& a, State& cur, uint32_t 
                                          uint32_t* __restrict__ key, uint32_t* __restrict__ count, uint32_t* __restrict__ count_halo, uint32_t* __restrict__ rank) {
 	const Geom& g = a.g;
 	uint32_t bin = KEY_NONE, mask = 0, sub = 0;      // bin: FINE bin (reference cell * S + x sub-bin)
+	int mcx = 0, mcy = 0, mcz = 0;
 	if (in_range && !live) key[s] = KEY_NONE;         // stale halo slot; fresh halo copies (halo.cu) are binned
 	if (live) {
 		if (g.periodic[0]) { double w = wrap_coord<0>(g, x); if (w != x) { x = w; cur.r[s] = w; } }
@@ -56,6 +83,7 @@ __device__ __forceinline__ void key_slot(const UpdArgs& a, State& cur, uint32_t 
 		if (out) { key[s] = g.ncells; bin = g.ncells * a.S; }
 		else {
 			const uint32_t cell = cell_index(g, cx, cy, cz);
+			mcx = cx; mcy = cy; mcz = cz;
 			mask = shift_mask<0>(g, x) | (shift_mask<1>(g, y) << 2) | (shift_mask<2>(g, z) << 4);
 			key[s] = cell | (mask << SHIFT_BITS);
 			if (a.S > 1) sub = (uint32_t) fine_sub(x, __ldg(a.bx + cx), a.finv, (int) a.S);      // S == 1: the reference cell is the bin
@@ -81,11 +109,16 @@ __device__ __forceinline__ void key_slot(const UpdArgs& a, State& cur, uint32_t 
 		if (bin != KEY_NONE) rank[s] = ((base + (uint32_t) (lane - start)) & RANK_MASK) | (sub << RANK_BITS);
 	}
 	if (mask) {
-		for (int c3 = 0; c3 < 3; c3++) for (int b3 = 0; b3 < 3; b3++) for (int a3 = 0; a3 < 3; a3++) {
+		CopyCells h;
+		copy_cells(a, mask, mcx, mcy, mcz, sub, x, y, z, h);
+		#pragma unroll
+		for (int c3 = 0; c3 < 3; c3++)
+		#pragma unroll
+		for (int b3 = 0; b3 < 3; b3++)
+		#pragma unroll
+		for (int a3 = 0; a3 < 3; a3++) {
 			if ((a3 | b3 | c3) == 0 || !code_valid(mask, a3, b3, c3)) continue;
-			const double xh = halo_coord<0>(g, x, a3);
-			const int hx = cell1d_tab<0>(g, a.bx, xh), hy = cell1d_tab<1>(g, a.by, halo_coord<1>(g, y, b3)), hz = cell1d_tab<2>(g, a.bz, halo_coord<2>(g, z, c3));
-			atomicAdd(&count_halo[(cell_index(g, hx, hy, hz) << a.logS) + (a.S > 1 ? (uint32_t) fine_sub(xh, __ldg(a.bx + hx), a.finv, (int) a.S) : 0u)], 1u);
+			atomicAdd(&count_halo[(cell_index(g, h.hx[a3], h.hy[b3], h.hz[c3]) << a.logS) + h.fsub[a3]], 1u);
 		}
 	}
 }
@@ -107,10 +140,10 @@ __global__ void __launch_bounds__(256) k_key(UpdArgs a, State cur, uint32_t* __r
 }
 
 // fused step, decomposed contexts: the imports the exchange appended behind the sorted slots (a few per cent of the slots) -- a small
-// grid that starts at n_sorted instead of a launch over the whole capacity
+// grid that starts at n_pre (the slots k_pre_key binned) instead of a launch over the whole capacity
 __global__ void __launch_bounds__(256) k_key_tail(UpdArgs a, State cur, uint32_t* __restrict__ key, uint32_t* __restrict__ count, uint32_t* __restrict__ count_halo,
                                                    uint32_t* __restrict__ rank, const DevScalars* __restrict__ scal) {
-	const uint32_t n = min(scal->n_slots2[a.parity], a.cap), first = min(scal->n_sorted, n);
+	const uint32_t n = min(scal->n_slots2[a.parity], a.cap), first = min(scal->n_pre, n);
 	for (uint32_t base = first + blockIdx.x * blockDim.x; base < n; base += gridDim.x * blockDim.x) {      // uniform per block: every warp calls key_slot together
 		const uint32_t s = base + threadIdx.x;
 		const bool in_range = s < n;
@@ -130,11 +163,12 @@ __global__ void __launch_bounds__(256) k_key_tail(UpdArgs a, State cur, uint32_t
 // load + upd_preF (half kick, drift) + the binning of k_key on the new position, which is still in registers: the slot state
 // is read and written once, the FP64 compares of the binning hide behind the memory traffic of the integration.
 // Same floating-point sequence per molecule as k_leapfrog_post -> k_scale -> k_leapfrog_pre -> k_key.
-__global__ void __launch_bounds__(256) k_pre_key(UpdArgs a, State cur, const double* __restrict__ F, const CompDev* __restrict__ comps, double dt, int use_beta, int post_kick,
+__global__ void __launch_bounds__(256, 8) k_pre_key(UpdArgs a, State cur, const double* __restrict__ F, const CompDev* __restrict__ comps, double dt, int use_beta, int post_kick,
                                                   uint32_t* __restrict__ key, uint32_t* __restrict__ count, uint32_t* __restrict__ count_halo, uint32_t* __restrict__ rank,
-                                                  const DevScalars* __restrict__ scal) {
+                                                  DevScalars* __restrict__ scal) {
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool in_range = s < min(scal->n_slots2[a.parity], a.cap);
+	if (s == 0) scal->n_pre = min(scal->n_slots2[a.parity], a.cap);      // the slots this kernel bins; what the exchange appends later lies behind
 	bool live = false;
 	double r[3] = {0., 0., 0.};
 	if (in_range) {
@@ -219,29 +253,27 @@ __global__ void __launch_bounds__(SCAN_T) k_scan_top(uint32_t* __restrict__ bsum
 // (n = ncells * S + 1 FINE bins; `coarse` = the reference cells' cell_start: entry c is the start of fine bin c * S)
 __global__ void __launch_bounds__(SCAN_T) k_scan_add(uint32_t* __restrict__ start, uint32_t* __restrict__ cursor, const uint32_t* __restrict__ count, const uint32_t* __restrict__ bsum,
                                                       const uint32_t* __restrict__ grand_total, uint32_t n, uint32_t cap, uint32_t parity, DevScalars* scal,
-                                                      uint32_t* __restrict__ coarse, uint32_t S) {
+                                                      uint32_t* __restrict__ coarse, uint32_t S, int tail) {
 	const uint32_t base = blockIdx.x * SCAN_B + threadIdx.x * SCAN_V;
-	const uint32_t off = bsum[blockIdx.x];
+	// tail: the bins of the imports of the overlapped step; their slots follow the n_sorted slots of the main sort
+	const uint32_t off = bsum[blockIdx.x] + (tail ? scal->n_sorted : 0u);
 	#pragma unroll
 	for (int k = 0; k < SCAN_V; k++) if (base + k < n) {
 		uint32_t v = start[base + k] + off; start[base + k] = v; cursor[base + k] = v + count[base + k];      // halo copies follow the ranked entries
 		if (coarse != start && ((base + k) & (S - 1u)) == 0) coarse[(base + k) / S] = v;
 	}
 	if (blockIdx.x == 0 && threadIdx.x == 0) {
-		const uint32_t total = *grand_total;
+		const uint32_t total = *grand_total + (tail ? scal->n_sorted : 0u);
 		start[n] = total;
 		if (coarse != start) coarse[(n - 1) / S + 1] = total;
 		scal->n_slots2[parity ^ 1u] = total;
-		scal->n_sorted = min(total, cap);
+		if (!tail) scal->n_sorted = min(total, cap);
 		if (total > cap) scal->overflow = 1;
 	}
 }
 
-__global__ void __launch_bounds__(256) k_scatter(UpdArgs a, State cur, const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ cell_start,
-                                                  uint32_t* __restrict__ cursor, uint32_t* __restrict__ entry, uint32_t* __restrict__ cell_of, const DevScalars* __restrict__ scal,
-                                                  uint64_t* __restrict__ ekey) {
-	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
-	if (s >= min(scal->n_slots2[a.parity], a.cap)) return;
+__device__ __forceinline__ void scatter_slot(const UpdArgs& a, const State& cur, uint32_t s, const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ cell_start,
+                                             uint32_t* __restrict__ cursor, uint32_t* __restrict__ entry, uint32_t* __restrict__ cell_of, uint64_t* __restrict__ ekey) {
 	const uint32_t k = key[s];
 	if (k == KEY_NONE) return;
 	const Geom& g = a.g;
@@ -255,26 +287,45 @@ __global__ void __launch_bounds__(256) k_scatter(UpdArgs a, State cur, const uin
 	if (p < a.cap) { entry[p] = s << 5; cell_of[p] = bin; if (ekey) ekey[p] = idk; }
 	if (mask) {
 		const double x = cur.r[s], y = cur.r[(size_t) a.cap + s], z = cur.r[2 * (size_t) a.cap + s];
-		for (int c3 = 0; c3 < 3; c3++) for (int b3 = 0; b3 < 3; b3++) for (int a3 = 0; a3 < 3; a3++) {
+		CopyCells h;
+		copy_cells(a, mask, (int) (cell % (uint32_t) g.cells[0]), (int) ((cell / (uint32_t) g.cells[0]) % (uint32_t) g.cells[1]), (int) (cell / (uint32_t) (g.cells[0] * g.cells[1])), rk >> RANK_BITS, x, y, z, h);
+		#pragma unroll
+		for (int c3 = 0; c3 < 3; c3++)
+		#pragma unroll
+		for (int b3 = 0; b3 < 3; b3++)
+		#pragma unroll
+		for (int a3 = 0; a3 < 3; a3++) {
 			if ((a3 | b3 | c3) == 0 || !code_valid(mask, a3, b3, c3)) continue;
-			const double xh = halo_coord<0>(g, x, a3);
-			const int hx = cell1d_tab<0>(g, a.bx, xh), hy = cell1d_tab<1>(g, a.by, halo_coord<1>(g, y, b3)), hz = cell1d_tab<2>(g, a.bz, halo_coord<2>(g, z, c3));
-			const uint32_t hb = (cell_index(g, hx, hy, hz) << a.logS) + (a.S > 1 ? (uint32_t) fine_sub(xh, __ldg(a.bx + hx), a.finv, (int) a.S) : 0u);
+			const uint32_t hb = (cell_index(g, h.hx[a3], h.hy[b3], h.hz[c3]) << a.logS) + h.fsub[a3];
 			p = atomicAdd(&cursor[hb], 1u);      // the periodic copies of a bin follow its ranked entries
 			if (p < a.cap) { entry[p] = (s << 5) | (uint32_t) (a3 + 3 * b3 + 9 * c3); cell_of[p] = hb; if (ekey) ekey[p] = idk | (uint64_t) (a3 + 3 * b3 + 9 * c3); }
 		}
 	}
 }
 
+// seg 0: every slot; 1: the slots k_pre_key binned (overlapped multi-GPU step: the exchange appends imports behind them meanwhile)
+__global__ void __launch_bounds__(256) k_scatter(UpdArgs a, State cur, const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ cell_start,
+                                                  uint32_t* __restrict__ cursor, uint32_t* __restrict__ entry, uint32_t* __restrict__ cell_of, const DevScalars* __restrict__ scal,
+                                                  uint64_t* __restrict__ ekey, int seg) {
+	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
+	if (s >= min(seg == 1 ? scal->n_pre : scal->n_slots2[a.parity], a.cap)) return;
+	scatter_slot(a, cur, s, key, rank, cell_start, cursor, entry, cell_of, ekey);
+}
+// the imports of the overlapped step, [n_pre, n_slots): their own histogram / cell_start (absolute slots behind n_sorted), small grid
+__global__ void __launch_bounds__(256) k_scatter_tail(UpdArgs a, State cur, const uint32_t* __restrict__ key, const uint32_t* __restrict__ rank, const uint32_t* __restrict__ cell_start,
+                                                       uint32_t* __restrict__ cursor, uint32_t* __restrict__ entry, uint32_t* __restrict__ cell_of, const DevScalars* __restrict__ scal,
+                                                       uint64_t* __restrict__ ekey) {
+	const uint32_t n = min(scal->n_slots2[a.parity], a.cap);
+	for (uint32_t s = min(scal->n_pre, n) + blockIdx.x * blockDim.x + threadIdx.x; s < n; s += gridDim.x * blockDim.x)
+		scatter_slot(a, cur, s, key, rank, cell_start, cursor, entry, cell_of, ekey);
+}
+
 template <class C>
-__global__ void __launch_bounds__(256) k_gather(UpdArgs a, State cur, State nxt, const uint32_t* __restrict__ entry, const uint32_t* __restrict__ cell_of,
-                                                 const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_of2,
-                                                 typename Vec4<C>::type* __restrict__ mpos, const DevScalars* __restrict__ scal, int rotates,
-                                                 double* __restrict__ F, double* __restrict__ Vi, double* __restrict__ M, const uint64_t* __restrict__ ekey,
-                                                 uint8_t* __restrict__ region_flag) {
-	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
-	const uint32_t n_slots = min(scal->n_slots2[a.parity ^ 1u], a.cap);
-	if (p >= n_slots) return;
+__device__ __forceinline__ void gather_slot(const UpdArgs& a, const State& cur, const State& nxt, uint32_t p, const uint32_t* __restrict__ entry, const uint32_t* __restrict__ cell_of,
+                                            const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_of2,
+                                            typename Vec4<C>::type* __restrict__ mpos, int rotates,
+                                            double* __restrict__ F, double* __restrict__ Vi, double* __restrict__ M, const uint64_t* __restrict__ ekey,
+                                            uint8_t* __restrict__ region_flag) {
 	const Geom& g = a.g;
 	const uint32_t e = entry[p], fb = cell_of[p];              // fine bin; cell_start is the FINE array
 	const uint32_t c = min(fb >> a.logS, g.ncells);            // reference cell (limbo: ncells)
@@ -290,6 +341,25 @@ __global__ void __launch_bounds__(256) k_gather(UpdArgs a, State cur, State nxt,
 		const int a3 = code % 3, b3 = (code / 3) % 3, c3 = code / 9;
 		x = halo_coord<0>(g, x, a3); y = halo_coord<1>(g, y, b3); z = halo_coord<2>(g, z, c3);
 		meta |= META_HALO;
+	}
+	if (a.fix_leavers && c < g.ncells) {
+		// A molecule this rank owned that now lies in the halo layer of a face shared with another rank has left: it stays behind as
+		// the halo copy of the molecule its new owner holds. k_export does this conversion in place while this kernel runs
+		// (overlapped step); applied again here it gives the same value whichever state this thread read.
+		const int cc[3] = {(int) (c % (uint32_t) g.cells[0]), (int) ((c / (uint32_t) g.cells[0]) % (uint32_t) g.cells[1]), (int) (c / (uint32_t) (g.cells[0] * g.cells[1]))};
+		double* rr[3] = {&x, &y, &z};
+		#pragma unroll
+		for (int d = 0; d < 3; d++) {
+			if (!a.cut[d]) continue;
+			double& v = *rr[d];
+			if (cc[d] == 0 && v < g.bmin[d]) {
+				meta |= META_HALO;
+				if (a.lo_wrap[d]) { double xl = __dadd_rn(v, a.glen[d]); if (xl >= a.gmax[d]) xl = a.wrap_hi[d]; double xh = __dsub_rn(xl, a.glen[d]); if (xh >= a.gmin[d]) xh = a.halo_lo[d]; v = xh; }
+			} else if (cc[d] == g.cells[d] - 1 && v >= g.bmax[d]) {
+				meta |= META_HALO;
+				if (a.hi_wrap[d]) { double xl = __dsub_rn(v, a.glen[d]); if (xl < a.gmin[d]) xl = a.gmin[d]; double xh = __dadd_rn(xl, a.glen[d]); if (xh < a.gmax[d]) xh = a.halo_hi[d]; v = xh; }
+			}
+		}
 	}
 	meta &= ~META_FRESH;      // a fresh halo copy of this step's exchange is an ordinary (stale after this sort) halo slot from here on
 	if (ekey) nxt.id[t] = cur.id[s];
@@ -311,6 +381,28 @@ __global__ void __launch_bounds__(256) k_gather(UpdArgs a, State cur, State nxt,
 	if (inert && !meta_halo(meta)) {   // an owned molecule no force kernel visits (halo-cell resident, limbo): its force is zero
 		for (int d = 0; d < 3; d++) { F[d * cap + t] = 0.; Vi[d * cap + t] = 0.; if (M) M[d * cap + t] = 0.; }
 	}
+}
+
+template <class C>
+__global__ void __launch_bounds__(256) k_gather(UpdArgs a, State cur, State nxt, const uint32_t* __restrict__ entry, const uint32_t* __restrict__ cell_of,
+                                                 const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_of2,
+                                                 typename Vec4<C>::type* __restrict__ mpos, const DevScalars* __restrict__ scal, int rotates,
+                                                 double* __restrict__ F, double* __restrict__ Vi, double* __restrict__ M, const uint64_t* __restrict__ ekey,
+                                                 uint8_t* __restrict__ region_flag, int seg) {
+	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
+	// seg 1 (overlapped multi-GPU step): the slots of THIS sort only -- the imports' sort, on the exchange stream, may already have added its own to n_slots2
+	if (p >= min(seg == 1 ? scal->n_sorted : scal->n_slots2[a.parity ^ 1u], a.cap)) return;
+	gather_slot<C>(a, cur, nxt, p, entry, cell_of, cell_start, cell_of2, mpos, rotates, F, Vi, M, ekey, region_flag);
+}
+// the imports of the overlapped step: destination slots [n_sorted, n_slots2[parity ^ 1]) (cell_start: the imports' own, absolute)
+template <class C>
+__global__ void __launch_bounds__(256) k_gather_tail(UpdArgs a, State cur, State nxt, const uint32_t* __restrict__ entry, const uint32_t* __restrict__ cell_of,
+                                                      const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_of2,
+                                                      typename Vec4<C>::type* __restrict__ mpos, const DevScalars* __restrict__ scal, int rotates,
+                                                      double* __restrict__ F, double* __restrict__ Vi, double* __restrict__ M, const uint64_t* __restrict__ ekey) {
+	const uint32_t n = min(scal->n_slots2[a.parity ^ 1u], a.cap);
+	for (uint32_t p = min(scal->n_sorted, n) + blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
+		gather_slot<C>(a, cur, nxt, p, entry, cell_of, cell_start, cell_of2, mpos, rotates, F, Vi, M, ekey, nullptr);
 }
 
 // ---- site expansion (FullMolecule::setupSoACache, molecules/FullMolecule.cpp:711-767; Quaternion::rotate, Quaternion.cpp:43-64)
@@ -354,12 +446,15 @@ __global__ void __launch_bounds__(128) k_sites(State st, uint32_t cap, uint32_t 
 
 // exclusive scan of cell_count + cell_count_halo over nb bins -> fstart (+ the reference cells' cell_start, the scatter cursor and
 // the slot count of the new order in DevScalars::n_slots2[parity ^ 1]); shared with the reduced-memory path (rmm.cu)
-int launch_bin_scan(ls1b200_ctx* c, uint32_t nb, uint32_t* fstart, uint32_t parity) {
+static int launch_bin_scan_ex(ls1b200_ctx* c, uint32_t nb, uint32_t* count, uint32_t* count_halo, uint32_t* fstart, uint32_t* scan_tmp, uint32_t* cursor, uint32_t* coarse, uint32_t parity, int tail) {
 	const uint32_t sb = (nb + SCAN_B - 1) / SCAN_B;
-	LS1_LAUNCH(c, PH_UPDATE, k_scan_block, sb, SCAN_T, 0, c->cell_count, c->cell_count_halo, fstart, c->scan_tmp, nb);
-	LS1_LAUNCH(c, PH_UPDATE, k_scan_top, 1, SCAN_T, 0, c->scan_tmp, sb, c->scan_tmp + sb);
-	LS1_LAUNCH(c, PH_UPDATE, k_scan_add, sb, SCAN_T, 0, fstart, c->cursor, c->cell_count, c->scan_tmp, c->scan_tmp + sb, nb, (uint32_t) c->cap, parity, c->d_scal, c->cell_start, c->fine_s);
+	LS1_LAUNCH(c, PH_UPDATE, k_scan_block, sb, SCAN_T, 0, count, count_halo, fstart, scan_tmp, nb);
+	LS1_LAUNCH(c, PH_UPDATE, k_scan_top, 1, SCAN_T, 0, scan_tmp, sb, scan_tmp + sb);
+	LS1_LAUNCH(c, PH_UPDATE, k_scan_add, sb, SCAN_T, 0, fstart, cursor, count, scan_tmp, scan_tmp + sb, nb, (uint32_t) c->cap, parity, c->d_scal, coarse, c->fine_s, tail);
 	return 0;
+}
+int launch_bin_scan(ls1b200_ctx* c, uint32_t nb, uint32_t* fstart, uint32_t parity) {
+	return launch_bin_scan_ex(c, nb, c->cell_count, c->cell_count_halo, fstart, c->scan_tmp, c->cursor, c->cell_start, parity, 0);
 }
 
 Region make_region(const ls1b200_ctx* c, int mode);      // integrate.cu
@@ -368,6 +463,13 @@ static UpdArgs make_upd_args(const ls1b200_ctx* c) {
 	UpdArgs a; a.g = c->geom; a.cap = (uint32_t) c->cap; a.parity = c->parity; for (int d = 0; d < 3; d++) a.cut[d] = c->dd.active && c->dd.grid[d] > 1;
 	a.S = c->fine_s; a.logS = c->fine_s == 8 ? 3u : c->fine_s == 4 ? 2u : c->fine_s == 2 ? 1u : 0u; a.finv = c->fine_inv;
 	a.bx = c->d_border; a.by = c->d_border + c->border_stride; a.bz = c->d_border + 2 * (size_t) c->border_stride;
+	a.fix_leavers = 0;
+	for (int d = 0; d < 3; d++) {
+		const auto& dd = c->dd;
+		a.lo_wrap[d] = dd.active && dd.coords[d] == 0; a.hi_wrap[d] = dd.active && dd.coords[d] == dd.grid[d] - 1;
+		a.gmin[d] = dd.gmin[d]; a.gmax[d] = dd.gmax[d]; a.glen[d] = dd.gmax[d] - dd.gmin[d];
+		a.wrap_hi[d] = dd.wrap_hi[d]; a.halo_hi[d] = dd.halo_hi[d]; a.halo_lo[d] = dd.halo_lo[d];
+	}
 	return a;
 }
 
@@ -390,19 +492,33 @@ int do_update(ls1b200_ctx* c, int part) {
 	if (c->n_owned == 0 && !c->dd.active) { c->sorted = true; return 0; }
 	if (c->cap == 0) return fail("ls1b200_update: call ls1b200_upload first");
 	LS1_TRY(span_begin(c, PH_UPDATE));
-	const UpdArgs a = make_upd_args(c);
+	UpdArgs a = make_upd_args(c);
+	a.fix_leavers = part == 4;
 	const uint32_t nb = c->geom.ncells * c->fine_s + 1;   // fine bins + limbo bin
 	// slot counts are only known on the device: every per-slot kernel is launched over the capacity, threads beyond exit
 	const uint32_t gs = (uint32_t) ((c->cap + 255) / 256);
 	if (part == 0 || part == 1) LS1_CUDA(cudaMemsetAsync(c->cell_count, 0, sizeof(uint32_t) * 2 * ((size_t) c->geom.ncells * c->fine_s + 4), c->stream));      // cell_count and cell_count_halo
 	// part 3: the sorted slots were binned by k_pre_key; only the imports the exchange appended behind them are left (decomposed contexts)
-	if (part == 3) {
+	// part 4: the overlapped multi-GPU step -- as part 3, but the imports are NOT part of this sort (the exchange is still appending them
+	// on its own stream; do_update_imports sorts them behind these slots later)
+	if (part == 4) {
+	} else if (part == 3) {
 		if (c->dd.active) LS1_LAUNCH(c, PH_UPDATE, k_key_tail, 592, 256, 0, a, c->cur, c->key, c->cell_count, c->cell_count_halo, c->rank, c->d_scal);
 	} else
 		LS1_LAUNCH(c, PH_UPDATE, k_key, gs, 256, 0, a, c->cur, c->key, c->cell_count, c->cell_count_halo, c->rank, c->d_scal, make_region(c, part == 0 ? 0 : part == 1 ? 2 : part == 2 ? 1 : 3));
 	if (part == 1) { LS1_TRY(span_end(c)); return 0; }
 	// cell_start_fine: exclusive scan over the fine bins; cell_start (the reference cells) is every S-th entry of it
 	uint32_t* fstart = c->fine_s > 1 ? c->cell_start_fine : c->cell_start;
+	if (part == 4) {
+		// the exchange is still walking the PREVIOUS order on its own stream, with the cell_start it was launched with: this sort writes the other buffer
+		if (c->fine_s != 1) return fail("ls1b200_update: the overlapped step needs one bin per cell");
+		if (!c->cell_start_alt) LS1_CUDA(cudaMalloc((void**) &c->cell_start_alt, sizeof(uint32_t) * ((size_t) c->geom.ncells + 4)));
+		std::swap(c->cell_start, c->cell_start_alt);
+		fstart = c->cell_start;
+		LS1_TRY(launch_bin_scan_ex(c, nb, c->cell_count, c->cell_count_halo, fstart, c->scan_tmp, c->cursor, fstart, a.parity, 0));
+		// from here the imports' sort may run (exchange stream): it needs n_sorted and writes behind the slots this sort fills
+		LS1_CUDA(cudaEventRecord(c->ev_m, c->stream));
+	} else
 	LS1_TRY(launch_bin_scan(c, nb, fstart, a.parity));
 	// The chunk list of the production 1CLJ kernel needs cell_start only: it is built on a side stream while scatter and gather
 	// (HBM bound) permute the state; the force kernel waits for it (force_1clj_tiled.cu). The reduced-memory path has its own sort.
@@ -418,18 +534,18 @@ int do_update(ls1b200_ctx* c, int part) {
 		LS1_CUDA(cudaStreamWaitEvent(c->stream_c, c->ev_c0, 0));
 		cudaStream_t main_stream = c->stream;
 		c->stream = c->stream_c;
-		const int rc = build_chunks_tiled_1clj(c, &c->chunks_nrows);
+		const int rc = build_chunks_tiled_1clj(c, &c->chunks_nrows, part == 4 ? 1 : 0);
 		c->stream = main_stream;
 		if (rc) return rc;
 		LS1_CUDA(cudaEventRecord(c->ev_c1, c->stream_c));
 		c->chunks_ready = true;
 	}
-	LS1_LAUNCH(c, PH_UPDATE, k_scatter, gs, 256, 0, a, c->cur, c->key, c->rank, (const uint32_t*) fstart, c->cursor, c->entry, c->cell_of, c->d_scal, c->dd.active ? c->ekey : (uint64_t*) nullptr);
+	LS1_LAUNCH(c, PH_UPDATE, k_scatter, gs, 256, 0, a, c->cur, c->key, c->rank, (const uint32_t*) fstart, c->cursor, c->entry, c->cell_of, c->d_scal, c->dd.active ? c->ekey : (uint64_t*) nullptr, part == 4 ? 1 : 0);
 	const uint32_t gc = gs;
 	if (c->mixed)
-		LS1_LAUNCH(c, PH_UPDATE, k_gather<float>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, (const uint32_t*) fstart, c->cell_of2, (float4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr, c->region_flag);
+		LS1_LAUNCH(c, PH_UPDATE, k_gather<float>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, (const uint32_t*) fstart, c->cell_of2, (float4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr, c->region_flag, part == 4 ? 1 : 0);
 	else
-		LS1_LAUNCH(c, PH_UPDATE, k_gather<double>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, (const uint32_t*) fstart, c->cell_of2, (double4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr, c->region_flag);
+		LS1_LAUNCH(c, PH_UPDATE, k_gather<double>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, (const uint32_t*) fstart, c->cell_of2, (double4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr, c->region_flag, part == 4 ? 1 : 0);
 	std::swap(c->cur, c->nxt);
 	c->parity ^= 1u;
 	if (!c->all_1clj) {
@@ -442,6 +558,40 @@ int do_update(ls1b200_ctx* c, int part) {
 	LS1_TRY(span_end(c));
 	c->sorted = true; c->ever_sorted = true;
 	c->forces_valid = false;
+	return 0;
+}
+
+// Overlapped multi-GPU step: the imports the exchange appended behind the n_pre slots of the OLD order (c->nxt after do_update(c, 4)
+// swapped the buffers) get a sort of their own -- histogram, scan, scatter, gather with their own bin arrays -- into the slots behind
+// the n_sorted slots of the main sort. cell_start_b[cell] is absolute: the force kernel reads a cell's molecules as two ranges.
+// Runs on c->stream (the caller puts the exchange stream there) after the main gather has finished.
+int do_update_imports(ls1b200_ctx* c) {
+	if (c->fine_s != 1) return fail("do_update_imports: one bin per cell");
+	const uint32_t nb = c->geom.ncells + 1;
+	if (!c->cell_count_b) {
+		const size_t nbb = (size_t) c->geom.ncells + 4;
+		uint32_t* p = nullptr;
+		LS1_CUDA(cudaMalloc((void**) &p, sizeof(uint32_t) * (4 * nbb + nbb / 2048 + 16)));
+		c->cell_count_b = p; c->cell_start_b = p + 2 * nbb; c->cursor_b = p + 3 * nbb; c->scan_tmp_b = p + 4 * nbb;
+	}
+	const size_t nbb = (size_t) c->geom.ncells + 4;
+	UpdArgs a = make_upd_args(c);
+	a.parity = c->parity ^ 1u;      // the order the imports were appended to
+	LS1_CUDA(cudaMemsetAsync(c->cell_count_b, 0, sizeof(uint32_t) * 2 * nbb, c->stream));
+	uint32_t* count = c->cell_count_b; uint32_t* count_halo = c->cell_count_b + nbb;
+	LS1_LAUNCH(c, PH_XCHG, k_key_tail, 296, 256, 0, a, c->nxt, c->key, count, count_halo, c->rank, c->d_scal);
+	LS1_TRY(launch_bin_scan_ex(c, nb, count, count_halo, c->cell_start_b, c->scan_tmp_b, c->cursor_b, c->cell_start_b, a.parity, 1));
+	LS1_LAUNCH(c, PH_XCHG, k_scatter_tail, 296, 256, 0, a, c->nxt, c->key, c->rank, (const uint32_t*) c->cell_start_b, c->cursor_b, c->entry, c->cell_of, c->d_scal, c->ekey);
+	if (c->mixed)
+		LS1_LAUNCH(c, PH_XCHG, k_gather_tail<float>, 296, 256, 0, a, c->nxt, c->cur, c->entry, c->cell_of, (const uint32_t*) c->cell_start_b, c->cell_of2, (float4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, (const uint64_t*) c->ekey);
+	else
+		LS1_LAUNCH(c, PH_XCHG, k_gather_tail<double>, 296, 256, 0, a, c->nxt, c->cur, c->entry, c->cell_of, (const uint32_t*) c->cell_start_b, c->cell_of2, (double4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, (const uint64_t*) c->ekey);
+	// the chunk list of the boundary pass (its own buffers: the inner chunks are being traversed on the main stream)
+	c->chunks_b_ready = false;
+	if (c->all_1clj && c->lj_kernel == 0) {
+		LS1_TRY(build_chunks_tiled_1clj(c, &c->chunks_b_nrows, 2, 1));
+		c->chunks_b_ready = true;
+	}
 	return 0;
 }
 

@@ -53,7 +53,7 @@ def components_xml(ens: Ensemble) -> str:
 
 def simulation_xml(ens: Ensemble, length, temperature, dt, steps, rc, rc_lj=None, epsilon_rf=1e10, phasespace_file=None,
                    generator_density=None, datastructure="LinkedCells", integrator="Leapfrog", longrange="none",
-                   result_prefix="res", extra_output="", datastructure_extra="") -> str:
+                   result_prefix="res", extra_output="", datastructure_extra="", cells_in_cutoff=1) -> str:
     """One <mardyn> document: NVT (velocity scaling to `temperature`), periodic box, C08 LinkedCells (or the B200 container),
     ReactionField epsilon, ResultWriter with 15 digits every step. `longrange="none"` (NoLRC) keeps U_pot and p the raw
     sums of the force path; pass "homogeneous" for the reference's default."""
@@ -79,7 +79,7 @@ def simulation_xml(ens: Ensemble, length, temperature, dt, steps, rc, rc_lj=None
   </ensemble>
   <algorithm>
    <parallelisation type="DomainDecomposition"></parallelisation>
-   <datastructure type="%s"><cellsInCutoffRadius>1</cellsInCutoffRadius>%s</datastructure>
+   <datastructure type="%s"><cellsInCutoffRadius>%d</cellsInCutoffRadius>%s</datastructure>
    <cutoffs type="CenterOfMass"><defaultCutoff unit="reduced">%r</defaultCutoff><radiusLJ unit="reduced">%r</radiusLJ></cutoffs>
    <electrostatic type="ReactionField"><epsilon>%r</epsilon></electrostatic>
    <longrange type="%s"></longrange>
@@ -88,4 +88,4 @@ def simulation_xml(ens: Ensemble, length, temperature, dt, steps, rc, rc_lj=None
  </simulation>
 </mardyn>
 """ % (integrator, float(dt), int(steps), float(temperature), float(length[0]), float(length[1]), float(length[2]),
-       components_xml(ens), psp, datastructure, datastructure_extra, float(rc), float(rc_lj), float(epsilon_rf), longrange, out, extra_output)
+       components_xml(ens), psp, datastructure, int(cells_in_cutoff), datastructure_extra, float(rc), float(rc_lj), float(epsilon_rf), longrange, out, extra_output)

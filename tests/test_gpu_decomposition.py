@@ -238,15 +238,19 @@ def test_balanced_blocks_on_one_device(capi, prec):
         assert sum(k.n_molecules for k in kg) == len(ps.id)
 
 
-@pytest.mark.parametrize("transport", ["peer", "nccl", "peer-overlap", "nccl-overlap"])
+@pytest.mark.parametrize("transport", ["peer", "nccl", "peer-overlap2", "nccl-overlap2", "peer-overlap1"])
 def test_nccl_two_gpus(capi, tmp_path, transport):
     """The transports inside the library (ls1b200_exchange inside ls1b200_simulate), one process per GPU: records stored
-    straight into the neighbour's memory over NVLink (CUDA IPC, ls1b200_peer_attach), and NCCL send / recv; "-overlap": the
-    exchange on its own stream beside the integration / binning of the inner slots (LS1B200_OVERLAP=1)."""
+    straight into the neighbour's memory over NVLink (CUDA IPC, ls1b200_peer_attach), and NCCL send / recv. Default: the exchange
+    in front of the sort. "-overlap2" (LS1B200_OVERLAP2=1): the exchange on its own stream beside the sort and the force traversal
+    of the inner chunks, the imports sorted behind the sorted slots, the boundary chunks reading every cell as two slot ranges
+    (1CLJ; the rotating system of the worker takes the in-line path); "-overlap1" (LS1B200_OVERLAP=1): the exchange beside the
+    integration / binning of the inner slots. Both overlapped variants are parity-green and measured slower (profiles/r02_multi_gpu.md)."""
     import torch
     if torch.cuda.device_count() < 2:
         pytest.skip("needs two GPUs (run under gpurun --gpus 2)")
     cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1", "--master-port", "29641",
            os.path.join(ROOT, "tests", "nccl_decomposition_worker.py")]
-    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PYTHONPATH=ROOT, LS1B200_TRANSPORT=transport.split("-")[0], LS1B200_OVERLAP="1" if transport.endswith("overlap") else "0"))
+    p = subprocess.run(cmd, capture_output=True, text=True, timeout=600, env=dict(os.environ, PYTHONPATH=ROOT, LS1B200_TRANSPORT=transport.split("-")[0], LS1B200_OVERLAP="1" if transport.endswith("overlap1") else "0",
+                                LS1B200_OVERLAP2="1" if transport.endswith("overlap2") else "0"))
     assert p.returncode == 0 and "NCCL-DECOMP-OK" in p.stdout, p.stdout[-3000:] + p.stderr[-3000:]

@@ -81,6 +81,40 @@ def test_argon_config0_through_the_adapter(tmp_path, prec, tol):
     assert err <= tol, (prec, "p", err)
 
 
+@pytest.mark.parametrize("prec,tol", [("double", 1e-9), ("mixed", 1e-6)])
+def test_cells_in_cutoff_radius_2(tmp_path, prec, tol):
+    """SURVEY.md 8f-4, <cellsInCutoffRadius>2</cellsInCutoffRadius> (LinkedCells.cpp:125: cells of half a cutoff radius, 5 x 5 x 5
+    neighbourhoods): the stock binary with that input against MarDyn_b200 with the same input. The adapter refines the host mirror
+    as asked and keeps one device cell per cutoff radius -- the pair set is decided by the cutoff test alone. 1CLJ liquid, 5 488
+    molecules, 40 steps, the reference's ResultWriter columns."""
+    ref = os.path.join(ROOT, "oracle", "_ref", prec, "MarDyn")
+    b200 = os.path.join(ROOT, "adapter", "_build", prec, "MarDyn_b200")
+    if not (os.path.exists(ref) and os.path.exists(b200)):
+        pytest.skip("reference / adapter binaries not built (oracle/build_ref.sh, adapter/build_adapter.sh)")
+    from ls1_mardyn_b200 import workloads
+    from ls1_mardyn_b200.xml_config import simulation_xml
+    wl = workloads.get("lj")
+    n, steps = 14, 40
+    N = 2 * n ** 3; L = (N / wl.rho) ** (1.0 / 3.0)
+    out = {}
+    for name, exe, ds, integ in (("ref", ref, "LinkedCells", "Leapfrog"), ("b200", b200, "LinkedCellsB200", "LeapfrogB200")):
+        d = tmp_path / name; d.mkdir()
+        (d / "config.xml").write_text(simulation_xml(wl.ensemble, [L, L, L], wl.temperature, wl.dt, steps, wl.rc, generator_density=N / L ** 3 * (1 + 1e-9),
+                                                     datastructure=ds, integrator=integ, longrange="homogeneous", cells_in_cutoff=2,
+                                                     datastructure_extra="<traversalSelector>mp</traversalSelector>"))      # the reference's traversals for 2 cells per cutoff: mp, nt (TraversalTuner.h:166)
+        out[name], log = run(exe, "config.xml", str(d), steps)
+        if name == "b200":
+            assert "applies to the host mirror" in log
+    a, b = out["b200"], out["ref"]
+    assert a.shape == b.shape and a.shape[0] >= steps and int(b[0, 11]) == N
+    for name, col in (("U_pot", 2), ("U_kin", 4), ("beta_trans", 8)):
+        err = np.abs(a[:, col] - b[:, col]).max() / np.abs(b[:, col]).max()
+        assert err <= tol, (prec, name, err)
+    rhoT = (N / L ** 3) * (2.0 * b[:, 4] / (3.0 * N))
+    err = np.abs(a[:, 6] - b[:, 6]).max() / max(np.abs(b[:, 6]).max(), rhoT.max())
+    assert err <= tol, (prec, "p", err)
+
+
 @pytest.mark.parametrize("prec,tol", [("double", 1e-9), ("mixed", 2e-5)])
 def test_checkpoints_written_from_the_host_mirror(tmp_path, prec, tol):
     """Host coherence: a molecule-iterating stock plugin (CheckpointWriter, io/CheckpointWriter.cpp; record layout
