@@ -234,6 +234,8 @@ struct ls1b200_ctx {
 	int force_pass = 0;               // overlapped multi-GPU step: which chunks the next force traversal visits (force_1clj_tiled.cu)
 	int overlap2 = 0;                 // LS1B200_OVERLAP2=1: the exchange on its own stream beside the sort and the inner chunks (measured slower, profiles/r02_multi_gpu.md: off by default)
 	cudaEvent_t ev_m = nullptr;       // overlapped step: the main sort has finished (the imports' sort may start)
+	// lazy permutation (fused step): the sort wrote perm[] instead of moving r and v; `cur` holds meta / id of the new order, `nxt` r and v of the previous one
+	uint32_t* perm = nullptr; bool state_lazy = false; bool lazy_next = false; int lazy = 1;      // LS1B200_LAZY=0: every sort moves the whole state
 	int fused = 1;                    // LS1B200_FUSED=0: ls1b200_simulate runs the phases as separate kernels
 	uint32_t partial_blocks = 0;
 	ls1b200::DevScalars* d_scal = nullptr;

@@ -67,7 +67,7 @@ void ctx_free_molecules(ls1b200_ctx* c) {
 	if (c->mpos) cudaFree(c->mpos); c->mpos = nullptr;
 	if (c->spos) cudaFree(c->spos); c->spos = nullptr;
 	if (c->sori) cudaFree(c->sori); c->sori = nullptr;
-	dev_free(c->sf); dev_free(c->partials); dev_free(c->partials_kin);
+	dev_free(c->sf); dev_free(c->partials); dev_free(c->partials_kin); dev_free(c->perm); c->state_lazy = false;
 	decomp_free(c);
 	c->cap = 0; c->n_owned = 0; c->n_slots = 0;
 }
@@ -266,6 +266,7 @@ int ls1b200_create(const ls1b200_config* cfg, ls1b200_ctx** out) {
 		c->lj_kernel = (k && std::string(k) == "global") ? 1 : (k && std::string(k) == "mma") ? 3 : (k && std::string(k) == "tc") ? 4 : (k && std::string(k) == "v3") ? 5 : (k && std::string(k) == "pf") ? 6 : 0;      // default: the tiled kernel (v3 measured slower, profiles/r02_force_kernel_experiments.md)
 		if (const char* pc = getenv("LS1B200_PF_CHECK")) c->pf_check = atoi(pc);
 		if (const char* fu = getenv("LS1B200_FUSED")) c->fused = atoi(fu);
+		if (const char* lz = getenv("LS1B200_LAZY")) c->lazy = atoi(lz);
 		if (const char* ce = getenv("LS1B200_CHUNKS_EARLY")) c->chunks_early = atoi(ce);
 		if (const char* o2 = getenv("LS1B200_OVERLAP2")) c->overlap2 = atoi(o2);
 		if (const char* tm = getenv("LS1B200_TILE_MAXCTAS")) c->tile_max_ctas = atoi(tm);

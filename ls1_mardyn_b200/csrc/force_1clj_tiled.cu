@@ -58,6 +58,7 @@ struct TArgs {
 	// fused step (ls1b200_simulate): the kinetic sum of Leapfrog::transition2to3 (Leapfrog.cpp:113-143), sum of m (v + dt/2m F)^2 over the
 	// molecules this kernel visits, from the force still in registers; the kick itself is applied by the next step's first kernel
 	const double* kin_v; double kin_dth; const CompDev* comps; double* partials_kin;      // partials_kin: [chunk][4 warps]
+	const uint32_t* kin_perm;      // lazy permutation: v of slot t is still at kin_perm[t] of the previous order (kin_v points there)
 	// overlapped multi-GPU step, boundary chunks (BND): the imports of this step's exchange are a second slot range per cell, sorted on
 	// their own behind the slots of the main sort (update.cu: do_update_imports); cell_start_b is absolute
 	const uint32_t* cell_start_b;
@@ -214,7 +215,8 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB, LS1_TILE_MINB) k_force_1clj_t
 				const size_t cp = a.cap;
 				if (!RMM && a.kin_v) {
 					const double mass = a.comps[cid_i].mass, am = a.kin_dth / mass;
-					const double v0 = a.kin_v[t] + am * Fd[0], v1 = a.kin_v[cp + t] + am * Fd[1], v2 = a.kin_v[2 * cp + t] + am * Fd[2];
+					const size_t tv = a.kin_perm ? a.kin_perm[t] : t;
+					const double v0 = a.kin_v[tv] + am * Fd[0], v1 = a.kin_v[cp + tv] + am * Fd[1], v2 = a.kin_v[2 * cp + tv] + am * Fd[2];
 					acc[2] += mass * (v0 * v0 + v1 * v1 + v2 * v2);
 				}
 				if (RMM) {
@@ -371,7 +373,8 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB, LS1_TILE_MINB) k_force_1clj_t
 				acc[1] += 0.5 * (Vd[l][0] + Vd[l][1] + Vd[l][2]);
 				if (!RMM && a.kin_v) {
 					const double mass = a.comps[cid_i[l]].mass, am = a.kin_dth / mass;
-					const double v0 = a.kin_v[t] + am * Fd[l][0], v1 = a.kin_v[cp + t] + am * Fd[l][1], v2 = a.kin_v[2 * cp + t] + am * Fd[l][2];
+					const size_t tv = a.kin_perm ? a.kin_perm[t] : t;
+					const double v0 = a.kin_v[tv] + am * Fd[l][0], v1 = a.kin_v[cp + tv] + am * Fd[l][1], v2 = a.kin_v[2 * cp + tv] + am * Fd[l][2];
 					acc[2] += mass * (v0 * v0 + v1 * v1 + v2 * v2);
 				}
 				if (RMM) {      // the kick in the epilogue: 12 B read + 12 B written per molecule instead of 48 B of F and Vi
@@ -470,7 +473,7 @@ static int launch_tiled(ls1b200_ctx* c, float* rmm_v = nullptr, float rmm_dt_m =
 	a.eps24_0 = (C) c->h_eps24[0]; a.sig2_0 = (C) c->h_sig2[0]; a.shift6_0 = (C) c->h_shift6[0];
 	a.rmm_v = rmm_v; a.rmm_dt_m = rmm_dt_m;
 	const bool kin = !RMM && c->kin_dth != 0.;
-	a.kin_v = kin ? c->cur.v : nullptr; a.kin_dth = c->kin_dth; a.comps = c->d_comps; a.partials_kin = c->partials_kin;
+	a.kin_v = kin ? (c->state_lazy ? c->nxt.v : c->cur.v) : nullptr; a.kin_perm = c->state_lazy ? c->perm : nullptr; a.kin_dth = c->kin_dth; a.comps = c->d_comps; a.partials_kin = c->partials_kin;
 	if (kin && !c->partials_kin) return fail("force_1clj_tiled: no buffer for the kinetic partial sums");
 	// the cell_start cache is padded by three rows: the compiler hoists the (guarded) loads of the next row's entries
 	a.cell_start_b = c->cell_start_b;

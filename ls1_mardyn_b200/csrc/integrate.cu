@@ -388,7 +388,10 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 		} else if (fused) {
 			LS1_TRY(do_pre_key(c, dt, target_temperature > 0., s > 0));
 			LS1_TRY(do_exchange(c));
-			LS1_TRY(do_update(c, 3));
+			c->lazy_next = kin_here && c->lazy;      // the next step starts with k_pre_key again: this sort leaves r and v where they are
+			const int urc = do_update(c, 3);
+			c->lazy_next = false;
+			if (urc) return urc;
 		} else {
 		LS1_TRY(do_leapfrog_pre(c, dt, target_temperature > 0.));
 		LS1_TRY(do_exchange(c));                 // multi-GPU: leaving molecules + halo copies over NCCL (no-op on one GPU)

@@ -163,9 +163,11 @@ __global__ void __launch_bounds__(256) k_key_tail(UpdArgs a, State cur, uint32_t
 // load + upd_preF (half kick, drift) + the binning of k_key on the new position, which is still in registers: the slot state
 // is read and written once, the FP64 compares of the binning hide behind the memory traffic of the integration.
 // Same floating-point sequence per molecule as k_leapfrog_post -> k_scale -> k_leapfrog_pre -> k_key.
+// `perm` (lazy permutation): the previous sort did not move r and v -- slot s of the current order still has them at perm[s] of the
+// previous order (`old`); this kernel, which reads and writes them anyway, puts them in place.
 __global__ void __launch_bounds__(256, 8) k_pre_key(UpdArgs a, State cur, const double* __restrict__ F, const CompDev* __restrict__ comps, double dt, int use_beta, int post_kick,
                                                   uint32_t* __restrict__ key, uint32_t* __restrict__ count, uint32_t* __restrict__ count_halo, uint32_t* __restrict__ rank,
-                                                  DevScalars* __restrict__ scal) {
+                                                  DevScalars* __restrict__ scal, const uint32_t* __restrict__ perm, State old) {
 	const uint32_t s = blockIdx.x * blockDim.x + threadIdx.x;
 	const bool in_range = s < min(scal->n_slots2[a.parity], a.cap);
 	if (s == 0) scal->n_pre = min(scal->n_slots2[a.parity], a.cap);      // the slots this kernel bins; what the exchange appends later lies behind
@@ -176,14 +178,16 @@ __global__ void __launch_bounds__(256, 8) k_pre_key(UpdArgs a, State cur, const 
 		const size_t c = a.cap;
 		if (!meta_halo(meta)) {
 			live = true;
+			const double* rs = perm ? old.r : cur.r; const double* vs = perm ? old.v : cur.v;
+			const size_t so = perm ? perm[s] : s;
 			#pragma unroll
-			for (int d = 0; d < 3; d++) r[d] = cur.r[d * c + s];
+			for (int d = 0; d < 3; d++) r[d] = rs[d * c + so];
 			if (!scal->overflow) {      // a failed step: the state stays as it is (k_leapfrog_pre)
 				const double bt = use_beta ? scal->beta_trans : 1.;
 				const double a0 = (.5 * dt) / comps[meta_cid(meta)].mass;
 				#pragma unroll
 				for (int d = 0; d < 3; d++) {
-					double v = cur.v[d * c + s];
+					double v = vs[d * c + so];
 					const double f = F[d * c + s];
 					if (post_kick) v += a0 * f;
 					if (use_beta) v *= bt;
@@ -192,6 +196,9 @@ __global__ void __launch_bounds__(256, 8) k_pre_key(UpdArgs a, State cur, const 
 					r[d] += dt * v;
 					cur.r[d * c + s] = r[d];
 				}
+			} else if (perm) {
+				#pragma unroll
+				for (int d = 0; d < 3; d++) { cur.v[d * c + s] = vs[d * c + so]; cur.r[d * c + s] = r[d]; }
 			}
 		} else if (meta_fresh(meta)) {
 			live = true;
@@ -325,7 +332,7 @@ __device__ __forceinline__ void gather_slot(const UpdArgs& a, const State& cur, 
                                             const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_of2,
                                             typename Vec4<C>::type* __restrict__ mpos, int rotates,
                                             double* __restrict__ F, double* __restrict__ Vi, double* __restrict__ M, const uint64_t* __restrict__ ekey,
-                                            uint8_t* __restrict__ region_flag) {
+                                            uint8_t* __restrict__ region_flag, uint32_t* __restrict__ perm) {
 	const Geom& g = a.g;
 	const uint32_t e = entry[p], fb = cell_of[p];              // fine bin; cell_start is the FINE array
 	const uint32_t c = min(fb >> a.logS, g.ncells);            // reference cell (limbo: ncells)
@@ -363,10 +370,13 @@ __device__ __forceinline__ void gather_slot(const UpdArgs& a, const State& cur, 
 	}
 	meta &= ~META_FRESH;      // a fresh halo copy of this step's exchange is an ordinary (stale after this sort) halo slot from here on
 	if (ekey) nxt.id[t] = cur.id[s];
-	nxt.r[t] = x; nxt.r[cap + t] = y; nxt.r[2 * cap + t] = z;
 	nxt.meta[t] = meta;
+	if (perm) perm[t] = s;      // lazy permutation (fused step, owned slots are not halo copies of anything): r and v move in the next k_pre_key
+	else {
+	nxt.r[t] = x; nxt.r[cap + t] = y; nxt.r[2 * cap + t] = z;
 	#pragma unroll
 	for (int d = 0; d < 3; d++) nxt.v[d * cap + t] = cur.v[d * cap + s];
+	}
 	if (rotates) {
 		#pragma unroll
 		for (int d = 0; d < 4; d++) nxt.q[d * cap + t] = cur.q[d * cap + s];
@@ -388,11 +398,11 @@ __global__ void __launch_bounds__(256) k_gather(UpdArgs a, State cur, State nxt,
                                                  const uint32_t* __restrict__ cell_start, uint32_t* __restrict__ cell_of2,
                                                  typename Vec4<C>::type* __restrict__ mpos, const DevScalars* __restrict__ scal, int rotates,
                                                  double* __restrict__ F, double* __restrict__ Vi, double* __restrict__ M, const uint64_t* __restrict__ ekey,
-                                                 uint8_t* __restrict__ region_flag, int seg) {
+                                                 uint8_t* __restrict__ region_flag, int seg, uint32_t* __restrict__ perm) {
 	const uint32_t p = blockIdx.x * blockDim.x + threadIdx.x;
 	// seg 1 (overlapped multi-GPU step): the slots of THIS sort only -- the imports' sort, on the exchange stream, may already have added its own to n_slots2
 	if (p >= min(seg == 1 ? scal->n_sorted : scal->n_slots2[a.parity ^ 1u], a.cap)) return;
-	gather_slot<C>(a, cur, nxt, p, entry, cell_of, cell_start, cell_of2, mpos, rotates, F, Vi, M, ekey, region_flag);
+	gather_slot<C>(a, cur, nxt, p, entry, cell_of, cell_start, cell_of2, mpos, rotates, F, Vi, M, ekey, region_flag, perm);
 }
 // the imports of the overlapped step: destination slots [n_sorted, n_slots2[parity ^ 1]) (cell_start: the imports' own, absolute)
 template <class C>
@@ -402,7 +412,7 @@ __global__ void __launch_bounds__(256) k_gather_tail(UpdArgs a, State cur, State
                                                       double* __restrict__ F, double* __restrict__ Vi, double* __restrict__ M, const uint64_t* __restrict__ ekey) {
 	const uint32_t n = min(scal->n_slots2[a.parity ^ 1u], a.cap);
 	for (uint32_t p = min(scal->n_sorted, n) + blockIdx.x * blockDim.x + threadIdx.x; p < n; p += gridDim.x * blockDim.x)
-		gather_slot<C>(a, cur, nxt, p, entry, cell_of, cell_start, cell_of2, mpos, rotates, F, Vi, M, ekey, nullptr);
+		gather_slot<C>(a, cur, nxt, p, entry, cell_of, cell_start, cell_of2, mpos, rotates, F, Vi, M, ekey, nullptr, nullptr);
 }
 
 // ---- site expansion (FullMolecule::setupSoACache, molecules/FullMolecule.cpp:711-767; Quaternion::rotate, Quaternion.cpp:43-64)
@@ -481,7 +491,9 @@ int do_pre_key(ls1b200_ctx* c, double dt, bool use_beta, bool post_kick) {
 	const UpdArgs a = make_upd_args(c);
 	const uint32_t gs = (uint32_t) ((c->cap + 255) / 256);
 	LS1_CUDA(cudaMemsetAsync(c->cell_count, 0, sizeof(uint32_t) * 2 * ((size_t) c->geom.ncells * c->fine_s + 4), c->stream));      // cell_count and cell_count_halo
-	LS1_LAUNCH(c, PH_PRE, k_pre_key, gs, 256, 0, a, c->cur, c->F, c->d_comps, dt, (int) use_beta, (int) post_kick, c->key, c->cell_count, c->cell_count_halo, c->rank, c->d_scal);
+	LS1_LAUNCH(c, PH_PRE, k_pre_key, gs, 256, 0, a, c->cur, c->F, c->d_comps, dt, (int) use_beta, (int) post_kick, c->key, c->cell_count, c->cell_count_halo, c->rank, c->d_scal,
+	           c->state_lazy ? (const uint32_t*) c->perm : (const uint32_t*) nullptr, c->nxt);
+	c->state_lazy = false;
 	LS1_TRY(span_end(c));
 	c->forces_valid = false;
 	return 0;
@@ -542,11 +554,18 @@ int do_update(ls1b200_ctx* c, int part) {
 	}
 	LS1_LAUNCH(c, PH_UPDATE, k_scatter, gs, 256, 0, a, c->cur, c->key, c->rank, (const uint32_t*) fstart, c->cursor, c->entry, c->cell_of, c->d_scal, c->dd.active ? c->ekey : (uint64_t*) nullptr, part == 4 ? 1 : 0);
 	const uint32_t gc = gs;
+	// lazy permutation: asked for by ls1b200_simulate for the steps whose successor starts with k_pre_key (it moves r and v itself)
+	uint32_t* lazy_perm = nullptr;
+	if (c->lazy_next && part == 3 && !c->rotates) {
+		if (!c->perm) LS1_CUDA(cudaMalloc((void**) &c->perm, sizeof(uint32_t) * c->cap));
+		lazy_perm = c->perm;
+	}
 	if (c->mixed)
-		LS1_LAUNCH(c, PH_UPDATE, k_gather<float>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, (const uint32_t*) fstart, c->cell_of2, (float4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr, c->region_flag, part == 4 ? 1 : 0);
+		LS1_LAUNCH(c, PH_UPDATE, k_gather<float>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, (const uint32_t*) fstart, c->cell_of2, (float4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr, c->region_flag, part == 4 ? 1 : 0, lazy_perm);
 	else
-		LS1_LAUNCH(c, PH_UPDATE, k_gather<double>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, (const uint32_t*) fstart, c->cell_of2, (double4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr, c->region_flag, part == 4 ? 1 : 0);
+		LS1_LAUNCH(c, PH_UPDATE, k_gather<double>, gc, 256, 0, a, c->cur, c->nxt, c->entry, c->cell_of, (const uint32_t*) fstart, c->cell_of2, (double4*) c->mpos, c->d_scal, (int) c->rotates, c->F, c->Vi, c->M, c->dd.active ? c->ekey : (const uint64_t*) nullptr, c->region_flag, part == 4 ? 1 : 0, lazy_perm);
 	std::swap(c->cur, c->nxt);
+	c->state_lazy = lazy_perm != nullptr;
 	c->parity ^= 1u;
 	if (!c->all_1clj) {
 		const uint32_t g2 = (uint32_t) ((c->cap + 127) / 128);
