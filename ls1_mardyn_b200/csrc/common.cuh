@@ -236,6 +236,7 @@ struct ls1b200_ctx {
 	cudaEvent_t ev_m = nullptr;       // overlapped step: the main sort has finished (the imports' sort may start)
 	// lazy permutation (fused step): the sort wrote perm[] instead of moving r and v; `cur` holds meta / id of the new order, `nxt` r and v of the previous one
 	uint32_t* perm = nullptr; bool state_lazy = false; bool lazy_next = false; int lazy = 1;      // LS1B200_LAZY=0: every sort moves the whole state
+	bool keys_valid = false;          // ls1b200_leapfrog_pre binned the slots it integrated (k_pre_key): the next ls1b200_update only bins what was appended since
 	int fused = 1;                    // LS1B200_FUSED=0: ls1b200_simulate runs the phases as separate kernels
 	uint32_t partial_blocks = 0;
 	ls1b200::DevScalars* d_scal = nullptr;

@@ -435,7 +435,7 @@ int ls1b200_upload(ls1b200_ctx* c, uint64_t n, const uint64_t* id, const uint32_
 	c->h_scal->n_slots2[0] = (uint32_t) n; c->h_scal->n_slots2[1] = 0; c->h_scal->overflow = 0;
 	c->h_scal->beta_trans = 1.; c->h_scal->beta_rot = 1.;
 	LS1_CUDA(cudaMemcpy(c->d_scal, c->h_scal, sizeof(DevScalars), cudaMemcpyHostToDevice));
-	c->sorted = false; c->ever_sorted = false; c->forces_valid = false;
+	c->sorted = false; c->ever_sorted = false; c->forces_valid = false; c->keys_valid = false;
 	return 0;
 }
 
@@ -474,11 +474,13 @@ static int sync_scalars(ls1b200_ctx* c, bool owned_index = false) {
 int ls1b200_update(ls1b200_ctx* c) {
 	if (!c) return fail("ls1b200_update: null context");
 	LS1_CUDA(cudaSetDevice(c->device));
+	const bool kv = c->keys_valid;      // ls1b200_leapfrog_pre already binned the slots it integrated
+	c->keys_valid = false;
 	if (c->split_test && c->dd.active && c->region_flag && c->ever_sorted) {      // LS1B200_SPLIT_TEST: inner slots' histogram first, then the rest + the sort
 		LS1_TRY(do_update(c, 1));
 		LS1_TRY(do_update(c, 2));
 	} else
-	LS1_TRY(do_update(c));
+	LS1_TRY(do_update(c, kv ? 3 : 0));
 	return sync_scalars(c);
 }
 
@@ -616,9 +618,9 @@ int ls1b200_set_field(ls1b200_ctx* c, int field, const void* src, uint64_t n) {
 	switch (field) {
 		// new positions / orientations: the cell order, the halo copies and the calc-precision records (mpos, spos, sori) are stale --
 		// ls1b200_traverse_cells must not run before the next ls1b200_update
-		case LS1B200_F_R: planes = c->cur.r; c->forces_valid = false; c->ever_sorted = false; c->sorted = false; break;      // arbitrary new positions: the exchange scans every slot
+		case LS1B200_F_R: planes = c->cur.r; c->forces_valid = false; c->ever_sorted = false; c->sorted = false; c->keys_valid = false; break;      // arbitrary new positions: the exchange scans every slot
 		case LS1B200_F_V: planes = c->cur.v; break;
-		case LS1B200_F_Q: planes = c->cur.q; dim = 4; if (c->cur.q) { c->forces_valid = false; c->sorted = false; } break;
+		case LS1B200_F_Q: planes = c->cur.q; dim = 4; if (c->cur.q) { c->forces_valid = false; c->sorted = false; c->keys_valid = false; } break;
 		case LS1B200_F_L: planes = c->cur.L; break;
 		case LS1B200_F_F: planes = c->F; break;
 		case LS1B200_F_M: planes = c->M; break;

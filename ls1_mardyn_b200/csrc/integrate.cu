@@ -270,6 +270,12 @@ int ls1b200_leapfrog_pre(ls1b200_ctx* c, double dt) {
 		LS1_TRY(do_leapfrog_pre(c, dt, false, 1));
 		return do_leapfrog_pre(c, dt, false, 2);
 	}
+	// ensembles without rotation: the binning of the next ls1b200_update rides on this kernel (the new position is in registers)
+	if (c->fused && !c->rotates && c->fine_s == 1 && c->components_set && c->cap) {
+		LS1_TRY(do_pre_key(c, dt, false, false));
+		c->keys_valid = true;
+		return 0;
+	}
 	return do_leapfrog_pre(c, dt, false);
 }
 
@@ -302,6 +308,7 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 	if (!c->forces_valid) return fail("ls1b200_simulate: forces are not valid (call ls1b200_update + ls1b200_traverse_cells first)");
 	LS1_CUDA(cudaSetDevice(c->device));
 	if (n_steps == 0) return 0;
+	c->keys_valid = false;
 	if (c->dd.active) {
 		if (global_n == 0 || !(global_volume > 0.)) return fail("ls1b200_simulate: a decomposed context needs global_n and global_volume");
 		if (!c->dd.comm) return fail("ls1b200_simulate: a decomposed context needs use_nccl = 1 (or drive the phases and move the messages yourself)");
