@@ -270,8 +270,12 @@ int ls1b200_leapfrog_pre(ls1b200_ctx* c, double dt) {
 		LS1_TRY(do_leapfrog_pre(c, dt, false, 1));
 		return do_leapfrog_pre(c, dt, false, 2);
 	}
-	// ensembles without rotation: the binning of the next ls1b200_update rides on this kernel (the new position is in registers)
-	if (c->fused && !c->rotates && c->fine_s == 1 && c->components_set && c->cap) {
+	// ensembles without rotation: the binning of the next ls1b200_update rides on this kernel (the new position is in registers).
+	// Not on decomposed contexts: binning wraps the coordinates of the dimensions a rank is periodic in by itself, and the staged
+	// exchange that follows must see them as the reference's messages carry them -- unwrapped until the receiver bins them
+	// (tests/test_gpu_decomposition.py compares the messages record by record; ls1b200_simulate, whose messages nobody sees, wraps first:
+	// the receiver ends up with the same bits either way)
+	if (c->fused && !c->rotates && !c->dd.active && c->fine_s == 1 && c->components_set && c->cap) {
 		LS1_TRY(do_pre_key(c, dt, false, false));
 		c->keys_valid = true;
 		return 0;
