@@ -107,7 +107,7 @@ def test_multicomponent_1clj_fast_path(capi):
         assert abs(ma.upot - mb.upot) <= TOL[prec] * abs(mb.upot)
 
 
-@pytest.mark.parametrize("kernel", ["tiled", "global", "mma", "tc", "v3", "v3:4", "v3:8:2"])
+@pytest.mark.parametrize("kernel", ["tiled", "global", "mma", "tc", "v3", "v3:4", "v3:8:2", "pf"])
 def test_1clj_kernel_variants_vs_oracle(capi, kernel):
     """The alternative 1CLJ force kernels (LS1B200_LJ_KERNEL): the global-memory v1 kernel, the two tensor-core prefilter
     experiments (mma.sync TF32 / tcgen05 FP16 with TMEM; both fall back to the tiled kernel in the double build) and the round-2
@@ -128,10 +128,12 @@ def test_1clj_kernel_variants_vs_oracle(capi, kernel):
                 os.environ["LS1B200_FINE_S"] = parts[1]
             if len(parts) > 2:
                 os.environ["LS1B200_V3_ALIGN"] = parts[2]
+            if parts[0] == "pf":
+                os.environ["LS1B200_PF_CHECK"] = "1"      # the prefilter kernel verifies that every window translation is exact
             try:
                 a = _mk(capi.Context, ps, 2.5, prec)
             finally:
-                for k in ("LS1B200_LJ_KERNEL", "LS1B200_FINE_S", "LS1B200_V3_ALIGN"):
+                for k in ("LS1B200_LJ_KERNEL", "LS1B200_FINE_S", "LS1B200_V3_ALIGN", "LS1B200_PF_CHECK"):
                     os.environ.pop(k, None)
             b = _mk(orc.OracleSim, ps, 2.5, prec)
             a.update(); b.update(); ma, mb = a.traverse_cells(), b.traverse_cells()
@@ -196,6 +198,39 @@ def test_simulate_trace_vs_oracle(capi, name, dt, nsteps, prec):
         assert err <= tol, f"{name} {prec} {k}: {err:.3g}"
     ok, worst = rel_close(a.download("R"), b.download("R"), 1e-7 if prec == "double" else 1e-4, scale=1.0)
     assert ok, worst
+
+
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_fused_step_switches(capi, prec):
+    """The fused step of ls1b200_simulate (k_pre_key, kinetic sum in the force epilogue, lazy permutation, chunk list beside the sort)
+    against the same loop with each of its parts switched off (LS1B200_FUSED / LS1B200_LAZY / LS1B200_CHUNKS_EARLY = 0): same
+    floating-point sequence per molecule; only the order of the kinetic sum differs between fused and phase-by-phase."""
+    import os
+    from ls1_mardyn_b200 import generators
+    ps = generators.lj_lattice(24, seed=9, jitter=0.1); ps.v *= 2.0
+    dt, T, n = 0.002, 0.85, 30
+
+    def run(env):
+        os.environ.update(env)
+        try:
+            c = capi.Context([0, 0, 0], list(ps.length), 2.5, precision=prec)
+        finally:
+            for k in env:
+                os.environ.pop(k, None)
+        c.set_components(ps.ensemble); c.upload(ps.id, ps.cid, ps.r, ps.v)
+        c.update(); c.traverse_cells()
+        rec = c.simulate(n, dt, T)
+        o = np.argsort(c.download("ID"))
+        return rec, c.download("R")[o], c.download("V")[o], c.download("F")[o]
+
+    ref = run({})
+    for env in ({"LS1B200_FUSED": "0"}, {"LS1B200_LAZY": "0"}, {"LS1B200_CHUNKS_EARLY": "0"}):
+        got = run(env)
+        for i in (0, 1, 2, 4, 5, 6):
+            err = np.abs(got[0][:, i] - ref[0][:, i]).max() / np.abs(ref[0][:, i]).max()
+            assert err <= 1e-12, (env, prec, i, err)
+        for k in (1, 2, 3):
+            assert np.allclose(got[k], ref[k], rtol=1e-11, atol=1e-11 * np.abs(ref[k]).max()), (env, prec, k)
 
 
 def test_simulate_equals_phase_calls(capi):
