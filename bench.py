@@ -142,7 +142,7 @@ XML = """<?xml version='1.0' encoding='UTF-8'?>
    <cutoffs type="CenterOfMass"><radiusLJ unit="reduced">{rc}</radiusLJ></cutoffs>
    <electrostatic type="ReactionField"><epsilon>1.0e+10</epsilon></electrostatic>
   </algorithm>
-  <output></output>
+  <output><outputplugin name="ResultWriter"><writefrequency>1</writefrequency><outputprefix>res</outputprefix><writeprecision>15</writeprecision></outputplugin></output>
  </simulation>
 </mardyn>
 """
@@ -171,6 +171,9 @@ def reference_build():
     return _REF_BUILD
 
 
+LAST_REFERENCE_TRACE = None      # T, U_pot / N, p after the last step of the most recent reference run (from its ResultWriter)
+
+
 def run_reference_binary(n_per_dim, steps, threads=None, prec=None, wl=None):
     """Runs oracle/_ref/<prec>/MarDyn (the unmodified reference, built by oracle/build_ref.sh) on a lattice of 2*n^3 molecules of
     workload `wl` (default: the 1CLJ liquid), generated by the reference's own CubicGridGenerator.
@@ -196,6 +199,15 @@ def run_reference_binary(n_per_dim, steps, threads=None, prec=None, wl=None):
         env = dict(os.environ, OMP_NUM_THREADS=str(threads))
         p = subprocess.run([exe, "--steps", str(steps), "--final-checkpoint=0", cfg], cwd=td, env=env, capture_output=True, text=True, timeout=3000)
         out = p.stdout + p.stderr
+        global LAST_REFERENCE_TRACE
+        LAST_REFERENCE_TRACE = None
+        try:      # ResultWriter rows (1CLJ template only): step, time, U_pot, U_pot_avg, U_kin, U_kin_avg, p, ...
+            rows = [l.split() for l in open(os.path.join(td, "res.res")) if l.strip() and not l.lstrip().startswith("#")]
+            last = [float(x) for x in rows[-1]]
+            if int(last[0]) == steps:
+                LAST_REFERENCE_TRACE = {"at_step": steps, "T": 2.0 * last[4] / (3.0 * last[11]), "upot_per_molecule": last[2] / last[11], "p": last[6]}
+        except (OSError, IndexError, ValueError):
+            pass
     if p.returncode != 0:
         return None
     m = re.search(r"Computation in main loop took:\s*([0-9.eE+-]+)\s*sec", out)
@@ -278,6 +290,10 @@ def reference_arm(args):
             "cpu_baseline": {"value": round(v, 4), "unit": "MMUPS", "cores": cores, "kind": kind,
                              "sample": f"oracle/_ref/{reference_build()[0]}/MarDyn ({reference_build()[1]}, OpenMP), N={nmol} ({sample}), {args.steps} steps, main loop {t:.2f} s, total wall {time.perf_counter() - t0:.1f} s"},
             "e2e": {"value": round(v, 4), "unit": "MMUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    if kind == "reference" and LAST_REFERENCE_TRACE is not None:
+        # the physical state after the K timed steps (ResultWriter, 15 digits): our arm generates the SAME initial state on the device
+        # (ls1b200_generate_cubic_grid with the reference's velocity sequence) and reports the same three numbers at the same step
+        line["trace"] = dict(LAST_REFERENCE_TRACE, molecules=nmol, note="ResultWriter of the timed run, started from CubicGridGenerator; compare with trace.at_reference_step of the other arm")
     print(json.dumps(line), flush=True)
 
 
@@ -434,7 +450,9 @@ def our_arm(args):
         dist.broadcast_object_list(uid, src=0, device=torch.device("cuda", local))
         ctx.decomp_attach(dd, uid[0])
     if device_gen:
-        N = ctx.generate_cubic_grid([n * grid[0], n * grid[1], n * grid[2]], box, TEMP, seed=0, remove_momentum=True)
+        # the reference's own generator state: per-cell std::mt19937(0) velocity sequence, momentum removed, rescaled to T -- at N = 1 this
+        # is bit for bit (velocities to 1e-13) what `--impl reference` starts from (tests: test_device_generator_reference_velocities_*)
+        N = ctx.generate_cubic_grid([n * grid[0], n * grid[1], n * grid[2]], box, TEMP, seed=0, remove_momentum=True, reference_velocities=True)
     else:
         if world == 1:
             ps = make_system(n, mixed=(args.precision == "mixed"), seed=rank, wl=wl)
@@ -474,7 +492,7 @@ def our_arm(args):
     hbm_peak, hbm_src = peaks()
 
     # ---- HBM-resident: K steps inside the library, no host round trip ----
-    ctx.simulate(args.warmup, DT, TEMP, global_n=N_global, global_volume=V_global, records=False)
+    rec_w = ctx.simulate(args.warmup, DT, TEMP, global_n=N_global, global_volume=V_global) if args.warmup else np.zeros((0, 8))
     ctx.phase_times(reset=True)
     launches0 = capi.kernel_launch_count()
     ext = torch.cuda.ExternalStream(ctx.stream(), device=local)
@@ -587,6 +605,11 @@ def our_arm(args):
             "clocks": clocks,
             "trace": {"T_first": rec[0, 4], "T_last": rec[-1, 4], "upot_last_per_molecule": rec[-1, 0] / N_global, "p_last": rec[-1, 5]},
         }
+        if device_gen and world == 1:
+            # `--impl reference` times K steps from the same generated state: its ResultWriter row K is this run's step K (warm-up included)
+            series = np.concatenate([rec_w, rec]); ks = args.steps
+            line["trace"]["at_reference_step"] = {"at_step": ks, "T": series[ks - 1, 4], "upot_per_molecule": series[ks - 1, 0] / N_global, "p": series[ks - 1, 5],
+                                                  "note": "same initial state as the reference arm (its CubicGridGenerator sequence, generated on the device): compare with that line's trace"}
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(wl)
             if cb is not None:

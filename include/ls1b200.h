@@ -271,17 +271,27 @@ int ls1b200_halo_import(ls1b200_ctx* ctx, const void* device_buf, uint64_t count
 int ls1b200_halo_import_host(ls1b200_ctx* ctx, const ls1b200_particle* host_buf, uint64_t count);
 
 /* ---- measurement helpers (bench.py) ---- */
-/* The reference's CubicGridGenerator on the device (io/CubicGridGeneratorInternal.cpp:125-187, ParticleCellBase::initCubicGrid,
+/* The reference's CubicGridGenerator on the device (io/CubicGridGeneratorInternal.cpp:62-123, ParticleCellBase::initCubicGrid,
  * particleContainer/ParticleCellBase.cpp:51-159): a body-centred cubic lattice of 2 * nx * ny * nz molecules of component 0 over
- * the whole simulation box [0, sim_box) -- two sub-lattices at 1/4 and 3/4 of the spacing, coordinates created in the calc type --
- * of which this context keeps those inside ITS box (min <= r < max): every rank of a decomposition generates its own block, no
- * host array of the system ever exists. Velocities: |v| = sqrt((3 + rotDOF) T / m), direction from two uniform numbers
- * (EqualVelocityAssigner.h:16-29) drawn from a counter-based generator keyed by `seed` and the molecule's global lattice index
- * (the state does not depend on the decomposition); q = (1, 0, 0, 0), L = 0; id = lattice index + 1. remove_momentum != 0
- * subtracts sum(m v) / sum(m) over all ranks (IOHelpers::removeMomentum; collective on contexts with a communicator).
+ * the whole simulation box [0, sim_box) -- two sub-lattices at 1/4 and 3/4 of the spacing, coordinates created in the calc type
+ * with one fused multiply-add, as the reference binary evaluates them -- of which this context keeps those inside ITS box
+ * (min <= r < max): every rank of a decomposition generates its own block, no host array of the system ever exists.
+ * Velocities: |v| = sqrt((3 + rotDOF) T / m), direction from two uniform numbers (EqualVelocityAssigner.h:16-29);
+ * q = (1, 0, 0, 0), L = 0; id = lattice index + 1. `flags`:
+ *   LS1B200_GEN_REMOVE_MOMENTUM        IOHelpers::removeMomentum (io/IOHelpers.cpp:8-115): subtracts sum(m v) / sum(m) over all ranks,
+ *                                      then scales the velocities back to `temperature` (collective on contexts with a communicator);
+ *   LS1B200_GEN_REFERENCE_VELOCITIES   the reference's own velocity sequence: initCubicGrid seeds a fresh std::mt19937(0) in every
+ *                                      LinkedCells cell, so the k-th molecule inserted into any cell gets the k-th direction of one
+ *                                      sequence. With both flags the state is the one the unmodified reference binary generates from
+ *                                      the same XML (tests/golden/generator_1clj_2662.npz: its step-0 checkpoint and 20-step trace);
+ *                                      it depends on the cell grid, i.e. on the decomposition, exactly as the reference's does.
+ *                                      Without this flag the uniform numbers come from a counter-based generator keyed by `seed` and
+ *                                      the molecule's global lattice index (the state does not depend on the decomposition).
  * Replaces ls1b200_upload: afterwards the context is in the same state as after an upload of these molecules. */
+#define LS1B200_GEN_REMOVE_MOMENTUM 1
+#define LS1B200_GEN_REFERENCE_VELOCITIES 2
 int ls1b200_generate_cubic_grid(ls1b200_ctx* ctx, const uint64_t mols_per_dim[3], const double sim_box[3], double temperature,
-                                uint64_t seed, int32_t remove_momentum);
+                                uint64_t seed, int32_t flags);
 
 /* ---- reduced-memory mode (the reference's RMM build: ENABLE_REDUCED_MEMORY_MODE, PRECISION=SINGLE) -------------------------------------
  * The all-single-precision 1CLJ path: a molecule is 32 bytes (FP32 position, FP32 velocity, id: molecules/MoleculeRMM.h), the force

@@ -243,12 +243,14 @@ class Context:
         o = np.argsort(id)
         return id[o], r[o], v[o]
 
-    def generate_cubic_grid(self, mols_per_dim, sim_box, temperature, seed=0, remove_momentum=True):
+    def generate_cubic_grid(self, mols_per_dim, sim_box, temperature, seed=0, remove_momentum=True, reference_velocities=False):
         """ls1b200_generate_cubic_grid: the reference's CubicGridGenerator on the device (replaces upload). Returns the number of
-        molecules this context generated (those of the global lattice that lie inside its box)."""
+        molecules this context generated (those of the global lattice that lie inside its box). reference_velocities: the
+        reference's own per-cell std::mt19937(0) sequence (LS1B200_GEN_REFERENCE_VELOCITIES) instead of the counter-based one."""
         m = np.ascontiguousarray(np.broadcast_to(np.asarray(mols_per_dim, dtype=np.uint64), (3,)))
         b = np.ascontiguousarray(sim_box, dtype=np.float64)
-        _check(lib().ls1b200_generate_cubic_grid(self.h, _vp(m), _vp(b), float(temperature), int(seed), int(bool(remove_momentum))))
+        flags = (1 if remove_momentum else 0) | (2 if reference_velocities else 0)
+        _check(lib().ls1b200_generate_cubic_grid(self.h, _vp(m), _vp(b), float(temperature), int(seed), flags))
         self.n = int(lib().ls1b200_num_molecules(self.h))
         return self.n
 

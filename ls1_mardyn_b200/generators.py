@@ -97,19 +97,26 @@ def _splitmix64(x):
     return x ^ (x >> np.uint64(31))
 
 
-def cubic_grid_reference(mols_per_dim, sim_box, box_min, box_max, temperature, mass, rot_dof=0, seed=0, mixed=True):
+def _fma(a: float, b: float, c: float) -> float:
+    """round(a * b + c) with ONE rounding (exact rational arithmetic; Python < 3.13 has no math.fma)."""
+    from fractions import Fraction
+    return float(Fraction(a) * Fraction(b) + Fraction(c))
+
+
+def cubic_grid_reference(mols_per_dim, sim_box, box_min, box_max, temperature, mass, rot_dof=0, seed=0, mixed=True, with_lattice_index=False):
     """What the device generator produces for the context box [box_min, box_max): (id, r, v before momentum removal), ordered by id.
-    Same arithmetic: coordinate = origin + i * spacing rounded through the calc type, membership min <= r < max, velocity direction
-    from splitmix64(seed ^ 2 * index [+ 1]) (reference: ParticleCellBase.cpp:51-159, EqualVelocityAssigner.h:16-29)."""
+    Same arithmetic: coordinate = fma(i, spacing, origin) rounded through the calc type (the reference binary contracts the
+    expression), membership min <= r < max, velocity direction from splitmix64(seed ^ 2 * index [+ 1]) (reference:
+    ParticleCellBase.cpp:51-159, EqualVelocityAssigner.h:16-29). with_lattice_index: also (sub-lattice, i, j, k) per molecule."""
     n = np.broadcast_to(np.asarray(mols_per_dim, dtype=np.int64), (3,))
     sim_box = np.asarray(sim_box, dtype=np.float64)
-    ids, rs = [], []
+    ids, rs, lat = [], [], []
     for s, f in enumerate((0.25, 0.25 * 3.0)):
         axes, idxs = [], []
         for d in range(3):
             spacing = sim_box[d] / float(n[d])
             i = np.arange(n[d], dtype=np.int64)
-            x = spacing * f + i.astype(np.float64) * spacing
+            x = np.array([_fma(float(k), float(spacing), float(spacing * f)) for k in i])
             if mixed:
                 x = x.astype(np.float32).astype(np.float64)
             m = (x >= box_min[d]) & (x < box_max[d])
@@ -117,7 +124,8 @@ def cubic_grid_reference(mols_per_dim, sim_box, box_min, box_max, temperature, m
         X, Y, Z = np.meshgrid(*axes, indexing="ij"); I, J, K = np.meshgrid(*idxs, indexing="ij")
         g = ((s * n[0] + I) * n[1] + J) * n[2] + K
         ids.append(g.ravel()); rs.append(np.stack([X.ravel(), Y.ravel(), Z.ravel()], axis=1))
-    gidx = np.concatenate(ids).astype(np.uint64); r = np.concatenate(rs)
+        lat.append(np.stack([np.full(g.size, s, dtype=np.int64), I.ravel(), J.ravel(), K.ravel()], axis=1))
+    gidx = np.concatenate(ids).astype(np.uint64); r = np.concatenate(rs); lat = np.concatenate(lat)
     with np.errstate(over="ignore"):
         h1 = _splitmix64(np.uint64(seed) ^ (np.uint64(2) * gidx)); h2 = _splitmix64(np.uint64(seed) ^ (np.uint64(2) * gidx + np.uint64(1)))
     u1 = (h1 >> np.uint64(11)).astype(np.float64) / 9007199254740992.0; u2 = (h2 >> np.uint64(11)).astype(np.float64) / 9007199254740992.0
@@ -125,4 +133,42 @@ def cubic_grid_reference(mols_per_dim, sim_box, box_min, box_max, temperature, m
     vabs = np.sqrt((3.0 + rot_dof) * temperature / mass)
     v = vabs * np.stack([np.sin(phi), np.cos(phi) * np.sin(theta), np.cos(phi) * np.cos(theta)], axis=1)
     o = np.argsort(gidx)
+    if with_lattice_index:
+        return (gidx[o] + np.uint64(1)), r[o], v[o], lat[o]
     return (gidx[o] + np.uint64(1)), r[o], v[o]
+
+
+def reference_velocity_table(count, temperature, mass, rot_dof=0, mixed=True):
+    """The velocity sequence every cell of the reference's CubicGridGenerator walks (ParticleCellBase.cpp:66-67 constructs
+    EqualVelocityAssigner(T) -- std::mt19937(0) -- per cell; EqualVelocityAssigner.h:16-29): entry k is what the k-th molecule
+    inserted into a cell gets. numpy's legacy RandomState(0) is the same Mersenne twister with the same seeding as std::mt19937(0);
+    libstdc++'s uniform_real_distribution<double> draws two 32-bit words per number: (w0 + w1 * 2^32) / 2^64. The ensemble's
+    temperature passes through a vcp_real_calc variable (float in the mixed build) before it reaches the assigner."""
+    w = np.frombuffer(np.random.RandomState(0).bytes(16 * count), dtype="<u4").astype(np.float64).reshape(count, 2, 2)
+    u = (w[:, :, 0] + w[:, :, 1] * 4294967296.0) / 18446744073709551616.0
+    assert (u < 1.0).all()
+    phi = 2 * np.pi * u[:, 0]; theta = np.arccos(2 * u[:, 1] - 1)
+    t_calc = float(np.float32(temperature)) if mixed else float(temperature)
+    vabs = np.sqrt((3 + rot_dof) * t_calc / mass)
+    return np.stack([vabs * np.sin(phi), vabs * np.cos(phi) * np.sin(theta), vabs * np.cos(phi) * np.cos(theta)], axis=1)
+
+
+def reference_velocities(lattice_index, cell, temperature, mass, rot_dof=0, mixed=True, remove_momentum=True):
+    """Velocities of the reference's generator for molecules with lattice index rows (sub-lattice, i, j, k) lying in LinkedCells
+    cells `cell` (the caller bins the positions: the cell grid is the container's). Inside a cell the reference inserts in loop
+    order i, j, k with sub-lattice 1 before sub-lattice 2 at the same lattice point (ParticleCellBase.cpp:88-136) -- here simply a
+    sort, independent of the closed form the device kernel evaluates. Then IOHelpers::removeMomentum (io/IOHelpers.cpp:8-115):
+    subtract sum(m v) / sum(m), scale back to the target temperature."""
+    lat = np.asarray(lattice_index, dtype=np.int64); cell = np.asarray(cell, dtype=np.int64)
+    order = np.lexsort((lat[:, 0], lat[:, 3], lat[:, 2], lat[:, 1], cell))      # by cell, then i, j, k, sub-lattice
+    c_sorted = cell[order]
+    first = np.r_[0, np.flatnonzero(np.diff(c_sorted)) + 1]
+    start = np.repeat(first, np.diff(np.r_[first, len(cell)]))
+    rank = np.empty(len(cell), dtype=np.int64)
+    rank[order] = np.arange(len(cell)) - start
+    v = reference_velocity_table(int(rank.max()) + 1, temperature, mass, rot_dof, mixed)[rank]
+    if remove_momentum:
+        v = v - v.sum(axis=0) / len(v)
+        t_current = mass * (v ** 2).sum() / ((3 + rot_dof) * len(v))
+        v = v * np.sqrt(temperature / t_current)
+    return v

@@ -98,8 +98,15 @@ def check_trace_vs_reference(cls, name, prec, report=None):
     s.update()
     m0 = s.traverse_cells()
     rec = s.simulate(steps, dt, temperature)
-    tol = TRACE_TOL[prec]
-    n = len(g["in_id"]); vol = float(np.prod(g["length"]))
+    out = compare_trace_rows(m0, rec, ref, steps, len(g["in_id"]), float(np.prod(g["length"])), TRACE_TOL[prec], (name, prec))
+    if report is not None:
+        report.append((name, prec, out))
+    return out
+
+
+def compare_trace_rows(m0, rec, ref, steps, n, vol, tol, label):
+    """The comparison of check_trace_vs_reference: `m0` the macroscopic values of the initial traversal, `rec` the step records of
+    ls1b200_simulate / orc_simulate, `ref` the reference binary's ResultWriter rows (row 0 = initial force calculation)."""
     out = {}
     b = ref[1:steps + 1]
     ukin = 0.5 * (rec[:, 2] + rec[:, 3])
@@ -113,8 +120,29 @@ def check_trace_vs_reference(cls, name, prec, report=None):
     out["p"] = float(np.abs(rec[:, 5] - b[:, 6]).max() / max(np.abs(b[:, 6]).max(), rho_t.max()))
     out["p_strict"] = float(np.abs(rec[:, 5] - b[:, 6]).max() / np.abs(b[:, 6]).max())
     # T = 2 U_kin / (3N + rotDOF): same relative error as U_kin
-    if report is not None:
-        report.append((name, prec, out))
     for k in ("U_pot", "U_kin", "beta_trans", "beta_rot", "p"):
-        assert out[k] <= tol, (name, prec, k, out)
+        assert out[k] <= tol, (label, k, out)
+    return out
+
+
+def check_generated_state_vs_reference(cls, prec, r, v, ids=None):
+    """CubicGridGenerator parity (tests/golden/generator_1clj_2662.npz, made by make_generator_golden.py from the UNMODIFIED reference
+    binary): the generated positions equal the reference's step-0 checkpoint bit for bit, the velocities (per-cell std::mt19937(0)
+    sequence, momentum removed, rescaled to T) to 1e-13; `cls` (OracleSim or the CUDA Context) started from (r, v) then follows the
+    reference binary's 20-step ResultWriter trace at the trace tolerance (1e-9 double / 1e-6 mixed)."""
+    from ls1_mardyn_b200.components import lj_fluid
+    g = dict(np.load(os.path.join(GOLD, "generator_1clj_2662.npz")))
+    L = float(g["length"]); rc = float(g["rc"]); steps = int(g["steps"]); n = len(g[prec + "_id"])
+    assert r.shape == (n, 3)
+    oa = np.lexsort(r.T[::-1]); ob = np.lexsort(g[prec + "_r"].T[::-1])
+    assert np.array_equal(r[oa], g[prec + "_r"][ob]), "lattice positions differ from the reference generator's"
+    dv = float(np.abs(v[oa] - g[prec + "_v"][ob]).max() / np.abs(g[prec + "_v"]).max())
+    assert dv <= 1e-13, ("velocities differ from the reference generator's", dv)
+    s = cls([0.0, 0.0, 0.0], [L, L, L], rc, precision=prec, geometry="xml", periodic=(1, 1, 1))
+    s.set_components(lj_fluid(rc=rc))
+    s.upload(np.arange(1, n + 1, dtype=np.uint64) if ids is None else ids, np.zeros(n, dtype=np.uint32), r, v, None, None)
+    s.update(); m0 = s.traverse_cells()
+    rec = s.simulate(steps, float(g["dt"]), float(g["temperature"]))
+    out = compare_trace_rows(m0, rec, g[prec + "_trace"], steps, n, L ** 3, TRACE_TOL[prec], ("generator", prec))
+    out["v"] = dv
     return out

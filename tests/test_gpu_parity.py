@@ -399,7 +399,10 @@ def test_device_cubic_grid_generator(capi, prec):
     # momentum removal
     ctx.generate_cubic_grid(n, box, T, seed=7, remove_momentum=True)
     v2 = ctx.download("V")
-    assert np.abs(v2.sum(axis=0)).max() <= 1e-9 and np.abs((v2 - v) - (v2 - v)[0]).max() <= 1e-13
+    # IOHelpers::removeMomentum: the mean velocity is subtracted, then the velocities are scaled back to the target temperature
+    vs = v - v.mean(axis=0)
+    assert np.abs(v2.sum(axis=0)).max() <= 1e-9 and np.abs(v2 - vs * np.sqrt(T / ((vs ** 2).sum() / (3 * N)))).max() <= 1e-13
+    assert abs((v2 ** 2).sum() / (3 * N) - T) <= 1e-13
     # the generated state is a normal state: forces against the oracle
     ctx.update(); m = ctx.traverse_cells()
     b = orc.OracleSim([0, 0, 0], box, rc, precision=prec, geometry="xml", periodic=(1, 1, 1))
@@ -423,6 +426,56 @@ def test_device_cubic_grid_generator(capi, prec):
         assert np.array_equal(rid[k], bid) and np.array_equal(br, rr[k]) and np.abs(c.download("V") - rv[k]).max() <= 1e-13 * np.abs(rv).max()
         seen.append(bid)
     assert np.array_equal(np.sort(np.concatenate(seen)), rid)
+
+
+@pytest.mark.parametrize("prec", ["mixed", "double"])
+def test_device_generator_reference_velocities_vs_reference_binary(capi, prec):
+    """ls1b200_generate_cubic_grid with LS1B200_GEN_REFERENCE_VELOCITIES | LS1B200_GEN_REMOVE_MOMENTUM against the UNMODIFIED reference
+    binary started from `<generator name="CubicGridGenerator">` (tests/golden/generator_1clj_2662.npz, make_generator_golden.py):
+    positions bit-identical to its step-0 checkpoint, velocities (per-cell std::mt19937(0) sequence -- the device evaluates every
+    molecule's insertion rank inside its LinkedCells cell in closed form --, momentum removed, rescaled to T) to 1e-13, and the
+    generated context then follows the reference binary's 20-step trace (U_pot, U_kin, p, beta at 1e-9 / 1e-6). Blocks of a
+    decomposition re-seed per cell of THEIR grid, like the ranks of the reference would: checked against the host mirror fed with
+    the block's own cells."""
+    import os
+    from helpers import GOLD, TRACE_TOL, check_generated_state_vs_reference, compare_trace_rows
+    from ls1_mardyn_b200 import generators
+    from ls1_mardyn_b200.components import lj_fluid
+    from ls1_mardyn_b200.decomposition import DomainDecomposition
+    g = dict(np.load(os.path.join(GOLD, "generator_1clj_2662.npz")))
+    n, L, T, rc, steps = int(g["n_per_dim"]), float(g["length"]), float(g["temperature"]), float(g["rc"]), int(g["steps"])
+    box = [L, L, L]; mixed = prec == "mixed"
+    ens = lj_fluid(rc=rc)
+    ctx = capi.Context([0, 0, 0], box, rc, precision=prec, geometry="xml", periodic=(1, 1, 1))
+    ctx.set_components(ens)
+    N = ctx.generate_cubic_grid(n, box, T, remove_momentum=True, reference_velocities=True)
+    assert N == 2 * n ** 3
+    r, v, ids = ctx.download("R"), ctx.download("V"), ctx.download("ID")
+    out = check_generated_state_vs_reference(capi.Context, prec, r, v, ids)      # state == checkpoint; an uploaded copy follows the trace
+    # ... and so does the generated context itself (no upload in between)
+    ctx.update(); m0 = ctx.traverse_cells()
+    rec = ctx.simulate(steps, float(g["dt"]), T)
+    out2 = compare_trace_rows(m0, rec, g[prec + "_trace"], steps, N, L ** 3, TRACE_TOL[prec], ("generated context", prec))
+    print(prec, {k: "%.2e" % x for k, x in out.items()}, {k: "%.2e" % x for k, x in out2.items()})
+    # blocks: a 2 x 2 x 2 decomposition and an uneven 3 x 1 x 2 one
+    for nranks, grid in ((8, (2, 2, 2)), (6, (3, 1, 2))):
+        total = 0
+        for rank in range(nranks):
+            dd = DomainDecomposition(rank, nranks, np.array(box), grid)
+            c = capi.Context(list(dd.box_min()), list(dd.box_max()), rc, precision=prec, geometry="xml", periodic=dd.periodic())
+            c.set_components(ens); c.decomp_attach(dd)
+            nb = c.generate_cubic_grid(n, box, T, remove_momentum=False, reference_velocities=True)
+            bid, br, bv = c.download("ID"), c.download("R"), c.download("V")
+            rid, rr, _, lat = generators.cubic_grid_reference(n, box, dd.box_min(), dd.box_max(), T, 1.0, mixed=mixed, with_lattice_index=True)
+            o = np.argsort(bid)
+            assert nb == len(rid) and np.array_equal(bid[o], rid) and np.array_equal(br[o], rr)
+            # the block's own cell grid, from a plain context over the same box
+            k = capi.Context(list(dd.box_min()), list(dd.box_max()), rc, precision=prec, geometry="xml", periodic=(0, 0, 0))
+            k.set_components(ens); k.upload(rid, np.zeros(len(rid), dtype=np.uint32), rr, np.zeros_like(rr), None, None); k.update()
+            mv = generators.reference_velocities(lat, k.download("CELL"), T, 1.0, mixed=mixed, remove_momentum=False)
+            assert np.abs(bv[o] - mv).max() <= 1e-13 * np.abs(mv).max(), (grid, rank)
+            total += nb
+        assert total == N
 
 
 def test_forces_one_million_molecules_vs_reference_on_the_fly(capi, tmp_path):

@@ -94,3 +94,28 @@ def test_trace_vs_reference_binary(name, prec):
     U_pot, U_kin (sum m v^2 + sum I w^2), p, beta_trans, beta_rot. water_432 and multi_250 rotate (beta_rot != 1)."""
     out = check_trace_vs_reference(orc.OracleSim, name, prec)
     print(name, prec, {k: "%.2e" % v for k, v in out.items()})
+
+
+@pytest.mark.parametrize("prec", ["double", "mixed"])
+def test_cubic_grid_generator_mirror_vs_reference_binary(prec):
+    """The reference's CubicGridGenerator restated (generators.cubic_grid_reference for the lattice -- coordinates are ONE fused
+    multiply-add, as the reference binary contracts them -- and generators.reference_velocities for the per-cell std::mt19937(0)
+    sequence, IOHelpers::removeMomentum and its rescaling to T) against the step-0 checkpoint and the 20-step trace of the
+    UNMODIFIED reference binary started from `<generator name="CubicGridGenerator">` (tests/golden/make_generator_golden.py).
+    The cell of a molecule -- the reference re-seeds per LinkedCells cell -- comes from the oracle's bit-exact binning."""
+    from helpers import GOLD, check_generated_state_vs_reference
+    from ls1_mardyn_b200 import generators
+    from ls1_mardyn_b200.components import lj_fluid
+    import os
+    g = dict(np.load(os.path.join(GOLD, "generator_1clj_2662.npz")))
+    n, L, T, rc = int(g["n_per_dim"]), float(g["length"]), float(g["temperature"]), float(g["rc"])
+    mixed = prec == "mixed"
+    ids, r, _, lat = generators.cubic_grid_reference(n, [L, L, L], [0, 0, 0], [L, L, L], T, 1.0, mixed=mixed, with_lattice_index=True)
+    s = orc.OracleSim([0, 0, 0], [L, L, L], rc, precision=prec, geometry="xml", periodic=(1, 1, 1))
+    s.set_components(lj_fluid(rc=rc))
+    s.upload(ids, np.zeros(len(ids), dtype=np.uint32), r, np.zeros_like(r), None, None)
+    s.update()
+    v = generators.reference_velocities(lat, s.download("CELL"), T, 1.0, mixed=mixed)
+    assert len(np.unique(np.round(v, 12), axis=0)) == len(np.unique(np.round(g[prec + "_v"], 12), axis=0))      # the cells share one sequence
+    out = check_generated_state_vs_reference(orc.OracleSim, prec, r, v, ids)
+    print(prec, {k: "%.2e" % x for k, x in out.items()})
