@@ -152,6 +152,15 @@ void LinkedCellsB200::traverseCells(CellProcessor& cellProcessor) {
 		ls1b200_macro mac{};
 		B200_CHECK(ls1b200_traverse_cells(_ctx, &mac));      // forces, torques, per-molecule virial stay on the device
 		Domain* domain = global_simulation->getDomain();
+		// The per-molecule part of the long-range correction: Homogeneous::calculateLongRange adds VirialCorr / 3N to every molecule's
+		// Vi right after the traversal (longRange/Homogeneous.cpp:143-155, Simulation.cpp:1175) -- a host loop that iterates nothing in
+		// device mode (and the view cannot open before Simulation::updateForces has run: calcFM would add the mirror's stale site
+		// forces). syncToHost() adds the term instead. Domain keeps VirialCorr private, but publishes _globalVirial / N
+		// (getAverageGlobalVirial, Domain.cpp:148, :187: _globalVirial = Virial + _VirialCorr): at this point it still holds the
+		// values Domain::calculateGlobalValues computed from the PREVIOUS traversal's virial. VirialCorr depends on N, V and the
+		// components only. (Sequential build: the local virial is the global one.)
+		if (_havePrevVirial) _virialCorr = domain->getAverageGlobalVirial() * (double) domain->getglobalNumMolecules(false) - _prevLocalVirial;
+		_prevLocalVirial = mac.virial; _havePrevVirial = true;
 		domain->setLocalVirial(mac.virial);                  // as VectorizedCellProcessor::endTraversal (.cpp:153-154)
 		domain->setLocalUpot(mac.upot);
 		return;
@@ -201,6 +210,8 @@ void LinkedCellsB200::syncToHost() {
 		at.reserve(n);
 		for (size_t i = 0; i < n; i++) at[id[i]] = i;
 	}
+	const unsigned long nGlobal = global_simulation->getDomain()->getglobalNumMolecules(false);
+	const double viAdd = nGlobal > 0 ? _virialCorr / (3. * (double) nGlobal) : 0.;
 	#if defined(_OPENMP)
 	#pragma omp parallel
 	#endif
@@ -217,12 +228,11 @@ void LinkedCellsB200::syncToHost() {
 		}
 		for (int d = 0; d < 3; d++) { m->setr(d, r[3 * i + d]); m->setv(d, v[3 * i + d]); m->setD(d, D[3 * i + d]); }
 		m->setq(Quaternion(q[4 * i], q[4 * i + 1], q[4 * i + 2], q[4 * i + 3]));
-		m->setF(&F[3 * i]); m->setM(&M[3 * i]); m->setVi(&Vi[3 * i]);
+		// pair virial from the device + what Homogeneous::calculateLongRange would have added to this molecule (see traverseCells)
+		const double vi[3] = {Vi[3 * i] + viAdd, Vi[3 * i + 1] + viAdd, Vi[3 * i + 2] + viAdd};
+		m->setF(&F[3 * i]); m->setM(&M[3 * i]); m->setVi(const_cast<double*>(vi));
 	}
 	LinkedCells::update();                   // re-sort the host mirror
-	// The per-molecule part of the long-range correction (Homogeneous::calculateLongRange adds VirialCorr / 3N to every Vi,
-	// longRange/Homogeneous.cpp:143-155) is applied by the stock step right after this point: LeapfrogB200 opens the host view
-	// before Simulation calls _longRangeCorrection->calculateLongRange(), so the refreshed molecules receive it like the reference's.
 }
 
 void LinkedCellsB200::syncToDevice() {

@@ -58,6 +58,10 @@ private:
 	bool _deviceMode = false;
 	bool _hostView = true;        // until the first time step: the init-time loops of prepare_start read the host mirror
 	unsigned long _numMolecules = 0;
+	// Homogeneous long-range correction, per-molecule part (see traverseCells): Domain's VirialCorr reconstructed from its public values
+	double _prevLocalVirial = 0.;
+	bool _havePrevVirial = false;
+	double _virialCorr = 0.;
 	unsigned long _hostSyncFrequency = 0;
 	bool _syncAtLastStep = true;
 	int _device = -1;

@@ -610,6 +610,20 @@ def our_arm(args):
             series = np.concatenate([rec_w, rec]); ks = args.steps
             line["trace"]["at_reference_step"] = {"at_step": ks, "T": series[ks - 1, 4], "upot_per_molecule": series[ks - 1, 0] / N_global, "p": series[ks - 1, 5],
                                                   "note": "same initial state as the reference arm (its CubicGridGenerator sequence, generated on the device): compare with that line's trace"}
+            # ... and against the committed ResultWriter rows of the unmodified reference on this very configuration (16 M molecules, 100 steps,
+            # tests/golden/make_reference_trace_16m.py): largest relative deviation over the steps both cover
+            fx = os.path.join(ROOT, "tests", "golden", "reference_trace_lj16M.npz")
+            if wl.name == "lj" and args.precision == "mixed" and os.path.exists(fx):
+                g = np.load(fx)
+                if int(g["molecules"]) == N_global:
+                    ref = g["trace"]; m = min(len(series), len(ref) - 1)
+                    b = ref[1:m + 1]
+                    line["trace"]["vs_reference_fixture"] = {
+                        "steps_compared": m, "fixture": "tests/golden/reference_trace_lj16M.npz (unmodified reference binary, the same 16 M-molecule configuration)",
+                        "U_pot_rel_max": float(np.abs(series[:m, 0] - b[:, 2]).max() / np.abs(b[:, 2]).max()),
+                        "T_rel_max": float(np.abs(0.5 * (series[:m, 2] + series[:m, 3]) - b[:, 4]).max() / np.abs(b[:, 4]).max()),
+                        "p_rel_max": float(np.abs(series[:m, 5] - b[:, 6]).max() / np.abs(b[:, 6]).max()),
+                        "beta_trans_abs_max": float(np.abs(series[:m, 6] - b[:, 8]).max()), "tolerance": 1e-6}
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(wl)
             if cb is not None:

@@ -162,3 +162,53 @@ def test_checkpoints_written_from_the_host_mirror(tmp_path, prec, tol):
     p = subprocess.run([ref, "--steps", "10", "config.xml"], cwd=str(d), capture_output=True, text=True, timeout=600, env=dict(os.environ, OMP_NUM_THREADS="8"))
     assert p.returncode == 0, (p.stdout + p.stderr)[-3000:]
     cmp(d / "config.restart.dat", runs["ref"] / "config.restart.dat", "restart")
+
+
+@pytest.mark.parametrize("prec", ["mixed", "double"])
+def test_per_molecule_virial_with_longrange_correction_through_a_stock_plugin(tmp_path, prec):
+    """Host coherence, per-molecule virial: the stock SpatialProfile plugin with its VirialProfile
+    (plugins/profiles/VirialProfile.h:29-33 sums Molecule::Vi per y-layer every step) on an ASCII phase space with the Homogeneous
+    long-range correction ACTIVE (U_pot shifts by ~9 %): in the reference every molecule's Vi is the pair virial from calcFM plus
+    VirialCorr / 3N added by Homogeneous::calculateLongRange (longRange/Homogeneous.cpp:143-155). In device mode that host loop
+    iterates nothing; LinkedCellsB200::syncToHost adds the term to the refreshed mirror (VirialCorr reconstructed from Domain's public
+    values). MarDyn_b200 with <hostSyncFrequency>1 writes the same profile files as the stock binary (6 printed digits)."""
+    ref = os.path.join(ROOT, "oracle", "_ref", prec, "MarDyn")
+    b200 = os.path.join(ROOT, "adapter", "_build", prec, "MarDyn_b200")
+    if not (os.path.exists(ref) and os.path.exists(b200)):
+        pytest.skip("reference / adapter binaries not built (oracle/build_ref.sh, adapter/build_adapter.sh)")
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    from helpers import load
+    from ls1_mardyn_b200.ascii_reader import PhaseSpace, write_phase_space
+    from ls1_mardyn_b200.xml_config import simulation_xml
+    g = load("periodic_1clj_1458")
+    steps, T, dt = 20, 0.85, 0.002
+    ps = PhaseSpace(np.array(g["length"]), T, float(g["epsilon_rf"]), g["ensemble"], g["in_id"], g["in_cid"], g["in_r"], g["in_v"], g["in_q"], g["in_L"])
+    plug = ('<plugin name="SpatialProfile"><mode>cartesian</mode><x>1</x><y>4</y><z>1</z><writefrequency>10</writefrequency><timesteps><init>1</init>'
+            "<recording>1</recording></timesteps><outputprefix>prof</outputprefix><profiledComponent>all</profiledComponent>"
+            "<profiles><density>true</density><virial>true</virial></profiles></plugin>")
+    out = {}
+    for name, exe, ds, integ, extra in (("ref", ref, "LinkedCells", "Leapfrog", ""), ("b200", b200, "LinkedCellsB200", "LeapfrogB200", "<hostSyncFrequency>1</hostSyncFrequency>")):
+        d = tmp_path / name; d.mkdir()
+        write_phase_space(str(d / "start.inp"), ps)
+        xml = simulation_xml(g["ensemble"], g["length"], T, dt, steps, float(g["cutoff"]), phasespace_file="start.inp", longrange="homogeneous",
+                             datastructure=ds, integrator=integ, datastructure_extra=extra).replace("</simulation>", plug + "</simulation>")
+        (d / "config.xml").write_text(xml)
+        res, _ = run(exe, "config.xml", str(d), steps)
+        prof = {}
+        for f in ("prof_10_1D-Y.Vipr", "prof_20_1D-Y.Vipr"):
+            rows = [l.split() for l in open(d / f) if l.strip() and not l.lstrip().startswith(("/", "#"))]
+            prof[f] = np.array([[float(x) for x in r] for r in rows if len(r) == 5])      # y, vn - vt, px, py, pz per layer
+            assert prof[f].shape == (4, 5), (f, prof[f].shape)
+        out[name] = (res, prof)
+    (ra, pa), (rb, pb) = out["b200"], out["ref"]
+    # the correction is active in this set-up (it is not with the generator input of the other drop-in tests: no molecule counts at init)
+    t = np.load(os.path.join(ROOT, "tests", "golden", "trace_1clj_1458.npz"))[prec]      # the same run with NoLRC
+    lrc_p = float(rb[0, 6] - t[0, 6])
+    assert abs(rb[0, 2] - t[0, 2]) > 0.05 * abs(t[0, 2]) and abs(lrc_p) > 0.1
+    assert np.abs(ra[:, 2] - rb[:, 2]).max() <= 1e-6 * np.abs(rb[:, 2]).max()
+    for f in pa:
+        # 6 printed digits; a missing correction would shift px, py, pz by ~lrc_p (0.5 of values around 2)
+        assert np.abs(pa[f][:, 2:] - pb[f][:, 2:]).max() <= 2e-5 * np.abs(pb[f][:, 2:]).max(), (f, pa[f], pb[f])
+        assert np.abs(pa[f][:, 1] - pb[f][:, 1]).max() <= 2e-5 * np.abs(pb[f][:, 2:]).max(), (f, pa[f], pb[f])
+    print(prec, "LRC pressure term", lrc_p, "largest profile deviation", max(float(np.abs(pa[f][:, 1:] - pb[f][:, 1:]).max()) for f in pa))

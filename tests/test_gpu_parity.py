@@ -478,6 +478,33 @@ def test_device_generator_reference_velocities_vs_reference_binary(capi, prec):
         assert total == N
 
 
+def test_benchmark_state_16M_vs_reference_binary(capi):
+    """Parity AT THE BENCHMARK'S FULL SIZE (BASELINE.json configs[1]: 16 000 000 1CLJ molecules, mixed precision): the device generator
+    builds the state the unmodified reference binary builds from its CubicGridGenerator, and ls1b200_simulate (the fused step that
+    bench.py times) is held against the reference binary's own ResultWriter rows on that configuration, 100 steps
+    (tests/golden/reference_trace_lj16M.npz, made by make_reference_trace_16m.py on the build container's host cores):
+    U_pot, U_kin (T), p, beta_trans at 1e-6 relative -- north_star's bound for T and p over 100 steps."""
+    import os
+    from helpers import GOLD, TRACE_TOL, compare_trace_rows
+    from ls1_mardyn_b200.components import lj_fluid
+    fx = os.path.join(GOLD, "reference_trace_lj16M.npz")
+    if not os.path.exists(fx):
+        pytest.skip("tests/golden/reference_trace_lj16M.npz not generated")
+    g = np.load(fx)
+    n, L, T, rc, dt, steps = int(g["n_per_dim"]), float(g["length"]), float(g["temperature"]), float(g["rc"]), float(g["dt"]), int(g["steps"])
+    ctx = capi.Context([0, 0, 0], [L, L, L], rc, precision="mixed", geometry="xml", periodic=(1, 1, 1))
+    ctx.set_components(lj_fluid(rc=rc))
+    N = ctx.generate_cubic_grid(n, [L, L, L], T, remove_momentum=True, reference_velocities=True)
+    assert N == int(g["molecules"]) == 16000000
+    ctx.update(); m0 = ctx.traverse_cells()
+    rec = ctx.simulate(steps, dt, T)
+    ctx.close()
+    for m in (20, 50, steps):      # how the deviation grows (printed before anything is asserted)
+        o = compare_trace_rows(m0, rec[:m], g["trace"], m, N, L ** 3, 1.0, ("16 M benchmark state", m))
+        print("16 M molecules, first", m, "steps vs the reference binary:", {k: "%.2e" % x for k, x in o.items()})
+    compare_trace_rows(m0, rec, g["trace"], steps, N, L ** 3, TRACE_TOL["mixed"], ("16 M benchmark state", "mixed"))
+
+
 def test_forces_one_million_molecules_vs_reference_on_the_fly(capi, tmp_path):
     """Parity at a size where the golden fixtures cannot go (they are 250 - 1 458 molecules): a 1 024 000-molecule jittered periodic
     1CLJ liquid (100 x 100 x... BCC lattice 2 * 80^3) is written out, the UNMODIFIED reference (oracle/_ref/mixed/refdump, the dump
