@@ -140,7 +140,20 @@ struct DevScalars {
 	uint32_t n_owned_dev;                         // owned molecules counted by the last count_owned() (decomposed mode)
 	uint32_t n_sorted;                            // slots in cell order (count of the last update); imports of the exchange follow behind
 	uint32_t n_pre;                               // fused step: slots binned by k_pre_key (the imports of this step's exchange are appended behind them)
+	// Domain's "explosion" heuristics (Domain.cpp:74-79, :259-314, :363-368), evaluated by k_globals: while a thermostat factor is below
+	// MIN_BETA = 0.9 and no error is pending, every molecule whose translational (rotational) kinetic energy exceeds 10 T (3 rotDOF T) is
+	// scaled down to that limit together with its force (torque). clip_limit > 0: that scaling is pending; like the thermostat factors
+	// it is applied on load by the next kernel that reads the velocities (k_pre_key, k_leapfrog_pre*, k_scale). The three counters are
+	// _universalSelectiveThermostatCounter / Warning / Error.
+	double clip_limit, clip_ti;
+	int32_t expl_counter, expl_warning, expl_error, expl_pad;
 };
+
+// the pending selective-thermostat scaling of one molecule (Domain.cpp:268-296): factor for v and F ...
+__device__ __forceinline__ double clip_factor_trans(double limit, double mass, double vx, double vy, double vz) {
+	const double utrans = 0.5 * mass * (vx * vx + vy * vy + vz * vz);      // FullMolecule::U_trans
+	return utrans > limit ? sqrt(limit / utrans) : 1.0;
+}
 
 }  // namespace ls1b200
 
@@ -177,6 +190,7 @@ struct ls1b200_ctx {
 	double* F = nullptr; double* M = nullptr; double* Vi = nullptr;   // [3][cap] each, slot order
 	bool sorted = false;          // update() has run since the last upload
 	bool ever_sorted = false;     // some update() has run since the last upload (cell_of2 / DevScalars::n_sorted describe it)
+	bool globals_initialised = false;      // ls1b200_simulate has evaluated the global values of the uploaded state once (Simulation::prepare_start)
 	bool forces_valid = false;
 
 	// cells
@@ -300,7 +314,7 @@ int do_pre_key(ls1b200_ctx* c, double dt, bool use_beta, bool post_kick);      /
 int do_forces(ls1b200_ctx* c);
 int do_leapfrog_pre(ls1b200_ctx* c, double dt, bool use_beta, int region = 0);      // region: see Region::mode
 int do_leapfrog_post(ls1b200_ctx* c, double dt);
-int do_globals(ls1b200_ctx* c, double target_T, uint64_t global_n, double global_volume, ls1b200_step_record* d_rec);
+int do_globals(ls1b200_ctx* c, double target_T, uint64_t global_n, double global_volume, ls1b200_step_record* d_rec, bool init = false);
 int force_general(ls1b200_ctx* c);
 int force_1clj(ls1b200_ctx* c);
 int force_1clj_tiled(ls1b200_ctx* c);

@@ -434,6 +434,7 @@ int ls1b200_upload(ls1b200_ctx* c, uint64_t n, const uint64_t* id, const uint32_
 	c->parity = 0; c->n_slots = (uint32_t) n;
 	c->h_scal->n_slots2[0] = (uint32_t) n; c->h_scal->n_slots2[1] = 0; c->h_scal->overflow = 0;
 	c->h_scal->beta_trans = 1.; c->h_scal->beta_rot = 1.;
+	c->h_scal->clip_limit = 0.; c->h_scal->expl_counter = c->h_scal->expl_warning = c->h_scal->expl_error = 0; c->globals_initialised = false;      // a new state: Domain's explosion heuristics start over
 	LS1_CUDA(cudaMemcpy(c->d_scal, c->h_scal, sizeof(DevScalars), cudaMemcpyHostToDevice));
 	c->sorted = false; c->ever_sorted = false; c->forces_valid = false; c->keys_valid = false;
 	return 0;

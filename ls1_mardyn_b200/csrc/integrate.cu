@@ -42,25 +42,37 @@ __global__ void __launch_bounds__(256) k_leapfrog_pre(State st, const double* __
 	const double bt = use_beta ? scal->beta_trans : 1., br = use_beta ? scal->beta_rot : 1.;
 	const double dth = .5 * dt, dtInv2m = dth / cp.mass;
 	const size_t c = cap;
+	const double clip = use_beta ? scal->clip_limit : 0.;      // pending selective thermostat (explosion heuristics): v, F (and L, M) scaled first
+	double vv[3] = {st.v[t], st.v[c + t], st.v[2 * c + t]};
+	const double vc = clip > 0. ? clip_factor_trans(clip, cp.mass, vv[0], vv[1], vv[2]) : 1.;
 	#pragma unroll
 	for (int d = 0; d < 3; d++) {
-		double v = st.v[d * c + t];
+		double v = vv[d] * vc;
 		if (use_beta) v *= bt;
-		v += dtInv2m * F[d * c + t];
+		v += dtInv2m * (F[d * c + t] * vc);
 		st.v[d * c + t] = v;
 		st.r[d * c + t] += dt * v;
 	}
 	if (rotates) {
 		double q[4], L[3], w[3], qh[4], qi[4];
 		for (int k = 0; k < 4; k++) q[k] = st.q[k * c + t];
-		for (int d = 0; d < 3; d++) { L[d] = st.L[d * c + t]; if (use_beta) L[d] *= br; }
+		for (int d = 0; d < 3; d++) L[d] = st.L[d * c + t];
+		double dc = 1.;
+		if (clip > 0. && cp.rot_dof > 0) {      // U_rot > 3 rotDOF T: D and M scaled to the limit (Domain.cpp:283-292)
+			q_rotateinv(q, L, w);
+			double Iw2 = 0.;
+			for (int d = 0; d < 3; d++) { w[d] *= cp.invI[d]; Iw2 += cp.I[d] * w[d] * w[d]; }
+			const double urot = 0.5 * Iw2, limit_rot = 3.0 * (double) cp.rot_dof * scal->clip_ti;
+			if (urot > limit_rot) dc = sqrt(limit_rot / urot);
+		}
+		for (int d = 0; d < 3; d++) { L[d] *= dc; if (use_beta) L[d] *= br; }
 		q_rotateinv(q, L, w);
 		for (int d = 0; d < 3; d++) w[d] *= cp.invI[d];
 		q_differentiate(q, w, qh);
 		for (int k = 0; k < 4; k++) qh[k] = qh[k] * dth + q[k];
 		double qc = 1. / sqrt(qh[0] * qh[0] + qh[1] * qh[1] + qh[2] * qh[2] + qh[3] * qh[3]);
 		for (int k = 0; k < 4; k++) qh[k] *= qc;
-		for (int d = 0; d < 3; d++) L[d] += dth * M[d * c + t];
+		for (int d = 0; d < 3; d++) L[d] += dth * (M[d * c + t] * dc);
 		q_rotateinv(qh, L, w);
 		for (int d = 0; d < 3; d++) w[d] *= cp.invI[d];
 		q_differentiate(qh, w, qi);
@@ -88,13 +100,22 @@ __global__ void __launch_bounds__(256) k_leapfrog_pre_v2(State st, const double*
 	const double dth = .5 * dt;
 	const double a0 = on0 ? dth / comps[meta_cid(m2.x)].mass : 0., a1 = on1 ? dth / comps[meta_cid(m2.y)].mass : 0.;
 	const size_t c = cap;
+	double2 v3[3];
+	#pragma unroll
+	for (int d = 0; d < 3; d++) v3[d] = *reinterpret_cast<const double2*>(st.v + d * c + t);
+	const double clip = use_beta ? scal->clip_limit : 0.;      // pending selective thermostat (explosion heuristics): v and F scaled first
+	double vc0 = 1., vc1 = 1.;
+	if (clip > 0.) {
+		if (on0) vc0 = clip_factor_trans(clip, comps[meta_cid(m2.x)].mass, v3[0].x, v3[1].x, v3[2].x);
+		if (on1) vc1 = clip_factor_trans(clip, comps[meta_cid(m2.y)].mass, v3[0].y, v3[1].y, v3[2].y);
+	}
 	#pragma unroll
 	for (int d = 0; d < 3; d++) {
-		double2 v = *reinterpret_cast<const double2*>(st.v + d * c + t);
+		double2 v = v3[d];
 		const double2 f = *reinterpret_cast<const double2*>(F + d * c + t);
 		double2 r = *reinterpret_cast<const double2*>(st.r + d * c + t);
-		if (on0) { if (use_beta) v.x *= bt; v.x += a0 * f.x; r.x += dt * v.x; }
-		if (on1) { if (use_beta) v.y *= bt; v.y += a1 * f.y; r.y += dt * v.y; }
+		if (on0) { v.x *= vc0; if (use_beta) v.x *= bt; v.x += a0 * (f.x * vc0); r.x += dt * v.x; }
+		if (on1) { v.y *= vc1; if (use_beta) v.y *= bt; v.y += a1 * (f.y * vc1); r.y += dt * v.y; }
 		*reinterpret_cast<double2*>(st.v + d * c + t) = v;
 		*reinterpret_cast<double2*>(st.r + d * c + t) = r;
 	}
@@ -171,20 +192,46 @@ __global__ void __launch_bounds__(1024) k_reduce_kinetic(const double* __restric
 	if (threadIdx.x == 0) { scal->summv2 = out[0]; scal->sum_iw2 = out[1]; scal->fault = scal->overflow ? 1. : 0.; }      // fault travels with the allreduce of the sums
 }
 
+// from_scal: what the next leapfrog_pre of a running ls1b200_simulate would have applied on load -- the pending selective-thermostat
+// scaling of the explosion heuristics (v, F and L, M of the molecules over the limit) and the thermostat factors
 __global__ void __launch_bounds__(256) k_scale(State st, uint32_t cap, double bt, double br, const DevScalars* __restrict__ scal, uint32_t parity,
-                                               int from_scal, int rotates) {
+                                               int from_scal, int rotates, double* __restrict__ F, double* __restrict__ M, const CompDev* __restrict__ comps) {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= min(scal->n_slots2[parity], cap)) return;
-	if (meta_halo(st.meta[t])) return;
+	const uint64_t meta = st.meta[t];
+	if (meta_halo(meta)) return;
 	if (from_scal) { bt = scal->beta_trans; br = scal->beta_rot; }
 	const size_t c = cap;
+	double vc = 1., dc = 1.;
+	const double clip = from_scal ? scal->clip_limit : 0.;
+	if (clip > 0.) {
+		const CompDev& cp = comps[meta_cid(meta)];
+		vc = clip_factor_trans(clip, cp.mass, st.v[t], st.v[c + t], st.v[2 * c + t]);
+		if (rotates && cp.rot_dof > 0) {
+			double q[4], L[3], w[3];
+			for (int k = 0; k < 4; k++) q[k] = st.q[k * c + t];
+			for (int d = 0; d < 3; d++) L[d] = st.L[d * c + t];
+			q_rotateinv(q, L, w);
+			double Iw2 = 0.;
+			for (int d = 0; d < 3; d++) { w[d] *= cp.invI[d]; Iw2 += cp.I[d] * w[d] * w[d]; }
+			const double urot = 0.5 * Iw2, limit_rot = 3.0 * (double) cp.rot_dof * scal->clip_ti;
+			if (urot > limit_rot) dc = sqrt(limit_rot / urot);
+		}
+		if (vc != 1.) for (int d = 0; d < 3; d++) F[d * c + t] *= vc;
+		if (dc != 1.) for (int d = 0; d < 3; d++) M[d * c + t] *= dc;
+	}
 	#pragma unroll
-	for (int d = 0; d < 3; d++) st.v[d * c + t] *= bt;
-	if (rotates) for (int d = 0; d < 3; d++) st.L[d * c + t] *= br;
+	for (int d = 0; d < 3; d++) st.v[d * c + t] = st.v[d * c + t] * vc * bt;
+	if (rotates) for (int d = 0; d < 3; d++) st.L[d * c + t] = st.L[d * c + t] * dc * br;
 }
 
-// Domain::calculateGlobalValues + getGlobalPressure for one rank (Domain.cpp:157-252, :142-146)
-__global__ void k_globals(DevScalars* scal, double target_T, unsigned long long N, unsigned long long rot_dof, double volume, ls1b200_step_record* rec) {
+// Domain::calculateGlobalValues + getGlobalPressure for one rank (Domain.cpp:157-314, :363-368, :142-146), incl. the heuristic handling
+// of an "explosion": a thermostat factor below MIN_BETA = 0.9 while no error is pending makes the NEXT kernel that loads the velocities
+// scale every molecule above 10 T (3 rotDOF T) of translational (rotational) kinetic energy down to that limit (clip_limit), beta_trans
+// becomes 1 and beta_rot its 0.0091-th power; the counters decide for how long (still there after 40 steps, or back within 4000: warning;
+// a second time: error -- the plain factors apply again). `init`: the evaluation of Simulation::prepare_start (Simulation.cpp:991) --
+// the heuristics see the state and start their counters, the factors are not applied.
+__global__ void k_globals(DevScalars* scal, double target_T, unsigned long long N, unsigned long long rot_dof, double volume, ls1b200_step_record* rec, int init) {
 	if (threadIdx.x != 0 || blockIdx.x != 0) return;
 	if (scal->fault != 0. && !scal->overflow) scal->overflow = 5;      // another rank failed: every rank freezes in the same step
 	const double upot = scal->upot6lj / 6.0 + scal->upot_xpoles + scal->my_rf;
@@ -197,6 +244,23 @@ __global__ void k_globals(DevScalars* scal, double target_T, unsigned long long 
 		bt = pow(3.0 * (double) N * target_T / summv2, 0.4);
 		br = (sumIw2 == 0.0) ? 1.0 : pow((double) rot_dof * target_T / sumIw2, 0.4);
 	}
+	double clip = 0.;
+	if ((bt < 0.9 || br < 0.9) && scal->expl_error <= 0 && !scal->overflow) {
+		clip = 10.0 * target_T;                                          // KINLIMIT_PER_T * Ti
+		const int reappearance_limit = 4000, vanish_grace_period = 40;
+		if (reappearance_limit - scal->expl_counter >= vanish_grace_period) {
+			if (scal->expl_warning > 0) scal->expl_error = scal->expl_warning;
+			if (scal->expl_counter > 0) scal->expl_warning = scal->expl_counter;
+			scal->expl_counter = reappearance_limit;
+		}
+		bt = 1.0;
+		br = pow(br, 0.0091);
+	}
+	if (scal->expl_counter > 0) scal->expl_counter--;
+	if (scal->expl_warning > 0) scal->expl_warning--;
+	if (scal->expl_error > 0) scal->expl_error--;
+	scal->clip_limit = clip; scal->clip_ti = target_T;
+	if (init) { bt = 1.; br = 1.; }
 	const double rho = (double) N / volume;
 	const double p = T * rho + rho * (virial / (double) N) / 3.;
 	scal->beta_trans = bt; scal->beta_rot = br;
@@ -248,12 +312,12 @@ int do_leapfrog_post(ls1b200_ctx* c, double dt) {
 	return 0;
 }
 
-int do_globals(ls1b200_ctx* c, double target_T, uint64_t global_n, double global_volume, ls1b200_step_record* d_rec) {
+int do_globals(ls1b200_ctx* c, double target_T, uint64_t global_n, double global_volume, ls1b200_step_record* d_rec, bool init) {
 	const uint64_t N = global_n ? global_n : c->n_owned;
 	double V = global_volume;
 	if (!(V > 0.)) V = c->geom.lbox[0] * c->geom.lbox[1] * c->geom.lbox[2];
 	const uint64_t rdof = c->dd.active ? c->dd.rot_dof_global : c->rot_dof_total;
-	LS1_LAUNCH(c, PH_POST, k_globals, 1, 32, 0, c->d_scal, target_T, (unsigned long long) N, (unsigned long long) rdof, V, d_rec);
+	LS1_LAUNCH(c, PH_POST, k_globals, 1, 32, 0, c->d_scal, target_T, (unsigned long long) N, (unsigned long long) rdof, V, d_rec, (int) init);
 	return 0;
 }
 
@@ -302,7 +366,7 @@ int ls1b200_scale_velocities(ls1b200_ctx* c, double beta_trans, double beta_rot)
 	LS1_CUDA(cudaSetDevice(c->device));
 	if (c->n_owned == 0 && !c->dd.active) return 0;
 	const uint32_t g = (uint32_t) ((c->cap + 255) / 256);
-	LS1_LAUNCH(c, PH_POST, k_scale, g, 256, 0, c->cur, (uint32_t) c->cap, beta_trans, beta_rot, c->d_scal, c->parity, 0, (int) c->rotates);
+	LS1_LAUNCH(c, PH_POST, k_scale, g, 256, 0, c->cur, (uint32_t) c->cap, beta_trans, beta_rot, c->d_scal, c->parity, 0, (int) c->rotates, c->F, c->M, c->d_comps);
 	return 0;
 }
 
@@ -334,9 +398,19 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 		LS1_CUDA(cudaMalloc((void**) &c->d_records, sizeof(ls1b200_step_record) * n_steps));
 		c->records_cap = n_steps;
 	}
-	// thermostat factors of the previous call have already been applied: start from 1
-	c->h_scal->beta_trans = 1.; c->h_scal->beta_rot = 1.;
+	// thermostat factors (and the selective-thermostat scaling of the explosion heuristics) of the previous call have already been applied: start from 1
+	c->h_scal->beta_trans = 1.; c->h_scal->beta_rot = 1.; c->h_scal->clip_limit = 0.;
 	LS1_CUDA(cudaMemcpyAsync(&c->d_scal->beta_trans, &c->h_scal->beta_trans, 2 * sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	LS1_CUDA(cudaMemcpyAsync(&c->d_scal->clip_limit, &c->h_scal->clip_limit, sizeof(double), cudaMemcpyHostToDevice, c->stream));
+	// The first call after an upload evaluates the global values once on the state as it is, like Simulation::prepare_start
+	// (Simulation.cpp:986-992: calculateVelocitySums + calculateGlobalValues): the factors are not applied there, but Domain's explosion
+	// heuristics see the initial state and start their counters. The sums come from a "second half kick" of length 0.
+	if (!c->globals_initialised && target_temperature > 0.) {
+		LS1_TRY(do_leapfrog_post(c, 0.));
+		LS1_TRY(do_allreduce_scalars(c));
+		LS1_TRY(do_globals(c, target_temperature, global_n, global_volume, nullptr, true));
+	}
+	c->globals_initialised = true;
 	// Multi-GPU: the exchange is overlapped with the work on the INNER slots (Region, common.cuh) -- the analogue of the reference's
 	// overlapping scheme (parallel/NonBlockingMPIMultiStepHandler.cpp:28-93: inner cells are processed while the messages travel), at
 	// the stages that do not need the imports: boundary slots are integrated first, then the three export / transport / import
@@ -441,7 +515,7 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 	}
 	if (target_temperature > 0.) {   // the scaling the next leapfrog_pre would have applied on load
 		const uint32_t g = (uint32_t) ((c->cap + 255) / 256);
-		LS1_LAUNCH(c, PH_POST, k_scale, g, 256, 0, c->cur, (uint32_t) c->cap, 1., 1., c->d_scal, c->parity, 1, (int) c->rotates);
+		LS1_LAUNCH(c, PH_POST, k_scale, g, 256, 0, c->cur, (uint32_t) c->cap, 1., 1., c->d_scal, c->parity, 1, (int) c->rotates, c->F, c->M, c->d_comps);
 	}
 	if (records) LS1_CUDA(cudaMemcpyAsync(records, c->d_records, sizeof(ls1b200_step_record) * n_steps, cudaMemcpyDeviceToHost, c->stream));
 	LS1_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));

@@ -158,6 +158,27 @@ __global__ void __launch_bounds__(256) k_key_tail(UpdArgs a, State cur, uint32_t
 	}
 }
 
+// k_pre_key's integration of one slot while the selective thermostat of Domain's explosion heuristics is pending (k_globals set
+// DevScalars::clip_limit): v and F of a molecule above the limit are scaled to it before the thermostat factor and the next half kick
+// (Domain.cpp:268-281). Returns the new position.
+__device__ __noinline__ double3 pre_key_clipped_slot(State cur, const double* __restrict__ vs, const double* __restrict__ F, size_t c, uint32_t s, size_t so, double a0, double mass,
+                                                     double bt, double dt, int post_kick, double limit, double rx, double ry, double rz) {
+	double w[3], f[3], r[3] = {rx, ry, rz};
+	#pragma unroll
+	for (int d = 0; d < 3; d++) { w[d] = vs[d * c + so]; f[d] = F[d * c + s]; if (post_kick) w[d] += a0 * f[d]; }
+	const double vc = clip_factor_trans(limit, mass, w[0], w[1], w[2]);
+	#pragma unroll
+	for (int d = 0; d < 3; d++) {
+		double v = w[d] * vc;
+		v *= bt;
+		v += a0 * (f[d] * vc);
+		cur.v[d * c + s] = v;
+		r[d] += dt * v;
+		cur.r[d * c + s] = r[d];
+	}
+	return make_double3(r[0], r[1], r[2]);
+}
+
 // The fused first kernel of a time step of ls1b200_simulate (ensembles without rotation): [the second half kick of the PREVIOUS
 // step (Leapfrog::transition2to3 -> upd_postF, whose sum of m v^2 the force kernel already delivered) +] thermostat factor on
 // load + upd_preF (half kick, drift) + the binning of k_key on the new position, which is still in registers: the slot state
@@ -185,6 +206,12 @@ __global__ void __launch_bounds__(256, 8) k_pre_key(UpdArgs a, State cur, const 
 			if (!scal->overflow) {      // a failed step: the state stays as it is (k_leapfrog_pre)
 				const double bt = use_beta ? scal->beta_trans : 1.;
 				const double a0 = (.5 * dt) / comps[meta_cid(meta)].mass;
+				if (use_beta && scal->clip_limit > 0.) {
+					// pending selective thermostat of Domain's explosion heuristics (k_globals). Rare: a function of its own (not inlined),
+					// so that the streaming loop below keeps its registers.
+					const double3 rn = pre_key_clipped_slot(cur, vs, F, c, s, so, a0, comps[meta_cid(meta)].mass, bt, dt, post_kick, scal->clip_limit, r[0], r[1], r[2]);
+					r[0] = rn.x; r[1] = rn.y; r[2] = rn.z;
+				} else {
 				#pragma unroll
 				for (int d = 0; d < 3; d++) {
 					double v = vs[d * c + so];
@@ -195,6 +222,7 @@ __global__ void __launch_bounds__(256, 8) k_pre_key(UpdArgs a, State cur, const 
 					cur.v[d * c + s] = v;
 					r[d] += dt * v;
 					cur.r[d * c + s] = r[d];
+				}
 				}
 			} else if (perm) {
 				#pragma unroll

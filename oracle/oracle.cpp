@@ -350,6 +350,11 @@ struct Sim {
 	// halo copies of the last update: owner index + shifted position
 	std::vector<long> halo_owner; std::vector<double> halo_r; std::vector<uint64_t> halo_cell;
 	FlopCount flops{};
+	// Domain's "explosion" heuristics (Domain.cpp:74-79, :259-314, :363-368): _universalSelectiveThermostatCounter / Warning / Error,
+	// and whether the evaluation of Simulation::prepare_start (Simulation.cpp:991) has happened for the uploaded state
+	int expl_counter = 0, expl_warning = 0, expl_error = 0;
+	bool globals_initialised = false;
+	uint64_t clipped = 0;      // molecules the selective thermostat rescaled so far (diagnostics)
 	size_t n() const { return id.size(); }
 };
 
@@ -690,8 +695,10 @@ int orc_upload(void* h, uint64_t n, const uint64_t* id, const uint32_t* cid, con
 	for (uint64_t i = 0; i < n; i++) { if (q) for (int k = 0; k < 4; k++) s.q[4 * i + k] = q[4 * i + k]; else s.q[4 * i] = 1.; }
 	if (L) s.L.assign(L, L + 3 * n);
 	s.F.assign(3 * n, 0.); s.M.assign(3 * n, 0.); s.Vi.assign(3 * n, 0.); s.cell.assign(n, 0);
+	s.expl_counter = s.expl_warning = s.expl_error = 0; s.globals_initialised = false; s.clipped = 0;
 	return 0;
 }
+uint64_t orc_clipped(void* h) { return ((Sim*) h)->clipped; }
 uint64_t orc_num_molecules(void* h) { return ((Sim*) h)->n(); }
 int orc_geometry(void* h, int32_t cpd[3], double clen[3], double hmin[3]) {
 	Sim& s = *(Sim*) h;
@@ -739,10 +746,72 @@ uint64_t orc_halo(void* h, int64_t* owner, double* r, uint64_t* cell) {
 }
 int orc_count_flops(void* h, FlopCount* out) { *out = ((Sim*) h)->flops; return 0; }
 
-// Simulation::simulate hot loop (Simulation.cpp:1076-1261) + Domain::calculateGlobalValues (Domain.cpp:157-252)
-// + VelocityScalingThermostat::apply. Forces must be valid on entry.
+// Domain::calculateGlobalValues for one global thermostat (Domain.cpp:232-314, :363-368): temperature, the velocity-scaling factors,
+// and the heuristic handling of an "explosion" -- a factor below MIN_BETA = 0.9 while no error is pending: every molecule whose
+// translational (rotational) kinetic energy exceeds 10 T (3 rotDOF T) is scaled down to that limit together with its force (torque),
+// beta_trans becomes 1, beta_rot its 0.0091-th power; three counters decide for how long this may go on (explosion still there after
+// 40 steps or back within 4000: warning; a second time: error, after which the plain factors apply again). Returns bt, br.
+static void global_values(Sim& s, const Kinetic& kin, uint64_t N, double Ttarget, double& bt, double& br) {
+	const double sumIw2 = kin.rot_dof > 0 ? kin.sum_iw2 : 0.0;
+	bt = 1.; br = 1.;
+	if (Ttarget > 0 && N > 0) {
+		bt = std::pow(3.0 * N * Ttarget / kin.summv2, 0.4);
+		br = (sumIw2 == 0.0) ? 1.0 : std::pow(kin.rot_dof * Ttarget / sumIw2, 0.4);
+	}
+	if ((bt < 0.9 || br < 0.9) && s.expl_error <= 0) {
+		const double limit_energy = 10.0 * Ttarget;
+		for (size_t i = 0; i < s.n(); i++) {
+			const Component& c = s.comps[s.cid[i]];
+			double* v = &s.v[3 * i];
+			const double Utrans = 0.5 * c.mass * (v[0] * v[0] + v[1] * v[1] + v[2] * v[2]);
+			bool hit = false;
+			if (Utrans > limit_energy) {
+				const double vcorr = std::sqrt(limit_energy / Utrans);
+				for (int d = 0; d < 3; d++) { v[d] *= vcorr; s.F[3 * i + d] *= vcorr; }
+				hit = true;
+			}
+			if (c.rot_dof > 0) {
+				const double limit_rot_energy = 3.0 * c.rot_dof * Ttarget;
+				double w[3]; q_rotateinv(&s.q[4 * i], &s.L[3 * i], w);
+				double Iw2 = 0;
+				for (int d = 0; d < 3; d++) { double invI = (c.inertia[d] != 0.) ? 1. / c.inertia[d] : 0.; w[d] *= invI; Iw2 += c.inertia[d] * w[d] * w[d]; }
+				const double Urot = 0.5 * Iw2;
+				if (Urot > limit_rot_energy) {
+					const double Dcorr = std::sqrt(limit_rot_energy / Urot);
+					for (int d = 0; d < 3; d++) { s.L[3 * i + d] *= Dcorr; s.M[3 * i + d] *= Dcorr; }
+					hit = true;
+				}
+			}
+			if (hit) s.clipped++;
+		}
+		const int explosionReappearanceLimit = 4000, explosionVanishGracePeriod = 40;
+		const int stepsSinceLastExplosion = explosionReappearanceLimit - s.expl_counter;
+		if (stepsSinceLastExplosion >= explosionVanishGracePeriod) {
+			if (s.expl_warning > 0) s.expl_error = s.expl_warning;
+			if (s.expl_counter > 0) s.expl_warning = s.expl_counter;
+			s.expl_counter = explosionReappearanceLimit;
+		}
+		bt = 1.0;
+		br = std::pow(br, 0.0091);
+	}
+	if (s.expl_counter > 0) s.expl_counter--;
+	if (s.expl_warning > 0) s.expl_warning--;
+	if (s.expl_error > 0) s.expl_error--;
+}
+
+// Simulation::simulate hot loop (Simulation.cpp:1076-1261) + Domain::calculateGlobalValues (Domain.cpp:157-314)
+// + VelocityScalingThermostat::apply. Forces must be valid on entry. The first call after an upload evaluates the global values
+// once on the state as it is, like Simulation::prepare_start (Simulation.cpp:986-992): nothing is scaled by the factors there, but
+// the explosion heuristics see the initial state (and start their counters).
 int orc_simulate(void* h, uint64_t nsteps, double dt, double Ttarget, uint64_t globalN, double globalV, StepRecord* rec) {
 	Sim& s = *(Sim*) h;
+	if (!s.globals_initialised && nsteps > 0) {
+		Kinetic kin;
+		leapfrog_post(s, 0.0, &kin);      // the sums of the state as it is (a kick of length 0)
+		double bt, br;
+		global_values(s, kin, globalN ? globalN : kin.n, Ttarget, bt, br);
+		s.globals_initialised = true;
+	}
 	for (uint64_t st = 0; st < nsteps; st++) {
 		leapfrog_pre(s, dt);
 		Macro mac; Kinetic kin;
@@ -754,10 +823,7 @@ int orc_simulate(void* h, uint64_t nsteps, double dt, double Ttarget, uint64_t g
 		double sumIw2 = kin.rot_dof > 0 ? kin.sum_iw2 : 0.0;
 		double T = (kin.summv2 + sumIw2) / (double) (3 * N + kin.rot_dof);
 		double bt = 1., br = 1.;
-		if (Ttarget > 0) {
-			bt = std::pow(3.0 * N * Ttarget / kin.summv2, 0.4);
-			br = (sumIw2 == 0.0) ? 1.0 : std::pow(kin.rot_dof * Ttarget / sumIw2, 0.4);
-		}
+		global_values(s, kin, N, Ttarget, bt, br);
 		double rho = N / V;
 		double p = T * rho + rho * (mac.virial / N) / 3.;
 		if (rec) rec[st] = StepRecord{mac.upot, mac.virial, kin.summv2, sumIw2, T, p, bt, br};

@@ -31,9 +31,13 @@ REFBIN = os.path.join(ROOT, "oracle", "_ref")
 # fixture (initial state), time step, thermostat target, steps. The rotating fixtures start with L = 0 and random orientations;
 # the torques spin the molecules up within a few steps, so beta_rot != 1 from the second step on.
 CASES = [
-    ("periodic_1clj_1458", 0.002, 0.85, 100),
-    ("periodic_water_432", 0.0166879, 9.437e-4, 100),      # dt / 4: keeps beta >= 0.9, outside Domain.cpp:260-306 ("explosion" heuristics, not on the path)
-    ("periodic_multi_250", 0.0667516, 8.55e-4, 100),
+    ("periodic_1clj_1458", 0.002, 0.85, 100, None),
+    ("periodic_water_432", 0.0166879, 9.437e-4, 100, None),      # dt / 4: keeps beta >= 0.9, i.e. outside Domain's "explosion" heuristics (Domain.cpp:259-314)
+    ("periodic_multi_250", 0.0667516, 8.55e-4, 100, None),
+    # ... and INSIDE them: the 1CLJ liquid at T = 0.85 with a thermostat target of 0.34 -- beta_trans = 0.4^0.4 = 0.69 < MIN_BETA, so the
+    # reference caps every molecule above 10 T_target = 4 kT of translational energy (a few per cent of them per step) with its force,
+    # holds beta_trans at 1, raises a warning after 40 steps and an error after 80, from where the plain factor applies
+    ("periodic_1clj_1458", 0.002, 0.34, 100, "trace_1clj_1458_explosion"),
 ]
 
 COLS = ("step", "time", "U_pot", "U_pot_avg", "U_kin", "U_kin_avg", "p", "p_avg", "beta_trans", "beta_rot", "c_v", "N")
@@ -59,15 +63,17 @@ def run_reference(prec, g, dt, temperature, steps, threads=4):
 
 
 def traces():
-    for name, dt, temperature, steps in CASES:
+    for name, dt, temperature, steps, outname in CASES:
         g = load(name)
         out = dict(dt=dt, temperature=temperature, steps=steps, fixture=np.array(name), columns=np.array(COLS))
         for prec in ("mixed", "double"):
             out[prec] = run_reference(prec, g, dt, temperature, steps)
-        np.savez_compressed(os.path.join(GOLD, "trace_" + name[len("periodic_"):] + ".npz"), **out)
+        np.savez_compressed(os.path.join(GOLD, (outname or "trace_" + name[len("periodic_"):]) + ".npz"), **out)
         d = out["double"]
         print("wrote trace of", name, "rows", d.shape[0], "U_pot", d[0, 2], "->", d[-1, 2], "beta_rot range", d[:, 9].min(), d[:, 9].max())
 
 
 if __name__ == "__main__":
+    if len(sys.argv) > 1:      # only the named outputs, e.g. trace_1clj_1458_explosion
+        CASES = [c for c in CASES if (c[4] or "trace_" + c[0][len("periodic_"):]) in sys.argv[1:]]
     traces()

@@ -362,7 +362,7 @@ def test_site_signature_kernels_vs_oracle(capi, name, prec):
         assert abs(ma.upot - mb.upot) <= tol * max(abs(mb.upot), terms) and abs(ma.virial - mb.virial) <= tol * max(abs(mb.virial), terms)
 
 
-@pytest.mark.parametrize("name", ["1clj_1458", "water_432", "multi_250"])
+@pytest.mark.parametrize("name", ["1clj_1458", "water_432", "multi_250", "1clj_1458_explosion"])
 @pytest.mark.parametrize("prec", ["double", "mixed"])
 def test_trace_vs_reference_binary(capi, name, prec):
     """ls1b200_simulate (k_leapfrog_pre / _post with quaternions, k_globals, thermostat on load) against 100 steps of the
@@ -428,35 +428,43 @@ def test_device_cubic_grid_generator(capi, prec):
     assert np.array_equal(np.sort(np.concatenate(seen)), rid)
 
 
+@pytest.mark.parametrize("fixture", ["generator_1clj_2662.npz", "generator_water_432.npz"])
 @pytest.mark.parametrize("prec", ["mixed", "double"])
-def test_device_generator_reference_velocities_vs_reference_binary(capi, prec):
+def test_device_generator_reference_velocities_vs_reference_binary(capi, prec, fixture):
     """ls1b200_generate_cubic_grid with LS1B200_GEN_REFERENCE_VELOCITIES | LS1B200_GEN_REMOVE_MOMENTUM against the UNMODIFIED reference
     binary started from `<generator name="CubicGridGenerator">` (tests/golden/generator_1clj_2662.npz, make_generator_golden.py):
     positions bit-identical to its step-0 checkpoint, velocities (per-cell std::mt19937(0) sequence -- the device evaluates every
     molecule's insertion rank inside its LinkedCells cell in closed form --, momentum removed, rescaled to T) to 1e-13, and the
-    generated context then follows the reference binary's 20-step trace (U_pot, U_kin, p, beta at 1e-9 / 1e-6). Blocks of a
+    generated context then follows the reference binary's trace (U_pot, U_kin, p, beta at 1e-9 / 1e-6). Blocks of a
     decomposition re-seed per cell of THEIR grid, like the ranks of the reference would: checked against the host mirror fed with
-    the block's own cells."""
+    the block's own cells. generator_water_432.npz: a rotating multi-site model whose generated state the reference treats as an
+    EXPLOSION -- 100 steps through Domain's heuristics on the device (k_globals, the selective scaling applied on load by
+    k_leapfrog_pre / k_scale), see tests/test_oracle_golden.py::test_cubic_grid_generator_mirror_vs_reference_binary."""
     import os
-    from helpers import GOLD, TRACE_TOL, check_generated_state_vs_reference, compare_trace_rows
-    from ls1_mardyn_b200 import generators
-    from ls1_mardyn_b200.components import lj_fluid
+    from helpers import GOLD, TOL, TRACE_TOL, check_generated_state_vs_reference, compare_trace_rows
+    from ls1_mardyn_b200 import generators, workloads
     from ls1_mardyn_b200.decomposition import DomainDecomposition
-    g = dict(np.load(os.path.join(GOLD, "generator_1clj_2662.npz")))
+    g = dict(np.load(os.path.join(GOLD, fixture)))
     n, L, T, rc, steps = int(g["n_per_dim"]), float(g["length"]), float(g["temperature"]), float(g["rc"]), int(g["steps"])
     box = [L, L, L]; mixed = prec == "mixed"
-    ens = lj_fluid(rc=rc)
+    water = str(g["workload"]) == "water"
+    ens = workloads.get(str(g["workload"])).ensemble
     ctx = capi.Context([0, 0, 0], box, rc, precision=prec, geometry="xml", periodic=(1, 1, 1))
     ctx.set_components(ens)
     N = ctx.generate_cubic_grid(n, box, T, remove_momentum=True, reference_velocities=True)
     assert N == 2 * n ** 3
     r, v, ids = ctx.download("R"), ctx.download("V"), ctx.download("ID")
-    out = check_generated_state_vs_reference(capi.Context, prec, r, v, ids)      # state == checkpoint; an uploaded copy follows the trace
+    out = check_generated_state_vs_reference(capi.Context, prec, r, v, ids, fixture)      # state == checkpoint; an uploaded copy follows the trace
     # ... and so does the generated context itself (no upload in between)
     ctx.update(); m0 = ctx.traverse_cells()
+    term_scale = tol_macro = None
+    if water and mixed:      # as in check_generated_state_vs_reference: cancelling U_pot, 40 steps
+        term_scale = float(np.abs(ctx.download("VI")).sum()); steps = 40; tol_macro = TOL["mixed"]
     rec = ctx.simulate(steps, float(g["dt"]), T)
-    out2 = compare_trace_rows(m0, rec, g[prec + "_trace"], steps, N, L ** 3, TRACE_TOL[prec], ("generated context", prec))
-    print(prec, {k: "%.2e" % x for k, x in out.items()}, {k: "%.2e" % x for k, x in out2.items()})
+    out2 = compare_trace_rows(m0, rec, g[prec + "_trace"], steps, N, L ** 3, TRACE_TOL[prec], ("generated context", prec), term_scale, tol_macro)
+    print(fixture, prec, {k: "%.2e" % x for k, x in out.items()}, {k: "%.2e" % x for k, x in out2.items()})
+    if water:
+        return      # (a box of three cutoff radii is too small for blocks)
     # blocks: a 2 x 2 x 2 decomposition and an uneven 3 x 1 x 2 one
     for nranks, grid in ((8, (2, 2, 2)), (6, (3, 1, 2))):
         total = 0
@@ -478,31 +486,46 @@ def test_device_generator_reference_velocities_vs_reference_binary(capi, prec):
         assert total == N
 
 
-def test_benchmark_state_16M_vs_reference_binary(capi):
-    """Parity AT THE BENCHMARK'S FULL SIZE (BASELINE.json configs[1]: 16 000 000 1CLJ molecules, mixed precision): the device generator
-    builds the state the unmodified reference binary builds from its CubicGridGenerator, and ls1b200_simulate (the fused step that
-    bench.py times) is held against the reference binary's own ResultWriter rows on that configuration, 100 steps
-    (tests/golden/reference_trace_lj16M.npz, made by make_reference_trace_16m.py on the build container's host cores):
-    U_pot, U_kin (T), p, beta_trans at 1e-6 relative -- north_star's bound for T and p over 100 steps."""
+@pytest.mark.parametrize("workload,prec,fixture", [("lj", "mixed", "reference_trace_lj16M.npz"), ("lj", "double", "reference_trace_lj16M_double.npz"),
+                                                   ("argon", "mixed", "reference_trace_argon_full.npz"), ("water", "mixed", "reference_trace_water_full.npz"),
+                                                   ("co2", "mixed", "reference_trace_co2_full.npz")])
+def test_benchmark_state_vs_reference_binary(capi, workload, prec, fixture):
+    """Parity AT THE BENCHMARK'S FULL SIZE (BASELINE.json configs[1]: 16 000 000 1CLJ molecules, mixed precision and the double build;
+    configs[0]: the Argon state point at 101 306 molecules): the device generator builds the state the unmodified reference binary
+    builds from its CubicGridGenerator, and ls1b200_simulate (the fused step that bench.py times) is held against the reference
+    binary's own ResultWriter rows on that configuration, 100 steps (tests/golden/reference_trace_*.npz, made by
+    make_reference_traces_full_size.py on the build container's host cores): U_pot, U_kin (T), p, beta_trans at 1e-6 relative
+    (mixed; north_star's bound for T and p over 100 steps) / 1e-9 (double).
+    configs[2] and [3] -- 4 000 752 water-like and 8 039 358 2CLJQ molecules, 20 steps: the generated state of a rotating model (all
+    molecules aligned, the whole thermal energy in the translation) is an EXPLOSION by the reference's definition, so these two runs go
+    through Domain's heuristics (beta_trans = 1, beta_rot^0.0091, per-molecule limits) on the device; their U_pot is what is left of
+    pair terms orders of magnitude larger, and is held -- like p -- to north_star's 1e-5 for mixed-precision energy and virial
+    sums, relative to the larger of the value and sum |Vi| (strict figure printed); U_kin and the thermostat factors to 1e-6."""
     import os
     from helpers import GOLD, TRACE_TOL, compare_trace_rows
-    from ls1_mardyn_b200.components import lj_fluid
-    fx = os.path.join(GOLD, "reference_trace_lj16M.npz")
+    from ls1_mardyn_b200 import workloads
+    fx = os.path.join(GOLD, fixture)
     if not os.path.exists(fx):
-        pytest.skip("tests/golden/reference_trace_lj16M.npz not generated")
+        pytest.skip("tests/golden/%s not generated" % fixture)
     g = np.load(fx)
+    wl = workloads.get(workload)
     n, L, T, rc, dt, steps = int(g["n_per_dim"]), float(g["length"]), float(g["temperature"]), float(g["rc"]), float(g["dt"]), int(g["steps"])
-    ctx = capi.Context([0, 0, 0], [L, L, L], rc, precision="mixed", geometry="xml", periodic=(1, 1, 1))
-    ctx.set_components(lj_fluid(rc=rc))
+    assert n == wl.n_per_dim and rc == wl.rc and dt == wl.dt
+    ctx = capi.Context([0, 0, 0], [L, L, L], rc, precision=prec, geometry="xml", periodic=(1, 1, 1))
+    ctx.set_components(wl.ensemble)
     N = ctx.generate_cubic_grid(n, [L, L, L], T, remove_momentum=True, reference_velocities=True)
-    assert N == int(g["molecules"]) == 16000000
+    assert N == int(g["molecules"]) == 2 * n ** 3
     ctx.update(); m0 = ctx.traverse_cells()
+    term_scale = tol_macro = None
+    if workload in ("water", "co2"):
+        from helpers import TOL
+        term_scale = float(np.abs(ctx.download("VI")).sum()); tol_macro = TOL[prec]
     rec = ctx.simulate(steps, dt, T)
     ctx.close()
-    for m in (20, 50, steps):      # how the deviation grows (printed before anything is asserted)
-        o = compare_trace_rows(m0, rec[:m], g["trace"], m, N, L ** 3, 1.0, ("16 M benchmark state", m))
-        print("16 M molecules, first", m, "steps vs the reference binary:", {k: "%.2e" % x for k, x in o.items()})
-    compare_trace_rows(m0, rec, g["trace"], steps, N, L ** 3, TRACE_TOL["mixed"], ("16 M benchmark state", "mixed"))
+    for m in sorted({min(20, steps), min(50, steps), steps}):      # how the deviation grows (printed before anything is asserted)
+        o = compare_trace_rows(m0, rec[:m], g["trace"], m, N, L ** 3, 1.0, (workload, prec, m), term_scale)
+        print(workload, prec, N, "molecules, first", m, "steps vs the reference binary:", {k: "%.2e" % x for k, x in o.items()})
+    compare_trace_rows(m0, rec, g["trace"], steps, N, L ** 3, TRACE_TOL[prec], (workload, prec, "full size"), term_scale, tol_macro)
 
 
 def test_forces_one_million_molecules_vs_reference_on_the_fly(capi, tmp_path):

@@ -86,7 +86,7 @@ def test_halo_copies_vs_reference(name, prec):
     assert mine == theirs
 
 
-@pytest.mark.parametrize("name", ["1clj_1458", "water_432", "multi_250"])
+@pytest.mark.parametrize("name", ["1clj_1458", "water_432", "multi_250", "1clj_1458_explosion"])
 @pytest.mark.parametrize("prec", ["double", "mixed"])
 def test_trace_vs_reference_binary(name, prec):
     """The integrator and the global values, pinned against the UNMODIFIED reference binary (stock Simulation loop, Leapfrog
@@ -96,26 +96,36 @@ def test_trace_vs_reference_binary(name, prec):
     print(name, prec, {k: "%.2e" % v for k, v in out.items()})
 
 
+@pytest.mark.parametrize("fixture", ["generator_1clj_2662.npz", "generator_water_432.npz"])
 @pytest.mark.parametrize("prec", ["double", "mixed"])
-def test_cubic_grid_generator_mirror_vs_reference_binary(prec):
+def test_cubic_grid_generator_mirror_vs_reference_binary(prec, fixture):
     """The reference's CubicGridGenerator restated (generators.cubic_grid_reference for the lattice -- coordinates are ONE fused
     multiply-add, as the reference binary contracts them -- and generators.reference_velocities for the per-cell std::mt19937(0)
-    sequence, IOHelpers::removeMomentum and its rescaling to T) against the step-0 checkpoint and the 20-step trace of the
-    UNMODIFIED reference binary started from `<generator name="CubicGridGenerator">` (tests/golden/make_generator_golden.py).
-    The cell of a molecule -- the reference re-seeds per LinkedCells cell -- comes from the oracle's bit-exact binning."""
+    sequence, IOHelpers::removeMomentum and its rescaling to T) against the step-0 checkpoint and the trace of the UNMODIFIED
+    reference binary started from `<generator name="CubicGridGenerator">` (tests/golden/make_generator_golden.py).
+    The cell of a molecule -- the reference re-seeds per LinkedCells cell -- comes from the oracle's bit-exact binning.
+    generator_water_432.npz: a rotating multi-site model, whose generated state the reference treats as an EXPLOSION (all thermal
+    energy in the translation: beta_trans = 0.5^0.4 < 0.9): 100 steps through Domain's heuristics (Domain.cpp:259-314, :363-368) --
+    beta_trans = 1, beta_rot^0.0091, per-molecule energy limits, and the warning / error counters that end the special handling at
+    step 80, after which the plain factors apply."""
     from helpers import GOLD, check_generated_state_vs_reference
-    from ls1_mardyn_b200 import generators
-    from ls1_mardyn_b200.components import lj_fluid
+    from ls1_mardyn_b200 import generators, workloads
     import os
-    g = dict(np.load(os.path.join(GOLD, "generator_1clj_2662.npz")))
+    g = dict(np.load(os.path.join(GOLD, fixture)))
+    wl = workloads.get(str(g["workload"]))
+    comp = wl.ensemble.components[0]
+    mass, rot_dof = float(comp.m()), int(comp.Ipa()[1])
     n, L, T, rc = int(g["n_per_dim"]), float(g["length"]), float(g["temperature"]), float(g["rc"])
     mixed = prec == "mixed"
-    ids, r, _, lat = generators.cubic_grid_reference(n, [L, L, L], [0, 0, 0], [L, L, L], T, 1.0, mixed=mixed, with_lattice_index=True)
+    ids, r, _, lat = generators.cubic_grid_reference(n, [L, L, L], [0, 0, 0], [L, L, L], T, mass, mixed=mixed, with_lattice_index=True)
     s = orc.OracleSim([0, 0, 0], [L, L, L], rc, precision=prec, geometry="xml", periodic=(1, 1, 1))
-    s.set_components(lj_fluid(rc=rc))
+    s.set_components(wl.ensemble)
     s.upload(ids, np.zeros(len(ids), dtype=np.uint32), r, np.zeros_like(r), None, None)
     s.update()
-    v = generators.reference_velocities(lat, s.download("CELL"), T, 1.0, mixed=mixed)
+    v = generators.reference_velocities(lat, s.download("CELL"), T, mass, rot_dof=rot_dof, mixed=mixed)
     assert len(np.unique(np.round(v, 12), axis=0)) == len(np.unique(np.round(g[prec + "_v"], 12), axis=0))      # the cells share one sequence
-    out = check_generated_state_vs_reference(orc.OracleSim, prec, r, v, ids)
-    print(prec, {k: "%.2e" % x for k, x in out.items()})
+    out = check_generated_state_vs_reference(orc.OracleSim, prec, r, v, ids, fixture)
+    tr = g[prec + "_trace"]
+    if str(g["workload"]) == "water":      # the fixture does go through the heuristics and out of them again
+        assert int(g[prec + "_explosions"]) == 81 and (tr[1:80, 8] == 1.0).all() and tr[81, 8] < 0.9 and abs(tr[-1, 8] - 1.0) < 0.05
+    print(fixture, prec, {k: "%.2e" % x for k, x in out.items()})
