@@ -7,6 +7,8 @@
 #include "utils/mardyn_assert.h"
 #include "utils/xmlfileUnits.h"
 
+#include <cmath>
+
 #include "ls1b200.h"
 
 static LinkedCellsB200* deviceContainer(ParticleContainer* pc) {
@@ -47,6 +49,19 @@ void LeapfrogB200::eventNewTimestep(ParticleContainer* moleculeContainer, Domain
 	// Domain's global betas (Domain.cpp:248-252) and are applied here, before the kick, which is the same arithmetic
 	// (Simulation.cpp:1235-1261; single global thermostat -- the component-wise variant needs a per-component factor table).
 	if (_thermostatPending && !domain->NVE()) {
+		// Domain's "explosion" heuristics (Domain.cpp:259-314): when a plain factor falls below MIN_BETA and no error is pending,
+		// calculateGlobalValues caps the kinetic energy of single molecules in a host loop -- vacuous in device mode -- and then reports
+		// beta_trans = 1 and beta_rot^0.0091. The decision stays Domain's; it is recognised here by exactly that signature (the plain
+		// factors follow from the sums this integrator handed to Domain), and the loop runs on the device before the factors are applied.
+		const double Ti = global_simulation->Tfactor(global_simulation->getSimulationStep() - 1) * domain->getTargetTemperature(0);
+		const double N = (double) domain->getglobalNumMolecules(false);
+		if (Ti > 0. && N > 0. && _lastSummv2 > 0.) {
+			const double btPlain = std::pow(3.0 * N * Ti / _lastSummv2, 0.4);
+			const double brPlain = (_lastSumIw2 == 0.0) ? 1.0 : std::pow((double) _lastRotDOF * Ti / _lastSumIw2, 0.4);
+			if ((btPlain < MIN_BETA || brPlain < MIN_BETA) && domain->getGlobalBetaTrans() == 1.0) {
+				if (ls1b200_selective_thermostat(c->context(), Ti) != 0) MARDYN_EXIT(ls1b200_last_error());
+			}
+		}
 		if (ls1b200_scale_velocities(c->context(), domain->getGlobalBetaTrans(), domain->getGlobalBetaRot()) != 0) MARDYN_EXIT(ls1b200_last_error());
 	}
 	if (ls1b200_leapfrog_pre(c->context(), _timestepLength) != 0) MARDYN_EXIT(ls1b200_last_error());
@@ -60,6 +75,7 @@ void LeapfrogB200::eventForcesCalculated(ParticleContainer* moleculeContainer, D
 	domain->setLocalSummv2(kin.summv2, 0);                        // Leapfrog.cpp:139-143
 	domain->setLocalSumIw2(kin.sum_iw2, 0);
 	domain->setLocalNrotDOF(0, kin.n_molecules, kin.rot_dof);
+	_lastSummv2 = kin.summv2; _lastSumIw2 = kin.rot_dof > 0 ? kin.sum_iw2 : 0.; _lastRotDOF = kin.rot_dof;      // sequential build: local sums are global
 	_thermostatPending = true;
 	// Host coherence: on the steps of the container's sync schedule -- and at the last step, for the final
 	// checkpoint -- the host mirror is refreshed HERE and the host view opens for the rest of the step. What follows in the stock

@@ -13,4 +13,6 @@ public:
 	void eventForcesCalculated(ParticleContainer* moleculeContainer, Domain* domain) override;  // transition2to3: upd_postF + sums
 private:
 	bool _thermostatPending = false;   // a step has completed: its velocity-scaling factors are applied before the next kick
+	double _lastSummv2 = 0., _lastSumIw2 = 0.;   // the kinetic sums of that step, as handed to Domain (eventForcesCalculated)
+	unsigned long _lastRotDOF = 0;
 };

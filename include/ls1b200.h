@@ -175,6 +175,12 @@ int ls1b200_leapfrog_pre(ls1b200_ctx* ctx, double dt);
 int ls1b200_leapfrog_post(ls1b200_ctx* ctx, double dt, ls1b200_kinetic* out);
 /* == VelocityScalingThermostat::apply, global variant (thermostats/VelocityScalingThermostat.cpp:68-89). */
 int ls1b200_scale_velocities(ls1b200_ctx* ctx, double beta_trans, double beta_rot);
+/* == the per-molecule loop of Domain's "explosion" heuristics (Domain.cpp:266-296; a thermostat factor below MIN_BETA = 0.9): every
+ * molecule whose translational kinetic energy exceeds KINLIMIT_PER_T * T = 10 T is scaled down to that limit together with its
+ * force, every molecule with more than 3 rotDOF T of rotational energy likewise with its angular momentum and torque. For
+ * phase-by-phase drivers whose host Domain takes the decision (the adapter); ls1b200_simulate evaluates the whole heuristics
+ * (decision, counters, beta_trans = 1, beta_rot^0.0091) on the device. */
+int ls1b200_selective_thermostat(ls1b200_ctx* ctx, double target_temperature);
 
 /* The whole hot path of Simulation::simulate for n_steps steps with the NVT velocity-scaling thermostat
  * (target_temperature > 0) or NVE (<= 0), without any host round trip inside the loop:

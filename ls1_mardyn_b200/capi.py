@@ -28,7 +28,7 @@ _FIELD_SHAPE = {0: (np.uint64, ()), 1: (np.uint32, ()), 2: (np.float64, (3,)), 3
 EXPORTS = ["ls1b200_last_error", "ls1b200_abi_version", "ls1b200_kernel_launch_count", "ls1b200_create", "ls1b200_destroy",
            "ls1b200_set_components", "ls1b200_upload", "ls1b200_num_molecules", "ls1b200_download", "ls1b200_set_field",
            "ls1b200_geometry", "ls1b200_update", "ls1b200_traverse_cells", "ls1b200_leapfrog_pre", "ls1b200_leapfrog_post",
-           "ls1b200_scale_velocities", "ls1b200_simulate", "ls1b200_halo_export", "ls1b200_halo_import",
+           "ls1b200_scale_velocities", "ls1b200_selective_thermostat", "ls1b200_simulate", "ls1b200_halo_export", "ls1b200_halo_import",
            "ls1b200_halo_import_host", "ls1b200_phase_times", "ls1b200_count_flops", "ls1b200_measure_fp32_peak", "ls1b200_measure_fp64_peak",
            "ls1b200_measure_hbm_copy", "ls1b200_stream", "ls1b200_nccl_unique_id", "ls1b200_decomp_attach", "ls1b200_download_begin", "ls1b200_download_end", "ls1b200_peer_handle", "ls1b200_peer_attach", "ls1b200_peer_detach", "ls1b200_exchange",
            "ls1b200_allreduce_macro", "ls1b200_halo_export_host", "ls1b200_generate_cubic_grid", "ls1b200_rmm_upload", "ls1b200_rmm_start", "ls1b200_rmm_simulate", "ls1b200_rmm_download", "ls1b200_rmm_state_bytes", "ls1b200_exchange_overlapped_ms"]
@@ -113,6 +113,7 @@ def lib():
         L.ls1b200_leapfrog_pre.argtypes = [C.c_void_p, C.c_double]
         L.ls1b200_leapfrog_post.argtypes = [C.c_void_p, C.c_double, C.c_void_p]
         L.ls1b200_scale_velocities.argtypes = [C.c_void_p, C.c_double, C.c_double]
+        L.ls1b200_selective_thermostat.argtypes = [C.c_void_p, C.c_double]
         L.ls1b200_simulate.argtypes = [C.c_void_p, C.c_uint64, C.c_double, C.c_double, C.c_uint64, C.c_double, C.c_void_p]
         L.ls1b200_phase_times.argtypes = [C.c_void_p, C.c_void_p, C.c_void_p, C.c_int]
         L.ls1b200_count_flops.argtypes = [C.c_void_p, C.c_void_p]
@@ -346,6 +347,10 @@ class Context:
 
     def scale_velocities(self, bt, br):
         _check(lib().ls1b200_scale_velocities(self.h, bt, br))
+
+    def selective_thermostat(self, target_temperature):
+        """ls1b200_selective_thermostat: the per-molecule energy limits of Domain's explosion heuristics (Domain.cpp:266-296)."""
+        _check(lib().ls1b200_selective_thermostat(self.h, float(target_temperature)))
 
     def download(self, field, out=None):
         f = FIELDS[field] if isinstance(field, str) else field

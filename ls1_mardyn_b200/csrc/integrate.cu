@@ -195,7 +195,8 @@ __global__ void __launch_bounds__(1024) k_reduce_kinetic(const double* __restric
 // from_scal: what the next leapfrog_pre of a running ls1b200_simulate would have applied on load -- the pending selective-thermostat
 // scaling of the explosion heuristics (v, F and L, M of the molecules over the limit) and the thermostat factors
 __global__ void __launch_bounds__(256) k_scale(State st, uint32_t cap, double bt, double br, const DevScalars* __restrict__ scal, uint32_t parity,
-                                               int from_scal, int rotates, double* __restrict__ F, double* __restrict__ M, const CompDev* __restrict__ comps) {
+                                               int from_scal, int rotates, double* __restrict__ F, double* __restrict__ M, const CompDev* __restrict__ comps,
+                                               double clip_arg, double ti_arg) {
 	const uint32_t t = blockIdx.x * blockDim.x + threadIdx.x;
 	if (t >= min(scal->n_slots2[parity], cap)) return;
 	const uint64_t meta = st.meta[t];
@@ -203,7 +204,7 @@ __global__ void __launch_bounds__(256) k_scale(State st, uint32_t cap, double bt
 	if (from_scal) { bt = scal->beta_trans; br = scal->beta_rot; }
 	const size_t c = cap;
 	double vc = 1., dc = 1.;
-	const double clip = from_scal ? scal->clip_limit : 0.;
+	const double clip = from_scal ? scal->clip_limit : clip_arg, clip_ti = from_scal ? scal->clip_ti : ti_arg;
 	if (clip > 0.) {
 		const CompDev& cp = comps[meta_cid(meta)];
 		vc = clip_factor_trans(clip, cp.mass, st.v[t], st.v[c + t], st.v[2 * c + t]);
@@ -214,7 +215,7 @@ __global__ void __launch_bounds__(256) k_scale(State st, uint32_t cap, double bt
 			q_rotateinv(q, L, w);
 			double Iw2 = 0.;
 			for (int d = 0; d < 3; d++) { w[d] *= cp.invI[d]; Iw2 += cp.I[d] * w[d] * w[d]; }
-			const double urot = 0.5 * Iw2, limit_rot = 3.0 * (double) cp.rot_dof * scal->clip_ti;
+			const double urot = 0.5 * Iw2, limit_rot = 3.0 * (double) cp.rot_dof * clip_ti;
 			if (urot > limit_rot) dc = sqrt(limit_rot / urot);
 		}
 		if (vc != 1.) for (int d = 0; d < 3; d++) F[d * c + t] *= vc;
@@ -366,7 +367,17 @@ int ls1b200_scale_velocities(ls1b200_ctx* c, double beta_trans, double beta_rot)
 	LS1_CUDA(cudaSetDevice(c->device));
 	if (c->n_owned == 0 && !c->dd.active) return 0;
 	const uint32_t g = (uint32_t) ((c->cap + 255) / 256);
-	LS1_LAUNCH(c, PH_POST, k_scale, g, 256, 0, c->cur, (uint32_t) c->cap, beta_trans, beta_rot, c->d_scal, c->parity, 0, (int) c->rotates, c->F, c->M, c->d_comps);
+	LS1_LAUNCH(c, PH_POST, k_scale, g, 256, 0, c->cur, (uint32_t) c->cap, beta_trans, beta_rot, c->d_scal, c->parity, 0, (int) c->rotates, c->F, c->M, c->d_comps, 0., 0.);
+	return 0;
+}
+
+int ls1b200_selective_thermostat(ls1b200_ctx* c, double target_temperature) {
+	if (!c) return fail("ls1b200_selective_thermostat: null context");
+	if (!(target_temperature > 0.)) return fail("ls1b200_selective_thermostat: target temperature must be positive");
+	LS1_CUDA(cudaSetDevice(c->device));
+	if (c->n_owned == 0 && !c->dd.active) return 0;
+	const uint32_t g = (uint32_t) ((c->cap + 255) / 256);
+	LS1_LAUNCH(c, PH_POST, k_scale, g, 256, 0, c->cur, (uint32_t) c->cap, 1., 1., c->d_scal, c->parity, 0, (int) c->rotates, c->F, c->M, c->d_comps, 10.0 * target_temperature, target_temperature);
 	return 0;
 }
 
@@ -515,7 +526,7 @@ int ls1b200_simulate(ls1b200_ctx* c, uint64_t n_steps, double dt, double target_
 	}
 	if (target_temperature > 0.) {   // the scaling the next leapfrog_pre would have applied on load
 		const uint32_t g = (uint32_t) ((c->cap + 255) / 256);
-		LS1_LAUNCH(c, PH_POST, k_scale, g, 256, 0, c->cur, (uint32_t) c->cap, 1., 1., c->d_scal, c->parity, 1, (int) c->rotates, c->F, c->M, c->d_comps);
+		LS1_LAUNCH(c, PH_POST, k_scale, g, 256, 0, c->cur, (uint32_t) c->cap, 1., 1., c->d_scal, c->parity, 1, (int) c->rotates, c->F, c->M, c->d_comps, 0., 0.);
 	}
 	if (records) LS1_CUDA(cudaMemcpyAsync(records, c->d_records, sizeof(ls1b200_step_record) * n_steps, cudaMemcpyDeviceToHost, c->stream));
 	LS1_CUDA(cudaMemcpyAsync(c->h_scal, c->d_scal, sizeof(DevScalars), cudaMemcpyDeviceToHost, c->stream));

@@ -15,7 +15,7 @@ and the `trace.vs_reference_fixture` entry of bench.py's JSON line.
 
 Run in the build container only (needs oracle/_ref, i.e. /root/reference); the .npz files (a few KB each) are committed.
 
-  python tests/golden/make_reference_traces_full_size.py [lj|lj:double|water|co2|argon ...]
+  python tests/golden/make_reference_traces_full_size.py [lj|lj:double|lj:rmm|water|co2|argon ...]
 """
 from __future__ import annotations
 
@@ -48,6 +48,9 @@ def make(name, prec="mixed"):
             text = bench.XML.format(dt=wl.dt, steps=steps, T=wl.temperature, L=repr(L), rho=repr(N / L ** 3 * (1 + 1e-9)), rc=wl.rc)
         else:      # what bench.run_reference_binary writes for the other workloads, with the ResultWriter on
             text = simulation_xml(wl.ensemble, [L, L, L], wl.temperature, wl.dt, steps, wl.rc, generator_density=N / L ** 3 * (1 + 1e-9), longrange="homogeneous")
+        if prec == "rmm":      # the reference's reduced-memory build (all FP32: MoleculeRMM, VCP1CLJRMM, LeapfrogRMM)
+            text = text.replace('integrator type="Leapfrog"', 'integrator type="LeapfrogRMM"')
+            steps = min(steps, 40)
         open(os.path.join(td, "config.xml"), "w").write(text)
         p = subprocess.run([exe, "--steps", str(steps), "--final-checkpoint=0", "config.xml"], cwd=td, capture_output=True, text=True,
                            env=dict(os.environ, OMP_NUM_THREADS=str(os.cpu_count() or 1)))
@@ -63,5 +66,5 @@ def make(name, prec="mixed"):
 
 
 if __name__ == "__main__":
-    for w in (sys.argv[1:] or ["lj", "lj:double", "water", "co2", "argon"]):      # "lj:double": the reference's double build (MARDYN_DPDP)
+    for w in (sys.argv[1:] or ["lj", "lj:double", "lj:rmm", "water", "co2", "argon"]):      # "lj:double": the reference's double build (MARDYN_DPDP); "lj:rmm": its reduced-memory build
         make(*w.split(":"))

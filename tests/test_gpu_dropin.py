@@ -212,3 +212,57 @@ def test_per_molecule_virial_with_longrange_correction_through_a_stock_plugin(tm
         assert np.abs(pa[f][:, 2:] - pb[f][:, 2:]).max() <= 2e-5 * np.abs(pb[f][:, 2:]).max(), (f, pa[f], pb[f])
         assert np.abs(pa[f][:, 1] - pb[f][:, 1]).max() <= 2e-5 * np.abs(pb[f][:, 2:]).max(), (f, pa[f], pb[f])
     print(prec, "LRC pressure term", lrc_p, "largest profile deviation", max(float(np.abs(pa[f][:, 1:] - pb[f][:, 1:]).max()) for f in pa))
+
+
+@pytest.mark.parametrize("prec,tol,steps", [("double", 1e-9, 100), ("mixed", 1e-6, 40)])
+def test_multisite_model_from_the_generator_through_the_adapter(tmp_path, prec, tol, steps):
+    """The drop-in with a ROTATING MULTI-SITE model (water-like: 1 LJ centre + 3 charges; quaternions, angular momenta, site tables
+    built from Comp2Param) started from the reference's own CubicGridGenerator: MarDyn_b200 against the stock binary on the same XML,
+    432 molecules. The generated state is an explosion by Domain's definition (all thermal energy in the translation): the host Domain
+    takes the decisions (beta_trans = 1, beta_rot^0.0091, counters, back to the plain factors at step 81), LeapfrogB200 recognises them
+    and runs the per-molecule limits on the device (ls1b200_selective_thermostat). Compared: every ResultWriter row. Mixed precision:
+    40 steps, U_pot and p at north_star's 1e-5 for mixed-precision sums (the aligned lattice's U_pot is a near-total cancellation),
+    as in test_cubic_grid_generator_mirror_vs_reference_binary; the stock binary's own trace is the committed generator_water_432.npz."""
+    ref = os.path.join(ROOT, "oracle", "_ref", prec, "MarDyn")
+    b200 = os.path.join(ROOT, "adapter", "_build", prec, "MarDyn_b200")
+    if not (os.path.exists(ref) and os.path.exists(b200)):
+        pytest.skip("reference / adapter binaries not built (oracle/build_ref.sh, adapter/build_adapter.sh)")
+    from ls1_mardyn_b200 import workloads
+    from ls1_mardyn_b200.xml_config import simulation_xml
+    wl = workloads.get("water")
+    n = 6; N = 2 * n ** 3; L = (N / wl.rho) ** (1.0 / 3.0)
+    out = {}
+    for name, exe, ds, integ in (("ref", ref, "LinkedCells", "Leapfrog"), ("b200", b200, "LinkedCellsB200", "LeapfrogB200")):
+        d = tmp_path / name; d.mkdir()
+        (d / "config.xml").write_text(simulation_xml(wl.ensemble, [L, L, L], wl.temperature, wl.dt, steps, wl.rc, generator_density=N / L ** 3 * (1 + 1e-9),
+                                                     datastructure=ds, integrator=integ, longrange="homogeneous"))
+        out[name], log = run(exe, "config.xml", str(d), steps)
+        if name == "ref":
+            assert log.count("Explosion!") == min(steps, 80) + 1      # the heuristics are what this run is about
+    a, b = out["b200"], out["ref"]
+    g = np.load(os.path.join(ROOT, "tests", "golden", "generator_water_432.npz"))[prec + "_trace"]
+    assert np.abs(b[:steps + 1, 2] - g[:steps + 1, 2]).max() <= 1e-6 * np.abs(g[:, 2]).max()      # the stock binary here == the committed fixture
+    assert a.shape == b.shape and a.shape[0] >= steps
+    tol_macro = tol if prec == "double" else 1e-5
+    term = 0.0
+    if prec == "mixed":
+        # the magnitude of the terms U_pot and the virial are summed from (sum of per-molecule |Vi| of the generated state): the same rule
+        # as check_generated_state_vs_reference / macro_close for this near-total cancellation; strict figures printed beside
+        from ls1_mardyn_b200 import capi
+        gs = np.load(os.path.join(ROOT, "tests", "golden", "generator_water_432.npz"))
+        c = capi.Context([0, 0, 0], [L, L, L], wl.rc, precision=prec, geometry="xml", periodic=(1, 1, 1))
+        c.set_components(wl.ensemble)
+        c.upload(gs[prec + "_id"].astype(np.uint64) + 1, np.zeros(N, dtype=np.uint32), gs[prec + "_r"], gs[prec + "_v"], None, None)
+        c.update(); c.traverse_cells()
+        term = float(np.abs(c.download("VI")).sum()); c.close()
+    err = {}
+    for name, col, t in (("U_pot", 2, tol_macro), ("U_kin", 4, tol), ("beta_trans", 8, tol), ("beta_rot", 9, tol)):
+        err[name + "_strict"] = float(np.abs(a[:, col] - b[:, col]).max() / np.abs(b[:, col]).max())
+        err[name] = float(np.abs(a[:, col] - b[:, col]).max() / max(np.abs(b[:, col]).max(), term if name == "U_pot" else 0.0))
+    rhoT = (N / L ** 3) * (2.0 * b[:, 4] / (6.0 * N))
+    err["p_strict"] = float(np.abs(a[:, 6] - b[:, 6]).max() / np.abs(b[:, 6]).max())
+    err["p"] = float(np.abs(a[:, 6] - b[:, 6]).max() / max(np.abs(b[:, 6]).max(), rhoT.max(), term / (3.0 * L ** 3)))
+    print(prec, steps, "steps, water-like model through the adapter vs the stock binary:", {k: "%.2e" % v for k, v in err.items()})
+    for name, t in (("U_pot", tol_macro), ("U_kin", tol), ("beta_trans", tol), ("beta_rot", tol), ("p", tol_macro)):
+        assert err[name] <= t, (prec, name, err)
+    assert (b[1:min(steps, 80), 8] == 1.0).all() and (a[1:min(steps, 80), 8] == 1.0).all()

@@ -80,3 +80,4 @@ def test_rmm_rejects_what_the_mode_does_not_cover(capi):
     c.set_components(g["ensemble"])
     with pytest.raises(Ls1B200Error):
         c.rmm_upload(g["in_id"], g["in_r"], g["in_v"])
+
