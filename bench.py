@@ -171,7 +171,7 @@ def reference_build():
     return _REF_BUILD
 
 
-LAST_REFERENCE_TRACE = None      # T, U_pot / N, p after the last step of the most recent reference run (from its ResultWriter)
+LAST_REFERENCE_TRACE = None      # U_kin / N, U_pot / N, p after the last step of the most recent reference run (from its ResultWriter)
 
 
 def run_reference_binary(n_per_dim, steps, threads=None, prec=None, wl=None):
@@ -192,7 +192,7 @@ def run_reference_binary(n_per_dim, steps, threads=None, prec=None, wl=None):
             text = XML.format(dt=dt, steps=steps, T=temp, L=repr(L), rho=repr(N / L ** 3 * (1 + 1e-9)), rc=rc)
         else:
             from ls1_mardyn_b200.xml_config import simulation_xml
-            text = simulation_xml(wl.ensemble, [L, L, L], temp, dt, steps, rc, generator_density=N / L ** 3 * (1 + 1e-9), longrange="homogeneous", result_prefix=None)
+            text = simulation_xml(wl.ensemble, [L, L, L], temp, dt, steps, rc, generator_density=N / L ** 3 * (1 + 1e-9), longrange="homogeneous")      # ResultWriter on: the trace
         if prec == "rmm":
             text = text.replace('integrator type="Leapfrog"', 'integrator type="LeapfrogRMM"')      # the reference's reduced-memory build
         open(cfg, "w").write(text)
@@ -205,7 +205,7 @@ def run_reference_binary(n_per_dim, steps, threads=None, prec=None, wl=None):
             rows = [l.split() for l in open(os.path.join(td, "res.res")) if l.strip() and not l.lstrip().startswith("#")]
             last = [float(x) for x in rows[-1]]
             if int(last[0]) == steps:
-                LAST_REFERENCE_TRACE = {"at_step": steps, "T": 2.0 * last[4] / (3.0 * last[11]), "upot_per_molecule": last[2] / last[11], "p": last[6]}
+                LAST_REFERENCE_TRACE = {"at_step": steps, "ukin_per_molecule": last[4] / last[11], "upot_per_molecule": last[2] / last[11], "p": last[6]}
         except (OSError, IndexError, ValueError):
             pass
     if p.returncode != 0:
@@ -305,20 +305,49 @@ def reference_arm(args):
 FORCE_TRAFFIC = {("lj", "mixed", 16000000): (279817216 + 728153088, "profiles/r02m_force_full.md (ncu --set full of this kernel at this size: dram__bytes_read.sum + dram__bytes_write.sum; algorithmic: 256 MB of calc records read + 768 MB of F, Vi written)")}
 
 
+REFERENCE_TRACES = {("lj", "mixed"): "reference_trace_lj16M.npz", ("lj", "double"): "reference_trace_lj16M_double.npz", ("argon", "mixed"): "reference_trace_argon_full.npz",
+                    ("water", "mixed"): "reference_trace_water_full.npz", ("co2", "mixed"): "reference_trace_co2_full.npz"}
+
+
+def vs_reference_fixture(wl_name, precision, n_molecules, series):
+    """The step records of a run that started from the reference's CubicGridGenerator state (generated on the device) against the
+    committed ResultWriter rows of the UNMODIFIED reference binary on the same full-size configuration
+    (tests/golden/make_reference_traces_full_size.py): largest relative deviation over the steps both cover. None if no fixture fits."""
+    f = REFERENCE_TRACES.get((wl_name, precision))
+    fx = os.path.join(ROOT, "tests", "golden", f) if f else None
+    if not fx or not os.path.exists(fx):
+        return None
+    g = np.load(fx)
+    if int(g["molecules"]) != int(n_molecules):
+        return None
+    ref = g["trace"]; m = min(len(series), len(ref) - 1)
+    if m < 1:
+        return None
+    b = ref[1:m + 1]
+    return {"steps_compared": m, "fixture": "tests/golden/%s (unmodified reference binary, the same %d-molecule configuration)" % (f, n_molecules),
+            "U_pot_rel_max": float(np.abs(series[:m, 0] - b[:, 2]).max() / np.abs(b[:, 2]).max()),
+            "T_rel_max": float(np.abs(0.5 * (series[:m, 2] + series[:m, 3]) - b[:, 4]).max() / np.abs(b[:, 4]).max()),
+            "p_rel_max": float(np.abs(series[:m, 5] - b[:, 6]).max() / np.abs(b[:, 6]).max()),
+            "beta_trans_abs_max": float(np.abs(series[:m, 6] - b[:, 8]).max()), "beta_rot_abs_max": float(np.abs(series[:m, 7] - b[:, 9]).max()),
+            "tolerance": "north_star: T and p within 1e-6 (mixed) / 1e-9 (double); U_pot and p of the rotating models' generated lattice are near-total cancellations (tests: 1e-5 of the terms)"}
+
+
 def run_secondary(name, local, fp32_peak, capi, with_cpu=True, steps=10, warmup=3):
     """One of the other single-GPU configurations of BASELINE.json, device-resident loop only: MMUPS, force-kernel time and its
     fraction of the FP32 peak (FlopCounter flops of the state), CPU baseline on a bounded sample."""
     from ls1_mardyn_b200 import workloads
     wl = workloads.get(name)
-    ps = make_system(wl.n_per_dim, mixed=True, seed=0, wl=wl)
-    ctx = capi.Context([0, 0, 0], list(ps.length), wl.rc, precision="mixed", geometry="xml", periodic=(1, 1, 1), device=local)
-    ctx.set_components(ps.ensemble)
-    rot = any(c.Ipa()[1] for c in wl.ensemble.components)
-    ctx.upload(ps.id, ps.cid, ps.r, ps.v, ps.q if rot else None, ps.L if rot else None)
-    N = len(ps.id)
+    # the state the reference's CubicGridGenerator builds (what this workload's cpu_baseline and `--impl reference` start from),
+    # generated on the device; for the rotating models that state is an "explosion" by Domain's definition -- both sides then run
+    # through the same heuristics (Domain.cpp:259-314)
+    n = wl.n_per_dim
+    N = 2 * n ** 3; L = (N / wl.rho) ** (1.0 / 3.0)
+    ctx = capi.Context([0, 0, 0], [L, L, L], wl.rc, precision="mixed", geometry="xml", periodic=(1, 1, 1), device=local)
+    ctx.set_components(wl.ensemble)
+    assert ctx.generate_cubic_grid(n, [L, L, L], wl.temperature, seed=0, remove_momentum=True, reference_velocities=True) == N
     ctx.update(); ctx.traverse_cells()
     fc0 = ctx.count_flops()
-    ctx.simulate(warmup, wl.dt, wl.temperature, records=False)
+    rec_w = ctx.simulate(warmup, wl.dt, wl.temperature) if warmup else np.zeros((0, 8))
     ctx.phase_times(reset=True)
     import torch
     torch.cuda.synchronize()
@@ -333,7 +362,9 @@ def run_secondary(name, local, fp32_peak, capi, with_cpu=True, steps=10, warmup=
     out = {"workload": wl.description, "molecules": N, "steps": steps, "warmup": warmup, "MMUPS": round(N * steps / t / 1e6, 2), "ms_per_step": round(1e3 * t / steps, 4),
            "phases_ms_per_step": {k: round(v / steps, 4) for k, v in ph_ms.items()},
            "kernel_ms": round(force_ms, 4), "flops_per_molecule": round(flops / N, 1), "achieved_tflops": round(flops / (force_ms * 1e-3) / 1e12, 3),
-           "frac": round(flops / (force_ms * 1e-3) / 1e12 / fp32_peak, 4), "T_last": rec[-1, 4], "upot_last_per_molecule": rec[-1, 0] / N}
+           "frac": round(flops / (force_ms * 1e-3) / 1e12 / fp32_peak, 4), "T_last": rec[-1, 4], "upot_last_per_molecule": rec[-1, 0] / N,
+           "data": "the reference's CubicGridGenerator state, generated on the device",
+           "vs_reference_fixture": vs_reference_fixture(wl.name, "mixed", N, np.concatenate([rec_w, rec]))}
     ctx.close()
     if with_cpu:
         out["cpu_baseline"] = cpu_baseline(wl)
@@ -434,7 +465,7 @@ def our_arm(args):
     RHO, TEMP, RC, DT = wl.rho, wl.temperature, wl.rc, wl.dt
     n = args.n_per_dim or wl.n_per_dim
     rot = any(c.Ipa()[1] for c in wl.ensemble.components)
-    device_gen = not rot and not args.host_gen      # 1CLJ systems are generated ON the device (ls1b200_generate_cubic_grid): no host array of the system exists
+    device_gen = (not rot or world == 1) and not args.host_gen      # generated ON the device (ls1b200_generate_cubic_grid): no host array of the system exists (rotating models on several GPUs: host blocks)
     grid = grid_for(world)
     L1 = (2 * n ** 3 / RHO) ** (1.0 / 3.0)             # box of one block
     box = np.array([L1 * grid[0], L1 * grid[1], L1 * grid[2]])
@@ -608,22 +639,13 @@ def our_arm(args):
         if device_gen and world == 1:
             # `--impl reference` times K steps from the same generated state: its ResultWriter row K is this run's step K (warm-up included)
             series = np.concatenate([rec_w, rec]); ks = args.steps
-            line["trace"]["at_reference_step"] = {"at_step": ks, "T": series[ks - 1, 4], "upot_per_molecule": series[ks - 1, 0] / N_global, "p": series[ks - 1, 5],
+            line["trace"]["at_reference_step"] = {"at_step": ks, "ukin_per_molecule": 0.5 * (series[ks - 1, 2] + series[ks - 1, 3]) / N_global, "upot_per_molecule": series[ks - 1, 0] / N_global, "p": series[ks - 1, 5],
                                                   "note": "same initial state as the reference arm (its CubicGridGenerator sequence, generated on the device): compare with that line's trace"}
-            # ... and against the committed ResultWriter rows of the unmodified reference on this very configuration (16 M molecules, 100 steps,
-            # tests/golden/make_reference_trace_16m.py): largest relative deviation over the steps both cover
-            fx = os.path.join(ROOT, "tests", "golden", "reference_trace_lj16M.npz")
-            if wl.name == "lj" and args.precision == "mixed" and os.path.exists(fx):
-                g = np.load(fx)
-                if int(g["molecules"]) == N_global:
-                    ref = g["trace"]; m = min(len(series), len(ref) - 1)
-                    b = ref[1:m + 1]
-                    line["trace"]["vs_reference_fixture"] = {
-                        "steps_compared": m, "fixture": "tests/golden/reference_trace_lj16M.npz (unmodified reference binary, the same 16 M-molecule configuration)",
-                        "U_pot_rel_max": float(np.abs(series[:m, 0] - b[:, 2]).max() / np.abs(b[:, 2]).max()),
-                        "T_rel_max": float(np.abs(0.5 * (series[:m, 2] + series[:m, 3]) - b[:, 4]).max() / np.abs(b[:, 4]).max()),
-                        "p_rel_max": float(np.abs(series[:m, 5] - b[:, 6]).max() / np.abs(b[:, 6]).max()),
-                        "beta_trans_abs_max": float(np.abs(series[:m, 6] - b[:, 8]).max()), "tolerance": 1e-6}
+            # ... and against the committed ResultWriter rows of the unmodified reference on this very configuration (full size;
+            # tests/golden/make_reference_traces_full_size.py): largest relative deviation over the steps both cover
+            cmpf = vs_reference_fixture(wl.name, args.precision, N_global, series)
+            if cmpf is not None:
+                line["trace"]["vs_reference_fixture"] = cmpf
         if world == 1 and not args.no_cpu_baseline:
             cb = cpu_baseline(wl)
             if cb is not None:
