@@ -187,7 +187,15 @@ int ls1b200_selective_thermostat(ls1b200_ctx* ctx, double target_temperature);
  *   leapfrog_pre -> update -> traverse_cells -> leapfrog_post -> Domain::calculateGlobalValues -> thermostat.
  * Forces must be valid on entry (call ls1b200_update + ls1b200_traverse_cells once first, as
  * Simulation::prepare_start does, Simulation.cpp:896-928). records (may be NULL) receives n_steps entries.
- * global_n / global_volume: N and V of the whole system (for rho in p); pass 0 to use this context's own. */
+ * global_n / global_volume: N and V of the whole system (for rho in p); pass 0 to use this context's own.
+ * Domain::calculateGlobalValues is evaluated in full (Domain.cpp:232-314, :363-368), i.e. with its heuristic handling of an
+ * "explosion": while a velocity-scaling factor is below MIN_BETA = 0.9 and no error is pending, molecules above 10 T of
+ * translational (3 rotDOF T of rotational) kinetic energy are scaled down to that limit with their force (torque), beta_trans is
+ * reported and applied as 1 and beta_rot as its 0.0091-th power, and the warning / error counters run (a persistent or returning
+ * explosion ends the special handling). The first call after an upload evaluates the global values once on the state as it is,
+ * like Simulation::prepare_start (Simulation.cpp:986-992): no factor is applied there, but the heuristics start. The reference's
+ * own CubicGridGenerator starts every rotating model inside these heuristics (all thermal energy in the translation).
+ * (The reduced-memory loop, ls1b200_rmm_simulate, applies the plain factors only.) */
 int ls1b200_simulate(ls1b200_ctx* ctx, uint64_t n_steps, double dt, double target_temperature,
                      uint64_t global_n, double global_volume, ls1b200_step_record* records);
 
