@@ -302,7 +302,7 @@ def reference_arm(args):
 # ----------------------------------------------------------------------------------------------------------------------
 # dram__bytes_read.sum + dram__bytes_write.sum per launch of the force kernel, from the `ncu --set full` captures under profiles/
 # (keyed by workload, precision, molecules): reported, with its source, as roofline.traffic
-FORCE_TRAFFIC = {("lj", "mixed", 16000000): (279817216 + 728153088, "profiles/r02m_force_full.md (ncu --set full of this kernel at this size: dram__bytes_read.sum + dram__bytes_write.sum; algorithmic: 256 MB of calc records read + 768 MB of F, Vi written)")}
+FORCE_TRAFFIC = {("lj", "mixed", 16000000): (734425088 + 748010240, "profiles/r02w_force_full.md (ncu --set full of a launch inside the fused step at this size: dram__bytes_read.sum + dram__bytes_write.sum; algorithmic: 256 MB of calc records + 384 MB of velocities and 64 MB of the lazy permutation for the kinetic-sum epilogue read, 768 MB of F, Vi written; the stand-alone traversal reads 280 MB, profiles/r02m_force_full.md)")}
 
 
 REFERENCE_TRACES = {("lj", "mixed"): "reference_trace_lj16M.npz", ("lj", "double"): "reference_trace_lj16M_double.npz", ("argon", "mixed"): "reference_trace_argon_full.npz",
