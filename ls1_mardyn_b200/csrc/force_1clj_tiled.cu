@@ -252,7 +252,7 @@ __global__ void __launch_bounds__(TileCfg<C>::TPB, LS1_TILE_MINB) k_force_1clj_t
 		// one contiguous range of the row's window); every candidate is ONE LDS.128 that serves the reference's molecule-distance
 		// test (strict <, bit-identical to calcDistLookup; in my own row SingleCellPolicy_ additionally masks pairs at distance 0,
 		// i.e. the molecule itself) of all RI molecules of the thread (register blocking: shared-memory wavefronts per test
-		// halve, the kernel is shared-memory bound -- profiles/r01p_force_full.md). A hit appends the candidate's shared-memory
+		// halve, the kernel is shared-memory bound -- profiles/r01r_force_full.md). A hit appends the candidate's shared-memory
 		// ADDRESS (it fits 16 bits) to the molecule's list. When a list is nearly full, or after the last row, phase 2 evaluates
 		// the lists densely (LJ 12-6; FP32 partial sums folded into FP64 like RealAccumVec) and empties them.
 		V4 mi[RI]; uint32_t cid_i[RI];

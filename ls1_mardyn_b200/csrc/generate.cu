@@ -199,7 +199,8 @@ extern "C" int ls1b200_generate_cubic_grid(ls1b200_ctx* c, const uint64_t mols_p
 	cap = (cap + 63) & ~63ull;
 	LS1_TRY(ctx_alloc_molecules(c, n, cap));
 	c->rot_dof_total = (uint64_t) comp.rot_dof * n;
-	double* d_vtab = nullptr;
+	struct DevBuf { double* p = nullptr; ~DevBuf() { if (p) cudaFree(p); } } vtab_guard;      // freed on every way out
+	double*& d_vtab = vtab_guard.p;
 	if (ref_vel && n) {
 		// The reference's velocity sequence (ParticleCellBase.cpp:66-67, EqualVelocityAssigner.h:11-29): a fresh std::mt19937(0) per cell,
 		// phi and theta from two draws of std::uniform_real_distribution<double>(0, 1) per molecule; the ensemble's temperature passes
@@ -223,7 +224,7 @@ extern "C" int ls1b200_generate_cubic_grid(ls1b200_ctx* c, const uint64_t mols_p
 	}
 	if (n) {
 		const uint32_t g = (uint32_t) ((n + 255) / 256);
-		if ((uint64_t) g > c->partial_blocks) { cudaFree(d_vtab); return fail("ls1b200_generate_cubic_grid: partials buffer too small"); }
+		if ((uint64_t) g > c->partial_blocks) return fail("ls1b200_generate_cubic_grid: partials buffer too small");
 		k_generate<<<g, 256, 0, c->stream>>>(a, c->cur, c->d_id, cap, c->partials); g_launches++;
 		LS1_CUDA(cudaGetLastError());
 		if (c->rotates) {
@@ -240,7 +241,7 @@ extern "C" int ls1b200_generate_cubic_grid(ls1b200_ctx* c, const uint64_t mols_p
 			int rc = allreduce_doubles(c, dsum, 4);
 			double h[4] = {0., 0., 0., 1.};
 			if (rc == 0) { cudaMemcpyAsync(h, dsum, sizeof(h), cudaMemcpyDeviceToHost, c->stream); cudaStreamSynchronize(c->stream); }
-			if (rc) { cudaFree(dsum); cudaFree(d_vtab); return rc; }
+			if (rc) { cudaFree(dsum); return rc; }
 			k_gen_shift<<<g, 256, 0, c->stream>>>(c->cur, n, cap, h[0] / h[3], h[1] / h[3], h[2] / h[3], c->partials); g_launches++;
 			// "After subtraction, the temperature was effectively changed": the velocities are scaled to the target temperature again
 			// (IOHelpers.cpp:75-115; T_current = 2 sum(m v^2 / 2) / sum(3 + rotDOF) over all ranks; L = 0 on a fresh lattice)
@@ -249,13 +250,12 @@ extern "C" int ls1b200_generate_cubic_grid(ls1b200_ctx* c, const uint64_t mols_p
 			rc = allreduce_doubles(c, dsum, 4);
 			if (rc == 0) { cudaMemcpyAsync(h, dsum, sizeof(h), cudaMemcpyDeviceToHost, c->stream); cudaStreamSynchronize(c->stream); }
 			cudaFree(dsum);
-			if (rc) { cudaFree(d_vtab); return rc; }
+			if (rc) return rc;
 			const double t_current = comp.mass * h[0] / ((3.0 + (double) comp.rot_dof) * h[3]);
 			if (t_current > 0.) { k_gen_scale<<<g, 256, 0, c->stream>>>(c->cur, n, cap, std::sqrt(temperature / t_current)); g_launches++; }
 		}
 		LS1_CUDA(cudaStreamSynchronize(c->stream));
 	}
-	if (d_vtab) cudaFree(d_vtab);
 	c->n_owned_local = n; c->rot_dof_local = c->rot_dof_total; c->dd.rot_dof_valid = false;
 	c->parity = 0; c->n_slots = (uint32_t) n;
 	c->h_scal->n_slots2[0] = (uint32_t) n; c->h_scal->n_slots2[1] = 0; c->h_scal->overflow = 0;
